@@ -1,0 +1,95 @@
+"""TEST INFRASTRUCTURE ONLY -- generates tests/golden/*.npz from the UNMODIFIED reference modules.
+
+Run in the build container (needs /root/reference):   python -m oracle.make_golden
+The fixtures hold only reference OUTPUTS; weights and inputs are regenerated from seeds by
+oracle.decoder_ref.seeded_params / seeded_inputs (no reference needed), so the fixtures stay small.
+"""
+import os
+
+import numpy as np
+import torch
+
+from . import decoder_ref as O
+from . import ref_shim as R
+
+GOLDEN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+# (name, kind, T, Hp, Wp, Q, param seed, input seed)
+DECODER_CASES = [
+    ("dec_frame_q100", "frame", 2, 64, 64, 100, 0, 1234),
+    ("dec_video_q100", "video", 3, 64, 96, 100, 1, 1235),
+    ("dec_san_frame_q100", "san_frame", 2, 64, 64, 100, 2, 1236),
+    ("dec_san_video_q100", "san_video", 2, 64, 64, 100, 3, 1237),
+    ("dec_frame_q200", "frame", 1, 96, 64, 200, 4, 1238),
+]
+
+
+def _ref_decoder(kind, Q):
+    d = R.decoders()
+    cls = {"frame": d.FrameMultiScaleMaskedTransformerDecoder,
+           "video": d.VideoMultiScaleMaskedTransformerDecoder,
+           "san_frame": d.SideAdapterFrameMultiScaleMaskedTransformerDecoder,
+           "san_video": d.SideAdapterVideoMultiScaleMaskedTransformerDecoder}[kind]
+    kw = R.decoder_kwargs(num_queries=Q)
+    if kind.startswith("san"):
+        kw["clip_heads"] = 12
+    return cls(**kw).eval()
+
+
+def run_reference_decoder(kind, T, Hp, Wp, Q, pseed, iseed):
+    m = _ref_decoder(kind, Q)
+    P = O.seeded_params(O.decoder_param_shapes(kind, Q=Q), pseed)
+    m.load_state_dict(P)
+    x, mf = O.seeded_inputs(T, Hp, Wp, seed=iseed)
+    with torch.no_grad():
+        return m(x, mf)
+
+
+def make_decoder_fixture(name, kind, T, Hp, Wp, Q, pseed, iseed):
+    out = run_reference_decoder(kind, T, Hp, Wp, Q, pseed, iseed)
+    rec = {"meta": np.array([T, Hp, Wp, Q, pseed, iseed])}
+    for k in ("pred_logits", "pred_masks", "pred_embeds", "class_attn_biases"):
+        if k in out:
+            rec[k] = out[k].numpy()
+    for i in (0, 4, 8):
+        a = out["aux_outputs"][i]
+        rec[f"aux{i}_pred_masks"] = a["pred_masks"].numpy().astype(np.float16)
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **rec)
+    print("wrote", name, {k: v.shape for k, v in rec.items()})
+
+
+def make_san_tail_fixture():
+    """SideAdapter._build_attn_biases + post_encode_image tail + cal_sim_logits on seeded inputs
+    (side_adapter.py:201-207, 234-270).  The three CLIP blocks in between are out of scope, so the tail
+    is exercised on a synthetic SOS-token tensor."""
+    s = R.side_adapter_module()
+    torch.manual_seed(3)
+    sa = s.SideAdapter(num_queries=7).eval()
+    g = torch.Generator().manual_seed(77)
+    bias = torch.randn(2, 12, 7, 24, 40, generator=g)
+    full = sa._build_attn_biases([bias], sa.num_heads, 3, target_shape=(14, 14))[0]
+    sos = torch.randn(2, 7, 768, generator=g)
+    text = torch.nn.functional.normalize(torch.randn(41, 512, generator=g), dim=-1)
+    cm = sa.clip_model
+    with torch.no_grad():
+        # the same three statements as side_adapter.py:203-205, on the reference's own parameters
+        f = torch.nn.functional.normalize(cm.visual.ln_post(sos) @ cm.visual.proj, dim=-1)
+        logits = sa.cal_sim_logits(text, f)
+    rec = dict(pooled=full[:, :7, -196:].numpy(), corner=full[0, :9, :9].numpy(),
+               row_last=full[0, -1].numpy(), clip_feats=f.numpy(), logits=logits.numpy(),
+               ln_w=cm.visual.ln_post.weight.detach().numpy(), ln_b=cm.visual.ln_post.bias.detach().numpy(),
+               proj=cm.visual.proj.detach().numpy().astype(np.float32),
+               logit_scale_exp=np.array(cm.logit_scale.exp().item()))
+    np.savez_compressed(os.path.join(GOLDEN, "san_tail.npz"), **rec)
+    print("wrote san_tail", {k: v.shape for k, v in rec.items()})
+
+
+def main():
+    os.makedirs(GOLDEN, exist_ok=True)
+    for case in DECODER_CASES:
+        make_decoder_fixture(*case)
+    make_san_tail_fixture()
+
+
+if __name__ == "__main__":
+    main()

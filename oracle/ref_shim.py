@@ -1,0 +1,164 @@
+"""TEST INFRASTRUCTURE ONLY -- loads the *unmodified* reference modules from /root/reference.
+
+This file never ships with the product path.  It exists so that, in the build container (where
+``/root/reference`` is mounted read-only), the CPU restatement in ``oracle/decoder_ref.py`` can be
+pinned against the reference's own PyTorch code and so that ``oracle/make_golden.py`` can generate the
+committed fixtures under ``tests/golden/``.  On the GPU box ``/root/reference`` does not exist and
+``available()`` returns False; nothing in ``-m gpu`` tests, ``smoke()`` or ``bench.py`` calls this.
+
+The reference decoder files import four names from packages that are not installed here
+(``detectron2.config.configurable``, ``detectron2.layers.Conv2d``, ``detectron2.utils.registry.Registry``,
+``fvcore.nn.weight_init.c2_xavier_fill``; video_mask2former_transformer_decoder.py:4,10-12).  They are
+stubbed in ``sys.modules``; the reference sources are loaded by path and are
+never copied into this repository.
+"""
+import importlib.util
+import os
+import sys
+import types
+
+import torch
+
+REF_ROOT = os.environ.get("OPENVIS_REFERENCE", "/root/reference")
+_DEC_DIR = os.path.join(REF_ROOT, "openvis/modeling/transformer_decoder")
+_CLIP_DIR = os.path.join(REF_ROOT, "openvis/modeling/clip_adapter")
+_MACLIP = os.path.join(REF_ROOT, "third_parties/mask_adapted_clip/mask_adapted_clip/model.py")
+
+_loaded = {}
+
+
+def available() -> bool:
+    return os.path.isfile(os.path.join(_DEC_DIR, "video_mask2former_transformer_decoder.py"))
+
+
+def _mod(name, **kw):
+    m = sys.modules.get(name)
+    if m is None:
+        m = types.ModuleType(name)
+        sys.modules[name] = m
+    m.__dict__.update(kw)
+    return m
+
+
+class _Registry(dict):
+    """Stand-in for detectron2.utils.registry.Registry (dict with a .register decorator)."""
+
+    def __init__(self, name):
+        super().__init__()
+        self.name = name
+
+    def register(self, obj=None):
+        def deco(o):
+            self[o.__name__] = o
+            return o
+
+        return deco if obj is None else deco(obj)
+
+
+def _c2_xavier_fill(m):
+    torch.nn.init.kaiming_uniform_(m.weight, a=1)
+    if m.bias is not None:
+        torch.nn.init.constant_(m.bias, 0)
+
+
+def _install_stubs():
+    if "detectron2" in sys.modules and not getattr(sys.modules["detectron2"], "_ovis_stub", False):
+        return  # a real detectron2 is importable: leave it alone
+    _mod("detectron2", _ovis_stub=True)
+    _mod("detectron2.config", configurable=lambda f=None, **k: f)
+    _mod("detectron2.layers", Conv2d=torch.nn.Conv2d)
+    _mod("detectron2.utils")
+    _mod("detectron2.utils.registry", Registry=_Registry)
+    _mod("detectron2.utils.comm", get_local_rank=lambda: 0, synchronize=lambda: None)
+    _mod("fvcore")
+    _mod("fvcore.nn")
+    _mod("fvcore.nn.weight_init", c2_xavier_fill=_c2_xavier_fill)
+
+
+def _load(pkg_name, pkg_dir, name):
+    full = f"{pkg_name}.{name}"
+    if full in sys.modules:
+        return sys.modules[full]
+    spec = importlib.util.spec_from_file_location(full, os.path.join(pkg_dir, name + ".py"))
+    m = importlib.util.module_from_spec(spec)
+    sys.modules[full] = m
+    spec.loader.exec_module(m)
+    return m
+
+
+def decoders():
+    """Returns a namespace with the reference decoder classes (unmodified)."""
+    if "dec" in _loaded:
+        return _loaded["dec"]
+    if not available():
+        raise RuntimeError(f"reference not found under {REF_ROOT}")
+    _install_stubs()
+    pkg = _mod("refdec")
+    pkg.__path__ = [_DEC_DIR]
+    pe = _load("refdec", _DEC_DIR, "position_encoding")
+    v = _load("refdec", _DEC_DIR, "video_mask2former_transformer_decoder")
+    f = _load("refdec", _DEC_DIR, "frame_mask2former_transformer_decoder")
+    sf = _load("refdec", _DEC_DIR, "side_adapter_frame_mask2former_transformer_decoder")
+    sv = _load("refdec", _DEC_DIR, "side_adapter_video_mask2former_transformer_decoder")
+    ns = types.SimpleNamespace(
+        position_encoding=pe,
+        video=v,
+        frame=f,
+        san_frame=sf,
+        san_video=sv,
+        VideoMultiScaleMaskedTransformerDecoder=v.VideoMultiScaleMaskedTransformerDecoder,
+        FrameMultiScaleMaskedTransformerDecoder=f.FrameMultiScaleMaskedTransformerDecoder,
+        SideAdapterFrameMultiScaleMaskedTransformerDecoder=sf.SideAdapterFrameMultiScaleMaskedTransformerDecoder,
+        SideAdapterVideoMultiScaleMaskedTransformerDecoder=sv.SideAdapterVideoMultiScaleMaskedTransformerDecoder,
+    )
+    _loaded["dec"] = ns
+    return ns
+
+
+def decoder_kwargs(num_queries=100, hidden_dim=256, nheads=8, dim_feedforward=2048, dec_layers=9,
+                   num_classes=1, mask_dim=None, num_frames=2):
+    return dict(in_channels=hidden_dim, mask_classification=True, num_classes=num_classes,
+                hidden_dim=hidden_dim, num_queries=num_queries, nheads=nheads,
+                dim_feedforward=dim_feedforward, dec_layers=dec_layers, pre_norm=False,
+                mask_dim=hidden_dim if mask_dim is None else mask_dim,
+                enforce_input_project=False, num_frames=num_frames)
+
+
+def side_adapter_module():
+    """Reference ``SideAdapter`` with the vendored mask_adapted_clip model standing in for OpenAI clip
+    (SURVEY.md Appendix A).  ``build_clip_model`` is replaced by a seeded random-init ViT-B/16 CLIP."""
+    if "san" in _loaded:
+        return _loaded["san"]
+    if not available():
+        raise RuntimeError(f"reference not found under {REF_ROOT}")
+    _install_stubs()
+    spec = importlib.util.spec_from_file_location("mask_adapted_clip.model", _MACLIP)
+    clip_model = importlib.util.module_from_spec(spec)
+    pkg = _mod("mask_adapted_clip")
+    pkg.__path__ = [os.path.dirname(_MACLIP)]
+    sys.modules["mask_adapted_clip.model"] = clip_model
+    spec.loader.exec_module(clip_model)
+    pkg.model = clip_model
+
+    def _no_tokenizer(*a, **k):
+        raise RuntimeError("clip.tokenize unavailable offline (ftfy missing); pass a text matrix")
+
+    _mod("clip", model=clip_model, tokenize=_no_tokenizer)
+    sys.modules["clip.model"] = clip_model
+    cpkg = _mod("refclip")
+    cpkg.__path__ = [_CLIP_DIR]
+    utils = _load("refclip", _CLIP_DIR, "utils")
+    sa = _load("refclip", _CLIP_DIR, "side_adapter")
+
+    def build_clip_model(*_a, **_k):
+        g = torch.random.get_rng_state()
+        torch.manual_seed(5)
+        m = clip_model.CLIP(512, 224, 12, 768, 16, 0, 77, 49408, 512, 8, 12).float().eval()
+        torch.random.set_rng_state(g)
+        return m
+
+    sa.build_clip_model = build_clip_model
+    utils.build_clip_model = build_clip_model
+    ns = types.SimpleNamespace(module=sa, SideAdapter=sa.SideAdapter, clip_model=clip_model)
+    _loaded["san"] = ns
+    return ns

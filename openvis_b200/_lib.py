@@ -1,0 +1,247 @@
+"""ctypes binding of the C-ABI library (include/openvis_b200.h) + thin torch-tensor wrappers.
+
+There is NO fallback: if the shared library is missing or the device is not sm_100, calls raise.
+PyTorch is used only for device memory (tensors) and the current CUDA stream.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libopenvis_b200.so")
+
+_c_int, _c_ll, _c_float, _vp = ctypes.c_int, ctypes.c_longlong, ctypes.c_float, ctypes.c_void_p
+
+# name -> (restype, argtypes); must list every symbol declared in include/openvis_b200.h
+SIGNATURES = {
+    "ovis_version": (_c_int, []),
+    "ovis_last_error": (ctypes.c_char_p, []),
+    "ovis_device_check": (_c_int, []),
+    "ovis_launch_count": (_c_ll, []),
+    "ovis_nchw_to_tokens_f16": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _vp]),
+    "ovis_maskfeat_prep": (_c_int, [_vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _vp]),
+    "ovis_cast_f16": (_c_int, [_vp, _vp, _c_ll, _vp]),
+    "ovis_init_queries": (_c_int, [_vp] * 9 + [_c_int, _c_int, _vp]),
+    "ovis_rownorm": (_c_int, [_vp] * 5 + [_c_int, _c_int, _c_int, _vp]),
+    "ovis_linear_f16": (_c_int, [_vp, _c_ll, _c_int, _c_int, _vp, _c_int, _vp, _c_float, _c_int, _vp, _c_int, _c_int, _vp]),
+    "ovis_linear_ln_f16": (_c_int, [_vp, _c_ll, _c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _c_int,
+                                    _vp, _vp, _vp, _vp, _vp, _vp]),
+    "ovis_kv_proj_f16": (_c_int, [_vp, _c_int, _c_int, _vp, _c_int, _vp, _vp, _vp, _vp, _c_int, _vp]),
+    "ovis_mask_bits": (_c_int, [_vp, _c_int, _c_int, _vp, _c_int, _vp, _vp, _c_int, _vp]),
+    "ovis_mask_logits": (_c_int, [_vp, _c_int, _c_int, _vp, _c_int, _c_int, _vp, _vp, _c_ll, _c_ll, _vp]),
+    "ovis_san_bias_logits": (_c_int, [_vp, _c_int, _c_int, _c_int, _vp, _c_int, _vp, _vp]),
+    "ovis_xattn_plan": (_c_int, [_c_int, _c_int, _c_int, ctypes.POINTER(_c_int), ctypes.POINTER(_c_int),
+                                 ctypes.POINTER(_c_ll), ctypes.POINTER(_c_ll)]),
+    "ovis_xattn": (_c_int, [_vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp]),
+    "ovis_self_attn": (_c_int, [_vp, _vp, _vp, _c_int, _c_int, _vp]),
+    "ovis_clip_aggregate": (_c_int, [_vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _vp]),
+    "ovis_san_attn_bias": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _vp]),
+}
+
+_lib = None
+
+
+def load():
+    """Loads libopenvis_b200.so (built in-tree by `python -m openvis_b200.build`)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: the CUDA extension must be built (python -m openvis_b200.build); "
+            "openvis_b200 has no CPU / PyTorch fallback path")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError here = header / library mismatch
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+class OvisError(RuntimeError):
+    pass
+
+
+def _check(rc):
+    if rc != 0:
+        raise OvisError(f"openvis_b200 error {rc}: {_lib.ovis_last_error().decode()}")
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _req(t, dtype, name):
+    if t is None:
+        return
+    if not t.is_cuda:
+        raise OvisError(f"{name}: expected a CUDA tensor (no CPU path)")
+    if t.dtype != dtype:
+        raise OvisError(f"{name}: expected {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise OvisError(f"{name}: expected a contiguous tensor")
+
+
+def launch_count():
+    return load().ovis_launch_count()
+
+
+def device_check():
+    _check(load().ovis_device_check())
+
+
+# ------------------------------------------------------------------------------------------ wrappers
+def nchw_to_tokens_f16(x, out=None):
+    """[B, C, h, w] fp32 -> [B, h*w, C] fp16."""
+    lib = load()
+    _req(x, torch.float32, "x")
+    B, C = x.shape[:2]
+    N = x[0, 0].numel()
+    if out is None:
+        out = torch.empty(B, N, C, dtype=torch.float16, device=x.device)
+    _check(lib.ovis_nchw_to_tokens_f16(_p(x), _p(out), B, C, N, _stream()))
+    return out
+
+
+def maskfeat_prep(F, outs=None):
+    """mask_features [B, C, H, W] fp32 -> (ft [B,HW,C], g0 [B,HW/64,C], g1 [B,HW/16,C], g2 [B,HW/4,C]) fp16."""
+    lib = load()
+    _req(F, torch.float32, "mask_features")
+    B, C, H, W = F.shape
+    if outs is None:
+        mk = lambda n: torch.empty(B, n, C, dtype=torch.float16, device=F.device)
+        outs = (mk(H * W), mk((H // 8) * (W // 8)), mk((H // 4) * (W // 4)), mk((H // 2) * (W // 2)))
+    ft, g0, g1, g2 = outs
+    _check(lib.ovis_maskfeat_prep(_p(F), _p(ft), _p(g0), _p(g1), _p(g2), B, C, H, W, _stream()))
+    return outs
+
+
+def cast_f16(x, out=None):
+    lib = load()
+    _req(x, torch.float32, "x")
+    if out is None:
+        out = torch.empty(x.shape, dtype=torch.float16, device=x.device)
+    _check(lib.ovis_cast_f16(_p(x), _p(out), x.numel(), _stream()))
+    return out
+
+
+def init_queries(query_feat, query_embed, dn_g, dn_b, G, outs):
+    lib = load()
+    Q = query_feat.shape[0]
+    z32, z16, ze16, d32, d16 = outs
+    _check(lib.ovis_init_queries(_p(query_feat), _p(query_embed), _p(dn_g), _p(dn_b), _p(z32), _p(z16), _p(ze16),
+                                 _p(d32), _p(d16), Q, G * Q, _stream()))
+
+
+def rownorm(x, g=None, b=None, layer_norm=False, l2=False, want32=True, want16=True):
+    lib = load()
+    _req(x, torch.float32, "x")
+    rows, D = x.shape
+    o32 = torch.empty_like(x) if want32 else None
+    o16 = torch.empty(rows, D, dtype=torch.float16, device=x.device) if want16 else None
+    mode = (1 if layer_norm else 0) | (2 if l2 else 0)
+    _check(lib.ovis_rownorm(_p(x), _p(g), _p(b), _p(o32), _p(o16), rows, D, mode, _stream()))
+    return o32, o16
+
+
+def linear_f16(x, w, bias=None, scale=1.0, relu=False, out=None, out_f32=False):
+    """x [rows, K] fp16 (row stride may exceed K), w [N, K] fp16 -> [rows, N] fp16 / fp32."""
+    lib = load()
+    assert x.dtype == torch.float16 and w.dtype == torch.float16 and x.stride(-1) == 1 and w.is_contiguous()
+    rows, K = x.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty(rows, N, dtype=torch.float32 if out_f32 else torch.float16, device=x.device)
+    _check(lib.ovis_linear_f16(_p(x), rows, K, x.stride(0), _p(w), N, _p(bias), float(scale), int(relu), _p(out),
+                               out.stride(0), int(out_f32), _stream()))
+    return out
+
+
+def linear_ln_f16(x, w, bias, resid, ln1, ln2=None, pe=None, y32=None, y16=None, ype16=None, d32=None, d16=None):
+    lib = load()
+    rows, K = x.shape
+    _check(lib.ovis_linear_ln_f16(_p(x), rows, K, _p(w), _p(bias), _p(resid), _p(ln1[0]), _p(ln1[1]),
+                                  _p(ln2[0]) if ln2 else None, _p(ln2[1]) if ln2 else None,
+                                  _p(pe), pe.shape[0] if pe is not None else 0,
+                                  _p(y32), _p(y16), _p(ype16), _p(d32), _p(d16), _stream()))
+
+
+def _ptr_array(tensors):
+    arr = (ctypes.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = _p(t)
+    return arr
+
+
+def kv_proj_f16(xt, groups, rows_per_group, w, outs, biases=None, tabs=None, tabs2=None, tab_period=1):
+    """xt [groups*rows_per_group, 256] fp16; w [n_tiles*256, 256] fp16; outs: n_tiles tensors [rows, 256] fp16."""
+    lib = load()
+    n_tiles = len(outs)
+    none = [None] * n_tiles
+    _check(lib.ovis_kv_proj_f16(_p(xt), groups, rows_per_group, _p(w), n_tiles, _ptr_array(outs),
+                                _ptr_array(biases or none), _ptr_array(tabs or none), _ptr_array(tabs2 or none),
+                                tab_period, _stream()))
+
+
+def mask_bits(gt, groups, rows_per_group, me, Q, bits, flags, q_stride):
+    lib = load()
+    _check(lib.ovis_mask_bits(_p(gt), groups, rows_per_group, _p(me), Q, _p(bits), _p(flags), q_stride, _stream()))
+
+
+def mask_logits(ft, groups, rows_per_group, me, me_group_stride, Q, out, t_group_stride, ldt, bias=None):
+    lib = load()
+    _check(lib.ovis_mask_logits(_p(ft), groups, rows_per_group, _p(me), me_group_stride, Q, _p(bias), _p(out),
+                                t_group_stride, ldt, _stream()))
+
+
+def san_bias_logits(af, B, P, heads, ae, Q, out):
+    lib = load()
+    _check(lib.ovis_san_bias_logits(_p(af), B, P, heads, _p(ae), Q, _p(out), _stream()))
+
+
+def xattn_plan(G, Q, keys):
+    lib = load()
+    s, qp, o, ml = _c_int(), _c_int(), _c_ll(), _c_ll()
+    _check(lib.ovis_xattn_plan(G, Q, keys, ctypes.byref(s), ctypes.byref(qp), ctypes.byref(o), ctypes.byref(ml)))
+    return s.value, qp.value, o.value, ml.value
+
+
+def xattn(q, k, v, bits, flags, G, Q, q_stride, keys, splits, o_part, ml_part, out):
+    lib = load()
+    _check(lib.ovis_xattn(_p(q), _p(k), _p(v), _p(bits), _p(flags), G, Q, q_stride, keys, splits, _p(o_part),
+                          _p(ml_part), _p(out), _stream()))
+
+
+def self_attn(qk, v, out, G, Q):
+    lib = load()
+    _check(lib.ovis_self_attn(_p(qk), _p(v), _p(out), G, Q, _stream()))
+
+
+def clip_aggregate(logits, valid):
+    """logits [T, Q, K] fp32, valid [T, Q] bool/uint8 -> (probs [Q, K], qvalid [Q] bool)."""
+    lib = load()
+    _req(logits, torch.float32, "logits")
+    T, Q, K = logits.shape
+    valid = valid.to(torch.uint8).contiguous()
+    probs = torch.empty(Q, K, dtype=torch.float32, device=logits.device)
+    qv = torch.empty(Q, dtype=torch.uint8, device=logits.device)
+    _check(lib.ovis_clip_aggregate(_p(logits), _p(valid), _p(probs), _p(qv), T, Q, K, _stream()))
+    return probs, qv.bool()
+
+
+def san_attn_bias(bias, grid_hw):
+    """bias [B, n, Q, h, w] fp32 -> [B*n, Q+1+L, Q+1+L] fp32."""
+    lib = load()
+    _req(bias, torch.float32, "bias")
+    B, n, Q, h, w = bias.shape
+    gh, gw = grid_hw
+    L = gh * gw
+    out = torch.empty(B * n, Q + 1 + L, Q + 1 + L, dtype=torch.float32, device=bias.device)
+    _check(lib.ovis_san_attn_bias(_p(bias), _p(out), B * n, Q, h, w, gh, gw, _stream()))
+    return out

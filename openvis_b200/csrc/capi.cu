@@ -1,0 +1,424 @@
+// C-ABI implementation (include/openvis_b200.h): argument checks, TMA tensor-map encoding, launches.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+#include <mutex>
+
+#include "../../include/openvis_b200.h"
+#include "gemm_tn.cuh"
+#include "prep.cuh"
+#include "xattn.cuh"
+
+using namespace ovis;
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const char* fmt, const char* a = "", long long b = 0, long long c = 0) {
+  snprintf(g_err, sizeof(g_err), fmt, a, b, c);
+  return code;
+}
+#define CHECK_ARG(cond, msg)                                      \
+  do {                                                            \
+    if (!(cond)) return fail(OVIS_ERR_ARG, "%s: " msg, __func__); \
+  } while (0)
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    snprintf(g_err, sizeof(g_err), "%s: launch failed: %s", what, cudaGetErrorString(e));
+    return OVIS_ERR_CUDA;
+  }
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return OVIS_OK;
+}
+
+struct DeviceInfo {
+  int ok = -1;      // -1 unknown, 0 good, else error code
+  int sms = 0;
+};
+DeviceInfo g_dev[64];
+std::mutex g_mu;
+
+int device_info(int* sms) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(OVIS_ERR_ARCH, "%s: no CUDA device", "ovis");
+  }
+  if (dev < 0 || dev >= 64) return fail(OVIS_ERR_ARCH, "%s: device index out of range", "ovis");
+  std::lock_guard<std::mutex> lk(g_mu);
+  DeviceInfo& d = g_dev[dev];
+  if (d.ok < 0) {
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) {
+      cudaGetLastError();
+      return fail(OVIS_ERR_ARCH, "%s: cannot query device", "ovis");
+    }
+    d.sms = p.multiProcessorCount;
+    d.ok = (p.major == 10) ? 0 : OVIS_ERR_ARCH;
+  }
+  if (d.ok != 0) return fail(OVIS_ERR_ARCH, "%s: kernels are built for sm_100a (B200) only; no fallback path", "ovis");
+  if (sms) *sms = d.sms;
+  return OVIS_OK;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+
+int get_encoder() {
+  if (g_encode) return OVIS_OK;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+  if (e != cudaSuccess || fn == nullptr || q != cudaDriverEntryPointSuccess) {
+    cudaGetLastError();
+    return fail(OVIS_ERR_CUDA, "%s: cuTensorMapEncodeTiled not available from the driver", "ovis");
+  }
+  g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  return OVIS_OK;
+}
+
+// fp16 row-major [rows][cols] (row stride ld elements) -> box {64 cols, box_rows}, 128B swizzle, zero OOB fill
+int make_map_f16(CUtensorMap* m, const void* base, unsigned long long rows, unsigned long long cols, unsigned long long ld,
+                 unsigned box_rows) {
+  int rc = get_encoder();
+  if (rc) return rc;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld * 2) % 16) return fail(OVIS_ERR_ARG, "%s: operand must be 16-byte aligned with a 16-byte-multiple row pitch", "tensor map");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(OVIS_ERR_CUDA, "%s: cuTensorMapEncodeTiled failed (%lld)", "tensor map", (long long)r);
+  return OVIS_OK;
+}
+
+void init_args(GemmArgs& a) {
+  memset(&a, 0, sizeof(a));
+  a.num_groups = 1;
+  a.a_k_mod = 1;
+  a.a_row_div = 1;
+  a.b_row_div = 1;
+  a.scale = 1.f;
+  a.tab_period = 1;
+  a.pe_period = 1;
+}
+
+template <int BN>
+int launch_gemm_bn(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a, int sms, cudaStream_t st) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr_done[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_done[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      snprintf(g_err, sizeof(g_err), "gemm: cudaFuncSetAttribute(smem) failed: %s", cudaGetErrorString(e));
+      return OVIS_ERR_CUDA;
+    }
+    attr_done[dev] = true;
+  }
+  const int m_tiles = (a.rows_per_group + 127) / 128;
+  const int n_tiles = (a.N + BN - 1) / BN;
+  const long long total = (long long)a.num_groups * m_tiles * n_tiles;
+  if (total <= 0) return OVIS_OK;
+  const int grid = (int)(total < sms ? total : sms);
+  gemm_tn_kernel<BN><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, a);
+  return check_launch("gemm_tn_kernel");
+}
+
+// A: [a_rows][a_cols] fp16 pitch lda; B: [b_rows][K] fp16 pitch ldb.
+int launch_gemm(const void* A, long long a_rows, long long a_cols, long long lda, const void* B, long long b_rows,
+                long long ldb, const GemmArgs& a, int bn, cudaStream_t st) {
+  int sms = 0;
+  int rc = device_info(&sms);
+  if (rc) return rc;
+  if (a.K <= 0 || a.K % 64) return fail(OVIS_ERR_ARG, "%s: K must be a positive multiple of 64", "gemm");
+  if ((a.N + bn - 1) / bn > GEMM_MAX_NTILES) return fail(OVIS_ERR_ARG, "%s: too many column tiles", "gemm");
+  CUtensorMap ta, tb;
+  rc = make_map_f16(&ta, A, a_rows, a_cols, lda, 128);
+  if (rc) return rc;
+  rc = make_map_f16(&tb, B, b_rows, a.K, ldb, bn);
+  if (rc) return rc;
+  return bn == 256 ? launch_gemm_bn<256>(ta, tb, a, sms, st) : launch_gemm_bn<128>(ta, tb, a, sms, st);
+}
+
+}  // namespace
+
+extern "C" {
+
+int ovis_version(void) { return 100; }
+const char* ovis_last_error(void) { return g_err; }
+int ovis_device_check(void) { return device_info(nullptr); }
+long long ovis_launch_count(void) { return g_launches.load(); }
+
+int ovis_nchw_to_tokens_f16(const float* in, void* out, int B, int C, int N, void* stream) {
+  CHECK_ARG(in && out && B > 0 && C > 0 && N > 0 && C % 2 == 0, "bad arguments");
+  int rc = device_info(nullptr);
+  if (rc) return rc;
+  dim3 grid((N + 63) / 64, (C + 63) / 64, B);
+  nchw_to_tokens_f16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, (__half*)out, C, N);
+  return check_launch("nchw_to_tokens_f16_kernel");
+}
+
+int ovis_maskfeat_prep(const float* F, void* ft, void* g0, void* g1, void* g2, int B, int C, int H, int W, void* stream) {
+  CHECK_ARG(F && ft && g0 && g1 && g2, "null pointer");
+  CHECK_ARG(B > 0 && C % 32 == 0 && H % 8 == 0 && W % 8 == 0 && H > 0 && W > 0, "needs C % 32 == 0, H % 8 == 0, W % 8 == 0");
+  int rc = device_info(nullptr);
+  if (rc) return rc;
+  dim3 grid(((W + 31) / 32) * (H / 8), C / 32, B);
+  maskfeat_prep_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(F, (__half*)ft, (__half*)g0, (__half*)g1, (__half*)g2, C, H, W);
+  return check_launch("maskfeat_prep_kernel");
+}
+
+int ovis_cast_f16(const float* in, void* out, long long n, void* stream) {
+  CHECK_ARG(in && out && n >= 0, "bad arguments");
+  int rc = device_info(nullptr);
+  if (rc) return rc;
+  if (n == 0) return OVIS_OK;
+  cast_f16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(in, (__half*)out, n);
+  return check_launch("cast_f16_kernel");
+}
+
+int ovis_init_queries(const float* qf, const float* qe, const float* g, const float* b, float* z32, void* z16, void* ze16,
+                      float* d32, void* d16, int Q, int rows, void* stream) {
+  CHECK_ARG(qf && qe && g && b && z32 && z16 && ze16 && d32 && d16 && Q > 0 && rows > 0, "bad arguments");
+  int rc = device_info(nullptr);
+  if (rc) return rc;
+  init_queries_kernel<<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(qf, qe, g, b, z32, (__half*)z16, (__half*)ze16, d32,
+                                                                        (__half*)d16, Q, rows);
+  return check_launch("init_queries_kernel");
+}
+
+int ovis_rownorm(const float* in, const float* g, const float* b, float* out32, void* out16, int rows, int D, int mode,
+                 void* stream) {
+  CHECK_ARG(in && rows > 0 && D > 0 && (out32 || out16), "bad arguments");
+  CHECK_ARG(!(mode & 1) || (g && b), "LayerNorm needs weight and bias");
+  int rc = device_info(nullptr);
+  if (rc) return rc;
+  rownorm_kernel<<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(in, g, b, out32, (__half*)out16, rows, D, mode);
+  return check_launch("rownorm_kernel");
+}
+
+int ovis_linear_f16(const void* x, long long rows, int K, int ldx, const void* w, int N, const float* bias, float scale,
+                    int relu, void* out, int ldo, int out_f32, void* stream) {
+  CHECK_ARG(x && w && out && rows > 0 && N > 0 && ldx >= K && ldo >= N, "bad arguments");
+  CHECK_ARG(rows < (1ll << 31), "too many rows");
+  GemmArgs a;
+  init_args(a);
+  a.rows_per_group = (int)rows;
+  a.a_group_stride = (int)rows;
+  a.N = N;
+  a.K = K;
+  a.epi = EPI_STORE;
+  const int bn = (N <= 128) ? 128 : 256;
+  const int nt = (N + bn - 1) / bn;
+  CHECK_ARG(nt <= GEMM_MAX_NTILES, "N too large");
+  for (int t = 0; t < nt; ++t) {
+    a.out[t] = out_f32 ? (void*)((float*)out + (long long)t * bn) : (void*)((__half*)out + (long long)t * bn);
+    a.bias[t] = bias ? bias + (long long)t * bn : nullptr;
+  }
+  a.ldo = ldo;
+  a.out_f32 = out_f32;
+  a.relu = relu;
+  a.scale = scale;
+  return launch_gemm(x, rows, K, ldx, w, N, K, a, bn, (cudaStream_t)stream);
+}
+
+int ovis_linear_ln_f16(const void* x, long long rows, int K, const void* w, const float* bias, const float* resid,
+                       const float* ln1_g, const float* ln1_b, const float* ln2_g, const float* ln2_b, const float* pe,
+                       int pe_period, float* y32, void* y16, void* ype16, float* d32, void* d16, void* stream) {
+  CHECK_ARG(x && w && bias && resid && ln1_g && ln1_b && rows > 0, "bad arguments");
+  CHECK_ARG((ln2_g == nullptr) == (ln2_b == nullptr), "second LayerNorm needs both weight and bias");
+  CHECK_ARG(!ype16 || (pe && pe_period > 0), "ype16 needs pe");
+  CHECK_ARG(rows < (1ll << 31), "too many rows");
+  GemmArgs a;
+  init_args(a);
+  a.rows_per_group = (int)rows;
+  a.a_group_stride = (int)rows;
+  a.N = 256;
+  a.K = K;
+  a.epi = EPI_LN;
+  a.bias[0] = bias;
+  a.resid = resid;
+  a.ln1_g = ln1_g; a.ln1_b = ln1_b; a.ln2_g = ln2_g; a.ln2_b = ln2_b;
+  a.pe = pe; a.pe_period = pe_period > 0 ? pe_period : 1;
+  a.y32 = y32; a.y16 = (__half*)y16; a.ype16 = (__half*)ype16; a.d32 = d32; a.d16 = (__half*)d16;
+  return launch_gemm(x, rows, K, K, w, 256, K, a, 256, (cudaStream_t)stream);
+}
+
+int ovis_kv_proj_f16(const void* xt, int groups, int rows_per_group, const void* w, int n_tiles, void* const* out,
+                     const float* const* bias, const float* const* tab, const float* const* tab2, int tab_period,
+                     void* stream) {
+  CHECK_ARG(xt && w && out && groups > 0 && rows_per_group > 0 && n_tiles > 0 && n_tiles <= GEMM_MAX_NTILES, "bad arguments");
+  CHECK_ARG((long long)groups * rows_per_group < (1ll << 31), "too many rows");
+  GemmArgs a;
+  init_args(a);
+  a.rows_per_group = rows_per_group;
+  a.num_groups = groups;
+  a.a_group_stride = rows_per_group;
+  a.N = n_tiles * 256;
+  a.K = 256;
+  a.epi = EPI_STORE;
+  for (int t = 0; t < n_tiles; ++t) {
+    CHECK_ARG(out[t] != nullptr, "null output tile");
+    a.out[t] = out[t];
+    a.bias[t] = bias ? bias[t] : nullptr;
+    a.tab[t] = tab ? tab[t] : nullptr;
+    a.tab2[t] = tab2 ? tab2[t] : nullptr;
+  }
+  a.ldo = 256;
+  a.tab_period = tab_period > 0 ? tab_period : 1;
+  a.tab_ld = 256;
+  return launch_gemm(xt, (long long)groups * rows_per_group, 256, 256, w, (long long)n_tiles * 256, 256, a, 256,
+                     (cudaStream_t)stream);
+}
+
+int ovis_mask_bits(const void* gt, int groups, int rows_per_group, const void* me, int Q, unsigned int* bits,
+                   unsigned char* flags, int q_stride, void* stream) {
+  CHECK_ARG(gt && me && bits && flags && groups > 0 && rows_per_group > 0 && Q > 0 && Q <= 256 && q_stride >= Q, "bad arguments");
+  CHECK_ARG((long long)groups * rows_per_group < (1ll << 31), "too many rows");
+  GemmArgs a;
+  init_args(a);
+  a.rows_per_group = rows_per_group;
+  a.num_groups = groups;
+  a.a_group_stride = rows_per_group;
+  a.b_group_stride = Q;
+  a.N = Q;
+  a.K = 256;
+  a.epi = EPI_SIGNBITS;
+  a.bits = bits;
+  a.flags = flags;
+  a.words_per_group = (rows_per_group + 31) / 32;
+  a.q_stride = q_stride;
+  return launch_gemm(gt, (long long)groups * rows_per_group, 256, 256, me, (long long)groups * Q, 256, a, Q <= 128 ? 128 : 256,
+                     (cudaStream_t)stream);
+}
+
+int ovis_mask_logits(const void* ft, int groups, int rows_per_group, const void* me, int me_group_stride, int Q,
+                     const float* bias, float* out, long long t_group_stride, long long ldt, void* stream) {
+  CHECK_ARG(ft && me && out && groups > 0 && rows_per_group > 0 && Q > 0 && me_group_stride >= 0, "bad arguments");
+  CHECK_ARG((long long)groups * rows_per_group < (1ll << 31), "too many rows");
+  GemmArgs a;
+  init_args(a);
+  a.rows_per_group = rows_per_group;
+  a.num_groups = groups;
+  a.a_group_stride = rows_per_group;
+  a.b_group_stride = me_group_stride;
+  a.N = Q;
+  a.K = 256;
+  a.epi = EPI_STORE_T;
+  const int bn = Q <= 128 ? 128 : 256;
+  const int nt = (Q + bn - 1) / bn;
+  CHECK_ARG(nt <= GEMM_MAX_NTILES, "too many output channels");
+  for (int t = 0; t < nt; ++t) a.bias[t] = bias ? bias + (long long)t * bn : nullptr;
+  a.out_t = out;
+  a.t_group_stride = t_group_stride;
+  a.ldt = ldt;
+  const long long b_rows = me_group_stride ? (long long)(groups - 1) * me_group_stride + Q : Q;
+  return launch_gemm(ft, (long long)groups * rows_per_group, 256, 256, me, b_rows, 256, a, bn, (cudaStream_t)stream);
+}
+
+int ovis_san_bias_logits(const void* af, int B, int P, int heads, const void* ae, int Q, float* out, void* stream) {
+  CHECK_ARG(af && ae && out && B > 0 && P > 0 && heads > 0 && Q > 0 && Q <= 256, "bad arguments");
+  GemmArgs a;
+  init_args(a);
+  a.rows_per_group = P;
+  a.num_groups = B * heads;
+  a.a_group_stride = P;
+  a.a_row_div = heads;
+  a.a_k_mod = heads;
+  a.a_k_offset_stride = 256;
+  a.b_group_stride = Q;
+  a.b_row_div = heads;
+  a.N = Q;
+  a.K = 256;
+  a.epi = EPI_STORE_T;
+  a.out_t = out;
+  a.t_group_stride = (long long)Q * P;
+  a.ldt = P;
+  return launch_gemm(af, (long long)B * P, (long long)heads * 256, (long long)heads * 256, ae, (long long)B * Q, 256, a,
+                     Q <= 128 ? 128 : 256, (cudaStream_t)stream);
+}
+
+int ovis_xattn_plan(int G, int Q, int keys, int* splits, int* q_pad, long long* o_floats, long long* ml_floats) {
+  CHECK_ARG(G > 0 && Q > 0 && Q <= 256 && keys > 0 && splits && q_pad && o_floats && ml_floats, "bad arguments");
+  int sms = 148;
+  device_info(&sms);   // sizing only: fall back to the B200 SM count when no device is visible
+  const int tiles = (keys + XA_KT - 1) / XA_KT;
+  // aim for ~4 CTAs per SM over (G * 8 heads * splits), at least 2 key tiles per split
+  int s = (4 * sms + G * 8 - 1) / (G * 8);
+  if (s > tiles / 2) s = tiles / 2;
+  if (s < 1) s = 1;
+  if (s > 256) s = 256;
+  int chunk = ((tiles + s - 1) / s) * XA_KT;
+  s = (keys + chunk - 1) / chunk;
+  *splits = s;
+  *q_pad = ((Q + 31) / 32) * 32;
+  *o_floats = (long long)G * s * 8 * (*q_pad) * 32;
+  *ml_floats = (long long)G * s * 8 * (*q_pad) * 2;
+  return OVIS_OK;
+}
+
+int ovis_xattn(const void* q, const void* k, const void* v, const unsigned int* bits, const unsigned char* flags, int G,
+               int Q, int q_stride, int keys, int splits, float* o_part, float* ml_part, void* out, void* stream) {
+  CHECK_ARG(q && k && v && bits && flags && o_part && ml_part && out, "null pointer");
+  CHECK_ARG(G > 0 && Q > 0 && Q <= 256 && keys > 0 && splits > 0 && q_stride >= Q, "bad arguments");
+  int rc = device_info(nullptr);
+  if (rc) return rc;
+  XattnArgs a;
+  a.q = (const __half*)q; a.k = (const __half*)k; a.v = (const __half*)v;
+  a.bits = bits; a.flags = flags; a.o_part = o_part; a.ml_part = ml_part;
+  a.Q = Q; a.q_pad = ((Q + 31) / 32) * 32; a.q_stride = q_stride;
+  a.keys = keys; a.W = (keys + 31) / 32; a.splits = splits;
+  const int tiles = (keys + XA_KT - 1) / XA_KT;
+  a.chunk = ((tiles + splits - 1) / splits) * XA_KT;
+  CHECK_ARG((long long)a.chunk * (splits - 1) < keys, "splits too large for the key count (use ovis_xattn_plan)");
+  dim3 grid(splits, 8, G);
+  xattn_split_kernel<<<grid, a.q_pad, 0, (cudaStream_t)stream>>>(a);
+  rc = check_launch("xattn_split_kernel");
+  if (rc) return rc;
+  xattn_combine_kernel<<<dim3(Q, G), 256, 0, (cudaStream_t)stream>>>(o_part, ml_part, (__half*)out, Q, a.q_pad, splits);
+  return check_launch("xattn_combine_kernel");
+}
+
+int ovis_self_attn(const void* qk, const void* v, void* out, int G, int Q, void* stream) {
+  CHECK_ARG(qk && v && out && G > 0 && Q > 0 && Q <= 256, "bad arguments");
+  int rc = device_info(nullptr);
+  if (rc) return rc;
+  SelfAttnArgs a;
+  a.qk = (const __half*)qk; a.v = (const __half*)v; a.out = (__half*)out; a.Q = Q;
+  a.scale_log2 = 0.17677669529663687f * 1.4426950408889634f;   // 32^-1/2 * log2(e)
+  const int threads = Q <= 128 ? 128 : 256;
+  self_attn_kernel<<<dim3(8, G), threads, (size_t)Q * 32 * 2 * sizeof(__half), (cudaStream_t)stream>>>(a);
+  return check_launch("self_attn_kernel");
+}
+
+int ovis_clip_aggregate(const float* logits, const unsigned char* valid, float* probs, unsigned char* qvalid, int T, int Q,
+                        int K, void* stream) {
+  CHECK_ARG(logits && valid && probs && qvalid && T > 0 && Q > 0 && K > 0 && K <= 12000, "bad arguments");
+  int rc = device_info(nullptr);
+  if (rc) return rc;
+  clip_aggregate_kernel<<<Q, 256, (size_t)K * sizeof(float), (cudaStream_t)stream>>>(logits, valid, probs, qvalid, T, Q, K);
+  return check_launch("clip_aggregate_kernel");
+}
+
+int ovis_san_attn_bias(const float* bias, float* out, int BN, int Q, int h, int w, int gh, int gw, void* stream) {
+  CHECK_ARG(bias && out && BN > 0 && Q > 0 && h > 0 && w > 0 && gh > 0 && gw > 0, "bad arguments");
+  int rc = device_info(nullptr);
+  if (rc) return rc;
+  san_attn_bias_kernel<<<dim3(Q + 1 + gh * gw, BN), 256, 0, (cudaStream_t)stream>>>(bias, out, Q, h, w, gh, gw);
+  return check_launch("san_attn_bias_kernel");
+}
+
+}  // extern "C"

@@ -1,0 +1,438 @@
+// Persistent tcgen05 GEMM for sm_100a:  D[rows, N] = A[rows, K] * B[N, K]^T   (fp16 operands, fp32 accumulate in TMEM)
+//
+//   * both operands K-major (row-major [rows][K] activations, PyTorch [out][in] weights), staged by TMA into
+//     128B-swizzled shared memory, consumed by tcgen05.mma (UMMA 128 x BN x 16) issued by one thread;
+//   * warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM owner), warps 2..5 = epilogue (one TMEM lane quarter each);
+//   * two TMEM accumulator stages so the epilogue of tile i overlaps the main loop of tile i+1;
+//   * "groups": the M axis is a batch of independent row blocks (frames / clips); B may be a different row block
+//     per group (b_group_stride) - this is how the per-frame mask-embed products run as one launch;
+//   * fused epilogues (see GemmArgs::epi).
+#pragma once
+#include "ptx.cuh"
+
+namespace ovis {
+
+enum GemmEpi : int {
+  EPI_STORE = 0,      // out[row][col] = act((acc + bias[col] + tab[r % period][col] + tab2[r / period][col]) * scale); fp16 or fp32
+  EPI_LN = 1,         // v = acc + bias + resid -> LayerNorm (-> optional 2nd LayerNorm); N == BN == 256
+  EPI_SIGNBITS = 2,   // bits[g][r/32][col] = ballot(acc < 0); flags[g][col] = any(acc >= 0)
+  EPI_STORE_T = 3,    // out[g*t_group_stride + col*ldt + r] = acc + bias[col]   (fp32, transposed / NCHW-style)
+};
+
+constexpr int GEMM_MAX_NTILES = 16;
+
+struct GemmArgs {
+  int rows_per_group;     // valid A rows in each group
+  int num_groups;
+  int a_group_stride;     // A rows between consecutive groups
+  int b_group_stride;     // B rows between consecutive groups (0 = one shared B)
+  int a_k_offset_stride;  // extra A column offset per (group % a_k_mod) (SAN per-head slices), usually 0
+  int a_k_mod;            // see above (>= 1)
+  int a_row_div;          // A row block index = group / a_row_div (>= 1)
+  int b_row_div;          // B row block index = group / b_row_div (>= 1)
+  int N;                  // valid output columns
+  int K;                  // reduction length, multiple of 64
+  int epi;
+  // ---- EPI_STORE
+  void* out[GEMM_MAX_NTILES];          // per n-tile base pointer (column 0 of that tile)
+  const float* bias[GEMM_MAX_NTILES];  // per n-tile bias (indexed by column within tile) or null
+  const float* tab[GEMM_MAX_NTILES];   // per n-tile additive table [period][BN-wide rows of ld tab_ld] or null
+  const float* tab2[GEMM_MAX_NTILES];  // per n-tile second table indexed by r / period, or null
+  int ldo;                // output row stride (elements)
+  int out_f32;            // 0: fp16 output, 1: fp32 output
+  int relu;
+  float scale;
+  int tab_period;
+  int tab_ld;
+  // ---- EPI_LN
+  const float* resid;     // [rows][256] fp32
+  const float* ln1_g; const float* ln1_b;
+  const float* ln2_g; const float* ln2_b;   // null -> no second norm
+  const float* pe;        // [pe_period][256] fp32 added for the "+pos" fp16 copy, or null
+  int pe_period;
+  float* y32; __half* y16; __half* ype16;   // LN1 outputs
+  float* d32; __half* d16;                  // LN2 outputs
+  // ---- EPI_SIGNBITS
+  uint32_t* bits;         // [G][W][q_stride]
+  unsigned char* flags;   // [G][q_stride]
+  int words_per_group;    // W = ceil(rows_per_group / 32)
+  int q_stride;
+  // ---- EPI_STORE_T
+  float* out_t;
+  long long t_group_stride;
+  long long ldt;
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int BM = 128, BK = 64;
+  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int TMEM_COLS = 2 * BN;   // 256 or 512: power of two
+  static constexpr int THREADS = 192;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1)
+gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs args) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = bars;                 // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;       // [STAGES]
+  uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]
+  uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int m_tiles = (args.rows_per_group + Cfg::BM - 1) / Cfg::BM;
+  const int n_tiles = (args.N + BN - 1) / BN;
+  const int total_tiles = args.num_groups * m_tiles * n_tiles;
+  const int k_blocks = args.K / Cfg::BK;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_holder, Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = tile % n_tiles;
+        const int mt = (tile / n_tiles) % m_tiles;
+        const int g = tile / (n_tiles * m_tiles);
+        const int a_row = (g / args.a_row_div) * args.a_group_stride + mt * Cfg::BM;
+        const int a_col = (g % args.a_k_mod) * args.a_k_offset_stride;
+        const int b_row = (g / args.b_row_div) * args.b_group_stride + nt * BN;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + Cfg::A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          tma_load_2d(sa, &tmA, &full_bar[stage], a_col + kb * Cfg::BK, a_row);
+          tma_load_2d(sb, &tmB, &full_bar[stage], kb * Cfg::BK, b_row);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(Cfg::BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t sb = sa + Cfg::A_BYTES;
+          const uint64_t adesc = umma_desc_k_sw128(sa);
+          const uint64_t bdesc = umma_desc_k_sw128(sb);
+#pragma unroll
+          for (int k = 0; k < Cfg::BK / 16; ++k) {
+            // advance 16 fp16 = 32 bytes along K inside the 128B swizzle atom: +2 in the (addr >> 4) field
+            umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);   // frees the smem slot when these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[acc]);       // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue warps (2..5) =====================
+    const int quarter = warp & 3;           // TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int nt = tile % n_tiles;
+      const int mt = (tile / n_tiles) % m_tiles;
+      const int g = tile / (n_tiles * m_tiles);
+      const int r = mt * Cfg::BM + quarter * 32 + lane;        // row within group
+      const bool row_ok = r < args.rows_per_group;
+      const long long grow = (long long)(g / args.a_row_div) * args.a_group_stride + r;   // global A/D row
+      const int col_base = nt * BN;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_acc = tmem_base + acc * BN + ((uint32_t)(quarter * 32) << 16);
+      uint32_t v[32];
+
+      if (args.epi == EPI_STORE) {
+        const float* bias = args.bias[nt];
+        const float* tab = args.tab[nt];
+        const float* tab2 = args.tab2[nt];
+        const float* trow = tab ? tab + (long long)(r % args.tab_period) * args.tab_ld : nullptr;
+        const float* trow2 = tab2 ? tab2 + (long long)(r / args.tab_period) * args.tab_ld : nullptr;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          if (col_base + c * 32 >= args.N) break;               // warp-uniform
+          tmem_ld_32x32(t_acc + c * 32, v);
+          tmem_ld_wait();
+          if (row_ok) {
+            float f[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+            if (bias) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] += __ldg(bias + c * 32 + j);
+            }
+            if (trow) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                float4 t = __ldg(reinterpret_cast<const float4*>(trow + c * 32 + j));
+                f[j] += t.x; f[j + 1] += t.y; f[j + 2] += t.z; f[j + 3] += t.w;
+              }
+            }
+            if (trow2) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                float4 t = __ldg(reinterpret_cast<const float4*>(trow2 + c * 32 + j));
+                f[j] += t.x; f[j + 1] += t.y; f[j + 2] += t.z; f[j + 3] += t.w;
+              }
+            }
+            if (args.scale != 1.f) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] *= args.scale;
+            }
+            if (args.relu) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+            }
+            const int ncols = min(32, args.N - (col_base + c * 32));
+            if (args.out_f32) {
+              float* o = reinterpret_cast<float*>(args.out[nt]) + grow * args.ldo + c * 32;
+              if (ncols == 32 && (args.ldo & 3) == 0) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+              } else {
+                for (int j = 0; j < ncols; ++j) o[j] = f[j];
+              }
+            } else {
+              __half* o = reinterpret_cast<__half*>(args.out[nt]) + grow * args.ldo + c * 32;
+              if (ncols == 32 && (args.ldo & 7) == 0) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                  uint4 u;
+                  u.x = pack_half2(f[j], f[j + 1]); u.y = pack_half2(f[j + 2], f[j + 3]);
+                  u.z = pack_half2(f[j + 4], f[j + 5]); u.w = pack_half2(f[j + 6], f[j + 7]);
+                  *reinterpret_cast<uint4*>(o + j) = u;
+                }
+              } else {
+                for (int j = 0; j < ncols; ++j) o[j] = __float2half_rn(f[j]);
+              }
+            }
+          }
+        }
+      } else if (args.epi == EPI_LN) {
+        // BN == 256 == N.  Row-per-thread LayerNorm; the biased+residual row is parked back in TMEM between passes.
+        const float* bias = args.bias[0];
+        const float* res = args.resid + grow * 256;
+        float sum = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < 8; ++c) {
+          tmem_ld_32x32(t_acc + c * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 rr = row_ok ? __ldg(reinterpret_cast<const float4*>(res + c * 32 + j)) : make_float4(0, 0, 0, 0);
+            float a0 = __uint_as_float(v[j]) + __ldg(bias + c * 32 + j) + rr.x;
+            float a1 = __uint_as_float(v[j + 1]) + __ldg(bias + c * 32 + j + 1) + rr.y;
+            float a2 = __uint_as_float(v[j + 2]) + __ldg(bias + c * 32 + j + 2) + rr.z;
+            float a3 = __uint_as_float(v[j + 3]) + __ldg(bias + c * 32 + j + 3) + rr.w;
+            sum += (a0 + a1) + (a2 + a3);
+            v[j] = __float_as_uint(a0); v[j + 1] = __float_as_uint(a1);
+            v[j + 2] = __float_as_uint(a2); v[j + 3] = __float_as_uint(a3);
+          }
+          tmem_st_32x32(t_acc + c * 32, v);
+        }
+        tmem_st_wait();
+        const float mean = sum * (1.f / 256.f);
+        float sq = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < 8; ++c) {
+          tmem_ld_32x32(t_acc + c * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { float d = __uint_as_float(v[j]) - mean; sq += d * d; }
+        }
+        const float rstd = rsqrtf(sq * (1.f / 256.f) + 1e-5f);
+        const bool two = args.ln2_g != nullptr;
+        const float* pe = args.pe ? args.pe + (long long)(r % args.pe_period) * 256 : nullptr;
+        float sum2 = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < 8; ++c) {
+          tmem_ld_32x32(t_acc + c * 32, v);
+          tmem_ld_wait();
+          float y[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            y[j] = (__uint_as_float(v[j]) - mean) * rstd * __ldg(args.ln1_g + c * 32 + j) + __ldg(args.ln1_b + c * 32 + j);
+            sum2 += y[j];
+          }
+          if (row_ok) {
+            if (args.y32) {
+              float* o = args.y32 + grow * 256 + c * 32;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
+            }
+            if (args.y16) {
+              __half* o = args.y16 + grow * 256 + c * 32;
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                uint4 u;
+                u.x = pack_half2(y[j], y[j + 1]); u.y = pack_half2(y[j + 2], y[j + 3]);
+                u.z = pack_half2(y[j + 4], y[j + 5]); u.w = pack_half2(y[j + 6], y[j + 7]);
+                *reinterpret_cast<uint4*>(o + j) = u;
+              }
+            }
+            if (args.ype16 && pe) {
+              __half* o = args.ype16 + grow * 256 + c * 32;
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                float4 p0 = __ldg(reinterpret_cast<const float4*>(pe + c * 32 + j));
+                float4 p1 = __ldg(reinterpret_cast<const float4*>(pe + c * 32 + j + 4));
+                uint4 u;
+                u.x = pack_half2(y[j] + p0.x, y[j + 1] + p0.y); u.y = pack_half2(y[j + 2] + p0.z, y[j + 3] + p0.w);
+                u.z = pack_half2(y[j + 4] + p1.x, y[j + 5] + p1.y); u.w = pack_half2(y[j + 6] + p1.z, y[j + 7] + p1.w);
+                *reinterpret_cast<uint4*>(o + j) = u;
+              }
+            }
+          }
+          if (two) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(y[j]);
+            tmem_st_32x32(t_acc + c * 32, v);
+          }
+        }
+        if (two) {
+          tmem_st_wait();
+          const float mean2 = sum2 * (1.f / 256.f);
+          float sq2 = 0.f;
+#pragma unroll 1
+          for (int c = 0; c < 8; ++c) {
+            tmem_ld_32x32(t_acc + c * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { float d = __uint_as_float(v[j]) - mean2; sq2 += d * d; }
+          }
+          const float rstd2 = rsqrtf(sq2 * (1.f / 256.f) + 1e-5f);
+#pragma unroll 1
+          for (int c = 0; c < 8; ++c) {
+            tmem_ld_32x32(t_acc + c * 32, v);
+            tmem_ld_wait();
+            if (row_ok) {
+              float y[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                y[j] = (__uint_as_float(v[j]) - mean2) * rstd2 * __ldg(args.ln2_g + c * 32 + j) + __ldg(args.ln2_b + c * 32 + j);
+              if (args.d32) {
+                float* o = args.d32 + grow * 256 + c * 32;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
+              }
+              if (args.d16) {
+                __half* o = args.d16 + grow * 256 + c * 32;
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                  uint4 u;
+                  u.x = pack_half2(y[j], y[j + 1]); u.y = pack_half2(y[j + 2], y[j + 3]);
+                  u.z = pack_half2(y[j + 4], y[j + 5]); u.w = pack_half2(y[j + 6], y[j + 7]);
+                  *reinterpret_cast<uint4*>(o + j) = u;
+                }
+              }
+            }
+          }
+        }
+      } else if (args.epi == EPI_SIGNBITS) {
+        // rows = keys / cells, columns = queries.  One ballot per column gives the 32-key word of this warp.
+        const int r0 = mt * Cfg::BM + quarter * 32;
+        const int word = r0 >> 5;
+        const int nvalid = max(0, min(32, args.rows_per_group - r0));
+        const uint32_t validmask = nvalid >= 32 ? 0xffffffffu : ((1u << nvalid) - 1u);
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          if (col_base + c * 32 >= args.N) break;
+          tmem_ld_32x32(t_acc + c * 32, v);
+          tmem_ld_wait();
+          uint32_t mine = 0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            // blocked  <=>  sigmoid(x) < 0.5  <=>  x < 0 ; rows past the group end count as blocked
+            const uint32_t w = __ballot_sync(0xffffffffu, !row_ok || __uint_as_float(v[j]) < 0.f);
+            if (lane == j) mine = w;
+          }
+          const int col = col_base + c * 32 + lane;
+          if (col < args.N && word < args.words_per_group) {
+            args.bits[((long long)g * args.words_per_group + word) * args.q_stride + col] = mine;
+            if ((~mine & validmask) != 0u) args.flags[(long long)g * args.q_stride + col] = 1;
+          }
+        }
+      } else {  // EPI_STORE_T
+        const float* bias = args.bias[nt];
+        float* obase = args.out_t + (long long)g * args.t_group_stride + r;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          if (col_base + c * 32 >= args.N) break;
+          tmem_ld_32x32(t_acc + c * 32, v);
+          tmem_ld_wait();
+          if (row_ok) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int col = col_base + c * 32 + j;
+              if (col < args.N) {
+                float f = __uint_as_float(v[j]);
+                if (bias) f += __ldg(bias + c * 32 + j);
+                __stcs(obase + (long long)col * args.ldt, f);
+              }
+            }
+          }
+        }
+      }
+      // release the accumulator stage
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+}  // namespace ovis

@@ -1,0 +1,264 @@
+"""Per-kernel parity tests (GPU): every C-ABI entry point against a plain torch fp32/fp64 evaluation of the same
+arithmetic on the same fp16-rounded operands, plus the oracle (oracle/decoder_ref.py) for the OV-head tails."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from openvis_b200 import _lib as L  # noqa: E402
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    L.device_check()
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+
+def _g(seed):
+    return torch.Generator(device="cpu").manual_seed(seed)
+
+
+def _randn(*shape, seed=0, scale=1.0):
+    return (torch.randn(*shape, generator=_g(seed)) * scale).cuda()
+
+
+def _maxerr(a, b):
+    return (a.double() - b.double()).abs().max().item()
+
+
+@pytest.mark.parametrize("rows,K,N", [(100, 256, 256), (3600, 256, 2048), (777, 2048, 256), (300, 512, 40),
+                                      (1000, 512, 1197), (129, 768, 512), (5000, 256, 768), (64, 64, 8)])
+@pytest.mark.parametrize("out_f32", [False, True])
+def test_linear(rows, K, N, out_f32):
+    x = _randn(rows, K, seed=1).half()
+    w = _randn(N, K, seed=2, scale=K ** -0.5).half()
+    b = _randn(N, seed=3)
+    ref = (x.double() @ w.double().T + b.double()) * 0.5
+    out = L.linear_f16(x, w, b, scale=0.5, relu=False, out_f32=out_f32)
+    torch.cuda.synchronize()
+    tol = 2e-4 if out_f32 else 4e-3
+    assert _maxerr(out, ref) < tol * max(1.0, ref.abs().max().item()), _maxerr(out, ref)
+    out = L.linear_f16(x, w, None, relu=True, out_f32=out_f32)
+    ref = (x.double() @ w.double().T).relu()
+    assert _maxerr(out, ref) < tol * max(1.0, ref.abs().max().item())
+
+
+def test_linear_strided_input():
+    base = _randn(500, 512, seed=4).half()
+    x = base[:, 256:]                     # row stride 512, K = 256
+    w = _randn(256, 256, seed=5, scale=1 / 16).half()
+    out = L.linear_f16(x, w, None, out_f32=True)
+    assert _maxerr(out, x.double() @ w.double().T) < 1e-3
+
+
+@pytest.mark.parametrize("rows,K,two", [(100, 256, False), (100, 2048, True), (3600, 256, True), (333, 2048, False)])
+def test_linear_ln(rows, K, two):
+    x = _randn(rows, K, seed=1).half()
+    w = _randn(256, K, seed=2, scale=K ** -0.5).half()
+    b = _randn(256, seed=3)
+    resid = _randn(rows, 256, seed=4)
+    g1, b1 = 1 + 0.1 * _randn(256, seed=5), 0.1 * _randn(256, seed=6)
+    g2, b2 = 1 + 0.1 * _randn(256, seed=7), 0.1 * _randn(256, seed=8)
+    pe = _randn(100, 256, seed=9)
+    y32 = torch.empty(rows, 256, device="cuda")
+    y16 = torch.empty(rows, 256, device="cuda", dtype=torch.float16)
+    ype16 = torch.empty_like(y16)
+    d32 = torch.empty_like(y32)
+    d16 = torch.empty_like(y16)
+    L.linear_ln_f16(x, w, b, resid, (g1, b1), (g2, b2) if two else None, pe, y32, y16, ype16, d32 if two else None,
+                    d16 if two else None)
+    v = x.double() @ w.double().T + b.double() + resid.double()
+    y = torch.nn.functional.layer_norm(v, (256,), g1.double(), b1.double(), 1e-5)
+    assert _maxerr(y32, y) < 2e-4
+    assert _maxerr(y16, y) < 4e-3
+    pidx = torch.arange(rows, device="cuda") % 100
+    assert _maxerr(ype16, y + pe.double()[pidx]) < 6e-3
+    if two:
+        d = torch.nn.functional.layer_norm(y, (256,), g2.double(), b2.double(), 1e-5)
+        assert _maxerr(d32, d) < 3e-4
+        assert _maxerr(d16, d) < 4e-3
+
+
+def test_nchw_to_tokens():
+    x = _randn(3, 256, 12, 20, seed=1)
+    out = L.nchw_to_tokens_f16(x)
+    ref = x.flatten(2).permute(0, 2, 1).half()
+    assert torch.equal(out, ref)
+
+
+@pytest.mark.parametrize("H,W", [(16, 16), (96, 160), (24, 40)])
+def test_maskfeat_prep(H, W):
+    F = _randn(2, 256, H, W, seed=2)
+    ft, g0, g1, g2 = L.maskfeat_prep(F)
+    assert torch.equal(ft, F.flatten(2).permute(0, 2, 1).half())
+    for g, s in ((g0, 8), (g1, 4), (g2, 2)):
+        # bilinear, align_corners=False, integer factor == centre 2x2 mean (SURVEY.md Finding 3)
+        ref = torch.nn.functional.interpolate(F, size=(H // s, W // s), mode="bilinear", align_corners=False)
+        ref = ref.flatten(2).permute(0, 2, 1)
+        assert _maxerr(g, ref) < 2e-3, (s, _maxerr(g, ref))
+
+
+@pytest.mark.parametrize("G,rows,Q", [(3, 240, 100), (1, 1200, 100), (2, 3840, 200), (5, 60, 100)])
+def test_mask_bits(G, rows, Q):
+    gt = _randn(G * rows, 256, seed=1).half()
+    me = _randn(G * Q, 256, seed=2).half()
+    W = (rows + 31) // 32
+    bits = torch.zeros(G, W, Q, dtype=torch.int32, device="cuda")
+    flags = torch.zeros(G, Q, dtype=torch.uint8, device="cuda")
+    L.mask_bits(gt, G, rows, me, Q, bits, flags, Q)
+    s = torch.einsum("grc,gqc->gqr", gt.view(G, rows, 256).double(), me.view(G, Q, 256).double())
+    blocked_ref = s < 0
+    r = torch.arange(rows, device="cuda")
+    got = ((bits.long()[:, r // 32, :] >> (r % 32)[None, :, None]) & 1).bool().permute(0, 2, 1)   # [G, Q, rows]
+    near0 = s.abs() < 1e-3
+    assert bool(((got == blocked_ref) | near0).all())
+    assert ((got != blocked_ref).float().mean().item()) < 1e-4
+    assert torch.equal(flags.bool(), (~got).any(-1))
+    # tail bits beyond `rows` are "blocked"
+    if rows % 32:
+        tail = bits.long()[:, -1, :] >> (rows % 32)
+        assert bool((tail == (1 << (32 - rows % 32)) - 1).all())
+
+
+@pytest.mark.parametrize("G,rows,Q,shared", [(2, 1000, 100, False), (1, 5000, 200, False), (3, 384, 300, True)])
+def test_mask_logits(G, rows, Q, shared):
+    ft = _randn(G * rows, 256, seed=1).half()
+    me = _randn((1 if shared else G) * Q, 256, seed=2, scale=0.1).half()
+    bias = _randn(Q, seed=3) if shared else None
+    out = torch.empty(Q, G * rows, device="cuda") if not shared else torch.empty(G, Q, rows, device="cuda")
+    if shared:
+        L.mask_logits(ft, G, rows, me, 0, Q, out, Q * rows, rows, bias)
+        ref = torch.einsum("grc,qc->gqr", ft.view(G, rows, 256).double(), me.double()) + bias.double()[None, :, None]
+    else:
+        L.mask_logits(ft, G, rows, me, Q, Q, out, rows, G * rows)
+        ref = torch.einsum("grc,gqc->qgr", ft.view(G, rows, 256).double(), me.view(G, Q, 256).double()).reshape(Q, -1)
+    assert _maxerr(out, ref) < 1e-3
+
+
+def test_kv_proj():
+    G, rows, nt = 2, 300, 6
+    xt = _randn(G * rows, 256, seed=1).half()
+    w = _randn(nt * 256, 256, seed=2, scale=1 / 16).half()
+    outs = [torch.empty(G * rows, 256, dtype=torch.float16, device="cuda") for _ in range(nt)]
+    biases = [_randn(256, seed=10 + i) if i % 2 else None for i in range(nt)]
+    tabs = [None if i % 2 else _randn(100, 256, seed=20 + i) for i in range(nt)]
+    tabs2 = [None if i % 2 else _randn(3, 256, seed=30 + i) for i in range(nt)]
+    L.kv_proj_f16(xt, G, rows, w, outs, biases, tabs, tabs2, tab_period=100)
+    r = torch.arange(rows, device="cuda")
+    for i in range(nt):
+        ref = xt.double() @ w[i * 256:(i + 1) * 256].double().T
+        if biases[i] is not None:
+            ref = ref + biases[i].double()
+        if tabs[i] is not None:
+            ref = ref + (tabs[i].double()[r % 100] + tabs2[i].double()[r // 100]).repeat(G, 1)
+        assert _maxerr(outs[i], ref) < 8e-3, i
+
+
+def _ref_xattn(q, k, v, blocked, G, Q, keys):
+    """q pre-scaled by d^-1/2*log2e -> softmax in base 2."""
+    qh = q.view(G, Q, 8, 32).permute(0, 2, 1, 3).double()
+    kh = k.view(G, keys, 8, 32).permute(0, 2, 1, 3).double()
+    vh = v.view(G, keys, 8, 32).permute(0, 2, 1, 3).double()
+    s = qh @ kh.transpose(-1, -2) * math.log(2.0)
+    full = blocked.all(-1, keepdim=True)
+    b = blocked & ~full
+    s = s.masked_fill(b[:, None], float("-inf"))
+    return (s.softmax(-1) @ vh).permute(0, 2, 1, 3).reshape(G * Q, 256)
+
+
+@pytest.mark.parametrize("G,Q,keys,density", [(3, 100, 240, 0.5), (2, 100, 3840, 0.5), (1, 100, 19200, 0.9),
+                                              (2, 200, 920, 0.5), (1, 100, 77, 0.3), (4, 100, 960, 0.99)])
+def test_xattn(G, Q, keys, density):
+    q = _randn(G * Q, 256, seed=1, scale=0.6).half()
+    k = _randn(G * keys, 256, seed=2).half()
+    v = _randn(G * keys, 256, seed=3).half()
+    blocked = torch.rand(G, Q, keys, generator=_g(4)).cuda() < density
+    blocked[0, 3] = True          # a fully blocked row -> must attend everywhere
+    blocked[-1, Q - 1] = True
+    blocked[0, 5] = False
+    W = (keys + 31) // 32
+    r = torch.arange(keys, device="cuda")
+    bits = torch.zeros(G, W, Q, dtype=torch.int64, device="cuda")
+    bits.scatter_add_(1, (r // 32)[None, :, None].expand(G, keys, Q),
+                      (blocked.permute(0, 2, 1).long() << (r % 32)[None, :, None]))
+    bits = bits.to(torch.int32)   # wraps bit 31 into the sign
+    flags = (~blocked).any(-1).to(torch.uint8).contiguous()
+    splits, q_pad, o_n, ml_n = L.xattn_plan(G, Q, keys)
+    o_part = torch.empty(o_n, device="cuda")
+    ml_part = torch.empty(ml_n, device="cuda")
+    out = torch.empty(G * Q, 256, dtype=torch.float16, device="cuda")
+    L.xattn(q, k, v, bits.contiguous(), flags, G, Q, Q, keys, splits, o_part, ml_part, out)
+    ref = _ref_xattn(q, k, v, blocked, G, Q, keys)
+    assert _maxerr(out, ref) < 6e-3, (_maxerr(out, ref), splits)
+
+
+@pytest.mark.parametrize("G,Q", [(1, 100), (5, 100), (2, 200)])
+def test_self_attn(G, Q):
+    qk = _randn(G * Q, 512, seed=1).half()
+    v = _randn(G * Q, 256, seed=2).half()
+    out = torch.empty(G * Q, 256, dtype=torch.float16, device="cuda")
+    L.self_attn(qk, v, out, G, Q)
+    qh = qk[:, :256].reshape(G, Q, 8, 32).permute(0, 2, 1, 3).double() * 32 ** -0.5
+    kh = qk[:, 256:].reshape(G, Q, 8, 32).permute(0, 2, 1, 3).double()
+    vh = v.view(G, Q, 8, 32).permute(0, 2, 1, 3).double()
+    ref = ((qh @ kh.transpose(-1, -2)).softmax(-1) @ vh).permute(0, 2, 1, 3).reshape(G * Q, 256)
+    assert _maxerr(out, ref) < 4e-3
+
+
+def test_init_queries_and_rownorm():
+    Q, G = 100, 3
+    qf, qe = _randn(Q, 256, seed=1), _randn(Q, 256, seed=2)
+    g, b = 1 + 0.1 * _randn(256, seed=3), 0.1 * _randn(256, seed=4)
+    mk32 = lambda: torch.empty(G * Q, 256, device="cuda")
+    mk16 = lambda: torch.empty(G * Q, 256, device="cuda", dtype=torch.float16)
+    z32, z16, ze16, d32, d16 = mk32(), mk16(), mk16(), mk32(), mk16()
+    L.init_queries(qf, qe, g, b, G, (z32, z16, ze16, d32, d16))
+    assert torch.equal(z32, qf.repeat(G, 1))
+    assert torch.equal(ze16, (qf + qe).half().repeat(G, 1))
+    ref = torch.nn.functional.layer_norm(qf.double(), (256,), g.double(), b.double(), 1e-5).repeat(G, 1)
+    assert _maxerr(d32, ref) < 1e-5
+    x = _randn(50, 768, seed=5)
+    gg, bb = 1 + 0.1 * _randn(768, seed=6), 0.1 * _randn(768, seed=7)
+    o32, o16 = L.rownorm(x, gg, bb, layer_norm=True)
+    assert _maxerr(o32, torch.nn.functional.layer_norm(x.double(), (768,), gg.double(), bb.double(), 1e-5)) < 1e-5
+    o32, _ = L.rownorm(x, l2=True)
+    assert _maxerr(o32, torch.nn.functional.normalize(x.double(), dim=-1)) < 1e-6
+
+
+def test_ov_tails_against_oracle():
+    from oracle import decoder_ref as O
+    # crop path: normalize + 100 * f @ text^T  (adapter.py:118-119,146-147), then the OpenVIS aggregation
+    T, Q, K = 5, 100, 40
+    f = _randn(T * Q, 512, seed=1)
+    text = torch.nn.functional.normalize(_randn(K, 512, seed=2), dim=-1)
+    _, f16 = L.rownorm(f, l2=True, want32=False)
+    logits = L.linear_f16(f16, text.half(), None, scale=100.0, out_f32=True)
+    ref = O.ov_cosine_logits(f.cpu(), text.cpu(), 100.0)
+    assert _maxerr(logits.cpu(), ref) < 0.06          # fp16 operands on |logit| <= 100
+    assert (logits.argmax(-1).cpu() == ref.argmax(-1)).float().mean().item() >= 0.999
+    valid = torch.rand(T, Q, generator=_g(3)) < 0.6
+    valid[:, 7] = False
+    probs, qv = L.clip_aggregate(ref.view(T, Q, K).cuda().contiguous(), valid.cuda())
+    rp, rv = O.openvis_clip_aggregate(ref[valid.flatten()], valid)
+    assert torch.equal(qv.cpu(), rv)
+    assert _maxerr(probs.cpu()[rv], rp) < 1e-6
+    # SAN path: bias matrix
+    bias = _randn(2, 12, 9, 24, 40, seed=4)
+    got = L.san_attn_bias(bias, (14, 14))
+    assert torch.equal(got.cpu(), O.san_build_attn_bias(bias.cpu(), (14, 14)))
+    # SAN tail: ln_post -> proj -> normalize -> scale * f @ text^T
+    sos = _randn(2 * 9, 768, seed=5)
+    lw, lb = 1 + 0.1 * _randn(768, seed=6), 0.1 * _randn(768, seed=7)
+    proj = _randn(768, 512, seed=8, scale=768 ** -0.5)
+    text = torch.nn.functional.normalize(_randn(41, 512, seed=9), dim=-1)
+    _, x16 = L.rownorm(sos, lw, lb, layer_norm=True, want32=False)
+    e = L.linear_f16(x16, proj.T.contiguous().half(), None, out_f32=True)
+    e32, e16 = L.rownorm(e, l2=True)
+    lg = L.linear_f16(e16, text.half(), None, scale=1 / 0.07, out_f32=True)
+    rf, rl = O.san_sos_tail(sos.cpu().view(2, 9, 768), lw.cpu(), lb.cpu(), proj.cpu(), text.cpu(), 1 / 0.07)
+    assert _maxerr(e32.cpu(), rf.reshape(-1, 512)) < 2e-3
+    assert _maxerr(lg.cpu(), rl.reshape(-1, 41)) < 0.03

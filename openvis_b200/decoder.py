@@ -1,0 +1,683 @@
+"""B200-native drop-in replacements for the reference's masked transformer decoders.
+
+Same class names, constructor keywords, ``from_config``, parameter names / shapes, ``forward``
+signature and output dictionaries as
+
+  VideoMultiScaleMaskedTransformerDecoder              openvis/modeling/transformer_decoder/video_mask2former_transformer_decoder.py:219-484
+  FrameMultiScaleMaskedTransformerDecoder              .../frame_mask2former_transformer_decoder.py:12-154
+  SideAdapterFrameMultiScaleMaskedTransformerDecoder   .../side_adapter_frame_mask2former_transformer_decoder.py:29-176
+  SideAdapterVideoMultiScaleMaskedTransformerDecoder   .../side_adapter_video_mask2former_transformer_decoder.py:28-149
+  (+ the Embedding*/Proposal* variants that only swap ``class_embed``)
+
+so that ``MaskFormerHead`` (mask_former_head.py:112-124) can build and call them unchanged.  The modules are
+parameter containers plus a launch schedule: every tensor operation on the hot path is one of the hand-written
+sm_100a kernels behind the C ABI (openvis_b200/_lib.py); PyTorch only allocates memory and provides the stream.
+Inference only (eval mode, no autograd), CUDA sm_100 only, no fallback.
+
+Design notes (DESIGN.md has the full account):
+  * a "group" is the set of frames that share one set of queries: the whole clip for the Video decoders (joint
+    attention over T*HW keys), a single frame for the Frame decoders;
+  * the per-layer attention mask is never materialised as bools: the mask head's GEMM epilogue writes one sign bit
+    per (query, key) and a per-row "has an unblocked key" flag; the cross-attention kernel expands them in-kernel;
+  * because bilinear down-sampling by an integer factor is the mean of the centre 2x2 pixels and the mask logit is
+    linear in the mask features, the intermediate heads multiply mask_embed with centre-pooled features (1/64, 1/16,
+    1/4 of the pixels) instead of the full-resolution map; only the last head produces full-resolution logits.
+    ``aux_outputs`` (never read in eval by the reference's meta-architectures) are computed on first access.
+"""
+import math
+from typing import List
+
+import torch
+from torch import nn
+
+from . import _lib as L
+
+HIDDEN = 256          # the kernels are specialised for hidden_dim 256 = 8 heads x 32
+NHEADS = 8
+LOG2E = 1.4426950408889634
+
+
+# ------------------------------------------------------------------------------------------------ registry
+class Registry(dict):
+    """Minimal stand-in for detectron2.utils.registry.Registry (video_..._decoder.py:16)."""
+
+    def __init__(self, name):
+        super().__init__()
+        self._name = name
+
+    def register(self, obj=None):
+        def deco(o):
+            self[o.__name__] = o
+            return o
+        return deco if obj is None else deco(obj)
+
+
+TRANSFORMER_DECODER_REGISTRY = Registry("TRANSFORMER_MODULE")
+
+
+def build_transformer_decoder(cfg, in_channels, mask_classification=True):
+    """Same contract as video_mask2former_transformer_decoder.py:21-26."""
+    name = cfg.MODEL.MASK_FORMER.TRANSFORMER_DECODER_NAME
+    return TRANSFORMER_DECODER_REGISTRY.get(name)(cfg, in_channels, mask_classification)
+
+
+def register_into(registry):
+    """Registers (overrides) the B200 decoders in the reference's own TRANSFORMER_DECODER_REGISTRY
+    (a detectron2 Registry or any mapping), see INTEGRATION.md."""
+    for name, cls in TRANSFORMER_DECODER_REGISTRY.items():
+        obj_map = getattr(registry, "_obj_map", registry)
+        obj_map[name] = cls
+
+
+# ------------------------------------------------------------------------------------------------ pos. embeddings
+def _sincos(coord, npf, temperature=10000.0):
+    i = torch.arange(npf, dtype=torch.float32, device=coord.device)
+    dim_t = temperature ** (2 * torch.div(i, 2, rounding_mode="floor") / npf)
+    ang = coord[..., None] / dim_t
+    return torch.stack((ang[..., 0::2].sin(), ang[..., 1::2].cos()), dim=-1).flatten(-2)
+
+
+def sine_pos_2d(h, w, device, npf=HIDDEN // 2):
+    """PositionEmbeddingSine2D(normalize=True) with no padding mask (position_encoding.py:78-103) -> [h*w, 2*npf]."""
+    eps, scale = 1e-6, 2 * math.pi
+    y = torch.arange(1, h + 1, dtype=torch.float32, device=device)
+    x = torch.arange(1, w + 1, dtype=torch.float32, device=device)
+    py = _sincos(y / (y[-1] + eps) * scale, npf)
+    px = _sincos(x / (x[-1] + eps) * scale, npf)
+    return torch.cat([py[:, None, :].expand(h, w, npf), px[None, :, :].expand(h, w, npf)], dim=-1).reshape(h * w, 2 * npf)
+
+
+def sine_pos_z(t, device, npf=HIDDEN // 2):
+    """frame term of PositionEmbeddingSine3D (position_encoding.py:141-163) -> [t, 2*npf]; pos3d = pos2d + pos_z."""
+    eps, scale = 1e-6, 2 * math.pi
+    z = torch.arange(1, t + 1, dtype=torch.float32, device=device)
+    return _sincos(z / (z[-1] + eps) * scale, 2 * npf)
+
+
+# ------------------------------------------------------------------------------------------------ containers
+class _AttnLayer(nn.Module):
+    """Parameter container with the reference layer's names (SelfAttentionLayer / CrossAttentionLayer)."""
+
+    def __init__(self, attn_name, d_model, nhead):
+        super().__init__()
+        setattr(self, attn_name, nn.MultiheadAttention(d_model, nhead, dropout=0.0))
+        self.norm = nn.LayerNorm(d_model)
+        for p in self.parameters():          # _reset_parameters (video_..._decoder.py:44-47)
+            if p.dim() > 1:
+                nn.init.xavier_uniform_(p)
+
+
+class _FFNLayer(nn.Module):
+    def __init__(self, d_model, dim_feedforward):
+        super().__init__()
+        self.linear1 = nn.Linear(d_model, dim_feedforward)
+        self.linear2 = nn.Linear(dim_feedforward, d_model)
+        self.norm = nn.LayerNorm(d_model)
+        for p in self.parameters():
+            if p.dim() > 1:
+                nn.init.xavier_uniform_(p)
+
+
+class MLP(nn.Module):
+    """Container matching MLP (video_..._decoder.py:204-216)."""
+
+    def __init__(self, input_dim, hidden_dim, output_dim, num_layers, affine_func=nn.Linear):
+        super().__init__()
+        self.num_layers = num_layers
+        h = [hidden_dim] * (num_layers - 1)
+        self.layers = nn.ModuleList(affine_func(n, k) for n, k in zip([input_dim] + h, h + [output_dim]))
+
+
+class _LazyDict(dict):
+    """dict whose values may be zero-argument callables resolved (once) on first access."""
+
+    def __getitem__(self, k):
+        v = super().__getitem__(k)
+        if callable(v) and getattr(v, "_ovis_lazy", False):
+            v = v()
+            super().__setitem__(k, v)
+        return v
+
+    def get(self, k, default=None):
+        return self[k] if k in self else default
+
+    def items(self):
+        return [(k, self[k]) for k in self.keys()]
+
+    def values(self):
+        return [self[k] for k in self.keys()]
+
+
+def _lazy(fn):
+    fn._ovis_lazy = True
+    return fn
+
+
+class LazyAuxOutputs(list):
+    """``aux_outputs`` of the reference (``_set_aux_loss``, video_..._decoder.py:473-484): one dict per intermediate
+    prediction head.  The reference's eval paths never read them (openvis.py:84-85, minvis.py:352-353), and writing
+    nine full-resolution mask tensors would make the whole path HBM-bound, so each entry is computed from the saved
+    per-layer query state the first time it is indexed."""
+
+    def __init__(self, n, compute):
+        super().__init__([None] * n)
+        self._compute = compute
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(len(self)))]
+        v = super().__getitem__(i)
+        if v is None:
+            v = self._compute(i if i >= 0 else len(self) + i)
+            super().__setitem__(i, v)
+        return v
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+
+# ------------------------------------------------------------------------------------------------ the decoder
+class _B200MaskedDecoderBase(nn.Module):
+    _version = 2
+    VIDEO = False     # joint attention over the clip (Video decoders) vs per-frame (Frame decoders)
+    SAN = False       # side-adapter variant (attention-bias branch instead of class_embed)
+
+    def __init__(self, in_channels=None, mask_classification=True, *, num_classes: int = None, hidden_dim: int = None,
+                 num_queries: int = None, nheads: int = None, dim_feedforward: int = None, dec_layers: int = None,
+                 pre_norm: bool = None, mask_dim: int = None, enforce_input_project: bool = None, num_frames=None,
+                 **extra):
+        super().__init__()
+        if hidden_dim != HIDDEN or nheads != NHEADS or mask_dim != HIDDEN:
+            raise NotImplementedError("openvis_b200 kernels are specialised for hidden_dim = mask_dim = 256, nheads = 8 "
+                                      f"(got hidden_dim={hidden_dim}, nheads={nheads}, mask_dim={mask_dim})")
+        if pre_norm:
+            raise NotImplementedError("PRE_NORM True is not supported (all shipped configs use post-norm)")
+        if in_channels != hidden_dim or enforce_input_project:
+            raise NotImplementedError("input_proj 1x1 convs are not supported (in_channels must equal hidden_dim, "
+                                      "ENFORCE_INPUT_PROJ False, as in every shipped config)")
+        if num_queries > 256:
+            raise NotImplementedError("at most 256 object queries")
+        self.mask_classification = mask_classification
+        self.num_frames = num_frames
+        self.num_heads = nheads
+        self.num_layers = dec_layers
+        self.num_queries = num_queries
+        self.num_feature_levels = 3
+        self.dim_feedforward = dim_feedforward
+        self.transformer_self_attention_layers = nn.ModuleList(
+            _AttnLayer("self_attn", hidden_dim, nheads) for _ in range(dec_layers))
+        self.transformer_cross_attention_layers = nn.ModuleList(
+            _AttnLayer("multihead_attn", hidden_dim, nheads) for _ in range(dec_layers))
+        self.transformer_ffn_layers = nn.ModuleList(_FFNLayer(hidden_dim, dim_feedforward) for _ in range(dec_layers))
+        self.decoder_norm = nn.LayerNorm(hidden_dim)
+        self.query_feat = nn.Embedding(num_queries, hidden_dim)
+        self.query_embed = nn.Embedding(num_queries, hidden_dim)
+        self.level_embed = nn.Embedding(3, hidden_dim)
+        self.input_proj = nn.ModuleList(nn.Sequential() for _ in range(3))
+        if self.mask_classification:
+            self.class_embed = nn.Linear(hidden_dim, num_classes + 1)
+        self.mask_embed = MLP(hidden_dim, hidden_dim, mask_dim, 3)
+        # non-reference knobs
+        self.materialize_aux = False      # True: compute all nine aux_outputs eagerly (API-exact mode)
+        self.debug_capture = None         # tests: set to a list to receive (head, level, bits, flags) clones
+        self._wcache = None
+        self._pcache = {}
+        self._ws = {}
+        self._generation = 0
+
+    # -- config ------------------------------------------------------------------------------------------------
+    @classmethod
+    def from_config(cls, cfg, in_channels, mask_classification):
+        """video_mask2former_transformer_decoder.py:351-378."""
+        ret = {"in_channels": in_channels, "mask_classification": mask_classification}
+        ret["num_classes"] = cfg.MODEL.SEM_SEG_HEAD.NUM_CLASSES
+        ret["hidden_dim"] = cfg.MODEL.MASK_FORMER.HIDDEN_DIM
+        ret["num_queries"] = cfg.MODEL.MASK_FORMER.NUM_OBJECT_QUERIES
+        ret["nheads"] = cfg.MODEL.MASK_FORMER.NHEADS
+        ret["dim_feedforward"] = cfg.MODEL.MASK_FORMER.DIM_FEEDFORWARD
+        assert cfg.MODEL.MASK_FORMER.DEC_LAYERS >= 1
+        ret["dec_layers"] = cfg.MODEL.MASK_FORMER.DEC_LAYERS - 1
+        ret["pre_norm"] = cfg.MODEL.MASK_FORMER.PRE_NORM
+        ret["enforce_input_project"] = cfg.MODEL.MASK_FORMER.ENFORCE_INPUT_PROJ
+        ret["mask_dim"] = cfg.MODEL.SEM_SEG_HEAD.MASK_DIM
+        ret["num_frames"] = cfg.INPUT.SAMPLING_FRAME_NUM
+        return ret
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+        """legacy-key upgrade of the reference (video_..._decoder.py:224-245): static_query -> query_feat."""
+        version = local_metadata.get("version", None)
+        if version is None or version < 2:
+            for k in list(state_dict.keys()):
+                if k.startswith(prefix) and "static_query" in k:
+                    state_dict[k.replace("static_query", "query_feat")] = state_dict.pop(k)
+        super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs)
+
+    # -- weight / table caches ---------------------------------------------------------------------------------
+    def _wkey(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def _weights(self):
+        """fp16 operand copies of the weights + fused biases; rebuilt whenever a parameter changes."""
+        key = self._wkey()
+        if self._wcache is not None and self._wcache["key"] == key:
+            return self._wcache
+        f16 = lambda t: L.cast_f16(t.detach().float().contiguous())
+        f32 = lambda t: t.detach().float().contiguous()
+        W = {"key": key, "layers": []}
+        C = HIDDEN
+        for i in range(self.num_layers):
+            ca = self.transformer_cross_attention_layers[i]
+            sa = self.transformer_self_attention_layers[i]
+            ff = self.transformer_ffn_layers[i]
+            cw, cb = ca.multihead_attn.in_proj_weight, ca.multihead_attn.in_proj_bias
+            sw, sb = sa.self_attn.in_proj_weight, sa.self_attn.in_proj_bias
+            W["layers"].append(dict(
+                xq_w=f16(cw[:C]), xq_b=f32(cb[:C]),
+                xk_w32=f32(cw[C:2 * C]), xk_b=f32(cb[C:2 * C]), xv_w32=f32(cw[2 * C:]), xv_b=f32(cb[2 * C:]),
+                xo_w=f16(ca.multihead_attn.out_proj.weight), xo_b=f32(ca.multihead_attn.out_proj.bias),
+                ln_x=(f32(ca.norm.weight), f32(ca.norm.bias)),
+                sqk_w=f16(sw[:2 * C]), sqk_b=f32(sb[:2 * C]), sv_w=f16(sw[2 * C:]), sv_b=f32(sb[2 * C:]),
+                so_w=f16(sa.self_attn.out_proj.weight), so_b=f32(sa.self_attn.out_proj.bias),
+                ln_s=(f32(sa.norm.weight), f32(sa.norm.bias)),
+                f1_w=f16(ff.linear1.weight), f1_b=f32(ff.linear1.bias),
+                f2_w=f16(ff.linear2.weight), f2_b=f32(ff.linear2.bias),
+                ln_f=(f32(ff.norm.weight), f32(ff.norm.bias)),
+            ))
+        # K/V projection weights of the layers that read level l, stacked [K_i, V_i, K_i+3, V_i+3, ...]
+        W["kv_w"], W["kv_layers"] = [], []
+        for l in range(3):
+            ids = [i for i in range(self.num_layers) if i % 3 == l]
+            W["kv_layers"].append(ids)
+            if ids:
+                stack = torch.cat([torch.cat([W["layers"][i]["xk_w32"], W["layers"][i]["xv_w32"]]) for i in ids])
+                W["kv_w"].append(L.cast_f16(stack.contiguous()))
+            else:
+                W["kv_w"].append(None)
+        le = f32(self.level_embed.weight)
+        for i, lw in enumerate(W["layers"]):
+            e = le[i % 3]
+            lw["v_bias"] = (lw["xv_b"] + lw["xv_w32"] @ e).contiguous()      # value = (x + level_embed) W_v^T + b_v
+            lw["k_const"] = (lw["xk_b"] + lw["xk_w32"] @ e).contiguous()     # constant part of the key projection
+        W["dn"] = (f32(self.decoder_norm.weight), f32(self.decoder_norm.bias))
+        W["qf"], W["qe"] = f32(self.query_feat.weight), f32(self.query_embed.weight)
+        W["mask_embed"] = [(f16(m.weight), f32(m.bias)) for m in self.mask_embed.layers]
+        if hasattr(self, "class_embed"):
+            ce = self.class_embed
+            W["class_embed"] = [(f16(m.weight), f32(m.bias)) for m in (ce.layers if isinstance(ce, MLP) else [ce])]
+        if self.SAN:
+            W["attn_embed"] = [(f16(m.weight), f32(m.bias)) for m in self.attn_embed.layers]
+            W["attn_mlp"] = [(f16(m.weight.flatten(1)), f32(m.bias)) for m in self.attn_mlp.layers]
+        self._wcache = W
+        self._pcache = {}
+        return W
+
+    def _pos_tables(self, W, T, sizes, device):
+        """Per layer: tab[i] = (pos2d_l) W_k^T + b_k + level_embed_l W_k^T   [N_l, 256] fp32
+        and, for the Video decoders, tab2[i] = pos_z W_k^T [T, 256]  (pos3d = pos2d + pos_z, position_encoding.py:163).
+        Input independent: cached per (weights, T, sizes)."""
+        key = (T if self.VIDEO else 0, tuple(sizes))
+        hit = self._pcache.get(key)
+        if hit is not None:
+            return hit
+        tabs, tabs2 = [], []
+        p2 = [sine_pos_2d(h, w, device) for (h, w) in sizes]
+        pz = sine_pos_z(T, device) if self.VIDEO else None
+        for i, lw in enumerate(W["layers"]):
+            tabs.append((p2[i % 3] @ lw["xk_w32"].T + lw["k_const"]).contiguous())
+            tabs2.append((pz @ lw["xk_w32"].T).contiguous() if self.VIDEO else None)
+        self._pcache[key] = (tabs, tabs2, p2, pz)
+        return self._pcache[key]
+
+    def _workspace(self, BT, H4, W4, device):
+        key = (BT, H4, W4, str(device))
+        ws = self._ws.get(key)
+        if ws is not None:
+            return ws
+        if len(self._ws) >= 2:           # keep at most two shapes resident (a clip-sized workspace is GBs)
+            self._ws.pop(next(iter(self._ws)))
+        Q, C = self.num_queries, HIDDEN
+        G = 1 if self.VIDEO else BT
+        Tg = BT // G
+        R = G * Q
+        N = [(H4 // s) * (W4 // s) for s in (8, 4, 2)]
+        M = H4 * W4
+        h = lambda *s: torch.empty(*s, dtype=torch.float16, device=device)
+        f = lambda *s: torch.empty(*s, dtype=torch.float32, device=device)
+        ws = dict(G=G, Tg=Tg, R=R, N=N, M=M)
+        ws["xt"] = [h(BT * n, C) for n in N]
+        ws["ft"] = h(BT * M, C)
+        ws["gt"] = [h(BT * n, C) for n in N]
+        ws["k"] = [h(BT * N[i % 3], C) for i in range(self.num_layers)]
+        ws["v"] = [h(BT * N[i % 3], C) for i in range(self.num_layers)]
+        ws["z32"], ws["z16"], ws["ze16"] = f(R, C), h(R, C), h(R, C)
+        ws["d32"] = f(R, C)
+        ws["d16"] = h(self.num_layers + 1, R, C)            # decoder_norm output of every head (lazy aux needs them)
+        ws["q16"], ws["att16"], ws["qk16"], ws["v16"], ws["sa16"] = h(R, C), h(R, C), h(R, 2 * C), h(R, C), h(R, C)
+        ws["h16"] = h(R, self.dim_feedforward)
+        ws["m1"], ws["m2"], ws["me16"] = h(R, C), h(R, C), h(R, C)
+        ws["bits"] = [torch.zeros(G, (Tg * n + 31) // 32, Q, dtype=torch.int32, device=device) for n in N]
+        ws["flags"] = torch.zeros(self.num_layers + 1, G, Q, dtype=torch.uint8, device=device)
+        plans = [L.xattn_plan(G, Q, Tg * n) for n in N]
+        ws["splits"] = [p[0] for p in plans]
+        ws["o_part"] = f(max(p[2] for p in plans))
+        ws["ml_part"] = f(max(p[3] for p in plans))
+        self._ws[key] = ws
+        return ws
+
+    # -- pieces of the schedule ----------------------------------------------------------------------------------
+    @staticmethod
+    def _mlp3(params, x16, t1, t2, out16):
+        L.linear_f16(x16, params[0][0], params[0][1], relu=True, out=t1)
+        L.linear_f16(t1, params[1][0], params[1][1], relu=True, out=t2)
+        L.linear_f16(t2, params[2][0], params[2][1], relu=False, out=out16)
+        return out16
+
+    def _check_inputs(self, x, mask_features):
+        if self.training:
+            raise RuntimeError("openvis_b200 decoders are inference-only: call .eval() (training / autograd is out of scope)")
+        if torch.is_grad_enabled() and any(t.requires_grad for t in list(x) + [mask_features]):
+            raise RuntimeError("openvis_b200 decoders do not support autograd; wrap the call in torch.no_grad()")
+        assert len(x) == self.num_feature_levels
+        if not mask_features.is_cuda:
+            raise L.OvisError("openvis_b200 has no CPU path: inputs must be CUDA tensors on an sm_100 device")
+        BT, C, H4, W4 = mask_features.shape
+        if C != HIDDEN or H4 % 8 or W4 % 8:
+            raise NotImplementedError(f"mask_features must be [BT, 256, H/4, W/4] with H, W multiples of 32, got {tuple(mask_features.shape)}")
+        sizes = []
+        for l, s in enumerate((8, 4, 2)):
+            exp = (BT, C, H4 // s, W4 // s)
+            if tuple(x[l].shape) != exp:
+                raise NotImplementedError(
+                    f"multi-scale feature {l} must be {exp} (strides 32/16/8 of a /32-padded input, coarsest first); "
+                    f"got {tuple(x[l].shape)}: the centre-2x2 mask down-sampling identity needs integer factors")
+            sizes.append((H4 // s, W4 // s))
+        return BT, H4, W4, sizes
+
+    @torch.no_grad()
+    def forward(self, x: List[torch.Tensor], mask_features: torch.Tensor, mask=None):
+        del mask                                  # "disable mask, it does not affect performance" (frame_...:59-60)
+        BT, H4, W4, sizes = self._check_inputs(x, mask_features)
+        dev = mask_features.device
+        x = [t.float().contiguous() for t in x]
+        mask_features_in = mask_features
+        mf = mask_features.float().contiguous()
+        with torch.cuda.device(dev):
+            return self._forward_impl(x, mf, mask_features_in, BT, H4, W4, sizes, dev)
+
+    def _forward_impl(self, x, mf, mask_features_in, BT, H4, W4, sizes, dev):
+        W = self._weights()
+        ws = self._workspace(BT, H4, W4, dev)
+        tabs, tabs2, p2, pz = self._pos_tables(W, BT, sizes, dev)
+        self._generation += 1
+        gen = self._generation
+        G, Tg, R, N, M = ws["G"], ws["Tg"], ws["R"], ws["N"], ws["M"]
+        Q, C, nl = self.num_queries, HIDDEN, self.num_layers
+
+        # ---- layout preparation (HBM-bound, once per call)
+        for l in range(3):
+            L.nchw_to_tokens_f16(x[l], out=ws["xt"][l])
+        L.maskfeat_prep(mf, (ws["ft"], ws["gt"][0], ws["gt"][1], ws["gt"][2]))
+        # ---- key / value projections of all layers, one launch per level
+        for l in range(3):
+            ids = W["kv_layers"][l]
+            if not ids:
+                continue
+            outs, biases, tb, tb2 = [], [], [], []
+            for i in ids:
+                outs += [ws["k"][i], ws["v"][i]]
+                biases += [None, W["layers"][i]["v_bias"]]
+                tb += [tabs[i], None]
+                tb2 += [tabs2[i], None]
+            L.kv_proj_f16(ws["xt"][l], 1, BT * N[l], W["kv_w"][l], outs, biases, tb, tb2, tab_period=N[l])
+
+        san = self._san_prepare(W, ws, BT, H4, W4) if self.SAN else None
+
+        ws["flags"].zero_()
+        L.init_queries(W["qf"], W["qe"], W["dn"][0], W["dn"][1], G, (ws["z32"], ws["z16"], ws["ze16"], ws["d32"], ws["d16"][0]))
+
+        def head_bits(hidx, level):
+            me = self._mlp3(W["mask_embed"], ws["d16"][hidx], ws["m1"], ws["m2"], ws["me16"])
+            L.mask_bits(ws["gt"][level], G, Tg * N[level], me, Q, ws["bits"][level], ws["flags"][hidx], Q)
+            if self.debug_capture is not None:
+                self.debug_capture.append((hidx, level, ws["bits"][level].clone(), ws["flags"][hidx].clone()))
+
+        head_bits(0, 0)
+        qscale = (C // NHEADS) ** -0.5 * LOG2E
+        for i in range(nl):
+            l = i % 3
+            lw = W["layers"][i]
+            # masked cross-attention (video_..._decoder.py:110-122)
+            L.linear_f16(ws["ze16"], lw["xq_w"], lw["xq_b"], scale=qscale, out=ws["q16"])
+            L.xattn(ws["q16"], ws["k"][i], ws["v"][i], ws["bits"][l], ws["flags"][i], G, Q, Q, Tg * N[l], ws["splits"][l],
+                    ws["o_part"], ws["ml_part"], ws["att16"])
+            L.linear_ln_f16(ws["att16"], lw["xo_w"], lw["xo_b"], ws["z32"], lw["ln_x"], None, W["qe"],
+                            y32=ws["z32"], y16=ws["z16"], ype16=ws["ze16"])
+            # self-attention (video_..._decoder.py:52-62)
+            L.linear_f16(ws["ze16"], lw["sqk_w"], lw["sqk_b"], out=ws["qk16"])
+            L.linear_f16(ws["z16"], lw["sv_w"], lw["sv_b"], out=ws["v16"])
+            L.self_attn(ws["qk16"], ws["v16"], ws["sa16"], G, Q)
+            L.linear_ln_f16(ws["sa16"], lw["so_w"], lw["so_b"], ws["z32"], lw["ln_s"], None, W["qe"],
+                            y32=ws["z32"], y16=ws["z16"], ype16=ws["ze16"])
+            # FFN (video_..._decoder.py:175-179) + decoder_norm of the following prediction head
+            L.linear_f16(ws["z16"], lw["f1_w"], lw["f1_b"], relu=True, out=ws["h16"])
+            L.linear_ln_f16(ws["h16"], lw["f2_w"], lw["f2_b"], ws["z32"], lw["ln_f"], W["dn"], W["qe"],
+                            y32=ws["z32"], y16=ws["z16"], ype16=ws["ze16"], d32=ws["d32"], d16=ws["d16"][i + 1])
+            if i + 1 < nl:
+                head_bits(i + 1, (i + 1) % 3)
+
+        # ---- final prediction head: full-resolution mask logits, class logits / attention biases
+        out = _LazyDict()
+        pred_masks = self._full_masks(W, ws, nl, BT, H4, W4)
+        pred_embeds = ws["d32"].clone()
+        cls = self._class_outputs(W, ws, nl, BT, san)
+        self._pack_outputs(out, cls, pred_masks, pred_embeds, x, mask_features_in, sizes, p2, pz, BT, san)
+
+        def compute_aux(j):
+            if gen != self._generation:
+                raise RuntimeError("aux_outputs must be read before the next forward() of the same decoder "
+                                   "(set decoder.materialize_aux = True to compute them eagerly)")
+            with torch.cuda.device(dev):
+                m = self._full_masks(W, ws, j, BT, H4, W4)
+                c = self._class_outputs(W, ws, j, BT, san)
+            d = {}
+            self._pack_head(d, c, m, BT)
+            return d
+
+        aux = LazyAuxOutputs(nl, compute_aux)
+        if self.materialize_aux:
+            list(aux)
+        out["aux_outputs"] = aux
+        return out
+
+    def _full_masks(self, W, ws, hidx, BT, H4, W4):
+        """einsum("bqc,bchw->bqhw") of head `hidx`, written directly in the reference's eval layout [1, Q, T, H, W]
+        ('(b t) q h w -> b q t h w', frame_...:117-118; video_...:459)."""
+        Q = self.num_queries
+        me = self._mlp3(W["mask_embed"], ws["d16"][hidx], ws["m1"], ws["m2"], ws["me16"])
+        out = torch.empty(1, Q, BT, H4, W4, dtype=torch.float32, device=me.device)
+        L.mask_logits(ws["ft"], ws["G"], ws["Tg"] * ws["M"], me, Q, Q, out, ws["Tg"] * ws["M"], BT * ws["M"])
+        return out
+
+    def _class_outputs(self, W, ws, hidx, BT, san):
+        if "class_embed" not in W:
+            return None
+        x = ws["d16"][hidx]
+        params = W["class_embed"]
+        for j, (w, b) in enumerate(params):
+            last = j == len(params) - 1
+            x = L.linear_f16(x, w, b, relu=not last, out_f32=last)
+        return x                                                   # [G*Q, cls] fp32
+
+    def _pack_head(self, d, cls, masks, BT):
+        Q = self.num_queries
+        if cls is not None:
+            d["pred_logits"] = cls.view(1, Q, -1) if self.VIDEO else cls.view(1, BT, Q, -1)
+        d["pred_masks"] = masks
+
+    def _pack_outputs(self, out, cls, pred_masks, pred_embeds, x, mask_features, sizes, p2, pz, BT, san):
+        self._pack_head(out, cls, pred_masks, BT)
+        if not self.VIDEO:
+            Q = self.num_queries
+            le = self.level_embed.weight.detach().float()
+            out["mask_feats"] = mask_features
+            # (frame_...:64-69) returned for API compatibility only; built on first access with torch glue
+            out["ms_feats"] = _lazy(lambda: [(x[l].flatten(2) + le[l][None, :, None]).permute(2, 0, 1) for l in range(3)])
+            out["ms_pos"] = _lazy(lambda: [p2[l][:, None, :].expand(-1, BT, -1) for l in range(3)])
+            out["size_list"] = [torch.Size(s) for s in sizes]
+            out["pred_embeds"] = pred_embeds.view(1, BT, Q, HIDDEN)
+
+    def _san_prepare(self, W, ws, BT, H4, W4):   # pragma: no cover - overridden
+        return None
+
+
+# ------------------------------------------------------------------------------------------------ public classes
+def _configurable_new(cls):
+    """Emulates detectron2's @configurable: Cls(cfg, in_channels, mask_classification) -> Cls(**from_config(...))."""
+    orig_init = cls.__init__
+
+    def __init__(self, *args, **kwargs):
+        if args and hasattr(args[0], "MODEL"):
+            kw = type(self).from_config(*args, **kwargs)
+            orig_init(self, **kw)
+        else:
+            orig_init(self, *args, **kwargs)
+
+    cls.__init__ = __init__
+    return cls
+
+
+@TRANSFORMER_DECODER_REGISTRY.register()
+@_configurable_new
+class VideoMultiScaleMaskedTransformerDecoder(_B200MaskedDecoderBase):
+    VIDEO = True
+
+
+@TRANSFORMER_DECODER_REGISTRY.register()
+@_configurable_new
+class FrameMultiScaleMaskedTransformerDecoder(_B200MaskedDecoderBase):
+    VIDEO = False
+
+
+class _EmbeddingMixin:
+    """Embedding* variants: class_embed = MLP(hidden, 2*clip_dims, clip_dims, 2) (video_..._decoder.py:487-523)."""
+
+    def __init__(self, clip_dims=None, mask_classification=True, **kwargs):
+        super().__init__(mask_classification=False, **kwargs)
+        self.mask_classification = mask_classification
+        if self.mask_classification:
+            self.class_embed = MLP(kwargs["hidden_dim"], clip_dims * 2, clip_dims, 2)
+
+    @classmethod
+    def from_config(cls, cfg, in_channels, mask_classification):
+        ret = super().from_config(cfg, in_channels, mask_classification)
+        ret["clip_dims"] = cfg.MODEL.CLIP_ADAPTER.CLIP_EMBED_DIMS
+        return ret
+
+
+class _ProposalMixin:
+    """Proposal* variants: class_embed = Linear(hidden, 2) (video_..._decoder.py:526-537)."""
+
+    def __init__(self, mask_classification=True, **kwargs):
+        super().__init__(mask_classification=False, **kwargs)
+        self.mask_classification = mask_classification
+        if self.mask_classification:
+            self.class_embed = nn.Linear(kwargs["hidden_dim"], 1 + 1)
+
+
+@TRANSFORMER_DECODER_REGISTRY.register()
+@_configurable_new
+class EmbeddingVideoMultiScaleMaskedTransformerDecoder(_EmbeddingMixin, _B200MaskedDecoderBase):
+    VIDEO = True
+
+
+@TRANSFORMER_DECODER_REGISTRY.register()
+@_configurable_new
+class ProposalVideoMultiScaleMaskedTransformerDecoder(_ProposalMixin, _B200MaskedDecoderBase):
+    VIDEO = True
+
+
+@TRANSFORMER_DECODER_REGISTRY.register()
+@_configurable_new
+class EmbeddingFrameMultiScaleMaskedTransformerDecoder(_EmbeddingMixin, _B200MaskedDecoderBase):
+    VIDEO = False
+
+
+@TRANSFORMER_DECODER_REGISTRY.register()
+@_configurable_new
+class ProposalFrameMultiScaleMaskedTransformerDecoder(_ProposalMixin, _B200MaskedDecoderBase):
+    VIDEO = False
+
+
+class _SideAdapterMixin:
+    """SAN decoders (side_adapter_frame_..._decoder.py:29-55): no class_embed; `attn_embed` MLP and the `attn_mlp`
+    1x1-conv branch that turns quarter-resolution mask features into per-CLIP-head attention-bias features."""
+    SAN = True
+
+    def __init__(self, clip_heads=None, mask_classification=True, **kwargs):
+        super().__init__(mask_classification=False, **kwargs)
+        hidden_dim = kwargs["hidden_dim"]
+        self.clip_heads = clip_heads
+        self.attn_embed = MLP(hidden_dim, hidden_dim, hidden_dim, 3)
+        self.attn_mlp = MLP(hidden_dim, hidden_dim, hidden_dim * clip_heads, 3,
+                            affine_func=lambda n, k: nn.Conv2d(n, k, kernel_size=1))
+
+    @classmethod
+    def from_config(cls, cfg, in_channels, mask_classification):
+        ret = super().from_config(cfg, in_channels, mask_classification)
+        ret["clip_heads"] = cfg.MODEL.CLIP_ADAPTER.CLIP_NUM_HEADS
+        return ret
+
+    def _san_prepare(self, W, ws, BT, H4, W4):
+        """attn_features = attn_mlp(bilinear 1/4 (mask_features)) (side_adapter_frame_...:67-71).  The bilinear 1/4
+        map is the centre-2x2 mean at stride 4, i.e. exactly the level-1 pooled features g1 already computed."""
+        nh, C = self.clip_heads, HIDDEN
+        P = ws["N"][1]
+        dev = ws["ft"].device
+        if "af_h1" not in ws:
+            ws["af_h1"] = torch.empty(BT * P, C, dtype=torch.float16, device=dev)
+            ws["af_h2"] = torch.empty(BT * P, C, dtype=torch.float16, device=dev)
+            ws["af16"] = torch.empty(BT * P, nh * C, dtype=torch.float16, device=dev)
+            ws["ae16"] = torch.empty(ws["R"], C, dtype=torch.float16, device=dev)
+        (w0, b0), (w1, b1), (w2, b2) = W["attn_mlp"]
+        L.linear_f16(ws["gt"][1], w0, b0, relu=True, out=ws["af_h1"])
+        L.linear_f16(ws["af_h1"], w1, b1, relu=True, out=ws["af_h2"])
+        # token-major fp16 copy (operand of the bias einsum) ...
+        L.linear_f16(ws["af_h2"], w2, b2, out=ws["af16"])
+        # ... and the fp32 NCHW tensor the reference returns as `attn_feats` [BT, heads, C, h, w]
+        attn_feats = torch.empty(BT, nh, C, H4 // 4, W4 // 4, dtype=torch.float32, device=dev)
+        L.mask_logits(ws["af_h2"], BT, P, w2, 0, nh * C, attn_feats, nh * C * P, P, bias=b2)
+        return dict(attn_feats=attn_feats, P=P, hw=(H4 // 4, W4 // 4))
+
+    def _class_outputs(self, W, ws, hidx, BT, san):
+        """class_attn_biases = einsum("bqc,bnchw->bnqhw") (side_adapter_frame_...:154-157) /
+        "bqc,btnchw->btnqhw" (side_adapter_video_...:128)."""
+        Q, nh = self.num_queries, self.clip_heads
+        ae = self._mlp3(W["attn_embed"], ws["d16"][hidx], ws["m1"], ws["m2"], ws["ae16"])
+        h, w = san["hw"]
+        out = torch.empty(BT, nh, Q, h, w, dtype=torch.float32, device=ae.device)
+        if self.VIDEO:
+            # one set of queries for all frames: replicate the [Q, 256] embedding block per frame (tiny)
+            ae = ae.repeat(BT, 1)
+        L.san_bias_logits(ws["af16"], BT, san["P"], nh, ae, Q, out)
+        return out
+
+    def _pack_head(self, d, cls, masks, BT):
+        d["class_attn_biases"] = cls[None]                       # [1, T, n, Q, h, w]
+        d["pred_masks"] = masks
+
+    def _pack_outputs(self, out, cls, pred_masks, pred_embeds, x, mask_features, sizes, p2, pz, BT, san):
+        super()._pack_outputs(out, cls, pred_masks, pred_embeds, x, mask_features, sizes, p2, pz, BT, san)
+        if not self.VIDEO:
+            out["attn_feats"] = san["attn_feats"]
+
+
+@TRANSFORMER_DECODER_REGISTRY.register()
+@_configurable_new
+class SideAdapterFrameMultiScaleMaskedTransformerDecoder(_SideAdapterMixin, _B200MaskedDecoderBase):
+    VIDEO = False
+
+
+@TRANSFORMER_DECODER_REGISTRY.register()
+@_configurable_new
+class SideAdapterVideoMultiScaleMaskedTransformerDecoder(_SideAdapterMixin, _B200MaskedDecoderBase):
+    VIDEO = True

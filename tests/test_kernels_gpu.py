@@ -120,7 +120,7 @@ def test_mask_bits(G, rows, Q):
     assert torch.equal(flags.bool(), (~got).any(-1))
     # tail bits beyond `rows` are "blocked"
     if rows % 32:
-        tail = bits.long()[:, -1, :] >> (rows % 32)
+        tail = (bits.long()[:, -1, :] & 0xFFFFFFFF) >> (rows % 32)
         assert bool((tail == (1 << (32 - rows % 32)) - 1).all())
 
 

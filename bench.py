@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""Headline benchmark: decoder + open-vocabulary head frames/sec (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            # this repository's CUDA path
+  python bench.py --impl reference [--gpus N] [--steps K] ...    # reference arm: the CPU restatement of the reference
+                                                                  # path (oracle/) on the host cores, bounded sample
+
+Workload (config.workload): BASELINE configs[1] -- OpenVIS R50 Video decoder on synthetic 36-frame 720x1280 clips
+(padded to 736x1280), 100 queries, followed by the OpenVIS OV tail (L2-normalise region features, 100 * f @ text^T
+against a cached 40-class text matrix, per-query mean over non-empty frames, softmax).  One step = one clip.
+Synthetic data: N(0,1) pixel-decoder outputs, seeded weights (oracle.decoder_ref.seeded_params), unit-norm text.
+
+One process per GPU (torchrun for N > 1); clips shard across ranks with no data-path collective; a single NCCL
+all_gather of the per-clip class scores closes the timed region.  value = frames of all ranks / max-over-ranks time.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (decoder kind, T, Hp, Wp, Q, K_vocab)
+    "openvis_video_36x720x1280_q100_k40": ("video", 36, 736, 1280, 100, 40),
+    "openvis_video_5x360x640_q100_k40": ("video", 5, 384, 640, 100, 40),
+}
+DEFAULT_WORKLOAD = "openvis_video_36x720x1280_q100_k40"
+METRIC = "decoder+OV-head frames/sec"
+UNIT = "frames/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=list(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """Samples SM clock / throttle reasons during the timed region (pynvml, else nvidia-smi)."""
+
+    def __init__(self, index):
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        self._nv = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self._nv = None
+
+    def _loop(self):
+        nv = self._nv
+        names = {}
+        if nv is not None:
+            for n in dir(nv):
+                if n.startswith("nvmlClocksEventReason") or n.startswith("nvmlClocksThrottleReason"):
+                    v = getattr(nv, n)
+                    if isinstance(v, int) and v:
+                        names[v] = n.replace("nvmlClocksEventReason", "").replace("nvmlClocksThrottleReason", "")
+        while not self._stop.is_set():
+            try:
+                if nv is not None:
+                    self.samples.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+                    try:
+                        r = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+                    except Exception:
+                        r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                    for bit, n in names.items():
+                        if r & bit and n not in ("GpuIdle", "None", "All"):
+                            self.reasons.add(n)
+                else:
+                    import subprocess
+                    o = subprocess.run(["nvidia-smi", f"--id={self.index}", "--query-gpu=clocks.sm,clocks.max.sm",
+                                        "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                    a, b = [int(v) for v in o.strip().split(",")]
+                    self.samples.append(a)
+                    self.max_mhz = b
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def start(self):
+        self._thr = threading.Thread(target=self._loop, daemon=True)
+        self._thr.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thr:
+            self._thr.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------------ helpers
+def algorithmic_flops_per_frame(T, Hp, Wp, Q, K, C=256, F=2048, L=9, cls=2):
+    """SURVEY.md section 8(d), Video decoder: query-side terms divided by T."""
+    N = [Hp * Wp // 1024, Hp * Wp // 256, Hp * Wp // 64]
+    M = Hp * Wp // 16
+    f_x = sum(4 * N[i % 3] * C * C + 4 * Q * N[i % 3] * C for i in range(L)) + L * 4 * Q * C * C / T
+    f_self = L * (8 * Q * C * C + 4 * Q * Q * C) / T
+    f_ffn = L * 4 * Q * C * F / T
+    f_head = (L + 1) * (6 * Q * C * C + 2 * Q * C * cls) / T + (L + 1) * 2 * Q * C * M
+    f_ov = 2 * Q * 512 * K
+    return f_x + f_self + f_ffn + f_head + f_ov
+
+
+def make_text(K, seed=7):
+    g = torch.Generator().manual_seed(seed)
+    return torch.nn.functional.normalize(torch.randn(K, 512, generator=g), dim=-1)
+
+
+def make_clip(T, Hp, Wp, Q, seed):
+    from openvis_b200.synthetic import seeded_inputs
+    x, mf = seeded_inputs(T, Hp, Wp, seed=seed)
+    g = torch.Generator().manual_seed(seed + 1)
+    feats = torch.randn(T, Q, 512, generator=g)
+    return x, mf, feats
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def oracle_step(P, x, mf, feats, text, kind):
+    from oracle import decoder_ref as O
+    out = O.decoder_forward(P, x, mf, kind=kind, return_attn_masks=False)
+    masks = out["pred_masks"][0]                                  # [Q, T, H, W]
+    valid = (masks > 0).flatten(2).any(-1).T                      # [T, Q]
+    logits = O.ov_cosine_logits(feats.reshape(-1, 512), text, 100.0)
+    if valid.any():
+        O.openvis_clip_aggregate(logits[valid.flatten()], valid)
+    return out
+
+
+def run_reference(args):
+    """CPU implementation of the path (the oracle port; the reference itself is Python and cannot travel to the GPU
+    box) on all host threads, each step a bounded sample (a 4-frame sub-clip at the workload's resolution)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import decoder_ref as O
+    kind, T, Hp, Wp, Q, K = WORKLOADS[args.workload]
+    Ts = min(T, 4)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.set_grad_enabled(False)
+    P = O.seeded_params(O.decoder_param_shapes(kind, Q=Q), 0)
+    text = make_text(K)
+    x, mf, feats = make_clip(Ts, Hp, Wp, Q, 1234)
+    for _ in range(max(1, min(args.warmup, 2))):
+        oracle_step(P, x, mf, feats, text, kind)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oracle_step(P, x, mf, feats, text, kind)
+    dt = time.perf_counter() - t0
+    v = args.steps * Ts / dt
+    sample = f"{Ts}-frame sub-clip of the {T}-frame {Hp}x{Wp} clip per step, fp32, torch CPU ({torch.get_num_threads()} threads)"
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "frames_per_step": Ts},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(kind, T, Hp, Wp, Q, K):
+    from oracle import decoder_ref as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    Ts = min(T, 4)
+    P = O.seeded_params(O.decoder_param_shapes(kind, Q=Q), 0)
+    text = make_text(K)
+    x, mf, feats = make_clip(Ts, Hp, Wp, Q, 1234)
+    with torch.no_grad():
+        oracle_step(P, x, mf, feats, text, kind)
+        best = 1e30
+        for _ in range(3):
+            t0 = time.perf_counter()
+            oracle_step(P, x, mf, feats, text, kind)
+            best = min(best, time.perf_counter() - t0)
+    return {"value": Ts / best, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"oracle port, {Ts}-frame sub-clip at {Hp}x{Wp}, fp32, best of 3, {torch.get_num_threads()} threads"}
+
+
+# ------------------------------------------------------------------------------------------------ B200 arm
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch.distributed as dist
+    from openvis_b200 import _lib as L
+    from openvis_b200 import decoder as D
+    from openvis_b200.ov_head import ClipLogitHead
+    from openvis_b200 import synthetic as O
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L.device_check()
+    torch.set_grad_enabled(False)
+
+    kind, T, Hp, Wp, Q, K = WORKLOADS[args.workload]
+    kw = dict(in_channels=256, mask_classification=True, num_classes=1, hidden_dim=256, num_queries=Q, nheads=8,
+              dim_feedforward=2048, dec_layers=9, pre_norm=False, mask_dim=256, enforce_input_project=False, num_frames=2)
+    dec = D.VideoMultiScaleMaskedTransformerDecoder(**kw)
+    dec.load_state_dict(O.seeded_params(O.decoder_param_shapes(kind, Q=Q), 0))
+    dec = dec.to(dev).eval()
+    head = ClipLogitHead()
+    text = make_text(K).to(dev)
+
+    # two distinct clips per rank, alternated, resident in HBM (each clip's inputs are ~2.9 GB >> 126 MB L2)
+    host_clips = [make_clip(T, Hp, Wp, Q, 1234 + 2 * rank + j) for j in range(2)]
+    dev_clips = [([t.to(dev) for t in x], mf.to(dev), f.to(dev)) for (x, mf, f) in host_clips]
+
+    xattn_events = []
+
+    def step(clip, record=False):
+        x, mf, feats = clip
+        if record:
+            L.PROFILE = xattn_events
+        out = dec(x, mf)
+        L.PROFILE = None
+        probs, qvalid = head.open_vocabulary_scores(feats, out["mask_valid"], text)
+        return out, probs, qvalid
+
+    # ---- device-resident throughput
+    for i in range(args.warmup):
+        step(dev_clips[i % 2])
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = L.launch_count()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    scores = []
+    for i in range(args.steps):
+        out, probs, qvalid = step(dev_clips[i % 2], record=True)
+        scores.append(probs)
+    if world > 1:   # the only collective of the path: gather of per-clip results
+        allp = [torch.empty_like(scores[-1]) for _ in range(world)]
+        dist.all_gather(allp, scores[-1])
+    e1.record()
+    torch.cuda.synchronize()
+    launches = L.launch_count() - l0
+    clocks = sampler.stop()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = ms.item()
+    value = world * args.steps * T / (ms * 1e-3)
+
+    # ---- dominant kernel roofline (masked cross-attention): CUDA events recorded around its launches in the timed region
+    flops_x = [4.0 * Q * (T * n) * 256 for n in (Hp * Wp // 1024, Hp * Wp // 256, Hp * Wp // 64)]
+    xt = [a.elapsed_time(b) for (_, a, b) in xattn_events]
+    names = [n for (n, _, _) in xattn_events]
+    per_layer = len(xt) // max(1, args.steps)
+    tot_flops = sum(flops_x[i % 3] for i in range(per_layer)) * args.steps if per_layer else 0.0
+    pk, src = peaks()
+    x_ms = sum(xt)
+    ach = tot_flops / (x_ms * 1e-3) / 1e12 if x_ms > 0 else 0.0
+    peak_tf = pk.get("bf16_tflops_sustained", pk.get("bf16_tflops"))
+    roofline = {"kernel": "xattn_split_kernel+xattn_combine_kernel", "bound": "tensor", "achieved": ach, "peak": peak_tf,
+                "unit": "TFLOP/s", "frac": ach / peak_tf if peak_tf else None, "traffic": None,
+                "peak_source": f"{src} bf16_tflops_sustained (kernel timed inside a long step)",
+                "share_of_step": x_ms / ms if ms > 0 else None, "launches_timed": len(xt)}
+
+    # ---- end to end through the public API with host buffers (pinned), H2D + forward + D2H every step
+    e2e = None
+    if not args.no_e2e:
+        pinned = [([t.pin_memory() for t in x], mf.pin_memory(), f.pin_memory()) for (x, mf, f) in host_clips]
+        h2d = sum(t.numel() * 4 for t in pinned[0][0]) + pinned[0][1].numel() * 4 + pinned[0][2].numel() * 4
+        copy_s = torch.cuda.Stream()
+        bufs = dev_clips                       # reuse the two resident buffers as the double-buffered staging area
+        ready = [torch.cuda.Event() for _ in range(2)]
+        done = [torch.cuda.Event() for _ in range(2)]
+        res_host = [(torch.empty(Q, K).pin_memory(), torch.empty(1, Q, 2).pin_memory(), torch.empty(Q, dtype=torch.bool).pin_memory())
+                    for _ in range(2)]
+        d2h = sum(t.numel() * t.element_size() for t in res_host[0])
+
+        def upload(j):
+            with torch.cuda.stream(copy_s):
+                copy_s.wait_event(done[j])
+                for dst, srcx in zip(bufs[j][0], pinned[j][0]):
+                    dst.copy_(srcx, non_blocking=True)
+                bufs[j][1].copy_(pinned[j][1], non_blocking=True)
+                bufs[j][2].copy_(pinned[j][2], non_blocking=True)
+                ready[j].record(copy_s)
+
+        def e2e_loop(n):
+            cur = torch.cuda.current_stream()
+            for j in range(2):
+                done[j].record(cur)
+            upload(0)
+            for i in range(n):
+                j = i % 2
+                if i + 1 < n:
+                    upload((i + 1) % 2)        # overlaps the next clip's H2D with this clip's kernels
+                cur.wait_event(ready[j])
+                out, probs, qvalid = step(bufs[j])
+                res_host[j][0].copy_(probs, non_blocking=True)
+                res_host[j][1].copy_(out["pred_logits"], non_blocking=True)
+                res_host[j][2].copy_(qvalid, non_blocking=True)
+                done[j].record(cur)
+            torch.cuda.synchronize()
+
+        e2e_loop(2)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        e2e_loop(args.steps)
+        dt = torch.tensor([time.perf_counter() - t0], device=dev)
+        if world > 1:
+            dist.barrier()
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * args.steps * T / dt.item(), "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h,
+               "note": "pinned host inputs -> device (double-buffered on a copy stream) -> decoder + OV head -> scores/logits "
+                       "to pinned host; pred_masks stay on the device for the (out-of-scope) post-processing"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(kind, T, Hp, Wp, Q, K)
+    flops_frame = algorithmic_flops_per_frame(T, Hp, Wp, Q, K)
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16 operands / f32 accumulate", "data": "synthetic",
+            "config": {"workload": args.workload, "frames_per_step_per_gpu": T, "queries": Q, "vocab": K,
+                       "l2": "inputs larger than L2 (2.9 GB per clip, two clips alternated)",
+                       "aux_outputs": "lazy (inference-minimal)", "parallelism": f"clip-sharded dp{world}"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu,
+            "whole_path": {"gflop_per_frame": flops_frame / 1e9,
+                           "tensor_frac_of_sustained": value / world * flops_frame / 1e12 / peak_tf if peak_tf else None}}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

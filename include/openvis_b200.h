@@ -81,9 +81,12 @@ int ovis_mask_bits(const void* gt_f16, int groups, int rows_per_group, const voi
                    unsigned int* bits, unsigned char* flags, int q_stride, void* stream);
 /* Full-resolution mask logits out[g*t_group_stride + q*ldt + r] = ft[g][r] . mask_embed[g][q] (+ bias[q]).
  * einsum("bqc,bchw->bqhw") / ("bqc,btchw->bqthw") (frame_...:144, video_...:459); also the 1x1-conv output of the
- * SAN attention-bias branch when bias != null (side_adapter_frame_...decoder.py:67-71). */
+ * SAN attention-bias branch when bias != null (side_adapter_frame_...decoder.py:67-71).
+ * posflags (optional, zeroed by the caller) [frames][Q]: set to 1 when frame/query has a positive logit, i.e. a
+ * non-empty mask -- the `valid` test of ClipAdapter._preprocess_image (clip_adapter/adapter.py:86-88). */
 int ovis_mask_logits(const void* ft_f16, int groups, int rows_per_group, const void* me_f16, int me_group_stride,
-                     int Q, const float* bias, float* out, long long t_group_stride, long long ldt, void* stream);
+                     int Q, const float* bias, float* out, long long t_group_stride, long long ldt,
+                     unsigned char* posflags, int rows_per_frame, void* stream);
 /* SAN per-head attention biases (side_adapter_frame_...decoder.py:157, einsum "bqc,bnchw->bnqhw"):
  * out[b][n][q][p] = af[b][p][n*256:(n+1)*256] . attn_embed[b][q];  af is the fp16 token-major copy
  * [B][P][heads*256] of attn_features. */

@@ -29,7 +29,7 @@ SIGNATURES = {
                                     _vp, _vp, _vp, _vp, _vp, _vp]),
     "ovis_kv_proj_f16": (_c_int, [_vp, _c_int, _c_int, _vp, _c_int, _vp, _vp, _vp, _vp, _c_int, _vp]),
     "ovis_mask_bits": (_c_int, [_vp, _c_int, _c_int, _vp, _c_int, _vp, _vp, _c_int, _vp]),
-    "ovis_mask_logits": (_c_int, [_vp, _c_int, _c_int, _vp, _c_int, _c_int, _vp, _vp, _c_ll, _c_ll, _vp]),
+    "ovis_mask_logits": (_c_int, [_vp, _c_int, _c_int, _vp, _c_int, _c_int, _vp, _vp, _c_ll, _c_ll, _vp, _c_int, _vp]),
     "ovis_san_bias_logits": (_c_int, [_vp, _c_int, _c_int, _c_int, _vp, _c_int, _vp, _vp]),
     "ovis_xattn_plan": (_c_int, [_c_int, _c_int, _c_int, ctypes.POINTER(_c_int), ctypes.POINTER(_c_int),
                                  ctypes.POINTER(_c_ll), ctypes.POINTER(_c_ll)]),
@@ -194,10 +194,11 @@ def mask_bits(gt, groups, rows_per_group, me, Q, bits, flags, q_stride):
     _check(lib.ovis_mask_bits(_p(gt), groups, rows_per_group, _p(me), Q, _p(bits), _p(flags), q_stride, _stream()))
 
 
-def mask_logits(ft, groups, rows_per_group, me, me_group_stride, Q, out, t_group_stride, ldt, bias=None):
+def mask_logits(ft, groups, rows_per_group, me, me_group_stride, Q, out, t_group_stride, ldt, bias=None,
+                posflags=None, rows_per_frame=0):
     lib = load()
     _check(lib.ovis_mask_logits(_p(ft), groups, rows_per_group, _p(me), me_group_stride, Q, _p(bias), _p(out),
-                                t_group_stride, ldt, _stream()))
+                                t_group_stride, ldt, _p(posflags), rows_per_frame, _stream()))
 
 
 def san_bias_logits(af, B, P, heads, ae, Q, out):
@@ -212,10 +213,20 @@ def xattn_plan(G, Q, keys):
     return s.value, qp.value, o.value, ml.value
 
 
+PROFILE = None   # bench.py: set to a list to receive ("xattn", start_event, end_event) per cross-attention call
+
+
 def xattn(q, k, v, bits, flags, G, Q, q_stride, keys, splits, o_part, ml_part, out):
     lib = load()
+    prof = PROFILE
+    if prof is not None:
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
     _check(lib.ovis_xattn(_p(q), _p(k), _p(v), _p(bits), _p(flags), G, Q, q_stride, keys, splits, _p(o_part),
                           _p(ml_part), _p(out), _stream()))
+    if prof is not None:
+        b.record()
+        prof.append(("xattn", a, b))
 
 
 def self_attn(qk, v, out, G, Q):

@@ -306,8 +306,11 @@ int ovis_mask_bits(const void* gt, int groups, int rows_per_group, const void* m
 }
 
 int ovis_mask_logits(const void* ft, int groups, int rows_per_group, const void* me, int me_group_stride, int Q,
-                     const float* bias, float* out, long long t_group_stride, long long ldt, void* stream) {
+                     const float* bias, float* out, long long t_group_stride, long long ldt,
+                     unsigned char* posflags, int rows_per_frame, void* stream) {
   CHECK_ARG(ft && me && out && groups > 0 && rows_per_group > 0 && Q > 0 && me_group_stride >= 0, "bad arguments");
+  CHECK_ARG(!posflags || (rows_per_frame > 0 && rows_per_frame % 32 == 0 && rows_per_group % rows_per_frame == 0),
+            "posflags needs rows_per_frame % 32 == 0 dividing rows_per_group");
   CHECK_ARG((long long)groups * rows_per_group < (1ll << 31), "too many rows");
   GemmArgs a;
   init_args(a);
@@ -325,6 +328,9 @@ int ovis_mask_logits(const void* ft, int groups, int rows_per_group, const void*
   a.out_t = out;
   a.t_group_stride = t_group_stride;
   a.ldt = ldt;
+  a.posflags = posflags;
+  a.rows_per_frame = rows_per_frame > 0 ? rows_per_frame : 32;
+  a.q_stride = Q;
   const long long b_rows = me_group_stride ? (long long)(groups - 1) * me_group_stride + Q : Q;
   return launch_gemm(ft, (long long)groups * rows_per_group, 256, 256, me, b_rows, 256, a, bn, (cudaStream_t)stream);
 }

@@ -61,6 +61,8 @@ struct GemmArgs {
   float* out_t;
   long long t_group_stride;
   long long ldt;
+  unsigned char* posflags;   // optional [frames][q_stride]: 1 when some logit of (frame, col) is > 0 (non-empty mask)
+  int rows_per_frame;        // multiple of 32
 };
 
 template <int BN>
@@ -415,6 +417,21 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (bias) f += __ldg(bias + c * 32 + j);
                 __stcs(obase + (long long)col * args.ldt, f);
               }
+            }
+          }
+          if (args.posflags) {
+            // all 32 rows of this warp belong to one frame (rows_per_frame % 32 == 0)
+            uint32_t mine = 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const uint32_t w = __ballot_sync(0xffffffffu, row_ok && __uint_as_float(v[j]) > 0.f);
+              if (lane == j) mine = w;
+            }
+            const int col = col_base + c * 32 + lane;
+            const int r0 = mt * Cfg::BM + quarter * 32;
+            if (col < args.N && mine != 0u && r0 < args.rows_per_group) {
+              const long long frame = (long long)g * (args.rows_per_group / args.rows_per_frame) + r0 / args.rows_per_frame;
+              args.posflags[frame * args.q_stride + col] = 1;
             }
           }
         }

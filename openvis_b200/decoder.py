@@ -467,7 +467,11 @@ class _B200MaskedDecoderBase(nn.Module):
 
         # ---- final prediction head: full-resolution mask logits, class logits / attention biases
         out = _LazyDict()
-        pred_masks = self._full_masks(W, ws, nl, BT, H4, W4)
+        valid = torch.zeros(BT, Q, dtype=torch.uint8, device=dev)
+        pred_masks = self._full_masks(W, ws, nl, BT, H4, W4, posflags=valid)
+        # extension (not a reference key): [T, Q] "mask is non-empty" = ClipAdapter._preprocess_image's `valid`
+        # (clip_adapter/adapter.py:86-88) evaluated on the stride-4 logits, produced by the mask GEMM's epilogue
+        out["mask_valid"] = valid
         pred_embeds = ws["d32"].clone()
         cls = self._class_outputs(W, ws, nl, BT, san)
         self._pack_outputs(out, cls, pred_masks, pred_embeds, x, mask_features_in, sizes, p2, pz, BT, san)
@@ -489,13 +493,14 @@ class _B200MaskedDecoderBase(nn.Module):
         out["aux_outputs"] = aux
         return out
 
-    def _full_masks(self, W, ws, hidx, BT, H4, W4):
+    def _full_masks(self, W, ws, hidx, BT, H4, W4, posflags=None):
         """einsum("bqc,bchw->bqhw") of head `hidx`, written directly in the reference's eval layout [1, Q, T, H, W]
         ('(b t) q h w -> b q t h w', frame_...:117-118; video_...:459)."""
         Q = self.num_queries
         me = self._mlp3(W["mask_embed"], ws["d16"][hidx], ws["m1"], ws["m2"], ws["me16"])
         out = torch.empty(1, Q, BT, H4, W4, dtype=torch.float32, device=me.device)
-        L.mask_logits(ws["ft"], ws["G"], ws["Tg"] * ws["M"], me, Q, Q, out, ws["Tg"] * ws["M"], BT * ws["M"])
+        L.mask_logits(ws["ft"], ws["G"], ws["Tg"] * ws["M"], me, Q, Q, out, ws["Tg"] * ws["M"], BT * ws["M"],
+                      posflags=posflags, rows_per_frame=ws["M"] if posflags is not None else 0)
         return out
 
     def _class_outputs(self, W, ws, hidx, BT, san):

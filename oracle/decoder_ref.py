@@ -316,74 +316,6 @@ def san_build_attn_bias(attn_bias, grid_hw):
 
 
 # --------------------------------------------------------------------------------------------
-# seeded synthetic parameters / inputs (shared by tests, bench and the golden generator)
+# seeded synthetic parameters / inputs: shared with bench.py, so they live in the (oracle-free) product package
 # --------------------------------------------------------------------------------------------
-def decoder_param_shapes(kind="frame", Q=100, C=256, F_=2048, L=9, num_classes=1, clip_heads=12):
-    """state_dict contract of the reference decoders."""
-    s = {}
-    for i in range(L):
-        for pre, att in ((f"transformer_self_attention_layers.{i}", "self_attn"),
-                         (f"transformer_cross_attention_layers.{i}", "multihead_attn")):
-            s[f"{pre}.{att}.in_proj_weight"] = (3 * C, C)
-            s[f"{pre}.{att}.in_proj_bias"] = (3 * C,)
-            s[f"{pre}.{att}.out_proj.weight"] = (C, C)
-            s[f"{pre}.{att}.out_proj.bias"] = (C,)
-            s[f"{pre}.norm.weight"] = (C,)
-            s[f"{pre}.norm.bias"] = (C,)
-        pre = f"transformer_ffn_layers.{i}"
-        s[f"{pre}.linear1.weight"] = (F_, C)
-        s[f"{pre}.linear1.bias"] = (F_,)
-        s[f"{pre}.linear2.weight"] = (C, F_)
-        s[f"{pre}.linear2.bias"] = (C,)
-        s[f"{pre}.norm.weight"] = (C,)
-        s[f"{pre}.norm.bias"] = (C,)
-    s["decoder_norm.weight"] = (C,)
-    s["decoder_norm.bias"] = (C,)
-    s["query_feat.weight"] = (Q, C)
-    s["query_embed.weight"] = (Q, C)
-    s["level_embed.weight"] = (3, C)
-    for i in range(3):
-        s[f"mask_embed.layers.{i}.weight"] = (C, C)
-        s[f"mask_embed.layers.{i}.bias"] = (C,)
-    if kind in ("san_frame", "san_video"):
-        for i in range(3):
-            s[f"attn_embed.layers.{i}.weight"] = (C, C)
-            s[f"attn_embed.layers.{i}.bias"] = (C,)
-        for i in range(3):
-            o = C * clip_heads if i == 2 else C
-            s[f"attn_mlp.layers.{i}.weight"] = (o, C, 1, 1)
-            s[f"attn_mlp.layers.{i}.bias"] = (o,)
-    else:
-        s["class_embed.weight"] = (num_classes + 1, C)
-        s["class_embed.bias"] = (num_classes + 1,)
-    return s
-
-
-def seeded_params(shapes, seed=0):
-    """Deterministic weights that do not need the reference to regenerate: names in sorted order, one
-    torch.Generator.  Scales mimic the reference's inits (xavier-like for matrices, N(0,1) embeddings,
-    LayerNorm weight near 1) so that activations / mask densities look like a random-init reference."""
-    g = torch.Generator().manual_seed(seed)
-    out = {}
-    for name in sorted(shapes):
-        shp = shapes[name]
-        if name.endswith("norm.weight"):
-            t = 1.0 + 0.1 * torch.randn(shp, generator=g)
-        elif name.endswith(".bias") or name.endswith("in_proj_bias"):
-            t = 0.05 * torch.randn(shp, generator=g)
-        elif name in ("query_feat.weight", "query_embed.weight", "level_embed.weight"):
-            t = torch.randn(shp, generator=g)
-        else:
-            fan_out, fan_in = shp[0], shp[1]
-            bound = math.sqrt(6.0 / (fan_in + fan_out))
-            t = (torch.rand(shp, generator=g) * 2 - 1) * bound
-        out[name] = t
-    return out
-
-
-def seeded_inputs(T, Hp, Wp, C=256, seed=1234):
-    """N(0,1) multi-scale features (coarsest first) and mask features."""
-    g = torch.Generator().manual_seed(seed)
-    x = [torch.randn(T, C, Hp // 32 * 2 ** l, Wp // 32 * 2 ** l, generator=g) for l in range(3)]
-    mf = torch.randn(T, C, Hp // 4, Wp // 4, generator=g)
-    return x, mf
+from openvis_b200.synthetic import decoder_param_shapes, seeded_inputs, seeded_params  # noqa: E402,F401

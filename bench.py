@@ -284,20 +284,46 @@ def main():
     ms = ms.item()
     value = world * args.steps * T / (ms * 1e-3)
 
-    # ---- dominant kernel roofline (masked cross-attention): CUDA events recorded around its launches in the timed region
-    flops_x = [4.0 * Q * (T * n) * 256 for n in (Hp * Wp // 1024, Hp * Wp // 256, Hp * Wp // 64)]
-    xt = [a.elapsed_time(b) for (_, a, b) in xattn_events]
-    names = [n for (n, _, _) in xattn_events]
-    per_layer = len(xt) // max(1, args.steps)
-    tot_flops = sum(flops_x[i % 3] for i in range(per_layer)) * args.steps if per_layer else 0.0
+    # ---- per-kernel-family device time (CUDA events recorded around every C-ABI call inside the timed region)
+    N3 = [Hp * Wp // 1024, Hp * Wp // 256, Hp * Wp // 64]
+    M = Hp * Wp // 16
+    rows3 = [T * n for n in N3]
+    work = {   # algorithmic work of ONE step (one clip), see DESIGN.md
+        "xattn": ("tensor", sum(4.0 * Q * rows3[i % 3] * 256 for i in range(9))),
+        "kv_proj": ("tensor", sum(2.0 * rows3[l] * 1536 * 256 for l in range(3))),
+        "prep": ("hbm", sum(r * 256 * (4 + 2 + 2) for r in rows3) + T * M * 256 * (4 + 2) + sum(rows3) * 256 * 2),
+        "mask_logits": ("hbm", T * M * 256 * 2 + Q * T * M * 4),
+        "mask_bits": ("hbm", sum(rows3[(i) % 3] * 256 * 2 + Q * rows3[i % 3] / 8 for i in range(9))),
+    }
+    fam_ms = {}
+    for (fam, a_, b_) in xattn_events:
+        fam_ms[fam] = fam_ms.get(fam, 0.0) + a_.elapsed_time(b_)
     pk, src = peaks()
-    x_ms = sum(xt)
-    ach = tot_flops / (x_ms * 1e-3) / 1e12 if x_ms > 0 else 0.0
     peak_tf = pk.get("bf16_tflops_sustained", pk.get("bf16_tflops"))
-    roofline = {"kernel": "xattn_split_kernel+xattn_combine_kernel", "bound": "tensor", "achieved": ach, "peak": peak_tf,
-                "unit": "TFLOP/s", "frac": ach / peak_tf if peak_tf else None, "traffic": None,
-                "peak_source": f"{src} bf16_tflops_sustained (kernel timed inside a long step)",
-                "share_of_step": x_ms / ms if ms > 0 else None, "launches_timed": len(xt)}
+    peak_bw = pk.get("hbm_gbs")
+    kernels = {}
+    for fam, t_ms in fam_ms.items():
+        ent = {"ms_per_step": t_ms / args.steps, "share_of_step": t_ms / ms if ms > 0 else None}
+        if fam in work and t_ms > 0:
+            bound, amount = work[fam]
+            if bound == "tensor":
+                ach = amount * args.steps / (t_ms * 1e-3) / 1e12
+                ent.update(bound="tensor", achieved=ach, peak=peak_tf, unit="TFLOP/s", frac=ach / peak_tf)
+            else:
+                ach = amount * args.steps / (t_ms * 1e-3) / 1e9
+                ent.update(bound="hbm", achieved=ach, peak=peak_bw, unit="GB/s", frac=ach / peak_bw)
+        kernels[fam] = ent
+    dom = max((f for f in kernels if f in work), key=lambda f: kernels[f]["ms_per_step"], default=None)
+    kname = {"xattn": "xattn_split_kernel+xattn_combine_kernel", "kv_proj": "gemm_tn_kernel<256> (key/value projection)",
+             "prep": "maskfeat_prep_kernel+nchw_to_tokens_f16_kernel", "mask_logits": "gemm_tn_kernel<128> (final mask logits)",
+             "mask_bits": "gemm_tn_kernel<128> (mask sign bits)"}
+    roofline = None
+    if dom is not None:
+        d = kernels[dom]
+        roofline = {"kernel": kname[dom], "bound": d["bound"], "achieved": d["achieved"], "peak": d["peak"], "unit": d["unit"],
+                    "frac": d["frac"], "traffic": None,
+                    "peak_source": f"{src} ({'bf16_tflops_sustained' if d['bound'] == 'tensor' else 'hbm_gbs'}; kernel timed inside a long step)",
+                    "share_of_step": d["share_of_step"]}
 
     # ---- end to end through the public API with host buffers (pinned), H2D + forward + D2H every step
     e2e = None
@@ -368,7 +394,7 @@ def main():
                        "l2": "inputs larger than L2 (2.9 GB per clip, two clips alternated)",
                        "aux_outputs": "lazy (inference-minimal)", "parallelism": f"clip-sharded dp{world}"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roofline, "cpu_baseline": cpu,
+            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,
             "whole_path": {"gflop_per_frame": flops_frame / 1e9,
                            "tensor_frac_of_sustained": value / world * flops_frame / 1e12 / peak_tf if peak_tf else None}}
     print(json.dumps(line), flush=True)

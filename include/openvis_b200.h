@@ -34,8 +34,11 @@ long long ovis_launch_count(void);
 
 /* ---- layout preparation ------------------------------------------------------------------------------
  * Multi-scale feature map x_l [B][C][N] fp32 (NCHW, N=h*w) -> token-major fp16 [B][N][C].
- * Replaces `src[-1].permute(2, 0, 1)` (frame_mask2former_transformer_decoder.py:65-69). */
-int ovis_nchw_to_tokens_f16(const float* in, void* out_f16, int B, int C, int N, void* stream);
+ * Replaces `src[-1].permute(2, 0, 1)` (frame_mask2former_transformer_decoder.py:65-69).  Optionally also writes
+ * out_pos = fp16(x + pos[n] + pos_t[b]), the `memory + pos` key operand (video_...decoder.py:115-116), with
+ * pos [N][C] = level_embed + 2-D sine embedding and pos_t [B][C] (or null) the frame term of the 3-D embedding. */
+int ovis_nchw_to_tokens_f16(const float* in, void* out_f16, void* out_pos_f16, const float* pos, const float* pos_t,
+                            int B, int C, int N, void* stream);
 /* mask_features [B][C][H][W] fp32 -> ft [B][H*W][C] f16 and centre-2x2-pooled g0/g1/g2 [B][(H/s)(W/s)][C] f16
  * (s = 8, 4, 2).  Replaces the operand side of einsum("bqc,bchw->bqhw") + F.interpolate(bilinear)
  * (frame_...decoder.py:144-148).  Requires H % 8 == 0, W % 8 == 0, C % 32 == 0. */
@@ -65,14 +68,12 @@ int ovis_linear_ln_f16(const void* x_f16, long long rows, int K, const void* w_f
                        const float* resid, const float* ln1_g, const float* ln1_b,
                        const float* ln2_g, const float* ln2_b, const float* pe, int pe_period,
                        float* y32, void* y16, void* ype16, float* d32, void* d16, void* stream);
-/* Key/value projections of all decoder layers that read one feature level, in one launch:
- * out[t] = xt * w[t*256:(t+1)*256]^T + bias[t] + tab[t][r % tab_period] + tab2[t][r / tab_period]
- * for n_tiles 256-wide column tiles (per-tile device pointers given in HOST arrays; tab/tab2/bias entries may be
- * null).  tab carries (pos + level_embed) W_k^T + b_k, i.e. `key=self.with_pos_embed(memory, pos)`
- * (video_...decoder.py:115-118); tab2 the frame term of the 3-D position embedding (position_encoding.py:135-165). */
-int ovis_kv_proj_f16(const void* xt_f16, int groups, int rows_per_group, const void* w_f16, int n_tiles,
-                     void* const* out_host, const float* const* bias_host, const float* const* tab_host,
-                     const float* const* tab2_host, int tab_period, void* stream);
+/* Key/value projections of all decoder layers that read one feature level, in one launch: for n_tiles 256-wide
+ * column tiles t, out[t] = (t even ? xk : xv) * w[t*256:(t+1)*256]^T + bias[t]; xk = memory + pos (+ level_embed),
+ * xv = memory, as in `key=self.with_pos_embed(memory, pos), value=memory` (video_...decoder.py:115-118).
+ * out / bias: HOST arrays of n_tiles device pointers (bias entries may be null). */
+int ovis_kv_proj_f16(const void* xk_f16, const void* xv_f16, long long rows, const void* w_f16, int n_tiles,
+                     void* const* out_host, const float* const* bias_host, void* stream);
 /* Next-layer attention mask: bits[g][r/32][q] bit (r%32) = (g_l[g][r] . mask_embed[g][q] < 0) and
  * flags[g][q] = 1 when some key is unblocked.  Replaces einsum + F.interpolate + sigmoid() < 0.5 + repeat(heads)
  * (frame_...decoder.py:144-152) and feeds the all-masked-row rule (frame_...decoder.py:87).

@@ -19,7 +19,7 @@ SIGNATURES = {
     "ovis_last_error": (ctypes.c_char_p, []),
     "ovis_device_check": (_c_int, []),
     "ovis_launch_count": (_c_ll, []),
-    "ovis_nchw_to_tokens_f16": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _vp]),
+    "ovis_nchw_to_tokens_f16": (_c_int, [_vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _vp]),
     "ovis_maskfeat_prep": (_c_int, [_vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _vp]),
     "ovis_cast_f16": (_c_int, [_vp, _vp, _c_ll, _vp]),
     "ovis_init_queries": (_c_int, [_vp] * 9 + [_c_int, _c_int, _vp]),
@@ -27,7 +27,7 @@ SIGNATURES = {
     "ovis_linear_f16": (_c_int, [_vp, _c_ll, _c_int, _c_int, _vp, _c_int, _vp, _c_float, _c_int, _vp, _c_int, _c_int, _vp]),
     "ovis_linear_ln_f16": (_c_int, [_vp, _c_ll, _c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _c_int,
                                     _vp, _vp, _vp, _vp, _vp, _vp]),
-    "ovis_kv_proj_f16": (_c_int, [_vp, _c_int, _c_int, _vp, _c_int, _vp, _vp, _vp, _vp, _c_int, _vp]),
+    "ovis_kv_proj_f16": (_c_int, [_vp, _vp, _c_ll, _vp, _c_int, _vp, _vp, _vp]),
     "ovis_mask_bits": (_c_int, [_vp, _c_int, _c_int, _vp, _c_int, _vp, _vp, _c_int, _vp]),
     "ovis_mask_logits": (_c_int, [_vp, _c_int, _c_int, _vp, _c_int, _c_int, _vp, _vp, _c_ll, _c_ll, _vp, _c_int, _vp]),
     "ovis_san_bias_logits": (_c_int, [_vp, _c_int, _c_int, _c_int, _vp, _c_int, _vp, _vp]),
@@ -88,6 +88,27 @@ def _req(t, dtype, name):
         raise OvisError(f"{name}: expected a contiguous tensor")
 
 
+PROFILE = None   # bench.py: set to a list to receive (family, start_event, end_event) for every wrapped call
+
+
+def _timed(family):
+    def deco(fn):
+        def wrapper(*a, **k):
+            prof = PROFILE
+            if prof is None:
+                return fn(*a, **k)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = fn(*a, **k)
+            e1.record()
+            prof.append((family, e0, e1))
+            return r
+        wrapper.__name__ = fn.__name__
+        wrapper.__doc__ = fn.__doc__
+        return wrapper
+    return deco
+
+
 def launch_count():
     return load().ovis_launch_count()
 
@@ -97,18 +118,20 @@ def device_check():
 
 
 # ------------------------------------------------------------------------------------------ wrappers
-def nchw_to_tokens_f16(x, out=None):
-    """[B, C, h, w] fp32 -> [B, h*w, C] fp16."""
+@_timed("prep")
+def nchw_to_tokens_f16(x, out=None, out_pos=None, pos=None, pos_t=None):
+    """[B, C, h, w] fp32 -> [B, h*w, C] fp16 (and optionally out_pos = fp16(x + pos[n] + pos_t[b]))."""
     lib = load()
     _req(x, torch.float32, "x")
     B, C = x.shape[:2]
     N = x[0, 0].numel()
     if out is None:
         out = torch.empty(B, N, C, dtype=torch.float16, device=x.device)
-    _check(lib.ovis_nchw_to_tokens_f16(_p(x), _p(out), B, C, N, _stream()))
+    _check(lib.ovis_nchw_to_tokens_f16(_p(x), _p(out), _p(out_pos), _p(pos), _p(pos_t), B, C, N, _stream()))
     return out
 
 
+@_timed("prep")
 def maskfeat_prep(F, outs=None):
     """mask_features [B, C, H, W] fp32 -> (ft [B,HW,C], g0 [B,HW/64,C], g1 [B,HW/16,C], g2 [B,HW/4,C]) fp16."""
     lib = load()
@@ -150,6 +173,7 @@ def rownorm(x, g=None, b=None, layer_norm=False, l2=False, want32=True, want16=T
     return o32, o16
 
 
+@_timed("query_side")
 def linear_f16(x, w, bias=None, scale=1.0, relu=False, out=None, out_f32=False):
     """x [rows, K] fp16 (row stride may exceed K), w [N, K] fp16 -> [rows, N] fp16 / fp32."""
     lib = load()
@@ -163,6 +187,7 @@ def linear_f16(x, w, bias=None, scale=1.0, relu=False, out=None, out_f32=False):
     return out
 
 
+@_timed("query_side")
 def linear_ln_f16(x, w, bias, resid, ln1, ln2=None, pe=None, y32=None, y16=None, ype16=None, d32=None, d16=None):
     lib = load()
     rows, K = x.shape
@@ -179,21 +204,23 @@ def _ptr_array(tensors):
     return arr
 
 
-def kv_proj_f16(xt, groups, rows_per_group, w, outs, biases=None, tabs=None, tabs2=None, tab_period=1):
-    """xt [groups*rows_per_group, 256] fp16; w [n_tiles*256, 256] fp16; outs: n_tiles tensors [rows, 256] fp16."""
+@_timed("kv_proj")
+def kv_proj_f16(xk, xv, w, outs, biases=None):
+    """xk, xv [rows, 256] fp16 (key / value operands); w [n_tiles*256, 256] fp16; outs: n_tiles tensors [rows, 256] fp16
+    (even tiles read xk, odd tiles read xv)."""
     lib = load()
     n_tiles = len(outs)
-    none = [None] * n_tiles
-    _check(lib.ovis_kv_proj_f16(_p(xt), groups, rows_per_group, _p(w), n_tiles, _ptr_array(outs),
-                                _ptr_array(biases or none), _ptr_array(tabs or none), _ptr_array(tabs2 or none),
-                                tab_period, _stream()))
+    _check(lib.ovis_kv_proj_f16(_p(xk), _p(xv), xk.shape[0], _p(w), n_tiles, _ptr_array(outs),
+                                _ptr_array(biases or [None] * n_tiles), _stream()))
 
 
+@_timed("mask_bits")
 def mask_bits(gt, groups, rows_per_group, me, Q, bits, flags, q_stride):
     lib = load()
     _check(lib.ovis_mask_bits(_p(gt), groups, rows_per_group, _p(me), Q, _p(bits), _p(flags), q_stride, _stream()))
 
 
+@_timed("mask_logits")
 def mask_logits(ft, groups, rows_per_group, me, me_group_stride, Q, out, t_group_stride, ldt, bias=None,
                 posflags=None, rows_per_frame=0):
     lib = load()
@@ -201,6 +228,7 @@ def mask_logits(ft, groups, rows_per_group, me, me_group_stride, Q, out, t_group
                                 t_group_stride, ldt, _p(posflags), rows_per_frame, _stream()))
 
 
+@_timed("san_bias")
 def san_bias_logits(af, B, P, heads, ae, Q, out):
     lib = load()
     _check(lib.ovis_san_bias_logits(_p(af), B, P, heads, _p(ae), Q, _p(out), _stream()))
@@ -213,22 +241,14 @@ def xattn_plan(G, Q, keys):
     return s.value, qp.value, o.value, ml.value
 
 
-PROFILE = None   # bench.py: set to a list to receive ("xattn", start_event, end_event) per cross-attention call
-
-
+@_timed("xattn")
 def xattn(q, k, v, bits, flags, G, Q, q_stride, keys, splits, o_part, ml_part, out):
     lib = load()
-    prof = PROFILE
-    if prof is not None:
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
     _check(lib.ovis_xattn(_p(q), _p(k), _p(v), _p(bits), _p(flags), G, Q, q_stride, keys, splits, _p(o_part),
                           _p(ml_part), _p(out), _stream()))
-    if prof is not None:
-        b.record()
-        prof.append(("xattn", a, b))
 
 
+@_timed("query_side")
 def self_attn(qk, v, out, G, Q):
     lib = load()
     _check(lib.ovis_self_attn(_p(qk), _p(v), _p(out), G, Q, _stream()))

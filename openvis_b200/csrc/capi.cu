@@ -110,12 +110,12 @@ void init_args(GemmArgs& a) {
   a.a_row_div = 1;
   a.b_row_div = 1;
   a.scale = 1.f;
-  a.tab_period = 1;
   a.pe_period = 1;
 }
 
 template <int BN>
-int launch_gemm_bn(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a, int sms, cudaStream_t st) {
+int launch_gemm_bn(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tb, const GemmArgs& a, int sms,
+                   cudaStream_t st) {
   using Cfg = GemmCfg<BN>;
   static bool attr_done[64] = {false};
   int dev = 0;
@@ -133,24 +133,26 @@ int launch_gemm_bn(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs&
   const long long total = (long long)a.num_groups * m_tiles * n_tiles;
   if (total <= 0) return OVIS_OK;
   const int grid = (int)(total < sms ? total : sms);
-  gemm_tn_kernel<BN><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, a);
+  gemm_tn_kernel<BN><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(ta, ta2, tb, a);
   return check_launch("gemm_tn_kernel");
 }
 
 // A: [a_rows][a_cols] fp16 pitch lda; B: [b_rows][K] fp16 pitch ldb.
 int launch_gemm(const void* A, long long a_rows, long long a_cols, long long lda, const void* B, long long b_rows,
-                long long ldb, const GemmArgs& a, int bn, cudaStream_t st) {
+                long long ldb, const GemmArgs& a, int bn, cudaStream_t st, const void* A2 = nullptr) {
   int sms = 0;
   int rc = device_info(&sms);
   if (rc) return rc;
   if (a.K <= 0 || a.K % 64) return fail(OVIS_ERR_ARG, "%s: K must be a positive multiple of 64", "gemm");
   if ((a.N + bn - 1) / bn > GEMM_MAX_NTILES) return fail(OVIS_ERR_ARG, "%s: too many column tiles", "gemm");
-  CUtensorMap ta, tb;
+  CUtensorMap ta, ta2, tb;
   rc = make_map_f16(&ta, A, a_rows, a_cols, lda, 128);
+  if (rc) return rc;
+  rc = make_map_f16(&ta2, A2 ? A2 : A, a_rows, a_cols, lda, 128);
   if (rc) return rc;
   rc = make_map_f16(&tb, B, b_rows, a.K, ldb, bn);
   if (rc) return rc;
-  return bn == 256 ? launch_gemm_bn<256>(ta, tb, a, sms, st) : launch_gemm_bn<128>(ta, tb, a, sms, st);
+  return bn == 256 ? launch_gemm_bn<256>(ta, ta2, tb, a, sms, st) : launch_gemm_bn<128>(ta, ta2, tb, a, sms, st);
 }
 
 }  // namespace
@@ -162,12 +164,14 @@ const char* ovis_last_error(void) { return g_err; }
 int ovis_device_check(void) { return device_info(nullptr); }
 long long ovis_launch_count(void) { return g_launches.load(); }
 
-int ovis_nchw_to_tokens_f16(const float* in, void* out, int B, int C, int N, void* stream) {
+int ovis_nchw_to_tokens_f16(const float* in, void* out, void* out_pos, const float* pos, const float* pos_t, int B, int C,
+                            int N, void* stream) {
   CHECK_ARG(in && out && B > 0 && C > 0 && N > 0 && C % 2 == 0, "bad arguments");
+  CHECK_ARG((out_pos == nullptr) == (pos == nullptr), "out_pos and pos go together");
   int rc = device_info(nullptr);
   if (rc) return rc;
   dim3 grid((N + 63) / 64, (C + 63) / 64, B);
-  nchw_to_tokens_f16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, (__half*)out, C, N);
+  nchw_to_tokens_f16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, (__half*)out, (__half*)out_pos, pos, pos_t, C, N);
   return check_launch("nchw_to_tokens_f16_kernel");
 }
 
@@ -257,31 +261,25 @@ int ovis_linear_ln_f16(const void* x, long long rows, int K, const void* w, cons
   return launch_gemm(x, rows, K, K, w, 256, K, a, 256, (cudaStream_t)stream);
 }
 
-int ovis_kv_proj_f16(const void* xt, int groups, int rows_per_group, const void* w, int n_tiles, void* const* out,
-                     const float* const* bias, const float* const* tab, const float* const* tab2, int tab_period,
-                     void* stream) {
-  CHECK_ARG(xt && w && out && groups > 0 && rows_per_group > 0 && n_tiles > 0 && n_tiles <= GEMM_MAX_NTILES, "bad arguments");
-  CHECK_ARG((long long)groups * rows_per_group < (1ll << 31), "too many rows");
+int ovis_kv_proj_f16(const void* xk, const void* xv, long long rows, const void* w, int n_tiles, void* const* out,
+                     const float* const* bias, void* stream) {
+  CHECK_ARG(xk && xv && w && out && rows > 0 && n_tiles > 0 && n_tiles <= GEMM_MAX_NTILES, "bad arguments");
+  CHECK_ARG(rows < (1ll << 31), "too many rows");
   GemmArgs a;
   init_args(a);
-  a.rows_per_group = rows_per_group;
-  a.num_groups = groups;
-  a.a_group_stride = rows_per_group;
+  a.rows_per_group = (int)rows;
+  a.a_group_stride = (int)rows;
   a.N = n_tiles * 256;
   a.K = 256;
   a.epi = EPI_STORE;
+  a.a_alt = 1;
   for (int t = 0; t < n_tiles; ++t) {
     CHECK_ARG(out[t] != nullptr, "null output tile");
     a.out[t] = out[t];
     a.bias[t] = bias ? bias[t] : nullptr;
-    a.tab[t] = tab ? tab[t] : nullptr;
-    a.tab2[t] = tab2 ? tab2[t] : nullptr;
   }
   a.ldo = 256;
-  a.tab_period = tab_period > 0 ? tab_period : 1;
-  a.tab_ld = 256;
-  return launch_gemm(xt, (long long)groups * rows_per_group, 256, 256, w, (long long)n_tiles * 256, 256, a, 256,
-                     (cudaStream_t)stream);
+  return launch_gemm(xk, rows, 256, 256, w, (long long)n_tiles * 256, 256, a, 256, (cudaStream_t)stream, xv);
 }
 
 int ovis_mask_bits(const void* gt, int groups, int rows_per_group, const void* me, int Q, unsigned int* bits,

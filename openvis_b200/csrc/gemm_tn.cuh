@@ -13,7 +13,7 @@
 namespace ovis {
 
 enum GemmEpi : int {
-  EPI_STORE = 0,      // out[row][col] = act((acc + bias[col] + tab[r % period][col] + tab2[r / period][col]) * scale); fp16 or fp32
+  EPI_STORE = 0,      // out[row][col] = act((acc + bias[col]) * scale); fp16 or fp32, smem-staged coalesced stores
   EPI_LN = 1,         // v = acc + bias + resid -> LayerNorm (-> optional 2nd LayerNorm); N == BN == 256
   EPI_SIGNBITS = 2,   // bits[g][r/32][col] = ballot(acc < 0); flags[g][col] = any(acc >= 0)
   EPI_STORE_T = 3,    // out[g*t_group_stride + col*ldt + r] = acc + bias[col]   (fp32, transposed / NCHW-style)
@@ -36,14 +36,11 @@ struct GemmArgs {
   // ---- EPI_STORE
   void* out[GEMM_MAX_NTILES];          // per n-tile base pointer (column 0 of that tile)
   const float* bias[GEMM_MAX_NTILES];  // per n-tile bias (indexed by column within tile) or null
-  const float* tab[GEMM_MAX_NTILES];   // per n-tile additive table [period][BN-wide rows of ld tab_ld] or null
-  const float* tab2[GEMM_MAX_NTILES];  // per n-tile second table indexed by r / period, or null
   int ldo;                // output row stride (elements)
   int out_f32;            // 0: fp16 output, 1: fp32 output
   int relu;
   float scale;
-  int tab_period;
-  int tab_ld;
+  int a_alt;              // 1: odd n-tiles read their A operand from the second tensor map (key / value operands)
   // ---- EPI_LN
   const float* resid;     // [rows][256] fp32
   const float* ln1_g; const float* ln1_b;
@@ -72,19 +69,22 @@ struct GemmCfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int STAGING_BYTES = 4 * 4096;   // epilogue store staging: 4 warps x [32 rows][128 B]
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int TMEM_COLS = 2 * BN;   // 256 or 512: power of two
   static constexpr int THREADS = 192;
 };
 
 template <int BN>
 __global__ void __launch_bounds__(192, 1)
-gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs args) {
+gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+               const __grid_constant__ CUtensorMap tmB, const GemmArgs args) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint8_t* stage_smem = smem + STAGES * Cfg::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_smem + Cfg::STAGING_BYTES);
   uint64_t* full_bar = bars;                 // [STAGES]
   uint64_t* empty_bar = bars + STAGES;       // [STAGES]
   uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]
@@ -101,6 +101,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmA2);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -130,12 +131,13 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int a_row = (g / args.a_row_div) * args.a_group_stride + mt * Cfg::BM;
         const int a_col = (g % args.a_k_mod) * args.a_k_offset_stride;
         const int b_row = (g / args.b_row_div) * args.b_group_stride + nt * BN;
+        const CUtensorMap* ta = (args.a_alt && (nt & 1)) ? &tmA2 : &tmA;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-          tma_load_2d(sa, &tmA, &full_bar[stage], a_col + kb * Cfg::BK, a_row);
+          tma_load_2d(sa, ta, &full_bar[stage], a_col + kb * Cfg::BK, a_row);
           tma_load_2d(sb, &tmB, &full_bar[stage], kb * Cfg::BK, b_row);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -192,36 +194,29 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
       if (args.epi == EPI_STORE) {
         const float* bias = args.bias[nt];
-        const float* tab = args.tab[nt];
-        const float* tab2 = args.tab2[nt];
-        const float* trow = tab ? tab + (long long)(r % args.tab_period) * args.tab_ld : nullptr;
-        const float* trow2 = tab2 ? tab2 + (long long)(r / args.tab_period) * args.tab_ld : nullptr;
+        const int cols_per_unit = args.out_f32 ? 32 : 64;        // 128 bytes of output per row per unit
+        const int esize = args.out_f32 ? 4 : 2;
+        uint4* stg = reinterpret_cast<uint4*>(stage_smem + (warp - 2) * 4096);   // [32 rows][8 x 16 B], XOR-swizzled
+        const int r_warp0 = mt * Cfg::BM + quarter * 32;          // first row (within group) of this warp
+        const long long grow0 = (long long)(g / args.a_row_div) * args.a_group_stride + r_warp0;
+        const bool vec_ok = (((long long)args.ldo * esize) & 15) == 0;
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-          if (col_base + c * 32 >= args.N) break;               // warp-uniform
-          tmem_ld_32x32(t_acc + c * 32, v);
-          tmem_ld_wait();
-          if (row_ok) {
+        for (int u0 = 0; u0 < BN; u0 += cols_per_unit) {
+          if (col_base + u0 >= args.N) break;                     // warp-uniform
+          const int ncols = min(cols_per_unit, args.N - (col_base + u0));
+          uint4 pk[8];
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            if (hh == 1 && args.out_f32) break;
+            tmem_ld_32x32(t_acc + u0 + hh * 32, v);
+            tmem_ld_wait();
             float f[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
             if (bias) {
+              const int nleft = args.N - (col_base + u0 + hh * 32);       // columns past N must not touch bias[]
 #pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] += __ldg(bias + c * 32 + j);
-            }
-            if (trow) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                float4 t = __ldg(reinterpret_cast<const float4*>(trow + c * 32 + j));
-                f[j] += t.x; f[j + 1] += t.y; f[j + 2] += t.z; f[j + 3] += t.w;
-              }
-            }
-            if (trow2) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                float4 t = __ldg(reinterpret_cast<const float4*>(trow2 + c * 32 + j));
-                f[j] += t.x; f[j + 1] += t.y; f[j + 2] += t.z; f[j + 3] += t.w;
-              }
+              for (int j = 0; j < 32; ++j) f[j] += (j < nleft) ? __ldg(bias + u0 + hh * 32 + j) : 0.f;
             }
             if (args.scale != 1.f) {
 #pragma unroll
@@ -231,30 +226,54 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
               for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
             }
-            const int ncols = min(32, args.N - (col_base + c * 32));
             if (args.out_f32) {
-              float* o = reinterpret_cast<float*>(args.out[nt]) + grow * args.ldo + c * 32;
-              if (ncols == 32 && (args.ldo & 3) == 0) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-              } else {
-                for (int j = 0; j < ncols; ++j) o[j] = f[j];
-              }
+              for (int j = 0; j < 8; ++j)
+                pk[j] = make_uint4(__float_as_uint(f[4 * j]), __float_as_uint(f[4 * j + 1]), __float_as_uint(f[4 * j + 2]),
+                                   __float_as_uint(f[4 * j + 3]));
             } else {
-              __half* o = reinterpret_cast<__half*>(args.out[nt]) + grow * args.ldo + c * 32;
-              if (ncols == 32 && (args.ldo & 7) == 0) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 8) {
-                  uint4 u;
-                  u.x = pack_half2(f[j], f[j + 1]); u.y = pack_half2(f[j + 2], f[j + 3]);
-                  u.z = pack_half2(f[j + 4], f[j + 5]); u.w = pack_half2(f[j + 6], f[j + 7]);
-                  *reinterpret_cast<uint4*>(o + j) = u;
+              for (int j = 0; j < 4; ++j)
+                pk[hh * 4 + j] = make_uint4(pack_half2(f[8 * j], f[8 * j + 1]), pack_half2(f[8 * j + 2], f[8 * j + 3]),
+                                            pack_half2(f[8 * j + 4], f[8 * j + 5]), pack_half2(f[8 * j + 6], f[8 * j + 7]));
+            }
+          }
+          // stage through shared memory so that each store instruction writes four full 128-byte rows
+#pragma unroll
+          for (int c = 0; c < 8; ++c) stg[lane * 8 + (c ^ (lane & 7))] = pk[c];
+          __syncwarp();
+          char* obase = reinterpret_cast<char*>(args.out[nt]) + (long long)u0 * esize;
+          if (ncols == cols_per_unit && vec_ok) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int row = it * 4 + (lane >> 3), c = lane & 7;
+              if (r_warp0 + row < args.rows_per_group) {
+                const uint4 val = stg[row * 8 + (c ^ (row & 7))];
+                *reinterpret_cast<uint4*>(obase + (grow0 + row) * args.ldo * esize + c * 16) = val;
+              }
+            }
+          } else {
+            // ragged tail (N not a multiple of the unit, or unaligned pitch): element-wise, still row-coalesced
+            const int epc = 16 / esize;                            // elements per 16 B chunk
+            for (int it = 0; it < 8; ++it) {
+              const int row = it * 4 + (lane >> 3), c = lane & 7;
+              if (r_warp0 + row < args.rows_per_group) {
+                const uint4 val = stg[row * 8 + (c ^ (row & 7))];
+                char* o = obase + (grow0 + row) * args.ldo * esize + c * 16;
+                if (esize == 4) {
+                  const uint32_t w[4] = {val.x, val.y, val.z, val.w};
+                  for (int e = 0; e < 4; ++e)
+                    if (c * epc + e < ncols) reinterpret_cast<uint32_t*>(o)[e] = w[e];
+                } else {
+                  const uint32_t w[4] = {val.x, val.y, val.z, val.w};
+                  for (int e = 0; e < 8; ++e)
+                    if (c * epc + e < ncols)
+                      reinterpret_cast<unsigned short*>(o)[e] = (unsigned short)((w[e >> 1] >> ((e & 1) * 16)) & 0xffffu);
                 }
-              } else {
-                for (int j = 0; j < ncols; ++j) o[j] = __float2half_rn(f[j]);
               }
             }
           }
+          __syncwarp();
         }
       } else if (args.epi == EPI_LN) {
         // BN == 256 == N.  Row-per-thread LayerNorm; the biased+residual row is parked back in TMEM between passes.
@@ -415,7 +434,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               if (col < args.N) {
                 float f = __uint_as_float(v[j]);
                 if (bias) f += __ldg(bias + c * 32 + j);
-                __stcs(obase + (long long)col * args.ldt, f);
+                __stcs(obase + (long long)col * args.ldt, f);   // col < N checked above
               }
             }
           }

@@ -4,10 +4,13 @@
 
 namespace ovis {
 
-// in [B][C][N] fp32 (NCHW, N = h*w)  ->  out [B][N][C] fp16 ("token-major", K-major GEMM operand).
+// in [B][C][N] fp32 (NCHW, N = h*w)  ->  out [B][N][C] fp16 ("token-major", K-major GEMM operand)
+// and optionally out_pos = fp16(in + pos[n][c] + pos_t[b][c]): the `key = memory + pos` operand
+// (with_pos_embed, video_..._decoder.py:115-116; pos3d = pos2d + pos_z, position_encoding.py:163).
 // Tile 64(n) x 64(c).  Reads are 256 B rows along n, writes 128 B rows along c.
 __global__ void __launch_bounds__(256)
-nchw_to_tokens_f16_kernel(const float* __restrict__ in, __half* __restrict__ out, int C, int N) {
+nchw_to_tokens_f16_kernel(const float* __restrict__ in, __half* __restrict__ out, __half* __restrict__ out_pos,
+                          const float* __restrict__ pos, const float* __restrict__ pos_t, int C, int N) {
   __shared__ float tile[64][65];
   const int b = blockIdx.z, c0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
   const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;     // 64 x 4
@@ -25,8 +28,19 @@ nchw_to_tokens_f16_kernel(const float* __restrict__ in, __half* __restrict__ out
   for (int i = 0; i < 8; ++i) {
     const int nl = ny + i * 8;
     const int n = n0 + nl;
-    if (n < N && c0 + cx < C)
-      *reinterpret_cast<__half2*>(ob + (long long)n * C + c0 + cx) = __floats2half2_rn(tile[cx][nl], tile[cx + 1][nl]);
+    if (n < N && c0 + cx < C) {
+      const float v0 = tile[cx][nl], v1 = tile[cx + 1][nl];
+      *reinterpret_cast<__half2*>(ob + (long long)n * C + c0 + cx) = __floats2half2_rn(v0, v1);
+      if (out_pos) {
+        // key operand: x + (level_embed + 2-D sine position)[n] (+ frame term of the 3-D embedding)
+        float2 p = __ldg(reinterpret_cast<const float2*>(pos + (long long)n * C + c0 + cx));
+        if (pos_t) {
+          const float2 pt = __ldg(reinterpret_cast<const float2*>(pos_t + (long long)b * C + c0 + cx));
+          p.x += pt.x; p.y += pt.y;
+        }
+        *reinterpret_cast<__half2*>(out_pos + ((long long)b * N + n) * C + c0 + cx) = __floats2half2_rn(v0 + p.x, v1 + p.y);
+      }
+    }
   }
 }
 

@@ -297,7 +297,6 @@ class _B200MaskedDecoderBase(nn.Module):
         for i, lw in enumerate(W["layers"]):
             e = le[i % 3]
             lw["v_bias"] = (lw["xv_b"] + lw["xv_w32"] @ e).contiguous()      # value = (x + level_embed) W_v^T + b_v
-            lw["k_const"] = (lw["xk_b"] + lw["xk_w32"] @ e).contiguous()     # constant part of the key projection
         W["dn"] = (f32(self.decoder_norm.weight), f32(self.decoder_norm.bias))
         W["qf"], W["qe"] = f32(self.query_feat.weight), f32(self.query_embed.weight)
         W["mask_embed"] = [(f16(m.weight), f32(m.bias)) for m in self.mask_embed.layers]
@@ -311,21 +310,22 @@ class _B200MaskedDecoderBase(nn.Module):
         self._pcache = {}
         return W
 
-    def _pos_tables(self, W, T, sizes, device):
-        """Per layer: tab[i] = (pos2d_l) W_k^T + b_k + level_embed_l W_k^T   [N_l, 256] fp32
-        and, for the Video decoders, tab2[i] = pos_z W_k^T [T, 256]  (pos3d = pos2d + pos_z, position_encoding.py:163).
-        Input independent: cached per (weights, T, sizes)."""
-        key = (T if self.VIDEO else 0, tuple(sizes))
+    def _pos_tables(self, T, sizes, device):
+        """Input-independent additive tables of the key operand: padd[l] = pos2d_l + level_embed_l  [N_l, 256] fp32 and,
+        for the Video decoders, pz = frame term [T, 256] (pos3d = pos2d + pos_z, position_encoding.py:163).
+        Cached per (level_embed version, T, sizes)."""
+        le = self.level_embed.weight
+        key = (T if self.VIDEO else 0, tuple(sizes), le.data_ptr(), le._version)
         hit = self._pcache.get(key)
         if hit is not None:
             return hit
-        tabs, tabs2 = [], []
         p2 = [sine_pos_2d(h, w, device) for (h, w) in sizes]
-        pz = sine_pos_z(T, device) if self.VIDEO else None
-        for i, lw in enumerate(W["layers"]):
-            tabs.append((p2[i % 3] @ lw["xk_w32"].T + lw["k_const"]).contiguous())
-            tabs2.append((pz @ lw["xk_w32"].T).contiguous() if self.VIDEO else None)
-        self._pcache[key] = (tabs, tabs2, p2, pz)
+        pz = sine_pos_z(T, device).contiguous() if self.VIDEO else None
+        lef = le.detach().float()
+        padd = [(p2[l] + lef[l][None, :]).contiguous() for l in range(3)]
+        if len(self._pcache) > 4:
+            self._pcache.clear()
+        self._pcache[key] = (padd, p2, pz)
         return self._pcache[key]
 
     def _workspace(self, BT, H4, W4, device):
@@ -344,7 +344,8 @@ class _B200MaskedDecoderBase(nn.Module):
         h = lambda *s: torch.empty(*s, dtype=torch.float16, device=device)
         f = lambda *s: torch.empty(*s, dtype=torch.float32, device=device)
         ws = dict(G=G, Tg=Tg, R=R, N=N, M=M)
-        ws["xt"] = [h(BT * n, C) for n in N]
+        ws["xt"] = [h(BT * n, C) for n in N]              # value operand: x
+        ws["xp"] = [h(BT * n, C) for n in N]              # key operand:   x + level_embed + pos
         ws["ft"] = h(BT * M, C)
         ws["gt"] = [h(BT * n, C) for n in N]
         ws["k"] = [h(BT * N[i % 3], C) for i in range(self.num_layers)]
@@ -407,7 +408,7 @@ class _B200MaskedDecoderBase(nn.Module):
     def _forward_impl(self, x, mf, mask_features_in, BT, H4, W4, sizes, dev):
         W = self._weights()
         ws = self._workspace(BT, H4, W4, dev)
-        tabs, tabs2, p2, pz = self._pos_tables(W, BT, sizes, dev)
+        padd, p2, pz = self._pos_tables(BT, sizes, dev)
         self._generation += 1
         gen = self._generation
         G, Tg, R, N, M = ws["G"], ws["Tg"], ws["R"], ws["N"], ws["M"]
@@ -415,20 +416,18 @@ class _B200MaskedDecoderBase(nn.Module):
 
         # ---- layout preparation (HBM-bound, once per call)
         for l in range(3):
-            L.nchw_to_tokens_f16(x[l], out=ws["xt"][l])
+            L.nchw_to_tokens_f16(x[l], out=ws["xt"][l], out_pos=ws["xp"][l], pos=padd[l], pos_t=pz)
         L.maskfeat_prep(mf, (ws["ft"], ws["gt"][0], ws["gt"][1], ws["gt"][2]))
         # ---- key / value projections of all layers, one launch per level
         for l in range(3):
             ids = W["kv_layers"][l]
             if not ids:
                 continue
-            outs, biases, tb, tb2 = [], [], [], []
+            outs, biases = [], []
             for i in ids:
                 outs += [ws["k"][i], ws["v"][i]]
-                biases += [None, W["layers"][i]["v_bias"]]
-                tb += [tabs[i], None]
-                tb2 += [tabs2[i], None]
-            L.kv_proj_f16(ws["xt"][l], 1, BT * N[l], W["kv_w"][l], outs, biases, tb, tb2, tab_period=N[l])
+                biases += [W["layers"][i]["xk_b"], W["layers"][i]["v_bias"]]
+            L.kv_proj_f16(ws["xp"][l], ws["xt"][l], W["kv_w"][l], outs, biases)
 
         san = self._san_prepare(W, ws, BT, H4, W4) if self.SAN else None
 

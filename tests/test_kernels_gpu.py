@@ -88,6 +88,12 @@ def test_nchw_to_tokens():
     out = L.nchw_to_tokens_f16(x)
     ref = x.flatten(2).permute(0, 2, 1).half()
     assert torch.equal(out, ref)
+    pos, pos_t = _randn(240, 256, seed=2), _randn(3, 256, seed=3)
+    out2 = torch.empty_like(out)
+    outp = torch.empty_like(out)
+    L.nchw_to_tokens_f16(x, out=out2, out_pos=outp, pos=pos, pos_t=pos_t)
+    assert torch.equal(out2, ref)
+    assert torch.equal(outp, (x.flatten(2).permute(0, 2, 1) + pos[None] + pos_t[:, None]).half())
 
 
 @pytest.mark.parametrize("H,W", [(16, 16), (96, 160), (24, 40)])
@@ -140,21 +146,17 @@ def test_mask_logits(G, rows, Q, shared):
 
 
 def test_kv_proj():
-    G, rows, nt = 2, 300, 6
-    xt = _randn(G * rows, 256, seed=1).half()
+    rows, nt = 700, 6
+    xk = _randn(rows, 256, seed=1).half()
+    xv = _randn(rows, 256, seed=11).half()
     w = _randn(nt * 256, 256, seed=2, scale=1 / 16).half()
-    outs = [torch.empty(G * rows, 256, dtype=torch.float16, device="cuda") for _ in range(nt)]
-    biases = [_randn(256, seed=10 + i) if i % 2 else None for i in range(nt)]
-    tabs = [None if i % 2 else _randn(100, 256, seed=20 + i) for i in range(nt)]
-    tabs2 = [None if i % 2 else _randn(3, 256, seed=30 + i) for i in range(nt)]
-    L.kv_proj_f16(xt, G, rows, w, outs, biases, tabs, tabs2, tab_period=100)
-    r = torch.arange(rows, device="cuda")
+    outs = [torch.empty(rows, 256, dtype=torch.float16, device="cuda") for _ in range(nt)]
+    biases = [_randn(256, seed=10 + i) if i != 2 else None for i in range(nt)]
+    L.kv_proj_f16(xk, xv, w, outs, biases)
     for i in range(nt):
-        ref = xt.double() @ w[i * 256:(i + 1) * 256].double().T
+        ref = (xk if i % 2 == 0 else xv).double() @ w[i * 256:(i + 1) * 256].double().T
         if biases[i] is not None:
             ref = ref + biases[i].double()
-        if tabs[i] is not None:
-            ref = ref + (tabs[i].double()[r % 100] + tabs2[i].double()[r // 100]).repeat(G, 1)
         assert _maxerr(outs[i], ref) < 8e-3, i
 
 

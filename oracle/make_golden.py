@@ -15,12 +15,14 @@ from . import ref_shim as R
 GOLDEN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 
 # (name, kind, T, Hp, Wp, Q, param seed, input seed)
+# Spatial size 128x192 (24 / 96 / 384 keys per frame): large enough that an isolated attention-mask bit flip at fp16
+# noise level does not dominate the comparison (at 64x64 the coarsest level has 4 keys), small enough to commit.
 DECODER_CASES = [
-    ("dec_frame_q100", "frame", 2, 64, 64, 100, 0, 1234),
-    ("dec_video_q100", "video", 3, 64, 96, 100, 1, 1235),
-    ("dec_san_frame_q100", "san_frame", 2, 64, 64, 100, 2, 1236),
-    ("dec_san_video_q100", "san_video", 2, 64, 64, 100, 3, 1237),
-    ("dec_frame_q200", "frame", 1, 96, 64, 200, 4, 1238),
+    ("dec_frame_q100", "frame", 2, 128, 192, 100, 0, 1234),
+    ("dec_video_q100", "video", 3, 128, 192, 100, 1, 1235),
+    ("dec_san_frame_q100", "san_frame", 2, 128, 192, 100, 2, 1236),
+    ("dec_san_video_q100", "san_video", 2, 128, 192, 100, 3, 1237),
+    ("dec_frame_q200", "frame", 1, 128, 192, 200, 4, 1238),
 ]
 
 
@@ -50,10 +52,10 @@ def make_decoder_fixture(name, kind, T, Hp, Wp, Q, pseed, iseed):
     rec = {"meta": np.array([T, Hp, Wp, Q, pseed, iseed])}
     for k in ("pred_logits", "pred_masks", "pred_embeds", "class_attn_biases"):
         if k in out:
-            rec[k] = out[k].numpy()
-    for i in (0, 4, 8):
-        a = out["aux_outputs"][i]
-        rec[f"aux{i}_pred_masks"] = a["pred_masks"].numpy().astype(np.float16)
+            rec[k] = out[k].numpy() if k == "pred_logits" else out[k].numpy().astype(np.float16)
+    rec["aux0_pred_masks"] = out["aux_outputs"][0]["pred_masks"].numpy().astype(np.float16)
+    for i in (4, 8):   # every 4th pixel in both directions
+        rec[f"aux{i}_pred_masks"] = out["aux_outputs"][i]["pred_masks"][..., ::4, ::4].numpy().astype(np.float16)
     np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **rec)
     print("wrote", name, {k: v.shape for k, v in rec.items()})
 

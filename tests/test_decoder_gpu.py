@@ -163,7 +163,7 @@ def test_decoder_matches_reference_golden(name, kind, golden_dir):
     x, mf = O.seeded_inputs(T, Hp, Wp, seed=iseed)
     out = m([t.cuda() for t in x], mf.cuda())
     g = lambda k: torch.as_tensor(gold[k]).float()
-    t = LOOSE                                         # fixtures are tiny (64x64 .. 96x64 inputs): see LOOSE above
+    t = LOOSE                                         # fixtures are small (128x192 inputs): see LOOSE above
     pm, gm = out["pred_masks"].cpu(), g("pred_masks")
     assert frac_within(pm, gm, t["pm_tol"]) >= t["pm_frac"]
     assert ((pm > 0) == (gm > 0)).float().mean().item() >= t["sign"]
@@ -178,7 +178,7 @@ def test_decoder_matches_reference_golden(name, kind, golden_dir):
     # the first head depends on no attention at all: it must match tightly
     assert frac_within(out["aux_outputs"][0]["pred_masks"].cpu(), g("aux0_pred_masks"), 0.08) >= 0.9999
     for i in (4, 8):
-        assert frac_within(out["aux_outputs"][i]["pred_masks"].cpu(), g(f"aux{i}_pred_masks"), 0.3) >= t["pm_frac"]
+        assert frac_within(out["aux_outputs"][i]["pred_masks"].cpu()[..., ::4, ::4], g(f"aux{i}_pred_masks"), 0.3) >= t["pm_frac"]
 
 
 def test_no_cpu_fallback_and_training_refused():

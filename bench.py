@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--streams", type=int, default=1, help="independent clips in flight per GPU (one decoder workspace each)")
+    ap.add_argument("--streams", type=int, default=3, help="independent clips in flight per GPU (one decoder workspace each)")
     return ap.parse_args()
 
 

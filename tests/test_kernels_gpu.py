@@ -93,7 +93,8 @@ def test_nchw_to_tokens():
     outp = torch.empty_like(out)
     L.nchw_to_tokens_f16(x, out=out2, out_pos=outp, pos=pos, pos_t=pos_t)
     assert torch.equal(out2, ref)
-    assert torch.equal(outp, (x.flatten(2).permute(0, 2, 1) + pos[None] + pos_t[:, None]).half())
+    refp = x.flatten(2).permute(0, 2, 1) + pos[None] + pos_t[:, None]
+    assert _maxerr(outp, refp) < 4e-3          # one fp16 ulp at |v| < 8 (summation order differs)
 
 
 @pytest.mark.parametrize("H,W", [(16, 16), (96, 160), (24, 40)])

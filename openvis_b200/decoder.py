@@ -379,8 +379,6 @@ class _B200MaskedDecoderBase(nn.Module):
         if torch.is_grad_enabled() and any(t.requires_grad for t in list(x) + [mask_features]):
             raise RuntimeError("openvis_b200 decoders do not support autograd; wrap the call in torch.no_grad()")
         assert len(x) == self.num_feature_levels
-        if not mask_features.is_cuda:
-            raise L.OvisError("openvis_b200 has no CPU path: inputs must be CUDA tensors on an sm_100 device")
         BT, C, H4, W4 = mask_features.shape
         if C != HIDDEN or H4 % 8 or W4 % 8:
             raise NotImplementedError(f"mask_features must be [BT, 256, H/4, W/4] with H, W multiples of 32, got {tuple(mask_features.shape)}")
@@ -392,6 +390,8 @@ class _B200MaskedDecoderBase(nn.Module):
                     f"multi-scale feature {l} must be {exp} (strides 32/16/8 of a /32-padded input, coarsest first); "
                     f"got {tuple(x[l].shape)}: the centre-2x2 mask down-sampling identity needs integer factors")
             sizes.append((H4 // s, W4 // s))
+        if not mask_features.is_cuda or any(not t.is_cuda for t in x):
+            raise L.OvisError("openvis_b200 has no CPU path: inputs must be CUDA tensors on an sm_100 device")
         return BT, H4, W4, sizes
 
     @torch.no_grad()

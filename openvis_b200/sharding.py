@@ -1,0 +1,35 @@
+"""Clip sharding across ranks and the end-of-run result gather.
+
+Mirrors the reference's evaluation pattern: `InferenceSampler` gives every rank a contiguous block of videos
+(openvis/data/build.py:238-247) and the per-video results are gathered on rank 0 once, at the end
+(openvis/data/evals/ytvis_eval.py:117-128, there via pickles over gloo).  Here the results are fixed-shape tensors
+and the gather is one `all_gather` (NCCL over NVLink on GPUs; gloo in the CPU tests).  Nothing on the decoding path
+communicates.
+"""
+from typing import List
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n_items: int, rank: int, world: int) -> range:
+    """Contiguous block of `n_items` for `rank` (same split as detectron2's InferenceSampler: the first
+    n % world ranks get one extra item)."""
+    base, rem = divmod(n_items, world)
+    begin = rank * base + min(rank, rem)
+    return range(begin, begin + base + (1 if rank < rem else 0))
+
+
+def gather_clip_results(local: torch.Tensor, n_items: int, group=None) -> torch.Tensor:
+    """local: [n_local, ...] results of this rank's block, in block order.  Returns [n_items, ...] in global clip order
+    on every rank.  Blocks may differ in length by one; shorter blocks are padded for the collective."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return local
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    n_max = -(-n_items // world)
+    pad = torch.zeros((n_max,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    parts: List[torch.Tensor] = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad, group=group)
+    out = [parts[r][: len(shard_range(n_items, r, world))] for r in range(world)]
+    return torch.cat(out, dim=0)

@@ -1,0 +1,111 @@
+"""CPU tests of the host-side mirror of the reference interface (no kernels run here)."""
+import types
+
+import pytest
+import torch
+
+from openvis_b200 import decoder as D
+from oracle import decoder_ref as O
+
+KW = dict(in_channels=256, mask_classification=True, num_classes=1, hidden_dim=256, num_queries=100, nheads=8,
+          dim_feedforward=2048, dec_layers=9, pre_norm=False, mask_dim=256, enforce_input_project=False, num_frames=2)
+
+
+def _cfg(name="FrameMultiScaleMaskedTransformerDecoder", queries=100):
+    ns = types.SimpleNamespace
+    return ns(MODEL=ns(SEM_SEG_HEAD=ns(NUM_CLASSES=1, MASK_DIM=256),
+                       MASK_FORMER=ns(HIDDEN_DIM=256, NUM_OBJECT_QUERIES=queries, NHEADS=8, DIM_FEEDFORWARD=2048,
+                                      DEC_LAYERS=10, PRE_NORM=False, ENFORCE_INPUT_PROJ=False,
+                                      TRANSFORMER_DECODER_NAME=name),
+                       CLIP_ADAPTER=ns(CLIP_NUM_HEADS=12, CLIP_EMBED_DIMS=512)),
+              INPUT=ns(SAMPLING_FRAME_NUM=2))
+
+
+@pytest.mark.parametrize("name,kind", [("FrameMultiScaleMaskedTransformerDecoder", "frame"),
+                                       ("VideoMultiScaleMaskedTransformerDecoder", "video"),
+                                       ("SideAdapterFrameMultiScaleMaskedTransformerDecoder", "san_frame"),
+                                       ("SideAdapterVideoMultiScaleMaskedTransformerDecoder", "san_video")])
+def test_state_dict_contract(name, kind):
+    """Parameter names and shapes equal the reference's; built through the registry from a cfg,
+    exactly as MaskFormerHead.from_config does (mask_former_head.py:112-116)."""
+    m = D.build_transformer_decoder(_cfg(name), 256, True)
+    got = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    assert got == O.decoder_param_shapes(kind)
+    assert m.num_layers == 9 and m.num_queries == 100 and m.num_heads == 8
+    m.load_state_dict(O.seeded_params(O.decoder_param_shapes(kind), 0))      # strict
+
+
+def test_registry_has_reference_names():
+    want = {"VideoMultiScaleMaskedTransformerDecoder", "EmbeddingVideoMultiScaleMaskedTransformerDecoder",
+            "ProposalVideoMultiScaleMaskedTransformerDecoder", "FrameMultiScaleMaskedTransformerDecoder",
+            "EmbeddingFrameMultiScaleMaskedTransformerDecoder", "ProposalFrameMultiScaleMaskedTransformerDecoder",
+            "SideAdapterVideoMultiScaleMaskedTransformerDecoder", "SideAdapterFrameMultiScaleMaskedTransformerDecoder"}
+    assert want <= set(D.TRANSFORMER_DECODER_REGISTRY)
+    target = {}
+    D.register_into(target)
+    assert want <= set(target)
+
+
+def test_embedding_and_proposal_variants():
+    e = D.EmbeddingFrameMultiScaleMaskedTransformerDecoder(clip_dims=512, **KW)
+    assert e.class_embed.layers[0].weight.shape == (1024, 256) and e.class_embed.layers[1].weight.shape == (512, 1024)
+    p = D.ProposalVideoMultiScaleMaskedTransformerDecoder(**KW)
+    assert p.class_embed.weight.shape == (2, 256)
+    e2 = D.build_transformer_decoder(_cfg("EmbeddingVideoMultiScaleMaskedTransformerDecoder"), 256, True)
+    assert e2.class_embed.layers[1].weight.shape == (512, 1024)
+
+
+def test_legacy_static_query_key_is_upgraded():
+    m = D.FrameMultiScaleMaskedTransformerDecoder(**KW)
+    sd = m.state_dict()
+    sd["static_query.weight"] = sd.pop("query_feat.weight") + 1.0
+    if hasattr(sd, "_metadata"):
+        sd._metadata[""] = {"version": 1}
+    m2 = D.FrameMultiScaleMaskedTransformerDecoder(**KW)
+    m2.load_state_dict(sd)
+    assert torch.equal(m2.query_feat.weight, sd["query_feat.weight"] if "query_feat.weight" in sd else m.query_feat.weight + 1.0)
+
+
+def test_unsupported_configs_fail_loudly():
+    for bad in (dict(hidden_dim=128, mask_dim=128, in_channels=128), dict(nheads=4), dict(pre_norm=True),
+                dict(enforce_input_project=True), dict(num_queries=300)):
+        with pytest.raises(NotImplementedError):
+            D.FrameMultiScaleMaskedTransformerDecoder(**{**KW, **bad})
+
+
+def test_position_tables_match_oracle():
+    for (h, w) in ((12, 20), (23, 40), (4, 6)):
+        a = D.sine_pos_2d(h, w, "cpu")                          # [h*w, 256]
+        b = O.sine_pos_2d(h, w).flatten(1).T
+        assert torch.allclose(a, b, atol=1e-6)
+    T, h, w = 5, 6, 8
+    p3 = O.sine_pos_3d(T, h, w).flatten(2).permute(0, 2, 1)      # [T, hw, C]
+    mine = D.sine_pos_2d(h, w, "cpu")[None] + D.sine_pos_z(T, "cpu")[:, None]
+    assert torch.allclose(mine, p3, atol=1e-6)
+
+
+def test_lazy_containers():
+    calls = []
+    aux = D.LazyAuxOutputs(3, lambda i: calls.append(i) or {"i": i})
+    assert len(aux) == 3 and calls == []
+    assert aux[1] == {"i": 1} and aux[1] == {"i": 1} and calls == [1]
+    assert aux[-1] == {"i": 2}
+    assert [a["i"] for a in aux] == [0, 1, 2] and sorted(calls) == [0, 1, 2]
+    d = D._LazyDict()
+    d["a"] = D._lazy(lambda: calls.append("a") or 7)
+    d["b"] = 3
+    assert d["a"] == 7 and d["a"] == 7 and calls.count("a") == 1
+    assert dict(d.items()) == {"a": 7, "b": 3}
+
+
+def test_inference_only_and_no_cpu_path():
+    m = D.FrameMultiScaleMaskedTransformerDecoder(**KW)
+    x, mf = O.seeded_inputs(1, 64, 64)
+    with pytest.raises(RuntimeError):
+        m(x, mf)                                  # training mode
+    m.eval()
+    with pytest.raises(Exception) as ei:
+        m(x, mf)                                  # CPU tensors: refused, never computed on the host
+    assert "CPU" in str(ei.value) or "CUDA" in str(ei.value)
+    with pytest.raises(NotImplementedError):
+        m([x[0], x[1], x[2][..., :-1]], mf)       # not the stride-32/16/8 pyramid of a /32-padded input

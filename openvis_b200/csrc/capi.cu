@@ -2,6 +2,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -11,6 +12,7 @@
 #include "gemm_tn.cuh"
 #include "prep.cuh"
 #include "xattn.cuh"
+#include "xattn_tc.cuh"
 
 using namespace ovis;
 
@@ -359,16 +361,17 @@ int ovis_xattn_plan(int G, int Q, int keys, int* splits, int* q_pad, long long* 
   CHECK_ARG(G > 0 && Q > 0 && Q <= 256 && keys > 0 && splits && q_pad && o_floats && ml_floats, "bad arguments");
   int sms = 148;
   device_info(&sms);   // sizing only: fall back to the B200 SM count when no device is visible
-  const int tiles = (keys + XA_KT - 1) / XA_KT;
-  // aim for ~4 CTAs per SM over (G * 8 heads * splits), at least 2 key tiles per split
-  int s = (4 * sms + G * 8 - 1) / (G * 8);
+  const int qtiles = (Q + 127) / 128;
+  const int tiles = (keys + XT_KT - 1) / XT_KT;
+  // one CTA per SM (the kernel owns all 512 TMEM columns and ~194 KB of shared memory): one wave of
+  // splits * qtiles * G CTAs, at least two key tiles per split
+  int s = sms / (G * qtiles);
   if (s > tiles / 2) s = tiles / 2;
   if (s < 1) s = 1;
-  if (s > 256) s = 256;
-  int chunk = ((tiles + s - 1) / s) * XA_KT;
+  const int chunk = ((tiles + s - 1) / s) * XT_KT;
   s = (keys + chunk - 1) / chunk;
   *splits = s;
-  *q_pad = ((Q + 31) / 32) * 32;
+  *q_pad = qtiles * 128;
   *o_floats = (long long)G * s * 8 * (*q_pad) * 32;
   *ml_floats = (long long)G * s * 8 * (*q_pad) * 2;
   return OVIS_OK;
@@ -378,21 +381,52 @@ int ovis_xattn(const void* q, const void* k, const void* v, const unsigned int* 
                int Q, int q_stride, int keys, int splits, float* o_part, float* ml_part, void* out, void* stream) {
   CHECK_ARG(q && k && v && bits && flags && o_part && ml_part && out, "null pointer");
   CHECK_ARG(G > 0 && Q > 0 && Q <= 256 && keys > 0 && splits > 0 && q_stride >= Q, "bad arguments");
+  CHECK_ARG((long long)G * keys < (1ll << 31), "too many keys");
   int rc = device_info(nullptr);
   if (rc) return rc;
-  XattnArgs a;
-  a.q = (const __half*)q; a.k = (const __half*)k; a.v = (const __half*)v;
-  a.bits = bits; a.flags = flags; a.o_part = o_part; a.ml_part = ml_part;
-  a.Q = Q; a.q_pad = ((Q + 31) / 32) * 32; a.q_stride = q_stride;
-  a.keys = keys; a.W = (keys + 31) / 32; a.splits = splits;
-  const int tiles = (keys + XA_KT - 1) / XA_KT;
-  a.chunk = ((tiles + splits - 1) / splits) * XA_KT;
-  CHECK_ARG((long long)a.chunk * (splits - 1) < keys, "splits too large for the key count (use ovis_xattn_plan)");
-  dim3 grid(splits, 8, G);
-  xattn_split_kernel<<<grid, a.q_pad, 0, (cudaStream_t)stream>>>(a);
-  rc = check_launch("xattn_split_kernel");
-  if (rc) return rc;
-  xattn_combine_kernel<<<dim3(Q, G), 256, 0, (cudaStream_t)stream>>>(o_part, ml_part, (__half*)out, Q, a.q_pad, splits);
+  const int qtiles = (Q + 127) / 128;
+  const int q_pad = qtiles * 128;
+  const int tiles = (keys + XT_KT - 1) / XT_KT;
+  const int chunk = ((tiles + splits - 1) / splits) * XT_KT;
+  CHECK_ARG((long long)chunk * (splits - 1) < keys, "splits too large for the key count (use ovis_xattn_plan)");
+  static const bool use_mma = getenv("OVIS_XATTN_MMA") != nullptr;   // round-1 mma.sync kernel, A/B testing only
+  if (use_mma) {
+    XattnArgs a;
+    a.q = (const __half*)q; a.k = (const __half*)k; a.v = (const __half*)v;
+    a.bits = bits; a.flags = flags; a.o_part = o_part; a.ml_part = ml_part;
+    a.Q = Q; a.q_pad = q_pad; a.q_stride = q_stride;
+    a.keys = keys; a.W = (keys + 31) / 32; a.splits = splits; a.chunk = chunk;
+    xattn_split_kernel<<<dim3(splits, 8, G), ((Q + 31) / 32) * 32, 0, (cudaStream_t)stream>>>(a);
+    rc = check_launch("xattn_split_kernel");
+    if (rc) return rc;
+  } else {
+    static bool attr_done[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_done[dev]) {
+      cudaError_t e = cudaFuncSetAttribute(xattn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XT_SMEM);
+      if (e != cudaSuccess) {
+        snprintf(g_err, sizeof(g_err), "xattn: cudaFuncSetAttribute(smem) failed: %s", cudaGetErrorString(e));
+        return OVIS_ERR_CUDA;
+      }
+      attr_done[dev] = true;
+    }
+    CUtensorMap tq, tk, tv;
+    rc = make_map_f16(&tq, q, (unsigned long long)G * Q, 256, 256, 128);
+    if (rc) return rc;
+    rc = make_map_f16(&tk, k, (unsigned long long)G * keys, 256, 256, XT_KT);
+    if (rc) return rc;
+    rc = make_map_f16(&tv, v, (unsigned long long)G * keys, 256, 256, XT_KT);
+    if (rc) return rc;
+    XattnTcArgs a;
+    a.bits = bits; a.flags = flags; a.o_part = o_part; a.ml_part = ml_part;
+    a.Q = Q; a.q_pad = q_pad; a.q_stride = q_stride;
+    a.keys = keys; a.W = (keys + 31) / 32; a.splits = splits; a.chunk = chunk;
+    xattn_tc_kernel<<<dim3(splits, qtiles, G), XT_THREADS, XT_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, a);
+    rc = check_launch("xattn_tc_kernel");
+    if (rc) return rc;
+  }
+  xattn_combine_kernel<<<dim3(Q, G), 256, 0, (cudaStream_t)stream>>>(o_part, ml_part, (__half*)out, Q, q_pad, splits);
   return check_launch("xattn_combine_kernel");
 }
 

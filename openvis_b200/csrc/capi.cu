@@ -139,6 +139,34 @@ int launch_gemm_bn(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensor
   return check_launch("gemm_tn_kernel");
 }
 
+template <int BN>
+int launch_gemm_bs(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tb, const GemmArgs& a, int sms,
+                   cudaStream_t st) {
+  using Cfg = GemmBsCfg<BN>;
+  static bool attr_done[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_done[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tn_bs_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      snprintf(g_err, sizeof(g_err), "gemm(bs): cudaFuncSetAttribute(smem) failed: %s", cudaGetErrorString(e));
+      return OVIS_ERR_CUDA;
+    }
+    attr_done[dev] = true;
+  }
+  const int m_tiles = (a.rows_per_group + 127) / 128;
+  const int n_tiles = (a.N + BN - 1) / BN;
+  const long long cols = (long long)a.num_groups * n_tiles;
+  if (cols <= 0 || m_tiles <= 0) return OVIS_OK;
+  // ncols x R CTAs: as many columns side by side as fit, R CTAs walking the m-tiles of each
+  const int ncols = (int)(cols < sms ? cols : sms);
+  int R = sms / ncols;
+  if (R > m_tiles) R = m_tiles;
+  if (R < 1) R = 1;
+  gemm_tn_bs_kernel<BN><<<ncols * R, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(ta, ta2, tb, a);
+  return check_launch("gemm_tn_bs_kernel");
+}
+
 // A: [a_rows][a_cols] fp16 pitch lda; B: [b_rows][K] fp16 pitch ldb.
 int launch_gemm(const void* A, long long a_rows, long long a_cols, long long lda, const void* B, long long b_rows,
                 long long ldb, const GemmArgs& a, int bn, cudaStream_t st, const void* A2 = nullptr) {
@@ -154,6 +182,11 @@ int launch_gemm(const void* A, long long a_rows, long long a_cols, long long lda
   if (rc) return rc;
   rc = make_map_f16(&tb, B, b_rows, a.K, ldb, bn);
   if (rc) return rc;
+  // HBM-heavy shapes (K <= 256, many row tiles): B-stationary kernel; small / long-K shapes: streaming kernel
+  const long long m_tiles_total = (long long)a.num_groups * ((a.rows_per_group + 127) / 128);
+  static const bool no_bs = getenv("OVIS_GEMM_NO_BS") != nullptr;    // A/B testing only
+  if (a.K <= 256 && m_tiles_total >= 64 && !no_bs)
+    return bn == 256 ? launch_gemm_bs<256>(ta, ta2, tb, a, sms, st) : launch_gemm_bs<128>(ta, ta2, tb, a, sms, st);
   return bn == 256 ? launch_gemm_bn<256>(ta, ta2, tb, a, sms, st) : launch_gemm_bn<128>(ta, ta2, tb, a, sms, st);
 }
 
@@ -426,7 +459,7 @@ int ovis_xattn(const void* q, const void* k, const void* v, const unsigned int* 
     rc = check_launch("xattn_tc_kernel");
     if (rc) return rc;
   }
-  xattn_combine_kernel<<<dim3(Q, G), 256, 0, (cudaStream_t)stream>>>(o_part, ml_part, (__half*)out, Q, q_pad, splits);
+  xattn_combine_kernel<<<dim3(Q, 8, G), 256, 0, (cudaStream_t)stream>>>(o_part, ml_part, (__half*)out, Q, q_pad, splits);
   return check_launch("xattn_combine_kernel");
 }
 

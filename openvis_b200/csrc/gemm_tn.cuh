@@ -75,6 +75,284 @@ struct GemmCfg {
   static constexpr int THREADS = 192;
 };
 
+// One 128 x BN accumulator tile: TMEM -> registers -> fused epilogue -> global.  Called by the four epilogue warps.
+template <int BN>
+__device__ __forceinline__ void gemm_epilogue_tile(const GemmArgs& args, int nt, int mt, int g, int warp, int lane,
+                                                   uint32_t t_acc_base, uint8_t* stage_smem) {
+  using Cfg = GemmCfg<BN>;
+  const int quarter = warp & 3;           // TMEM lane quarter this warp may access
+  const int r = mt * Cfg::BM + quarter * 32 + lane;        // row within group
+  const bool row_ok = r < args.rows_per_group;
+  const long long grow = (long long)(g / args.a_row_div) * args.a_group_stride + r;   // global A/D row
+  const int col_base = nt * BN;
+  const uint32_t t_acc = t_acc_base + ((uint32_t)(quarter * 32) << 16);
+  uint32_t v[32];
+
+  if (args.epi == EPI_STORE) {
+    const float* bias = args.bias[nt];
+    const int cols_per_unit = args.out_f32 ? 32 : 64;        // 128 bytes of output per row per unit
+    const int esize = args.out_f32 ? 4 : 2;
+    uint4* stg = reinterpret_cast<uint4*>(stage_smem + (warp - 2) * 4096);   // [32 rows][8 x 16 B], XOR-swizzled
+    const int r_warp0 = mt * Cfg::BM + quarter * 32;          // first row (within group) of this warp
+    const long long grow0 = (long long)(g / args.a_row_div) * args.a_group_stride + r_warp0;
+    const bool vec_ok = (((long long)args.ldo * esize) & 15) == 0;
+#pragma unroll 1
+    for (int u0 = 0; u0 < BN; u0 += cols_per_unit) {
+      if (col_base + u0 >= args.N) break;                     // warp-uniform
+      const int ncols = min(cols_per_unit, args.N - (col_base + u0));
+      uint4 pk[8];
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        if (hh == 1 && args.out_f32) break;
+        tmem_ld_32x32(t_acc + u0 + hh * 32, v);
+        tmem_ld_wait();
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        if (bias) {
+          const int nleft = args.N - (col_base + u0 + hh * 32);       // columns past N must not touch bias[]
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] += (j < nleft) ? __ldg(bias + u0 + hh * 32 + j) : 0.f;
+        }
+        if (args.scale != 1.f) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] *= args.scale;
+        }
+        if (args.relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+        }
+        if (args.out_f32) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            pk[j] = make_uint4(__float_as_uint(f[4 * j]), __float_as_uint(f[4 * j + 1]), __float_as_uint(f[4 * j + 2]),
+                               __float_as_uint(f[4 * j + 3]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            pk[hh * 4 + j] = make_uint4(pack_half2(f[8 * j], f[8 * j + 1]), pack_half2(f[8 * j + 2], f[8 * j + 3]),
+                                        pack_half2(f[8 * j + 4], f[8 * j + 5]), pack_half2(f[8 * j + 6], f[8 * j + 7]));
+        }
+      }
+      // stage through shared memory so that each store instruction writes four full 128-byte rows
+#pragma unroll
+      for (int c = 0; c < 8; ++c) stg[lane * 8 + (c ^ (lane & 7))] = pk[c];
+      __syncwarp();
+      char* obase = reinterpret_cast<char*>(args.out[nt]) + (long long)u0 * esize;
+      if (ncols == cols_per_unit && vec_ok) {
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int row = it * 4 + (lane >> 3), c = lane & 7;
+          if (r_warp0 + row < args.rows_per_group) {
+            const uint4 val = stg[row * 8 + (c ^ (row & 7))];
+            *reinterpret_cast<uint4*>(obase + (grow0 + row) * args.ldo * esize + c * 16) = val;
+          }
+        }
+      } else {
+        // ragged tail (N not a multiple of the unit, or unaligned pitch): element-wise, still row-coalesced
+        const int epc = 16 / esize;                            // elements per 16 B chunk
+        for (int it = 0; it < 8; ++it) {
+          const int row = it * 4 + (lane >> 3), c = lane & 7;
+          if (r_warp0 + row < args.rows_per_group) {
+            const uint4 val = stg[row * 8 + (c ^ (row & 7))];
+            char* o = obase + (grow0 + row) * args.ldo * esize + c * 16;
+            if (esize == 4) {
+              const uint32_t w[4] = {val.x, val.y, val.z, val.w};
+              for (int e = 0; e < 4; ++e)
+                if (c * epc + e < ncols) reinterpret_cast<uint32_t*>(o)[e] = w[e];
+            } else {
+              const uint32_t w[4] = {val.x, val.y, val.z, val.w};
+              for (int e = 0; e < 8; ++e)
+                if (c * epc + e < ncols)
+                  reinterpret_cast<unsigned short*>(o)[e] = (unsigned short)((w[e >> 1] >> ((e & 1) * 16)) & 0xffffu);
+            }
+          }
+        }
+      }
+      __syncwarp();
+    }
+  } else if (args.epi == EPI_LN) {
+    // BN == 256 == N.  Row-per-thread LayerNorm; the biased+residual row is parked back in TMEM between passes.
+    const float* bias = args.bias[0];
+    const float* res = args.resid + grow * 256;
+    float sum = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < 8; ++c) {
+      tmem_ld_32x32(t_acc + c * 32, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        float4 rr = row_ok ? __ldg(reinterpret_cast<const float4*>(res + c * 32 + j)) : make_float4(0, 0, 0, 0);
+        float a0 = __uint_as_float(v[j]) + __ldg(bias + c * 32 + j) + rr.x;
+        float a1 = __uint_as_float(v[j + 1]) + __ldg(bias + c * 32 + j + 1) + rr.y;
+        float a2 = __uint_as_float(v[j + 2]) + __ldg(bias + c * 32 + j + 2) + rr.z;
+        float a3 = __uint_as_float(v[j + 3]) + __ldg(bias + c * 32 + j + 3) + rr.w;
+        sum += (a0 + a1) + (a2 + a3);
+        v[j] = __float_as_uint(a0); v[j + 1] = __float_as_uint(a1);
+        v[j + 2] = __float_as_uint(a2); v[j + 3] = __float_as_uint(a3);
+      }
+      tmem_st_32x32(t_acc + c * 32, v);
+    }
+    tmem_st_wait();
+    const float mean = sum * (1.f / 256.f);
+    float sq = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < 8; ++c) {
+      tmem_ld_32x32(t_acc + c * 32, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) { float d = __uint_as_float(v[j]) - mean; sq += d * d; }
+    }
+    const float rstd = rsqrtf(sq * (1.f / 256.f) + 1e-5f);
+    const bool two = args.ln2_g != nullptr;
+    const float* pe = args.pe ? args.pe + (long long)(r % args.pe_period) * 256 : nullptr;
+    float sum2 = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < 8; ++c) {
+      tmem_ld_32x32(t_acc + c * 32, v);
+      tmem_ld_wait();
+      float y[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        y[j] = (__uint_as_float(v[j]) - mean) * rstd * __ldg(args.ln1_g + c * 32 + j) + __ldg(args.ln1_b + c * 32 + j);
+        sum2 += y[j];
+      }
+      if (row_ok) {
+        if (args.y32) {
+          float* o = args.y32 + grow * 256 + c * 32;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
+        }
+        if (args.y16) {
+          __half* o = args.y16 + grow * 256 + c * 32;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint4 u;
+            u.x = pack_half2(y[j], y[j + 1]); u.y = pack_half2(y[j + 2], y[j + 3]);
+            u.z = pack_half2(y[j + 4], y[j + 5]); u.w = pack_half2(y[j + 6], y[j + 7]);
+            *reinterpret_cast<uint4*>(o + j) = u;
+          }
+        }
+        if (args.ype16 && pe) {
+          __half* o = args.ype16 + grow * 256 + c * 32;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            float4 p0 = __ldg(reinterpret_cast<const float4*>(pe + c * 32 + j));
+            float4 p1 = __ldg(reinterpret_cast<const float4*>(pe + c * 32 + j + 4));
+            uint4 u;
+            u.x = pack_half2(y[j] + p0.x, y[j + 1] + p0.y); u.y = pack_half2(y[j + 2] + p0.z, y[j + 3] + p0.w);
+            u.z = pack_half2(y[j + 4] + p1.x, y[j + 5] + p1.y); u.w = pack_half2(y[j + 6] + p1.z, y[j + 7] + p1.w);
+            *reinterpret_cast<uint4*>(o + j) = u;
+          }
+        }
+      }
+      if (two) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(y[j]);
+        tmem_st_32x32(t_acc + c * 32, v);
+      }
+    }
+    if (two) {
+      tmem_st_wait();
+      const float mean2 = sum2 * (1.f / 256.f);
+      float sq2 = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 8; ++c) {
+        tmem_ld_32x32(t_acc + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { float d = __uint_as_float(v[j]) - mean2; sq2 += d * d; }
+      }
+      const float rstd2 = rsqrtf(sq2 * (1.f / 256.f) + 1e-5f);
+#pragma unroll 1
+      for (int c = 0; c < 8; ++c) {
+        tmem_ld_32x32(t_acc + c * 32, v);
+        tmem_ld_wait();
+        if (row_ok) {
+          float y[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            y[j] = (__uint_as_float(v[j]) - mean2) * rstd2 * __ldg(args.ln2_g + c * 32 + j) + __ldg(args.ln2_b + c * 32 + j);
+          if (args.d32) {
+            float* o = args.d32 + grow * 256 + c * 32;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
+          }
+          if (args.d16) {
+            __half* o = args.d16 + grow * 256 + c * 32;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 u;
+              u.x = pack_half2(y[j], y[j + 1]); u.y = pack_half2(y[j + 2], y[j + 3]);
+              u.z = pack_half2(y[j + 4], y[j + 5]); u.w = pack_half2(y[j + 6], y[j + 7]);
+              *reinterpret_cast<uint4*>(o + j) = u;
+            }
+          }
+        }
+      }
+    }
+  } else if (args.epi == EPI_SIGNBITS) {
+    // rows = keys / cells, columns = queries.  One ballot per column gives the 32-key word of this warp.
+    const int r0 = mt * Cfg::BM + quarter * 32;
+    const int word = r0 >> 5;
+    const int nvalid = max(0, min(32, args.rows_per_group - r0));
+    const uint32_t validmask = nvalid >= 32 ? 0xffffffffu : ((1u << nvalid) - 1u);
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      if (col_base + c * 32 >= args.N) break;
+      tmem_ld_32x32(t_acc + c * 32, v);
+      tmem_ld_wait();
+      uint32_t mine = 0;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        // blocked  <=>  sigmoid(x) < 0.5  <=>  x < 0 ; rows past the group end count as blocked
+        const uint32_t w = __ballot_sync(0xffffffffu, !row_ok || __uint_as_float(v[j]) < 0.f);
+        if (lane == j) mine = w;
+      }
+      const int col = col_base + c * 32 + lane;
+      if (col < args.N && word < args.words_per_group) {
+        args.bits[((long long)g * args.words_per_group + word) * args.q_stride + col] = mine;
+        if ((~mine & validmask) != 0u) args.flags[(long long)g * args.q_stride + col] = 1;
+      }
+    }
+  } else {  // EPI_STORE_T
+    const float* bias = args.bias[nt];
+    float* obase = args.out_t + (long long)g * args.t_group_stride + r;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      if (col_base + c * 32 >= args.N) break;
+      tmem_ld_32x32(t_acc + c * 32, v);
+      tmem_ld_wait();
+      if (row_ok) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int col = col_base + c * 32 + j;
+          if (col < args.N) {
+            float f = __uint_as_float(v[j]);
+            if (bias) f += __ldg(bias + c * 32 + j);
+            __stcs(obase + (long long)col * args.ldt, f);   // col < N checked above
+          }
+        }
+      }
+      if (args.posflags) {
+        // all 32 rows of this warp belong to one frame (rows_per_frame % 32 == 0)
+        uint32_t mine = 0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const uint32_t w = __ballot_sync(0xffffffffu, row_ok && __uint_as_float(v[j]) > 0.f);
+          if (lane == j) mine = w;
+        }
+        const int col = col_base + c * 32 + lane;
+        const int r0 = mt * Cfg::BM + quarter * 32;
+        if (col < args.N && mine != 0u && r0 < args.rows_per_group) {
+          const long long frame = (long long)g * (args.rows_per_group / args.rows_per_frame) + r0 / args.rows_per_frame;
+          args.posflags[frame * args.q_stride + col] = 1;
+        }
+      }
+    }
+  }
+}
+
 template <int BN>
 __global__ void __launch_bounds__(192, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
@@ -176,290 +454,174 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     // ===================== epilogue warps (2..5) =====================
-    const int quarter = warp & 3;           // TMEM lane quarter this warp may access
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int nt = tile % n_tiles;
       const int mt = (tile / n_tiles) % m_tiles;
       const int g = tile / (n_tiles * m_tiles);
-      const int r = mt * Cfg::BM + quarter * 32 + lane;        // row within group
-      const bool row_ok = r < args.rows_per_group;
-      const long long grow = (long long)(g / args.a_row_div) * args.a_group_stride + r;   // global A/D row
-      const int col_base = nt * BN;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const uint32_t t_acc = tmem_base + acc * BN + ((uint32_t)(quarter * 32) << 16);
-      uint32_t v[32];
-
-      if (args.epi == EPI_STORE) {
-        const float* bias = args.bias[nt];
-        const int cols_per_unit = args.out_f32 ? 32 : 64;        // 128 bytes of output per row per unit
-        const int esize = args.out_f32 ? 4 : 2;
-        uint4* stg = reinterpret_cast<uint4*>(stage_smem + (warp - 2) * 4096);   // [32 rows][8 x 16 B], XOR-swizzled
-        const int r_warp0 = mt * Cfg::BM + quarter * 32;          // first row (within group) of this warp
-        const long long grow0 = (long long)(g / args.a_row_div) * args.a_group_stride + r_warp0;
-        const bool vec_ok = (((long long)args.ldo * esize) & 15) == 0;
-#pragma unroll 1
-        for (int u0 = 0; u0 < BN; u0 += cols_per_unit) {
-          if (col_base + u0 >= args.N) break;                     // warp-uniform
-          const int ncols = min(cols_per_unit, args.N - (col_base + u0));
-          uint4 pk[8];
-#pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            if (hh == 1 && args.out_f32) break;
-            tmem_ld_32x32(t_acc + u0 + hh * 32, v);
-            tmem_ld_wait();
-            float f[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-            if (bias) {
-              const int nleft = args.N - (col_base + u0 + hh * 32);       // columns past N must not touch bias[]
-#pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] += (j < nleft) ? __ldg(bias + u0 + hh * 32 + j) : 0.f;
-            }
-            if (args.scale != 1.f) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] *= args.scale;
-            }
-            if (args.relu) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
-            }
-            if (args.out_f32) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j)
-                pk[j] = make_uint4(__float_as_uint(f[4 * j]), __float_as_uint(f[4 * j + 1]), __float_as_uint(f[4 * j + 2]),
-                                   __float_as_uint(f[4 * j + 3]));
-            } else {
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                pk[hh * 4 + j] = make_uint4(pack_half2(f[8 * j], f[8 * j + 1]), pack_half2(f[8 * j + 2], f[8 * j + 3]),
-                                            pack_half2(f[8 * j + 4], f[8 * j + 5]), pack_half2(f[8 * j + 6], f[8 * j + 7]));
-            }
-          }
-          // stage through shared memory so that each store instruction writes four full 128-byte rows
-#pragma unroll
-          for (int c = 0; c < 8; ++c) stg[lane * 8 + (c ^ (lane & 7))] = pk[c];
-          __syncwarp();
-          char* obase = reinterpret_cast<char*>(args.out[nt]) + (long long)u0 * esize;
-          if (ncols == cols_per_unit && vec_ok) {
-#pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              const int row = it * 4 + (lane >> 3), c = lane & 7;
-              if (r_warp0 + row < args.rows_per_group) {
-                const uint4 val = stg[row * 8 + (c ^ (row & 7))];
-                *reinterpret_cast<uint4*>(obase + (grow0 + row) * args.ldo * esize + c * 16) = val;
-              }
-            }
-          } else {
-            // ragged tail (N not a multiple of the unit, or unaligned pitch): element-wise, still row-coalesced
-            const int epc = 16 / esize;                            // elements per 16 B chunk
-            for (int it = 0; it < 8; ++it) {
-              const int row = it * 4 + (lane >> 3), c = lane & 7;
-              if (r_warp0 + row < args.rows_per_group) {
-                const uint4 val = stg[row * 8 + (c ^ (row & 7))];
-                char* o = obase + (grow0 + row) * args.ldo * esize + c * 16;
-                if (esize == 4) {
-                  const uint32_t w[4] = {val.x, val.y, val.z, val.w};
-                  for (int e = 0; e < 4; ++e)
-                    if (c * epc + e < ncols) reinterpret_cast<uint32_t*>(o)[e] = w[e];
-                } else {
-                  const uint32_t w[4] = {val.x, val.y, val.z, val.w};
-                  for (int e = 0; e < 8; ++e)
-                    if (c * epc + e < ncols)
-                      reinterpret_cast<unsigned short*>(o)[e] = (unsigned short)((w[e >> 1] >> ((e & 1) * 16)) & 0xffffu);
-                }
-              }
-            }
-          }
-          __syncwarp();
-        }
-      } else if (args.epi == EPI_LN) {
-        // BN == 256 == N.  Row-per-thread LayerNorm; the biased+residual row is parked back in TMEM between passes.
-        const float* bias = args.bias[0];
-        const float* res = args.resid + grow * 256;
-        float sum = 0.f;
-#pragma unroll 1
-        for (int c = 0; c < 8; ++c) {
-          tmem_ld_32x32(t_acc + c * 32, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 rr = row_ok ? __ldg(reinterpret_cast<const float4*>(res + c * 32 + j)) : make_float4(0, 0, 0, 0);
-            float a0 = __uint_as_float(v[j]) + __ldg(bias + c * 32 + j) + rr.x;
-            float a1 = __uint_as_float(v[j + 1]) + __ldg(bias + c * 32 + j + 1) + rr.y;
-            float a2 = __uint_as_float(v[j + 2]) + __ldg(bias + c * 32 + j + 2) + rr.z;
-            float a3 = __uint_as_float(v[j + 3]) + __ldg(bias + c * 32 + j + 3) + rr.w;
-            sum += (a0 + a1) + (a2 + a3);
-            v[j] = __float_as_uint(a0); v[j + 1] = __float_as_uint(a1);
-            v[j + 2] = __float_as_uint(a2); v[j + 3] = __float_as_uint(a3);
-          }
-          tmem_st_32x32(t_acc + c * 32, v);
-        }
-        tmem_st_wait();
-        const float mean = sum * (1.f / 256.f);
-        float sq = 0.f;
-#pragma unroll 1
-        for (int c = 0; c < 8; ++c) {
-          tmem_ld_32x32(t_acc + c * 32, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) { float d = __uint_as_float(v[j]) - mean; sq += d * d; }
-        }
-        const float rstd = rsqrtf(sq * (1.f / 256.f) + 1e-5f);
-        const bool two = args.ln2_g != nullptr;
-        const float* pe = args.pe ? args.pe + (long long)(r % args.pe_period) * 256 : nullptr;
-        float sum2 = 0.f;
-#pragma unroll 1
-        for (int c = 0; c < 8; ++c) {
-          tmem_ld_32x32(t_acc + c * 32, v);
-          tmem_ld_wait();
-          float y[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            y[j] = (__uint_as_float(v[j]) - mean) * rstd * __ldg(args.ln1_g + c * 32 + j) + __ldg(args.ln1_b + c * 32 + j);
-            sum2 += y[j];
-          }
-          if (row_ok) {
-            if (args.y32) {
-              float* o = args.y32 + grow * 256 + c * 32;
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
-            }
-            if (args.y16) {
-              __half* o = args.y16 + grow * 256 + c * 32;
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                uint4 u;
-                u.x = pack_half2(y[j], y[j + 1]); u.y = pack_half2(y[j + 2], y[j + 3]);
-                u.z = pack_half2(y[j + 4], y[j + 5]); u.w = pack_half2(y[j + 6], y[j + 7]);
-                *reinterpret_cast<uint4*>(o + j) = u;
-              }
-            }
-            if (args.ype16 && pe) {
-              __half* o = args.ype16 + grow * 256 + c * 32;
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                float4 p0 = __ldg(reinterpret_cast<const float4*>(pe + c * 32 + j));
-                float4 p1 = __ldg(reinterpret_cast<const float4*>(pe + c * 32 + j + 4));
-                uint4 u;
-                u.x = pack_half2(y[j] + p0.x, y[j + 1] + p0.y); u.y = pack_half2(y[j + 2] + p0.z, y[j + 3] + p0.w);
-                u.z = pack_half2(y[j + 4] + p1.x, y[j + 5] + p1.y); u.w = pack_half2(y[j + 6] + p1.z, y[j + 7] + p1.w);
-                *reinterpret_cast<uint4*>(o + j) = u;
-              }
-            }
-          }
-          if (two) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(y[j]);
-            tmem_st_32x32(t_acc + c * 32, v);
-          }
-        }
-        if (two) {
-          tmem_st_wait();
-          const float mean2 = sum2 * (1.f / 256.f);
-          float sq2 = 0.f;
-#pragma unroll 1
-          for (int c = 0; c < 8; ++c) {
-            tmem_ld_32x32(t_acc + c * 32, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) { float d = __uint_as_float(v[j]) - mean2; sq2 += d * d; }
-          }
-          const float rstd2 = rsqrtf(sq2 * (1.f / 256.f) + 1e-5f);
-#pragma unroll 1
-          for (int c = 0; c < 8; ++c) {
-            tmem_ld_32x32(t_acc + c * 32, v);
-            tmem_ld_wait();
-            if (row_ok) {
-              float y[32];
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                y[j] = (__uint_as_float(v[j]) - mean2) * rstd2 * __ldg(args.ln2_g + c * 32 + j) + __ldg(args.ln2_b + c * 32 + j);
-              if (args.d32) {
-                float* o = args.d32 + grow * 256 + c * 32;
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
-              }
-              if (args.d16) {
-                __half* o = args.d16 + grow * 256 + c * 32;
-#pragma unroll
-                for (int j = 0; j < 32; j += 8) {
-                  uint4 u;
-                  u.x = pack_half2(y[j], y[j + 1]); u.y = pack_half2(y[j + 2], y[j + 3]);
-                  u.z = pack_half2(y[j + 4], y[j + 5]); u.w = pack_half2(y[j + 6], y[j + 7]);
-                  *reinterpret_cast<uint4*>(o + j) = u;
-                }
-              }
-            }
-          }
-        }
-      } else if (args.epi == EPI_SIGNBITS) {
-        // rows = keys / cells, columns = queries.  One ballot per column gives the 32-key word of this warp.
-        const int r0 = mt * Cfg::BM + quarter * 32;
-        const int word = r0 >> 5;
-        const int nvalid = max(0, min(32, args.rows_per_group - r0));
-        const uint32_t validmask = nvalid >= 32 ? 0xffffffffu : ((1u << nvalid) - 1u);
-#pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-          if (col_base + c * 32 >= args.N) break;
-          tmem_ld_32x32(t_acc + c * 32, v);
-          tmem_ld_wait();
-          uint32_t mine = 0;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            // blocked  <=>  sigmoid(x) < 0.5  <=>  x < 0 ; rows past the group end count as blocked
-            const uint32_t w = __ballot_sync(0xffffffffu, !row_ok || __uint_as_float(v[j]) < 0.f);
-            if (lane == j) mine = w;
-          }
-          const int col = col_base + c * 32 + lane;
-          if (col < args.N && word < args.words_per_group) {
-            args.bits[((long long)g * args.words_per_group + word) * args.q_stride + col] = mine;
-            if ((~mine & validmask) != 0u) args.flags[(long long)g * args.q_stride + col] = 1;
-          }
-        }
-      } else {  // EPI_STORE_T
-        const float* bias = args.bias[nt];
-        float* obase = args.out_t + (long long)g * args.t_group_stride + r;
-#pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-          if (col_base + c * 32 >= args.N) break;
-          tmem_ld_32x32(t_acc + c * 32, v);
-          tmem_ld_wait();
-          if (row_ok) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int col = col_base + c * 32 + j;
-              if (col < args.N) {
-                float f = __uint_as_float(v[j]);
-                if (bias) f += __ldg(bias + c * 32 + j);
-                __stcs(obase + (long long)col * args.ldt, f);   // col < N checked above
-              }
-            }
-          }
-          if (args.posflags) {
-            // all 32 rows of this warp belong to one frame (rows_per_frame % 32 == 0)
-            uint32_t mine = 0;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const uint32_t w = __ballot_sync(0xffffffffu, row_ok && __uint_as_float(v[j]) > 0.f);
-              if (lane == j) mine = w;
-            }
-            const int col = col_base + c * 32 + lane;
-            const int r0 = mt * Cfg::BM + quarter * 32;
-            if (col < args.N && mine != 0u && r0 < args.rows_per_group) {
-              const long long frame = (long long)g * (args.rows_per_group / args.rows_per_frame) + r0 / args.rows_per_frame;
-              args.posflags[frame * args.q_stride + col] = 1;
-            }
-          }
-        }
-      }
+      gemm_epilogue_tile<BN>(args, nt, mt, g, warp, lane, tmem_base + acc * BN, stage_smem);
       // release the accumulator stage
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// B-stationary variant for K <= 256 (every HBM-heavy GEMM of this path: K/V projection, mask bits, full-resolution
+// mask logits, SAN bias branch).  A CTA keeps one [BN x K] B tile (weights / mask embeddings of one group) resident in
+// shared memory and streams only A tiles through the TMA ring, so the ring is twice as deep for the same shared
+// memory and B is read from L2 once per CTA instead of once per tile.  Work decomposition: "columns" = (group, n-tile);
+// the grid is laid out as ncols x R CTAs, CTA (col, r) walks m-tiles r, r+R, ... of its column(s), so the CTAs that
+// share an A tile (same m-tile, different n-tile) run at the same time and the tile is fetched from HBM once.
+template <int BN>
+struct GemmBsCfg {
+  static constexpr int BM = 128, BK = 64, KB_MAX = 4;           // K <= 256
+  static constexpr int B_BYTES = BN * BK * 2 * KB_MAX;           // 128 KB (BN 256) / 64 KB (BN 128)
+  static constexpr int A_BYTES = BM * BK * 2;                    // 16 KB per ring stage
+  static constexpr int STAGES = (BN == 256) ? 4 : 8;
+  static constexpr int STAGING_BYTES = 4 * 4096;
+  static constexpr int SMEM_BYTES = B_BYTES + STAGES * A_BYTES + STAGING_BYTES + 1024 + 256;
+  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int THREADS = 192;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1)
+gemm_tn_bs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+                  const __grid_constant__ CUtensorMap tmB, const GemmArgs args) {
+  using Cfg = GemmBsCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sB = smem;
+  uint8_t* sA = smem + Cfg::B_BYTES;
+  uint8_t* stage_smem = sA + STAGES * Cfg::A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_smem + Cfg::STAGING_BYTES);
+  uint64_t* full_bar = bars;                      // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;            // [STAGES]
+  uint64_t* tfull_bar = bars + 2 * STAGES;        // [2]
+  uint64_t* tempty_bar = bars + 2 * STAGES + 2;   // [2]
+  uint64_t* bfull_bar = bars + 2 * STAGES + 4;    // [1]
+  uint64_t* bempty_bar = bars + 2 * STAGES + 5;   // [1]
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 6);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m_tiles = (args.rows_per_group + Cfg::BM - 1) / Cfg::BM;
+  const int n_tiles = (args.N + BN - 1) / BN;
+  const int cols = args.num_groups * n_tiles;
+  const int k_blocks = args.K / Cfg::BK;
+  const int ncols_cta = min(cols, (int)gridDim.x);      // columns processed concurrently
+  const int R = (int)gridDim.x / ncols_cta;             // CTAs per column
+  const int col0 = (int)blockIdx.x % ncols_cta;
+  const int r0 = (int)blockIdx.x / ncols_cta;
+  const bool active = r0 < R;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmA2);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
+    mbar_init(bfull_bar, 1);
+    mbar_init(bempty_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_holder, Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (active) {
+    if (warp == 0) {
+      // ===================== TMA producer =====================
+      if (lane == 0) {
+        int stage = 0;
+        uint32_t phase = 0, bphase = 0;
+        for (int col = col0; col < cols; col += ncols_cta) {
+          const int nt = col % n_tiles;
+          const int g = col / n_tiles;
+          const int b_row = (g / args.b_row_div) * args.b_group_stride + nt * BN;
+          const int a_col = (g % args.a_k_mod) * args.a_k_offset_stride;
+          const int a_row0 = (g / args.a_row_div) * args.a_group_stride;
+          const CUtensorMap* ta = (args.a_alt && (nt & 1)) ? &tmA2 : &tmA;
+          mbar_wait(bempty_bar, bphase ^ 1);               // previous column's MMAs have retired
+          mbar_arrive_expect_tx(bfull_bar, (uint32_t)(k_blocks * BN * Cfg::BK * 2));
+          for (int kb = 0; kb < k_blocks; ++kb) tma_load_2d(sB + kb * (BN * Cfg::BK * 2), &tmB, bfull_bar, kb * Cfg::BK, b_row);
+          bphase ^= 1;
+          for (int mt = r0; mt < m_tiles; mt += R) {
+            for (int kb = 0; kb < k_blocks; ++kb) {
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              mbar_arrive_expect_tx(&full_bar[stage], Cfg::A_BYTES);
+              tma_load_2d(sA + stage * Cfg::A_BYTES, ta, &full_bar[stage], a_col + kb * Cfg::BK, a_row0 + mt * Cfg::BM);
+              if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+    } else if (warp == 1) {
+      // ===================== MMA issuer =====================
+      if (lane == 0) {
+        constexpr uint32_t idesc = umma_idesc_f16(Cfg::BM, BN);
+        int stage = 0, acc = 0;
+        uint32_t phase = 0, acc_phase = 0, bphase = 0;
+        const uint32_t b_addr = smem_u32(sB);
+        for (int col = col0; col < cols; col += ncols_cta) {
+          mbar_wait(bfull_bar, bphase);
+          bphase ^= 1;
+          tc_fence_after();
+          for (int mt = r0; mt < m_tiles; mt += R) {
+            mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * BN;
+            for (int kb = 0; kb < k_blocks; ++kb) {
+              mbar_wait(&full_bar[stage], phase);
+              tc_fence_after();
+              const uint64_t adesc = umma_desc_k_sw128(smem_u32(sA + stage * Cfg::A_BYTES));
+              const uint64_t bdesc = umma_desc_k_sw128(b_addr + kb * (BN * Cfg::BK * 2));
+#pragma unroll
+              for (int k = 0; k < Cfg::BK / 16; ++k)
+                umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              umma_commit(&empty_bar[stage]);
+              if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(&tfull_bar[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+          }
+          umma_commit(bempty_bar);                       // B tile may be overwritten once everything above retired
+        }
+      }
+    } else {
+      // ===================== epilogue warps (2..5) =====================
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int col = col0; col < cols; col += ncols_cta) {
+        const int nt = col % n_tiles;
+        const int g = col / n_tiles;
+        for (int mt = r0; mt < m_tiles; mt += R) {
+          mbar_wait(&tfull_bar[acc], acc_phase);
+          tc_fence_after();
+          gemm_epilogue_tile<BN>(args, nt, mt, g, warp, lane, tmem_base + acc * BN, stage_smem);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+      }
     }
   }
 

@@ -241,25 +241,41 @@ xattn_split_kernel(const XattnArgs a) {
 }
 
 // Merge the key splits: out[g*Q+q][h*32+d] = sum_s 2^(m_s-M) O_s / sum_s 2^(m_s-M) l_s   (fp16 for the out-proj GEMM)
+// grid (Q, 8 heads, G), 256 threads = 8 split lanes x 32 channels; each lane folds its splits online, then a smem merge.
 __global__ void __launch_bounds__(256)
 xattn_combine_kernel(const float* __restrict__ o_part, const float* __restrict__ ml_part, __half* __restrict__ out,
                      int Q, int q_pad, int splits) {
-  const int q = blockIdx.x, g = blockIdx.y;
-  const int h = threadIdx.x >> 5, d = threadIdx.x & 31;
-  float M = -INFINITY;
-  for (int s = 0; s < splits; ++s) {
+  __shared__ float sm_m[8], sm_den[8], sm_num[8][32];
+  const int q = blockIdx.x, h = blockIdx.y, g = blockIdx.z;
+  const int d = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  float M = -INFINITY, num = 0.f, den = 0.f;
+  for (int s = sl; s < splits; s += 8) {
     const long long r = (((long long)g * splits + s) * 8 + h) * q_pad + q;
-    M = fmaxf(M, ml_part[r * 2]);
+    const float2 ml = __ldg(reinterpret_cast<const float2*>(ml_part + r * 2));
+    const float o = __ldg(o_part + r * 32 + d);
+    if (ml.x == -INFINITY) continue;
+    const float Mn = fmaxf(M, ml.x);
+    const float c0 = exp2f(M - Mn), c1 = exp2f(ml.x - Mn);      // exp2f(-inf) = 0 on the first contribution
+    num = num * c0 + o * c1;
+    den = den * c0 + ml.y * c1;
+    M = Mn;
   }
-  float num = 0.f, den = 0.f;
-  for (int s = 0; s < splits; ++s) {
-    const long long r = (((long long)g * splits + s) * 8 + h) * q_pad + q;
-    const float m = ml_part[r * 2];
-    const float w = (m == -INFINITY) ? 0.f : exp2f(m - M);
-    num += w * o_part[r * 32 + d];
-    den += w * ml_part[r * 2 + 1];
+  sm_num[sl][d] = num;
+  if (d == 0) { sm_m[sl] = M; sm_den[sl] = den; }
+  __syncthreads();
+  if (sl == 0) {
+    float Mt = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) Mt = fmaxf(Mt, sm_m[i]);
+    float n = 0.f, dn = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float w = (sm_m[i] == -INFINITY) ? 0.f : exp2f(sm_m[i] - Mt);
+      n += w * sm_num[i][d];
+      dn += w * sm_den[i];
+    }
+    out[((long long)g * Q + q) * 256 + h * 32 + d] = __float2half_rn(n / dn);
   }
-  out[((long long)g * Q + q) * 256 + h * 32 + d] = __float2half_rn(num / den);
 }
 
 // Self-attention over the Q object queries (SelfAttentionLayer.forward_post, video_..._decoder.py:52-62).

@@ -69,6 +69,12 @@ __device__ __forceinline__ void tmem_ld_32x32_nowait(uint32_t taddr, uint32_t* r
       : "memory");
 }
 
+__device__ __forceinline__ float fast_ex2(float x) {      // MUFU.EX2, flush-to-zero: exactly what a probability needs
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __global__ void __launch_bounds__(XT_THREADS, 1)
 xattn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const XattnTcArgs a) {
@@ -102,8 +108,8 @@ xattn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     for (int s = 0; s < XT_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int i = 0; i < 4; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_empty[i], 128);
-      mbar_init(&p_full[i], 128);
+      mbar_init(&s_empty[i], 4);        // one elected arrival per softmax warp
+      mbar_init(&p_full[i], 4);
       mbar_init(&p_empty[i], 1);
     }
     mbar_init(done, 1);
@@ -198,19 +204,27 @@ xattn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
     for (int j = 0; j < 4; ++j) { m_run[j] = -INFINITY; l_run[j] = 0.f; }
 
-    for (int t = 0; t < ntiles; ++t) {
+    // mask words of a 64-key tile (shared by all heads); the next tile's words are prefetched one tile ahead
+    auto load_words = [&](int t, uint32_t (&dst)[2]) {
       const int kb = k_begin + t * XT_KT;
-      // mask words of this 64-key tile (shared by all heads)
-      uint32_t mw[2];
 #pragma unroll
       for (int x = 0; x < 2; ++x) {
         const int wi = (kb >> 5) + x;
-        uint32_t bw = 0u;
-        if (use_mask && wi < a.W) bw = __ldg(bits_q + (long long)wi * a.q_stride);
+        dst[x] = (use_mask && t < ntiles && wi < a.W) ? __ldg(bits_q + (long long)wi * a.q_stride) : 0u;
+      }
+    };
+    uint32_t nw[2];
+    load_words(0, nw);
+    for (int t = 0; t < ntiles; ++t) {
+      const int kb = k_begin + t * XT_KT;
+      uint32_t mw[2];
+#pragma unroll
+      for (int x = 0; x < 2; ++x) {
         const int nvalid = k_end - (kb + x * 32);
         const uint32_t inval = nvalid >= 32 ? 0u : (nvalid <= 0 ? 0xffffffffu : ~((1u << nvalid) - 1u));
-        mw[x] = bw | inval;
+        mw[x] = nw[x] | inval;
       }
+      load_words(t + 1, nw);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int b = j & 1;
@@ -224,16 +238,18 @@ xattn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tmem_ld_32x32_nowait(s_addr + 32, sv + 32);
         tmem_ld_wait();
         tc_fence_before();
-        mbar_arrive(&s_empty[bi]);
-        // mask + tile max
-        float mx = -INFINITY;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[bi]);
+        // mask + tile max (four independent chains)
+        float mxa[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
         for (int k = 0; k < 64; ++k) {
           float s = __uint_as_float(sv[k]);
-          if ((mw[k >> 5] >> (k & 31)) & 1u) s = -INFINITY;
+          if (mw[k >> 5] & (1u << (k & 31))) s = -INFINITY;
           sv[k] = __float_as_uint(s);
-          mx = fmaxf(mx, s);
+          mxa[k & 3] = fmaxf(mxa[k & 3], s);
         }
+        const float mx = fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3]));
         // lazy rescaling: keep the stale reference max unless the new one exceeds it by more than 2^8
         const float m_old = m_run[j];
         float m_use = m_old;
@@ -243,7 +259,7 @@ xattn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         mbar_wait(&p_empty[bi], ph ^ 1u);
         tc_fence_after();
         if (__any_sync(0xffffffffu, grow)) {
-          const float f = grow ? exp2f(m_old - m_use) : 1.f;
+          const float f = grow ? fast_ex2(m_old - m_use) : 1.f;
           uint32_t ov[32];
           const uint32_t o_addr = tmem_base + lane_off + 256u + (uint32_t)((2 * j + w) * 32);
           tmem_ld_32x32_nowait(o_addr, ov);
@@ -256,25 +272,26 @@ xattn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
         m_run[j] = m_use;
         const float m_sub = (m_use == -INFINITY) ? 0.f : m_use;
-        float lsum = 0.f;
+        float ls[4] = {0.f, 0.f, 0.f, 0.f};
         uint8_t* prow = p_base + b * XT_P_BYTES;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {                     // 8 chunks of 8 keys = 16 bytes
           float p[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
-            p[e] = exp2f(__uint_as_float(sv[c * 8 + e]) - m_sub);
-            lsum += p[e];
+            p[e] = fast_ex2(__uint_as_float(sv[c * 8 + e]) - m_sub);
+            ls[e & 3] += p[e];
           }
           uint4 u;
           u.x = pack_half2(p[0], p[1]); u.y = pack_half2(p[2], p[3]);
           u.z = pack_half2(p[4], p[5]); u.w = pack_half2(p[6], p[7]);
           *reinterpret_cast<uint4*>(prow + ((c ^ (r & 7)) << 4)) = u;
         }
-        l_run[j] += lsum;
+        l_run[j] += (ls[0] + ls[1]) + (ls[2] + ls[3]);
         fence_async_proxy();            // generic-proxy smem writes -> visible to the tensor core (async proxy)
         tc_fence_before();
-        mbar_arrive(&p_full[bi]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[bi]);
       }
     }
     // ---- all MMAs retired: write the split's partial O (un-normalised) and (max, sum)

@@ -92,27 +92,53 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmArgs& args, int nt,
     const float* bias = args.bias[nt];
     const int cols_per_unit = args.out_f32 ? 32 : 64;        // 128 bytes of output per row per unit
     const int esize = args.out_f32 ? 4 : 2;
-    uint4* stg = reinterpret_cast<uint4*>(stage_smem + (warp - 2) * 4096);   // [32 rows][8 x 16 B], XOR-swizzled
+    const uint32_t stg = smem_u32(stage_smem + (warp - 2) * 4096);   // [32 rows][8 x 16 B], XOR-swizzled
     const int r_warp0 = mt * Cfg::BM + quarter * 32;          // first row (within group) of this warp
     const long long grow0 = (long long)(g / args.a_row_div) * args.a_group_stride + r_warp0;
     const bool vec_ok = (((long long)args.ldo * esize) & 15) == 0;
+    const bool bias_vec = bias && ((reinterpret_cast<uintptr_t>(bias) & 15) == 0);
 #pragma unroll 1
     for (int u0 = 0; u0 < BN; u0 += cols_per_unit) {
       if (col_base + u0 >= args.N) break;                     // warp-uniform
       const int ncols = min(cols_per_unit, args.N - (col_base + u0));
+      const int nh = args.out_f32 ? 1 : 2;
+      uint32_t vv[2][32];
+      // issue all TMEM loads of the unit, fetch the bias while they are in flight, wait once
+      tmem_ld_32x32_raw(t_acc + u0, vv[0]);
+      if (nh == 2) tmem_ld_32x32_raw(t_acc + u0 + 32, vv[1]);
+      float4 bv[2][8];
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        if (hh >= nh) break;
+        const int nleft = args.N - (col_base + u0 + hh * 32);          // columns past N must not touch bias[]
+        if (bias_vec && nleft >= 32) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) bv[hh][j] = __ldg(reinterpret_cast<const float4*>(bias + u0 + hh * 32) + j);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int c = 4 * j;
+            bv[hh][j] = make_float4((bias && c < nleft) ? __ldg(bias + u0 + hh * 32 + c) : 0.f,
+                                    (bias && c + 1 < nleft) ? __ldg(bias + u0 + hh * 32 + c + 1) : 0.f,
+                                    (bias && c + 2 < nleft) ? __ldg(bias + u0 + hh * 32 + c + 2) : 0.f,
+                                    (bias && c + 3 < nleft) ? __ldg(bias + u0 + hh * 32 + c + 3) : 0.f);
+          }
+        }
+      }
+      tmem_ld_wait();
+      reg_fence32(vv[0]);
+      if (nh == 2) reg_fence32(vv[1]);
       uint4 pk[8];
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
-        if (hh == 1 && args.out_f32) break;
-        tmem_ld_32x32(t_acc + u0 + hh * 32, v);
-        tmem_ld_wait();
+        if (hh >= nh) break;
         float f[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-        if (bias) {
-          const int nleft = args.N - (col_base + u0 + hh * 32);       // columns past N must not touch bias[]
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] += (j < nleft) ? __ldg(bias + u0 + hh * 32 + j) : 0.f;
+        for (int j = 0; j < 8; ++j) {
+          f[4 * j] = __uint_as_float(vv[hh][4 * j]) + bv[hh][j].x;
+          f[4 * j + 1] = __uint_as_float(vv[hh][4 * j + 1]) + bv[hh][j].y;
+          f[4 * j + 2] = __uint_as_float(vv[hh][4 * j + 2]) + bv[hh][j].z;
+          f[4 * j + 3] = __uint_as_float(vv[hh][4 * j + 3]) + bv[hh][j].w;
         }
         if (args.scale != 1.f) {
 #pragma unroll
@@ -136,17 +162,21 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmArgs& args, int nt,
       }
       // stage through shared memory so that each store instruction writes four full 128-byte rows
 #pragma unroll
-      for (int c = 0; c < 8; ++c) stg[lane * 8 + (c ^ (lane & 7))] = pk[c];
+      for (int c = 0; c < 8; ++c) st_shared_v4(stg + (uint32_t)((lane * 8 + (c ^ (lane & 7))) << 4), pk[c]);
       __syncwarp();
       char* obase = reinterpret_cast<char*>(args.out[nt]) + (long long)u0 * esize;
       if (ncols == cols_per_unit && vec_ok) {
+        uint4 val[8];
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
           const int row = it * 4 + (lane >> 3), c = lane & 7;
-          if (r_warp0 + row < args.rows_per_group) {
-            const uint4 val = stg[row * 8 + (c ^ (row & 7))];
-            *reinterpret_cast<uint4*>(obase + (grow0 + row) * args.ldo * esize + c * 16) = val;
-          }
+          val[it] = ld_shared_v4(stg + (uint32_t)((row * 8 + (c ^ (row & 7))) << 4));
+        }
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int row = it * 4 + (lane >> 3), c = lane & 7;
+          if (r_warp0 + row < args.rows_per_group)
+            *reinterpret_cast<uint4*>(obase + (grow0 + row) * args.ldo * esize + c * 16) = val[it];
         }
       } else {
         // ragged tail (N not a multiple of the unit, or unaligned pitch): element-wise, still row-coalesced
@@ -154,14 +184,13 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmArgs& args, int nt,
         for (int it = 0; it < 8; ++it) {
           const int row = it * 4 + (lane >> 3), c = lane & 7;
           if (r_warp0 + row < args.rows_per_group) {
-            const uint4 val = stg[row * 8 + (c ^ (row & 7))];
+            const uint4 val = ld_shared_v4(stg + (uint32_t)((row * 8 + (c ^ (row & 7))) << 4));
             char* o = obase + (grow0 + row) * args.ldo * esize + c * 16;
+            const uint32_t w[4] = {val.x, val.y, val.z, val.w};
             if (esize == 4) {
-              const uint32_t w[4] = {val.x, val.y, val.z, val.w};
               for (int e = 0; e < 4; ++e)
                 if (c * epc + e < ncols) reinterpret_cast<uint32_t*>(o)[e] = w[e];
             } else {
-              const uint32_t w[4] = {val.x, val.y, val.z, val.w};
               for (int e = 0; e < 8; ++e)
                 if (c * epc + e < ncols)
                   reinterpret_cast<unsigned short*>(o)[e] = (unsigned short)((w[e >> 1] >> ((e & 1) * 16)) & 0xffffu);

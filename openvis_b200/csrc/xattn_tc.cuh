@@ -237,6 +237,8 @@ xattn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tmem_ld_32x32_nowait(s_addr, sv);
         tmem_ld_32x32_nowait(s_addr + 32, sv + 32);
         tmem_ld_wait();
+        reg_fence32(sv);
+        reg_fence32(sv + 32);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_empty[bi]);
@@ -264,6 +266,7 @@ xattn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           const uint32_t o_addr = tmem_base + lane_off + 256u + (uint32_t)((2 * j + w) * 32);
           tmem_ld_32x32_nowait(o_addr, ov);
           tmem_ld_wait();
+          reg_fence32(ov);
 #pragma unroll
           for (int c = 0; c < 32; ++c) ov[c] = __float_as_uint(__uint_as_float(ov[c]) * f);
           tmem_st_32x32(o_addr, ov);
@@ -304,6 +307,7 @@ xattn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       uint32_t ov[32];
       tmem_ld_32x32_nowait(tmem_base + lane_off + 256u + (uint32_t)(h * 32), ov);
       tmem_ld_wait();
+      reg_fence32(ov);
       if (q < a.q_pad) {
         float* op = a.o_part + (pb + (long long)h * a.q_pad) * 32;
 #pragma unroll

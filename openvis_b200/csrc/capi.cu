@@ -66,7 +66,12 @@ int device_info(int* sms) {
     d.ok = (p.major == 10) ? 0 : OVIS_ERR_ARCH;
   }
   if (d.ok != 0) return fail(OVIS_ERR_ARCH, "%s: kernels are built for sm_100a (B200) only; no fallback path", "ovis");
-  if (sms) *sms = d.sms;
+  if (sms) {
+    // OVIS_SM_BUDGET=n: persistent kernels use at most n SMs, leaving the rest to concurrently running clips' small
+    // (latency-bound) kernels on other streams
+    static const int budget = getenv("OVIS_SM_BUDGET") ? atoi(getenv("OVIS_SM_BUDGET")) : 0;
+    *sms = (budget > 0 && budget < d.sms) ? budget : d.sms;
+  }
   return OVIS_OK;
 }
 

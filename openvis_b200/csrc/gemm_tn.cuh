@@ -69,10 +69,10 @@ struct GemmCfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGING_BYTES = 4 * 4096;   // epilogue store staging: 4 warps x [32 rows][128 B]
+  static constexpr int STAGING_BYTES = 8 * 4096;   // epilogue store staging: 8 warps x [32 rows][128 B]
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int TMEM_COLS = 2 * BN;   // 256 or 512: power of two
-  static constexpr int THREADS = 192;
+  static constexpr int THREADS = 320;   // TMA warp, MMA warp, 8 epilogue warps (two per TMEM lane quarter)
 };
 
 // One 128 x BN accumulator tile: TMEM -> registers -> fused epilogue -> global.  Called by the four epilogue warps.
@@ -81,6 +81,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmArgs& args, int nt,
                                                    uint32_t t_acc_base, uint8_t* stage_smem) {
   using Cfg = GemmCfg<BN>;
   const int quarter = warp & 3;           // TMEM lane quarter this warp may access
+  const int half = (warp - 2) >> 2;       // which half of the tile's columns this warp handles (warps 2-5: 0, 6-9: 1)
   const int r = mt * Cfg::BM + quarter * 32 + lane;        // row within group
   const bool row_ok = r < args.rows_per_group;
   const long long grow = (long long)(g / args.a_row_div) * args.a_group_stride + r;   // global A/D row
@@ -98,7 +99,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmArgs& args, int nt,
     const bool vec_ok = (((long long)args.ldo * esize) & 15) == 0;
     const bool bias_vec = bias && ((reinterpret_cast<uintptr_t>(bias) & 15) == 0);
 #pragma unroll 1
-    for (int u0 = 0; u0 < BN; u0 += cols_per_unit) {
+    for (int u0 = half * (BN / 2); u0 < (half + 1) * (BN / 2); u0 += cols_per_unit) {
       if (col_base + u0 >= args.N) break;                     // warp-uniform
       const int ncols = min(cols_per_unit, args.N - (col_base + u0));
       const int nh = args.out_f32 ? 1 : 2;
@@ -202,6 +203,8 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmArgs& args, int nt,
     }
   } else if (args.epi == EPI_LN) {
     // BN == 256 == N.  Row-per-thread LayerNorm; the biased+residual row is parked back in TMEM between passes.
+    // (row statistics span all 256 columns: only the first warp of each lane quarter works here)
+    if (half != 0) return;
     const float* bias = args.bias[0];
     const float* res = args.resid + grow * 256;
     float sum = 0.f;
@@ -327,7 +330,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmArgs& args, int nt,
     const int nvalid = max(0, min(32, args.rows_per_group - r0));
     const uint32_t validmask = nvalid >= 32 ? 0xffffffffu : ((1u << nvalid) - 1u);
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
+    for (int c = half * (BN / 64); c < (half + 1) * (BN / 64); ++c) {
       if (col_base + c * 32 >= args.N) break;
       tmem_ld_32x32(t_acc + c * 32, v);
       tmem_ld_wait();
@@ -341,14 +344,17 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmArgs& args, int nt,
       const int col = col_base + c * 32 + lane;
       if (col < args.N && word < args.words_per_group) {
         args.bits[((long long)g * args.words_per_group + word) * args.q_stride + col] = mine;
-        if ((~mine & validmask) != 0u) args.flags[(long long)g * args.q_stride + col] = 1;
+        if ((~mine & validmask) != 0u) {
+          unsigned char* fl = args.flags + (long long)g * args.q_stride + col;
+          if (__ldcg(fl) == 0) *fl = 1;
+        }
       }
     }
   } else {  // EPI_STORE_T
     const float* bias = args.bias[nt];
     float* obase = args.out_t + (long long)g * args.t_group_stride + r;
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
+    for (int c = half * (BN / 64); c < (half + 1) * (BN / 64); ++c) {
       if (col_base + c * 32 >= args.N) break;
       tmem_ld_32x32(t_acc + c * 32, v);
       tmem_ld_wait();
@@ -365,17 +371,19 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmArgs& args, int nt,
       }
       if (args.posflags) {
         // all 32 rows of this warp belong to one frame (rows_per_frame % 32 == 0)
-        uint32_t mine = 0;
+        // bit j of `pos` = this row has a positive logit in column j; OR-reduce over the 32 rows of the warp
+        uint32_t pos = 0;
+        if (row_ok) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const uint32_t w = __ballot_sync(0xffffffffu, row_ok && __uint_as_float(v[j]) > 0.f);
-          if (lane == j) mine = w;
+          for (int j = 0; j < 32; ++j) pos |= (__uint_as_float(v[j]) > 0.f ? 1u : 0u) << j;
         }
+        const uint32_t anyrow = __reduce_or_sync(0xffffffffu, pos);
         const int col = col_base + c * 32 + lane;
         const int r0 = mt * Cfg::BM + quarter * 32;
-        if (col < args.N && mine != 0u && r0 < args.rows_per_group) {
+        if (col < args.N && ((anyrow >> lane) & 1u) && r0 < args.rows_per_group) {
           const long long frame = (long long)g * (args.rows_per_group / args.rows_per_frame) + r0 / args.rows_per_frame;
-          args.posflags[frame * args.q_stride + col] = 1;
+          unsigned char* fl = args.posflags + frame * args.q_stride + col;
+          if (__ldcg(fl) == 0) *fl = 1;       // test first: thousands of warps would otherwise hammer the same bytes
         }
       }
     }
@@ -383,7 +391,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmArgs& args, int nt,
 }
 
 template <int BN>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                const __grid_constant__ CUtensorMap tmB, const GemmArgs args) {
   using Cfg = GemmCfg<BN>;
@@ -416,7 +424,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4);
+      mbar_init(&tempty_bar[s], 8);
     }
     fence_mbar_init();
   }
@@ -521,14 +529,14 @@ struct GemmBsCfg {
   static constexpr int B_BYTES = BN * BK * 2 * KB_MAX;           // 128 KB (BN 256) / 64 KB (BN 128)
   static constexpr int A_BYTES = BM * BK * 2;                    // 16 KB per ring stage
   static constexpr int STAGES = (BN == 256) ? 4 : 8;
-  static constexpr int STAGING_BYTES = 4 * 4096;
+  static constexpr int STAGING_BYTES = 8 * 4096;
   static constexpr int SMEM_BYTES = B_BYTES + STAGES * A_BYTES + STAGING_BYTES + 1024 + 256;
   static constexpr int TMEM_COLS = 2 * BN;
-  static constexpr int THREADS = 192;
+  static constexpr int THREADS = 320;   // TMA warp, MMA warp, 8 epilogue warps (two per TMEM lane quarter)
 };
 
 template <int BN>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 gemm_tn_bs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                   const __grid_constant__ CUtensorMap tmB, const GemmArgs args) {
   using Cfg = GemmBsCfg<BN>;
@@ -564,7 +572,7 @@ gemm_tn_bs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     tma_prefetch_desc(&tmA2);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 8); }
     mbar_init(bfull_bar, 1);
     mbar_init(bempty_bar, 1);
     fence_mbar_init();

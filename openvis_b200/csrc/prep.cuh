@@ -7,7 +7,8 @@ namespace ovis {
 // in [B][C][N] fp32 (NCHW, N = h*w)  ->  out [B][N][C] fp16 ("token-major", K-major GEMM operand)
 // and optionally out_pos = fp16(in + pos[n][c] + pos_t[b][c]): the `key = memory + pos` operand
 // (with_pos_embed, video_..._decoder.py:115-116; pos3d = pos2d + pos_z, position_encoding.py:163).
-// Tile 64(n) x 64(c).  Reads are 256 B rows along n, writes 128 B rows along c.
+// Tile 64(n) x 64(c).  Reads are 256 B rows along n; every thread then writes 16 B (8 channels) so that a warp
+// store covers four full 128-byte token rows.
 __global__ void __launch_bounds__(256)
 nchw_to_tokens_f16_kernel(const float* __restrict__ in, __half* __restrict__ out, __half* __restrict__ out_pos,
                           const float* __restrict__ pos, const float* __restrict__ pos_t, int C, int N) {
@@ -22,24 +23,32 @@ nchw_to_tokens_f16_kernel(const float* __restrict__ in, __half* __restrict__ out
     tile[c][tx] = (n < N && c0 + c < C) ? __ldg(ib + (long long)(c0 + c) * N + n) : 0.f;
   }
   __syncthreads();
-  __half* ob = out + (long long)b * N * C;
-  const int cx = (threadIdx.x & 31) * 2, ny = threadIdx.x >> 5;  // 32 half2 x 8 rows
-#pragma unroll 4
-  for (int i = 0; i < 8; ++i) {
-    const int nl = ny + i * 8;
-    const int n = n0 + nl;
-    if (n < N && c0 + cx < C) {
-      const float v0 = tile[cx][nl], v1 = tile[cx + 1][nl];
-      *reinterpret_cast<__half2*>(ob + (long long)n * C + c0 + cx) = __floats2half2_rn(v0, v1);
-      if (out_pos) {
-        // key operand: x + (level_embed + 2-D sine position)[n] (+ frame term of the 3-D embedding)
-        float2 p = __ldg(reinterpret_cast<const float2*>(pos + (long long)n * C + c0 + cx));
-        if (pos_t) {
-          const float2 pt = __ldg(reinterpret_cast<const float2*>(pos_t + (long long)b * C + c0 + cx));
-          p.x += pt.x; p.y += pt.y;
-        }
-        *reinterpret_cast<__half2*>(out_pos + ((long long)b * N + n) * C + c0 + cx) = __floats2half2_rn(v0 + p.x, v1 + p.y);
+  // item = (token, 8-channel group): 64 tokens x 8 groups = 512 items, two per thread
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int item = i * 256 + threadIdx.x;
+    const int cg = item & 7, nl = item >> 3;
+    const int n = n0 + nl, c = c0 + cg * 8;
+    if (n >= N || c >= C) continue;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = tile[cg * 8 + e][nl];
+    const long long o = ((long long)b * N + n) * C + c;
+    *reinterpret_cast<uint4*>(out + o) =
+        make_uint4(pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]), pack_half2(v[6], v[7]));
+    if (out_pos) {
+      // key operand: x + (level_embed + 2-D sine position)[n] (+ frame term of the 3-D embedding)
+      const float4 p0 = __ldg(reinterpret_cast<const float4*>(pos + (long long)n * C + c));
+      const float4 p1 = __ldg(reinterpret_cast<const float4*>(pos + (long long)n * C + c) + 1);
+      float p[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+      if (pos_t) {
+        const float4 t0 = __ldg(reinterpret_cast<const float4*>(pos_t + (long long)b * C + c));
+        const float4 t1 = __ldg(reinterpret_cast<const float4*>(pos_t + (long long)b * C + c) + 1);
+        p[0] += t0.x; p[1] += t0.y; p[2] += t0.z; p[3] += t0.w; p[4] += t1.x; p[5] += t1.y; p[6] += t1.z; p[7] += t1.w;
       }
+      *reinterpret_cast<uint4*>(out_pos + o) =
+          make_uint4(pack_half2(v[0] + p[0], v[1] + p[1]), pack_half2(v[2] + p[2], v[3] + p[3]),
+                     pack_half2(v[4] + p[4], v[5] + p[5]), pack_half2(v[6] + p[6], v[7] + p[7]));
     }
   }
 }
@@ -67,17 +76,21 @@ maskfeat_prep_kernel(const float* __restrict__ F, __half* __restrict__ ft, __hal
     tile[ch][ty * 32 + tx] = inx ? __ldg(fb + (long long)ch * H * W + (long long)(y0 + ty) * W + x0 + tx) : 0.f;
   __syncthreads();
 
-  // ---- full-resolution token-major fp16 copy
+  // ---- full-resolution token-major fp16 copy: item = (pixel, 8-channel group), 16-byte stores
   {
     __half* ob = ft + (long long)b * H * W * C + c0;
-#pragma unroll 4
-    for (int i = 0; i < 16; ++i) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
       const int item = i * 256 + threadIdx.x;
-      const int cp = item & 15, pix = item >> 4;
+      const int cg = item & 3, pix = item >> 2;
       const int py = pix >> 5, px = pix & 31;
-      if (x0 + px < W)
-        *reinterpret_cast<__half2*>(ob + ((long long)(y0 + py) * W + x0 + px) * C + cp * 2) =
-            __floats2half2_rn(tile[cp * 2][pix], tile[cp * 2 + 1][pix]);
+      if (x0 + px < W) {
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = tile[cg * 8 + e][pix];
+        *reinterpret_cast<uint4*>(ob + ((long long)(y0 + py) * W + x0 + px) * C + cg * 8) =
+            make_uint4(pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]), pack_half2(v[6], v[7]));
+      }
     }
   }
   // ---- level 2: 2x2 blocks (all four pixels are "centre"), 4 x 16 cells

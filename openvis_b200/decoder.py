@@ -219,6 +219,10 @@ class _B200MaskedDecoderBase(nn.Module):
         self.mask_embed = MLP(hidden_dim, hidden_dim, mask_dim, 3)
         # non-reference knobs
         self.materialize_aux = False      # True: compute all nine aux_outputs eagerly (API-exact mode)
+        # Video decoders only: number of independent clips stacked along the frame axis of one call.  The reference
+        # forces bs = 1 in eval (video_..._decoder.py:382-383); >1 is a throughput extension (same arithmetic as its
+        # training-mode bs > 1): the query-side GEMMs then run on clips_per_call * Q rows per launch.
+        self.clips_per_call = 1
         self.debug_capture = None         # tests: set to a list to receive (head, level, bits, flags) clones
         self._wcache = None
         self._pcache = {}
@@ -328,15 +332,23 @@ class _B200MaskedDecoderBase(nn.Module):
         self._pcache[key] = (padd, p2, pz)
         return self._pcache[key]
 
+    def _groups(self, BT):
+        if not self.VIDEO:
+            return BT
+        G = int(self.clips_per_call)
+        if G < 1 or BT % G:
+            raise ValueError(f"clips_per_call={G} does not divide the {BT} frames of this call")
+        return G
+
     def _workspace(self, BT, H4, W4, device):
-        key = (BT, H4, W4, str(device))
+        key = (BT, H4, W4, str(device), self._groups(BT))
         ws = self._ws.get(key)
         if ws is not None:
             return ws
         if len(self._ws) >= 2:           # keep at most two shapes resident (a clip-sized workspace is GBs)
             self._ws.pop(next(iter(self._ws)))
         Q, C = self.num_queries, HIDDEN
-        G = 1 if self.VIDEO else BT
+        G = self._groups(BT)
         Tg = BT // G
         R = G * Q
         N = [(H4 // s) * (W4 // s) for s in (8, 4, 2)]
@@ -408,7 +420,9 @@ class _B200MaskedDecoderBase(nn.Module):
     def _forward_impl(self, x, mf, mask_features_in, BT, H4, W4, sizes, dev):
         W = self._weights()
         ws = self._workspace(BT, H4, W4, dev)
-        padd, p2, pz = self._pos_tables(BT, sizes, dev)
+        padd, p2, pz = self._pos_tables(BT // self._groups(BT), sizes, dev)
+        if pz is not None and self._groups(BT) > 1:
+            pz = pz.repeat(self._groups(BT), 1)            # frame b of the call is frame b % Tg of its clip
         self._generation += 1
         gen = self._generation
         G, Tg, R, N, M = ws["G"], ws["Tg"], ws["R"], ws["N"], ws["M"]
@@ -497,9 +511,17 @@ class _B200MaskedDecoderBase(nn.Module):
         ('(b t) q h w -> b q t h w', frame_...:117-118; video_...:459)."""
         Q = self.num_queries
         me = self._mlp3(W["mask_embed"], ws["d16"][hidx], ws["m1"], ws["m2"], ws["me16"])
-        out = torch.empty(1, Q, BT, H4, W4, dtype=torch.float32, device=me.device)
-        L.mask_logits(ws["ft"], ws["G"], ws["Tg"] * ws["M"], me, Q, Q, out, ws["Tg"] * ws["M"], BT * ws["M"],
-                      posflags=posflags, rows_per_frame=ws["M"] if posflags is not None else 0)
+        G, Tg, M = ws["G"], ws["Tg"], ws["M"]
+        if self.VIDEO:
+            # [clips, Q, Tg, H, W]: out[g][q][t*M + p]
+            out = torch.empty(G, Q, Tg, H4, W4, dtype=torch.float32, device=me.device)
+            L.mask_logits(ws["ft"], G, Tg * M, me, Q, Q, out, Q * Tg * M, Tg * M,
+                          posflags=posflags, rows_per_frame=M if posflags is not None else 0)
+        else:
+            # frames as groups, written as [1, Q, T, H, W]: out[q][g*M + p]
+            out = torch.empty(1, Q, BT, H4, W4, dtype=torch.float32, device=me.device)
+            L.mask_logits(ws["ft"], G, M, me, Q, Q, out, M, BT * M,
+                          posflags=posflags, rows_per_frame=M if posflags is not None else 0)
         return out
 
     def _class_outputs(self, W, ws, hidx, BT, san):
@@ -515,7 +537,7 @@ class _B200MaskedDecoderBase(nn.Module):
     def _pack_head(self, d, cls, masks, BT):
         Q = self.num_queries
         if cls is not None:
-            d["pred_logits"] = cls.view(1, Q, -1) if self.VIDEO else cls.view(1, BT, Q, -1)
+            d["pred_logits"] = cls.view(-1, Q, cls.shape[-1]) if self.VIDEO else cls.view(1, BT, Q, -1)
         d["pred_masks"] = masks
 
     def _pack_outputs(self, out, cls, pred_masks, pred_embeds, x, mask_features, sizes, p2, pz, BT, san):
@@ -660,13 +682,15 @@ class _SideAdapterMixin:
         h, w = san["hw"]
         out = torch.empty(BT, nh, Q, h, w, dtype=torch.float32, device=ae.device)
         if self.VIDEO:
-            # one set of queries for all frames: replicate the [Q, 256] embedding block per frame (tiny)
-            ae = ae.repeat(BT, 1)
+            # one set of queries per clip: replicate its [Q, 256] embedding block for each of its frames (tiny)
+            G = ws["G"]
+            ae = ae.view(G, 1, Q, HIDDEN).expand(G, BT // G, Q, HIDDEN).reshape(BT * Q, HIDDEN).contiguous()
         L.san_bias_logits(ws["af16"], BT, san["P"], nh, ae, Q, out)
         return out
 
     def _pack_head(self, d, cls, masks, BT):
-        d["class_attn_biases"] = cls[None]                       # [1, T, n, Q, h, w]
+        G = self._groups(BT) if self.VIDEO else 1
+        d["class_attn_biases"] = cls.view(G, BT // G, *cls.shape[1:])    # [1, T, n, Q, h, w] (reference: b = 1)
         d["pred_masks"] = masks
 
     def _pack_outputs(self, out, cls, pred_masks, pred_embeds, x, mask_features, sizes, p2, pz, BT, san):

@@ -150,6 +150,30 @@ def test_frame_outputs_api():
     assert out2["aux_outputs"][1]["pred_masks"].shape == ref["aux_outputs"][1]["pred_masks"].shape
 
 
+@pytest.mark.parametrize("kind", ["video", "san_video"])
+def test_video_multi_clip_call_equals_single_clip_calls(kind):
+    """clips_per_call > 1 (throughput extension) must reproduce the per-clip results."""
+    T, Hp, Wp, Q = 3, 128, 192, 100
+    m, P = build(kind, Q, 0)
+    clips = [O.seeded_inputs(T, Hp, Wp, seed=50 + i) for i in range(2)]
+    singles = []
+    for x, mf in clips:
+        o = m([t.cuda() for t in x], mf.cuda())
+        singles.append({k: o[k].clone() for k in ("pred_masks", "mask_valid") + (("pred_logits",) if kind == "video" else ("class_attn_biases",))})
+    m.clips_per_call = 2
+    xs = [torch.cat([clips[0][0][l], clips[1][0][l]]).cuda() for l in range(3)]
+    mfs = torch.cat([clips[0][1], clips[1][1]]).cuda()
+    o = m(xs, mfs)
+    assert o["pred_masks"].shape == (2, Q, T, Hp // 4, Wp // 4)
+    for g in range(2):
+        assert torch.equal(o["pred_masks"][g], singles[g]["pred_masks"][0])
+        assert torch.equal(o["mask_valid"][g * T:(g + 1) * T], singles[g]["mask_valid"])
+        if kind == "video":
+            assert torch.equal(o["pred_logits"][g], singles[g]["pred_logits"][0])
+        else:
+            assert torch.equal(o["class_attn_biases"][g], singles[g]["class_attn_biases"][0])
+
+
 GOLDEN_CASES = [("dec_frame_q100", "frame"), ("dec_video_q100", "video"), ("dec_san_frame_q100", "san_frame"),
                 ("dec_san_video_q100", "san_video"), ("dec_frame_q200", "frame")]
 

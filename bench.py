@@ -45,7 +45,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--streams", type=int, default=2, help="independent decoder calls in flight per GPU (one workspace each)")
-    ap.add_argument("--clips", type=int, default=2, help="clips stacked into one decoder call (step = this many clips)")
+    ap.add_argument("--clips", type=int, default=4, help="clips stacked into one decoder call (step = this many clips)")
     return ap.parse_args()
 
 
@@ -214,6 +214,9 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    # persistent kernels leave a few SMs to the other in-flight call's small latency-bound kernels
+    if args.streams > 1:
+        os.environ.setdefault("OVIS_SM_BUDGET", "140")
     import torch.distributed as dist
     from openvis_b200 import _lib as L
     from openvis_b200 import decoder as D
@@ -357,11 +360,21 @@ def main():
     kname = {"xattn": "xattn_split_kernel+xattn_combine_kernel", "kv_proj": "gemm_tn_kernel<256> (key/value projection)",
              "prep": "maskfeat_prep_kernel+nchw_to_tokens_f16_kernel", "mask_logits": "gemm_tn_kernel<128> (final mask logits)",
              "mask_bits": "gemm_tn_kernel<128> (mask sign bits)"}
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic_r1.json")
+    if os.path.isfile(tp):
+        try:
+            traffic = json.load(open(tp))
+        except Exception:
+            traffic = None
     roofline = None
     if dom is not None:
         d = kernels[dom]
         roofline = {"kernel": kname[dom], "bound": d["bound"], "achieved": d["achieved"], "peak": d["peak"], "unit": d["unit"],
-                    "frac": d["frac"], "traffic": None,
+                    "frac": d["frac"],
+                    "traffic": (traffic or {}).get(dom, {}).get("dram_bytes_per_clip") if traffic else None,
+                    "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of this family's launches for ONE clip (ncu, "
+                                    "profiles/ncu_traffic_r1.json); algorithmic bytes/flops above are per step = clips_per_step clips",
                     "peak_source": f"{src} ({'bf16_tflops_sustained' if d['bound'] == 'tensor' else 'hbm_gbs'}; kernel timed inside a long step)",
                     "share_of_step": d["share_of_step"]}
 
@@ -433,7 +446,7 @@ def main():
             "config": {"workload": args.workload, "frames_per_step_per_gpu": C_ * T, "clips_per_step": C_, "queries": Q, "vocab": K,
                        "l2": "inputs larger than L2 (2.9 GB per clip, two input sets alternated)",
                        "aux_outputs": "lazy (inference-minimal)", "parallelism": f"clip-sharded dp{world}",
-                       "decoder_calls_in_flight_per_gpu": len(decs)},
+                       "decoder_calls_in_flight_per_gpu": len(decs), "sm_budget": os.environ.get("OVIS_SM_BUDGET")},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,
             "whole_path": {"gflop_per_frame": flops_frame / 1e9,

@@ -1,0 +1,31 @@
+"""Turns an ncu CSV (metrics gpu__time_duration.sum, dram__bytes_read.sum, dram__bytes_write.sum over the launches of ONE
+clips=1 decoder call) into profiles/ncu_traffic_r1.json + a readable per-kernel summary."""
+import csv, collections, json, sys
+src, out_json, out_txt = sys.argv[1:4]
+lines = [l for l in open(src) if not l.startswith("==")]
+rows = list(csv.DictReader(lines))
+per = collections.OrderedDict()
+for r in rows:
+    k = (r["ID"], r["Kernel Name"].split("(")[0])
+    v = float(r["Metric Value"].replace(",", ""))
+    u = r["Metric Unit"]
+    m = r["Metric Name"]
+    if m.startswith("gpu__time"):
+        v = v / 1e3 if u == "ns" else (v * 1e3 if u == "ms" else v)          # -> us
+    else:
+        v = v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
+    per.setdefault(k, {})[m] = v
+fam = lambda n: ("xattn" if "xattn" in n else "prep" if ("maskfeat" in n or "nchw" in n) else "gemm" if "gemm" in n else "other")
+agg = collections.defaultdict(lambda: [0, 0.0, 0.0, 0.0])
+byname = collections.defaultdict(lambda: [0, 0.0, 0.0, 0.0])
+for (i, n), m in per.items():
+    for d in (agg[fam(n)], byname[n]):
+        d[0] += 1; d[1] += m.get("gpu__time_duration.sum", 0); d[2] += m.get("dram__bytes_read.sum", 0); d[3] += m.get("dram__bytes_write.sum", 0)
+js = {f: {"launches": v[0], "us": v[1], "dram_bytes_per_clip": v[2] + v[3], "read": v[2], "write": v[3]} for f, v in agg.items()}
+json.dump(js, open(out_json, "w"), indent=1)
+with open(out_txt, "w") as f:
+    f.write(f"# {src}: one decoder call, clips=1, cfg 2 (36x736x1280, Q=100); ncu times are cold-cache & serialised\n")
+    f.write(f"{'kernel':60s} {'n':>4s} {'us':>10s} {'dram_read_MB':>13s} {'dram_write_MB':>14s}\n")
+    for n, v in sorted(byname.items(), key=lambda x: -x[1][1]):
+        f.write(f"{n[:60]:60s} {v[0]:4d} {v[1]:10.1f} {v[2]/1e6:13.1f} {v[3]/1e6:14.1f}\n")
+print(open(out_txt).read())

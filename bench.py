@@ -357,7 +357,7 @@ def main():
                 ent.update(bound="hbm", achieved=ach, peak=peak_bw, unit="GB/s", frac=ach / peak_bw)
         kernels[fam] = ent
     dom = max((f for f in kernels if f in work), key=lambda f: kernels[f]["ms_per_step"], default=None)
-    kname = {"xattn": "xattn_split_kernel+xattn_combine_kernel", "kv_proj": "gemm_tn_kernel<256> (key/value projection)",
+    kname = {"xattn": "xattn_tc_kernel+xattn_combine_kernel", "kv_proj": "gemm_tn_kernel<256> (key/value projection)",
              "prep": "maskfeat_prep_kernel+nchw_to_tokens_f16_kernel", "mask_logits": "gemm_tn_kernel<128> (final mask logits)",
              "mask_bits": "gemm_tn_kernel<128> (mask sign bits)"}
     traffic = None

@@ -51,6 +51,27 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {     // pure poll, never suspends
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_poll(uint64_t* bar, uint32_t parity) {
+  long long t0 = 0;
+  int n = 0;
+  while (!mbar_test_wait(bar, parity)) {
+    if ((++n & 0xffff) == 0) {
+      if (t0 == 0) t0 = clock64();
+      else if (clock64() - t0 > 4000000000LL) { printf("ovis: mbarrier timeout (poll) block %d thread %d\n", (int)blockIdx.x, (int)threadIdx.x); __trap(); }
+    }
+  }
+}
 // Bounded wait: a broken pipeline must not hang the GPU box.  ~2 s at 2 GHz, then trap.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;

@@ -38,7 +38,8 @@ constexpr int XT_STAGES = 4;
 constexpr int XT_Q_BYTES = 4 * 128 * 128;       // 4 k-blocks [128 rows][64 ch] fp16
 constexpr int XT_KV_STAGE = 2 * XT_KT * 128;    // K box + V box
 constexpr int XT_P_BYTES = 128 * 128;           // [128 q][64 keys] fp16
-constexpr int XT_SMEM = XT_Q_BYTES + XT_STAGES * XT_KV_STAGE + 4 * XT_P_BYTES + 1024 + 512;
+constexpr int XT_STATS_BYTES = 256 * 8 * 4;
+constexpr int XT_SMEM = XT_Q_BYTES + XT_STAGES * XT_KV_STAGE + 4 * XT_P_BYTES + XT_STATS_BYTES + 1024 + 512;
 constexpr int XT_THREADS = 320;
 
 // kind::f16 instruction descriptors (cute::UMMA::InstrDescriptor): fp16 x fp16 -> fp32
@@ -83,7 +84,8 @@ xattn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint8_t* sQ = smem;
   uint8_t* sKV = smem + XT_Q_BYTES;
   uint8_t* sP = sKV + XT_STAGES * XT_KV_STAGE;                       // [wg][buf][16 KB]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 4 * XT_P_BYTES);
+  float* stats = reinterpret_cast<float*>(sP + 4 * XT_P_BYTES);                   // [256 threads][4 max, 4 sum]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 4 * XT_P_BYTES + XT_STATS_BYTES);
   uint64_t* q_full = bars;               // [1]
   uint64_t* full = bars + 1;             // [4]   TMA -> MMA
   uint64_t* empty = bars + 5;            // [4]   MMA -> TMA
@@ -200,7 +202,11 @@ xattn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint32_t* bits_q = a.bits + (long long)g * a.W * a.q_stride + q;
     uint8_t* p_base = sP + (w * 2) * XT_P_BYTES + (r >> 3) * 1024 + (r & 7) * 128;
 
-    float m_run[4], l_run[4];
+    // running (max, sum) of this row for the warpgroup's four heads live in shared memory so that the head-pair loop
+    // can stay rolled: fully unrolled, the loop body (4 x ~550 instructions) overflows the instruction cache and the
+    // kernel becomes fetch-bound (ncu: stall_no_inst 34 %) whatever the arithmetic does
+    float* m_run = stats + (((warp - 2) * 32 + lane) * 8);
+    float* l_run = m_run + 4;
 #pragma unroll
     for (int j = 0; j < 4; ++j) { m_run[j] = -INFINITY; l_run[j] = 0.f; }
 
@@ -225,7 +231,7 @@ xattn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         mw[x] = nw[x] | inval;
       }
       load_words(t + 1, nw);
-#pragma unroll
+#pragma unroll 1
       for (int j = 0; j < 4; ++j) {
         const int b = j & 1;
         const uint32_t ph = (uint32_t)((j >> 1) & 1);       // (step >> 1) & 1 with step = 4t + j

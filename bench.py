@@ -252,8 +252,17 @@ def main():
     text = make_text(K).to(dev)
 
     # two distinct clips per rank, alternated, resident in HBM (each clip's inputs are ~2.9 GB >> 126 MB L2)
-    host_clips = [make_clip(T * C_, Hp, Wp, Q, 1234 + 2 * rank + j) for j in range(2)]
-    dev_clips = [([t.to(dev) for t in x], mf.to(dev), f.to(dev)) for (x, mf, f) in host_clips]
+    # Synthetic inputs are drawn on the device (seeded), which keeps start-up short and host memory small at 8 ranks;
+    # the end-to-end leg below copies them once into pinned host memory and uploads from there every step.
+    def device_clip(seed):
+        g = torch.Generator(device=dev).manual_seed(seed)
+        TT_ = T * C_
+        x = [torch.randn(TT_, 256, Hp // 32 * 2 ** l, Wp // 32 * 2 ** l, generator=g, device=dev) for l in range(3)]
+        mf = torch.randn(TT_, 256, Hp // 4, Wp // 4, generator=g, device=dev)
+        feats = torch.randn(TT_, Q, 512, generator=g, device=dev)
+        return x, mf, feats
+
+    dev_clips = [device_clip(1234 + 2 * rank + j) for j in range(2)]
 
     xattn_events = []
 
@@ -381,7 +390,14 @@ def main():
     # ---- end to end through the public API with host buffers (pinned), H2D + forward + D2H every step
     e2e = None
     if not args.no_e2e:
-        pinned = [([t.pin_memory() for t in x], mf.pin_memory(), f.pin_memory()) for (x, mf, f) in host_clips]
+        def to_pinned(t):
+            h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            h.copy_(t)
+            return h
+        x0, mf0, f0 = dev_clips[0]
+        one = ([to_pinned(t) for t in x0], to_pinned(mf0), to_pinned(f0))     # one pinned host input set (11.6 GB at 4 clips)
+        pinned = [one, one]
+        torch.cuda.synchronize()
         h2d = sum(t.numel() * 4 for t in pinned[0][0]) + pinned[0][1].numel() * 4 + pinned[0][2].numel() * 4
         copy_s = torch.cuda.Stream()
         bufs = dev_clips                       # reuse the two resident buffers as the double-buffered staging area

@@ -248,26 +248,57 @@ xattn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_empty[bi]);
-        // mask + tile max (four independent chains)
+        // Fused optimistic pass: mask select + max (ALU pipe) interleaved element by element with exp2 against the
+        // *stale* reference max (MUFU pipe), so both pipes work at the same time inside one warp.  With lazy rescaling
+        // the stale max is the one that will be used anyway unless the tile max exceeds it by more than 2^8 (or this is
+        // the row's first unblocked tile); only then the probabilities are recomputed (rare after the first tiles).
+        const float m_old = m_run[j];
+        const float m_opt = (m_old == -INFINITY) ? 0.f : m_old;
         float mxa[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        float ls[4] = {0.f, 0.f, 0.f, 0.f};
+        uint32_t pk[32];
 #pragma unroll
-        for (int k = 0; k < 64; ++k) {
-          float s = __uint_as_float(sv[k]);
-          if (mw[k >> 5] & (1u << (k & 31))) s = -INFINITY;
-          sv[k] = __float_as_uint(s);
-          mxa[k & 3] = fmaxf(mxa[k & 3], s);
+        for (int c = 0; c < 8; ++c) {                     // 8 chunks of 8 keys = 16 bytes
+          float p[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int k = c * 8 + e;
+            float sc = __uint_as_float(sv[k]);
+            if (mw[k >> 5] & (1u << (k & 31))) sc = -INFINITY;
+            sv[k] = __float_as_uint(sc);
+            mxa[k & 3] = fmaxf(mxa[k & 3], sc);
+            p[e] = fast_ex2(sc - m_opt);
+            ls[e & 3] += p[e];
+          }
+          pk[c * 4 + 0] = pack_half2(p[0], p[1]); pk[c * 4 + 1] = pack_half2(p[2], p[3]);
+          pk[c * 4 + 2] = pack_half2(p[4], p[5]); pk[c * 4 + 3] = pack_half2(p[6], p[7]);
         }
         const float mx = fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3]));
-        // lazy rescaling: keep the stale reference max unless the new one exceeds it by more than 2^8
-        const float m_old = m_run[j];
         float m_use = m_old;
         bool grow = false;
-        if (mx > m_old + 8.f || m_old == -INFINITY) { m_use = fmaxf(m_old, mx); grow = (m_old != -INFINITY) && (m_use != m_old); }
+        if (mx > m_old + 8.f || m_old == -INFINITY) {
+          m_use = fmaxf(m_old, mx);
+          grow = (m_old != -INFINITY) && (m_use != m_old);
+          if (m_use != m_old) {                            // reference changed: recompute this tile's probabilities
+            ls[0] = ls[1] = ls[2] = ls[3] = 0.f;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              float p[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                p[e] = fast_ex2(__uint_as_float(sv[c * 8 + e]) - m_use);
+                ls[e & 3] += p[e];
+              }
+              pk[c * 4 + 0] = pack_half2(p[0], p[1]); pk[c * 4 + 1] = pack_half2(p[2], p[3]);
+              pk[c * 4 + 2] = pack_half2(p[4], p[5]); pk[c * 4 + 3] = pack_half2(p[6], p[7]);
+            }
+          }
+        }
+        const float f = grow ? fast_ex2(m_old - m_use) : 1.f;
         // the P buffer (and the O accumulator of this head) are free once the PV product of step i-2 has retired
         mbar_wait(&p_empty[bi], ph ^ 1u);
         tc_fence_after();
         if (__any_sync(0xffffffffu, grow)) {
-          const float f = grow ? fast_ex2(m_old - m_use) : 1.f;
           uint32_t ov[32];
           const uint32_t o_addr = tmem_base + lane_off + 256u + (uint32_t)((2 * j + w) * 32);
           tmem_ld_32x32_nowait(o_addr, ov);
@@ -277,26 +308,13 @@ xattn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           for (int c = 0; c < 32; ++c) ov[c] = __float_as_uint(__uint_as_float(ov[c]) * f);
           tmem_st_32x32(o_addr, ov);
           tmem_st_wait();
-          l_run[j] *= f;
         }
         m_run[j] = m_use;
-        const float m_sub = (m_use == -INFINITY) ? 0.f : m_use;
-        float ls[4] = {0.f, 0.f, 0.f, 0.f};
+        l_run[j] = l_run[j] * f + ((ls[0] + ls[1]) + (ls[2] + ls[3]));
         uint8_t* prow = p_base + b * XT_P_BYTES;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {                     // 8 chunks of 8 keys = 16 bytes
-          float p[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            p[e] = fast_ex2(__uint_as_float(sv[c * 8 + e]) - m_sub);
-            ls[e & 3] += p[e];
-          }
-          uint4 u;
-          u.x = pack_half2(p[0], p[1]); u.y = pack_half2(p[2], p[3]);
-          u.z = pack_half2(p[4], p[5]); u.w = pack_half2(p[6], p[7]);
-          *reinterpret_cast<uint4*>(prow + ((c ^ (r & 7)) << 4)) = u;
-        }
-        l_run[j] += (ls[0] + ls[1]) + (ls[2] + ls[3]);
+        for (int c = 0; c < 8; ++c)
+          *reinterpret_cast<uint4*>(prow + ((c ^ (r & 7)) << 4)) = make_uint4(pk[c * 4], pk[c * 4 + 1], pk[c * 4 + 2], pk[c * 4 + 3]);
         fence_async_proxy();            // generic-proxy smem writes -> visible to the tensor core (async proxy)
         tc_fence_before();
         __syncwarp();

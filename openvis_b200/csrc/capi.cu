@@ -13,6 +13,7 @@
 #include "prep.cuh"
 #include "xattn.cuh"
 #include "xattn_tc.cuh"
+#include "xattn_tc2.cuh"
 
 using namespace ovis;
 
@@ -395,19 +396,38 @@ int ovis_san_bias_logits(const void* af, int B, int P, int heads, const void* ae
                      Q <= 128 ? 128 : 256, (cudaStream_t)stream);
 }
 
+// which masked cross-attention kernel runs: 2 = head-pair CTAs, four softmax warpgroups (default);
+// OVIS_XATTN=1 -> first tcgen05 layout, OVIS_XATTN=0 -> round-1 mma.sync kernel (A/B testing only)
+static int xattn_variant() {
+  static const int v = getenv("OVIS_XATTN") ? atoi(getenv("OVIS_XATTN")) : 2;
+  return v;
+}
+
 int ovis_xattn_plan(int G, int Q, int keys, int* splits, int* q_pad, long long* o_floats, long long* ml_floats) {
   CHECK_ARG(G > 0 && Q > 0 && Q <= 256 && keys > 0 && splits && q_pad && o_floats && ml_floats, "bad arguments");
   int sms = 148;
   device_info(&sms);   // sizing only: fall back to the B200 SM count when no device is visible
   const int qtiles = (Q + 127) / 128;
   const int tiles = (keys + XT_KT - 1) / XT_KT;
-  // one CTA per SM (the kernel owns all 512 TMEM columns and ~194 KB of shared memory): one wave of
-  // splits * qtiles * G CTAs, at least two key tiles per split
-  int s = sms / (G * qtiles);
-  if (s > tiles / 2) s = tiles / 2;
-  if (s < 1) s = 1;
-  const int chunk = ((tiles + s - 1) / s) * XT_KT;
-  s = (keys + chunk - 1) / chunk;
+  int s;
+  if (xattn_variant() == 2) {
+    // one CTA per SM per (key chunk, head pair, query tile, group); every chunk yields two partials per head (the
+    // even and the odd key tiles), so the partial count is 2 * chunks
+    int c = sms / (4 * G * qtiles);
+    if (c > tiles / 4) c = tiles / 4;
+    if (c < 1) c = 1;
+    const int chunk = ((tiles + c - 1) / c) * XT_KT;
+    c = (keys + chunk - 1) / chunk;
+    s = 2 * c;
+  } else {
+    // one CTA per SM (the kernel owns all 512 TMEM columns and ~194 KB of shared memory): one wave of
+    // splits * qtiles * G CTAs, at least two key tiles per split
+    s = sms / (G * qtiles);
+    if (s > tiles / 2) s = tiles / 2;
+    if (s < 1) s = 1;
+    const int chunk = ((tiles + s - 1) / s) * XT_KT;
+    s = (keys + chunk - 1) / chunk;
+  }
   *splits = s;
   *q_pad = qtiles * 128;
   *o_floats = (long long)G * s * 8 * (*q_pad) * 32;
@@ -425,10 +445,12 @@ int ovis_xattn(const void* q, const void* k, const void* v, const unsigned int* 
   const int qtiles = (Q + 127) / 128;
   const int q_pad = qtiles * 128;
   const int tiles = (keys + XT_KT - 1) / XT_KT;
-  const int chunk = ((tiles + splits - 1) / splits) * XT_KT;
-  CHECK_ARG((long long)chunk * (splits - 1) < keys, "splits too large for the key count (use ovis_xattn_plan)");
-  static const bool use_mma = getenv("OVIS_XATTN_MMA") != nullptr;   // round-1 mma.sync kernel, A/B testing only
-  if (use_mma) {
+  const int variant = xattn_variant();
+  const int chunks = variant == 2 ? splits / 2 : splits;
+  CHECK_ARG(variant != 2 || (splits % 2 == 0), "the split count must come from ovis_xattn_plan (even)");
+  const int chunk = ((tiles + chunks - 1) / chunks) * XT_KT;
+  CHECK_ARG((long long)chunk * (chunks - 1) < keys, "splits too large for the key count (use ovis_xattn_plan)");
+  if (variant == 0) {
     XattnArgs a;
     a.q = (const __half*)q; a.k = (const __half*)k; a.v = (const __half*)v;
     a.bits = bits; a.flags = flags; a.o_part = o_part; a.ml_part = ml_part;
@@ -443,6 +465,7 @@ int ovis_xattn(const void* q, const void* k, const void* v, const unsigned int* 
     cudaGetDevice(&dev);
     if (!attr_done[dev]) {
       cudaError_t e = cudaFuncSetAttribute(xattn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XT_SMEM);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(xattn_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, X2_SMEM);
       if (e != cudaSuccess) {
         snprintf(g_err, sizeof(g_err), "xattn: cudaFuncSetAttribute(smem) failed: %s", cudaGetErrorString(e));
         return OVIS_ERR_CUDA;
@@ -460,8 +483,13 @@ int ovis_xattn(const void* q, const void* k, const void* v, const unsigned int* 
     a.bits = bits; a.flags = flags; a.o_part = o_part; a.ml_part = ml_part;
     a.Q = Q; a.q_pad = q_pad; a.q_stride = q_stride;
     a.keys = keys; a.W = (keys + 31) / 32; a.splits = splits; a.chunk = chunk;
-    xattn_tc_kernel<<<dim3(splits, qtiles, G), XT_THREADS, XT_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, a);
-    rc = check_launch("xattn_tc_kernel");
+    if (variant == 2) {
+      xattn_tc2_kernel<<<dim3(chunks * 4, qtiles, G), X2_THREADS, X2_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, a);
+      rc = check_launch("xattn_tc2_kernel");
+    } else {
+      xattn_tc_kernel<<<dim3(splits, qtiles, G), XT_THREADS, XT_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, a);
+      rc = check_launch("xattn_tc_kernel");
+    }
     if (rc) return rc;
   }
   xattn_combine_kernel<<<dim3(Q, 8, G), 256, 0, (cudaStream_t)stream>>>(o_part, ml_part, (__half*)out, Q, q_pad, splits);

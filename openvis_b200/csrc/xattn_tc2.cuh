@@ -1,0 +1,357 @@
+// Masked flash cross-attention on tcgen05 / TMEM / TMA, second layout (reference: CrossAttentionLayer.forward_post ->
+// nn.MultiheadAttention with a bool attn_mask, video_mask2former_transformer_decoder.py:110-122; all-masked-row rule
+// frame_mask2former_transformer_decoder.py:87).
+//
+// What the first layout (xattn_tc.cuh) taught (profiles/experiments/xattn_tc_r1_findings.md + tools/ubench/softmax_loop.cu):
+// the softmax instruction stream alone runs at the MUFU.EX2 rate (~14 elements/clk/SM, 130 us for the cfg-2 level-2
+// launch) once 16 warps per SM execute it, but the kernel needed 350 us because only 8 softmax warps were resident and
+// each of them serialises TMEM load -> mask/max -> exp2 -> store -> fence -> arrive.  So this layout is built for
+// thread-level parallelism and a deep K/V ring instead of a smarter inner loop:
+//
+//   CTA = (key chunk, head PAIR, query tile, group): Q is one 16 KB box, a 64-key K/V stage is 16 KB, so the ring is
+//         8 stages deep (three tiles in flight cover the HBM latency at the target rate of ~0.6 us per tile);
+//   four softmax warpgroups (16 warps, 96 registers: 5 warps on one scheduler cap it): warpgroup (w, b) owns head w of the pair and the key tiles of
+//         parity b, with its own S buffer, P buffer, O accumulator and running (max, sum) -- the two parities of a head
+//         are simply two interleaved key splits, merged with the others by xattn_combine_kernel;
+//   three single-thread roles on their own warps: TMA producer, S = Q K^T issuer, O += P V issuer; the issuers serve
+//         the warpgroups out of order, so S for a warpgroup's next tile is issued the moment the warpgroup has drained its S buffer into registers.
+//
+// TMEM (512 columns allocated): S[4 wg] x 64 fp32 columns at 0, O[4 wg] x 32 at 256.
+#pragma once
+#include "ptx.cuh"
+#include "xattn_tc.cuh"
+
+namespace ovis {
+
+constexpr int X2_KT = 64;                        // keys per tile
+constexpr int X2_STAGES = 8;
+constexpr int X2_Q_BYTES = 128 * 128;            // [128 rows][64 ch] fp16 (one head pair)
+constexpr int X2_KV_STAGE = 2 * X2_KT * 128;     // K box + V box
+constexpr int X2_P_BYTES = 128 * 128;            // [128 q][64 keys] fp16
+constexpr int X2_SMEM = X2_Q_BYTES + X2_STAGES * X2_KV_STAGE + 4 * X2_P_BYTES + 1024 + 512;
+constexpr int X2_THREADS = 19 * 32;
+
+__global__ void __launch_bounds__(X2_THREADS, 1)
+xattn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                 const __grid_constant__ CUtensorMap tmV, const XattnTcArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sKV = smem + X2_Q_BYTES;
+  uint8_t* sP = sKV + X2_STAGES * X2_KV_STAGE;                       // [wg][16 KB]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 4 * X2_P_BYTES);
+  uint64_t* q_full = bars;                      // [1]
+  uint64_t* full = bars + 1;                    // [8]  TMA -> S issuer
+  uint64_t* empty = bars + 9;                   // [8]  PV issuer -> TMA
+  uint64_t* s_full = bars + 17;                 // [4 wg]  S issuer -> softmax
+  uint64_t* s_empty = bars + 21;                // [4]     softmax -> S issuer (S drained into registers)
+  uint64_t* p_full = bars + 25;                 // [4]     softmax -> PV issuer (P written)
+  uint64_t* p_empty = bars + 29;                // [4]     PV issuer -> softmax (PV retired: P buffer and O free)
+  uint64_t* done = bars + 33;                   // [1]
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 34);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int chunk_id = blockIdx.x >> 2, hp = blockIdx.x & 3, qt = blockIdx.y, g = blockIdx.z;
+  const int k_begin = chunk_id * a.chunk;
+  const int k_end = min(k_begin + a.chunk, a.keys);
+  const int ntiles = (k_end - k_begin + X2_KT - 1) / X2_KT;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < X2_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_empty[i], 4);        // one elected arrival per softmax warp
+      mbar_init(&p_full[i], 4);
+      mbar_init(&p_empty[i], 1);
+    }
+    mbar_init(done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 17) tmem_alloc(tmem_holder, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 16) {
+    // ============================ TMA producer ============================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, X2_Q_BYTES);
+      tma_load_2d(sQ, &tmQ, q_full, hp * 64, g * a.Q + qt * 128);
+      for (int t = 0; t < ntiles; ++t) {
+        const int st = t % X2_STAGES;
+        mbar_wait(&empty[st], (uint32_t)(((t / X2_STAGES) & 1) ^ 1));
+        uint8_t* dst = sKV + st * X2_KV_STAGE;
+        const int krow = g * a.keys + k_begin + t * X2_KT;
+        mbar_arrive_expect_tx(&full[st], X2_KV_STAGE);
+        tma_load_2d(dst, &tmK, &full[st], hp * 64, krow);
+        tma_load_2d(dst + X2_KT * 128, &tmV, &full[st], hp * 64, krow);
+      }
+    }
+  } else if (warp == 17) {
+    // ============================ S = Q K^T issuer ============================
+    // Serves the four warpgroups out of order: whichever has drained its S buffer (and whose K tile has landed) gets
+    // its next S first, so one slow warpgroup never delays the others.
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = xt_idesc(128, X2_KT, 0);     // M128 N64, A and B K-major
+      const uint32_t q_addr = smem_u32(sQ);
+      const uint32_t kv_addr = smem_u32(sKV);
+      mbar_wait(q_full, 0);
+      int nxt[4];                          // per warpgroup: local index n of its next tile (t = 2n + b)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) nxt[i] = 0;
+      int remaining = 0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) remaining += (ntiles - (i >> 1) + 1) >> 1;
+      long long t0 = 0;
+      int spins = 0;
+      while (remaining > 0) {
+        bool any = false;
+#pragma unroll
+        for (int wg = 0; wg < 4; ++wg) {
+          const int w = wg & 1, b = wg >> 1;
+          const int n = nxt[wg], t = 2 * n + b;
+          if (t >= ntiles) continue;
+          const int st = t % X2_STAGES;
+          if (!mbar_test_wait(&s_empty[wg], (uint32_t)((n & 1) ^ 1))) continue;
+          if (!mbar_test_wait(&full[st], (uint32_t)((t / X2_STAGES) & 1))) continue;
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + (uint32_t)(wg * 64);
+          const uint64_t adesc = umma_desc_k_sw128(q_addr + w * 64);
+          const uint64_t bdesc = umma_desc_k_sw128(kv_addr + st * X2_KV_STAGE + w * 64);
+          umma_f16(d_tmem, adesc, bdesc, idesc_s, 0u);
+          umma_f16(d_tmem, adesc + 2, bdesc + 2, idesc_s, 1u);
+          umma_commit(&s_full[wg]);
+          nxt[wg] = n + 1;
+          --remaining;
+          any = true;
+        }
+        if (any) { spins = 0; t0 = 0; }
+        else if ((++spins & 0xfff) == 0) {                      // bounded: a broken pipeline must not hang the GPU box
+          if (t0 == 0) t0 = clock64();
+          else if (clock64() - t0 > 4000000000LL) { printf("ovis: xattn S issuer timeout block %d\n", (int)blockIdx.x); __trap(); }
+        }
+      }
+    }
+  } else if (warp == 18) {
+    // ============================ O += P V issuer (out of order as well) ============================
+    if (lane == 0) {
+      constexpr uint32_t idesc_o = xt_idesc(128, 32, 1);        // M128 N32, B (V) MN-major
+      const uint32_t kv_addr = smem_u32(sKV);
+      const uint32_t p_addr = smem_u32(sP);
+      int nxt[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) nxt[i] = 0;
+      int remaining = 0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) remaining += (ntiles - (i >> 1) + 1) >> 1;
+      uint32_t half_done = 0;              // bit st: one of the two heads of the tile in stage st has been issued
+      long long t0 = 0;
+      int spins = 0;
+      while (remaining > 0) {
+        bool any = false;
+#pragma unroll
+        for (int wg = 0; wg < 4; ++wg) {
+          const int w = wg & 1, b = wg >> 1;
+          const int n = nxt[wg], t = 2 * n + b;
+          if (t >= ntiles) continue;
+          if (!mbar_test_wait(&p_full[wg], (uint32_t)(n & 1))) continue;
+          tc_fence_after();
+          const int st = t % X2_STAGES;
+          const uint32_t d_tmem = tmem_base + 256u + (uint32_t)(wg * 32);
+          const uint64_t adesc = umma_desc_k_sw128(p_addr + wg * X2_P_BYTES);
+          const uint64_t bdesc = umma_desc_mn_sw128(kv_addr + st * X2_KV_STAGE + X2_KT * 128 + w * 64);
+#pragma unroll
+          for (int kk = 0; kk < X2_KT / 16; ++kk)
+            umma_f16(d_tmem, adesc + 2 * kk, bdesc + (uint64_t)(kk * (2048 >> 4)), idesc_o, (n > 0 || kk > 0) ? 1u : 0u);
+          umma_commit(&p_empty[wg]);
+          if (half_done & (1u << st)) {     // both heads of this tile issued: the K/V stage is free once they retire
+            umma_commit(&empty[st]);
+            half_done &= ~(1u << st);
+          } else {
+            half_done |= 1u << st;
+          }
+          nxt[wg] = n + 1;
+          --remaining;
+          any = true;
+        }
+        if (any) { spins = 0; t0 = 0; }
+        else if ((++spins & 0xfff) == 0) {
+          if (t0 == 0) t0 = clock64();
+          else if (clock64() - t0 > 4000000000LL) { printf("ovis: xattn PV issuer timeout block %d\n", (int)blockIdx.x); __trap(); }
+        }
+      }
+      umma_commit(done);
+    }
+  } else {
+    // ============================ softmax warpgroups ============================
+    const int wg = warp >> 2;                            // 0..3
+    const int w = wg & 1, b = wg >> 1;                   // head within the pair, key-tile parity
+    const int quarter = warp & 3;                        // TMEM lane quarter of this warp
+    const int r = quarter * 32 + lane;                   // query row within the tile
+    const int q = qt * 128 + r;
+    const bool use_mask = (q < a.Q) && (a.flags[(long long)g * a.q_stride + q] != 0);
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    const uint32_t* bits_q = a.bits + (long long)g * a.W * a.q_stride + q;
+    uint8_t* prow = sP + wg * X2_P_BYTES + (r >> 3) * 1024 + (r & 7) * 128;
+    const uint32_t s_addr = tmem_base + lane_off + (uint32_t)(wg * 64);
+    const uint32_t o_addr = tmem_base + lane_off + 256u + (uint32_t)(wg * 32);
+    float m_run = -INFINITY, l_run = 0.f;
+
+    auto load_words = [&](int t, uint32_t (&dst)[2]) {
+      const int kb = k_begin + t * X2_KT;
+#pragma unroll
+      for (int x = 0; x < 2; ++x) {
+        const int wi = (kb >> 5) + x;
+        dst[x] = (use_mask && t < ntiles && wi < a.W) ? __ldg(bits_q + (long long)wi * a.q_stride) : 0u;
+      }
+    };
+    uint32_t nw[2];
+    load_words(b, nw);
+    for (int t = b, n = 0; t < ntiles; t += 2, ++n) {
+      const int kb = k_begin + t * X2_KT;
+      uint32_t mw[2];
+#pragma unroll
+      for (int x = 0; x < 2; ++x) {
+        const int nvalid = k_end - (kb + x * 32);
+        const uint32_t inval = nvalid >= 32 ? 0u : (nvalid <= 0 ? 0xffffffffu : ~((1u << nvalid) - 1u));
+        mw[x] = nw[x] | inval;
+      }
+      load_words(t + 2, nw);
+      const uint32_t ph = (uint32_t)(n & 1);
+      mbar_wait(&s_full[wg], ph);
+      tc_fence_after();
+      // Online softmax in base 2 with a lazily updated reference max (one 32-key half at a time to stay inside the
+      // register budget): probabilities are computed optimistically against the running reference; only when a half's
+      // max exceeds it by more than 2^8 (or the row had no unblocked key so far) the half is recomputed against the new
+      // reference and everything accumulated so far is rescaled.
+      uint32_t pk[32];
+      float m_cur = m_run;
+      float f_all = 1.f;                                  // rescale factor for l_run / O from before this tile
+      bool grow_any = false;
+      float sum_tile = 0.f;
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        // 32 S columns at a time (registers: 18 warps leave 96 per thread); the S buffer is handed back to the issuer
+        // as soon as the second half sits in registers
+        uint32_t sv[32];
+        __syncwarp();                                     // (re-converged after the per-lane recompute branch)
+        tmem_ld_32x32_nowait(s_addr + hf * 32, sv);
+        tmem_ld_wait();
+        reg_fence32(sv);
+        if (hf == 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s_empty[wg]);
+        }
+        const uint32_t word = mw[hf];
+        const float m_opt = (m_cur == -INFINITY) ? 0.f : m_cur;
+        float mxa[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        float ls[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          float p[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int k = e + u;
+            float sc = __uint_as_float(sv[k]);
+            if (word & (1u << k)) sc = -INFINITY;
+            sv[k] = __float_as_uint(sc);
+            mxa[k & 3] = fmaxf(mxa[k & 3], sc);
+            p[u] = fast_ex2(sc - m_opt);
+            ls[k & 3] += p[u];
+          }
+          pk[hf * 16 + (e >> 1)] = pack_half2(p[0], p[1]);
+        }
+        const float mx = fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3]));
+        if (mx > m_cur + 8.f || (m_cur == -INFINITY && mx != -INFINITY)) {
+          const float m_new = fmaxf(m_cur, mx);
+          ls[0] = ls[1] = ls[2] = ls[3] = 0.f;
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            const float p0 = fast_ex2(__uint_as_float(sv[e]) - m_new);
+            const float p1 = fast_ex2(__uint_as_float(sv[e + 1]) - m_new);
+            ls[e & 3] += p0;
+            ls[(e + 1) & 3] += p1;
+            pk[hf * 16 + (e >> 1)] = pack_half2(p0, p1);
+          }
+          if (m_cur != -INFINITY) {
+            const float f = fast_ex2(m_cur - m_new);
+            f_all *= f;
+            grow_any = true;
+            sum_tile *= f;
+            if (hf == 1) {                                // first half was packed against the old reference
+              const __half2 fh = __float2half2_rn(f);
+#pragma unroll
+              for (int c = 0; c < 16; ++c) {
+                __half2 v = *reinterpret_cast<__half2*>(&pk[c]);
+                v = __hmul2(v, fh);
+                pk[c] = *reinterpret_cast<uint32_t*>(&v);
+              }
+            }
+          }
+          m_cur = m_new;
+        }
+        sum_tile += (ls[0] + ls[1]) + (ls[2] + ls[3]);
+      }
+      // the P buffer and the O accumulator of this warpgroup are free once the PV product of its previous tile retired
+      mbar_wait(&p_empty[wg], ph ^ 1u);
+      tc_fence_after();
+      if (__any_sync(0xffffffffu, grow_any)) {
+        uint32_t ov[32];
+        tmem_ld_32x32_nowait(o_addr, ov);
+        tmem_ld_wait();
+        reg_fence32(ov);
+#pragma unroll
+        for (int c = 0; c < 32; ++c) ov[c] = __float_as_uint(__uint_as_float(ov[c]) * f_all);
+        tmem_st_32x32(o_addr, ov);
+        tmem_st_wait();
+      }
+      m_run = m_cur;
+      l_run = l_run * f_all + sum_tile;
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        *reinterpret_cast<uint4*>(prow + ((c ^ (r & 7)) << 4)) = make_uint4(pk[c * 4], pk[c * 4 + 1], pk[c * 4 + 2], pk[c * 4 + 3]);
+      fence_async_proxy();            // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[wg]);
+    }
+    // ---- all MMAs retired: write this (head, parity) partial: un-normalised O and (max, sum)
+    mbar_wait(done, 0);
+    tc_fence_after();
+    const int h = 2 * hp + w;
+    const int split = 2 * chunk_id + b;
+    const long long pr = ((((long long)g * a.splits + split) * 8) + h) * a.q_pad + q;
+    uint32_t ov[32];
+    if (b < ntiles) {                                   // (a warpgroup without tiles never had its accumulator written)
+      tmem_ld_32x32_nowait(o_addr, ov);
+      tmem_ld_wait();
+      reg_fence32(ov);
+    } else {
+#pragma unroll
+      for (int c = 0; c < 32; ++c) ov[c] = 0u;
+    }
+    if (q < a.q_pad) {
+      float* op = a.o_part + pr * 32;
+#pragma unroll
+      for (int c = 0; c < 32; c += 4)
+        *reinterpret_cast<float4*>(op + c) = make_float4(__uint_as_float(ov[c]), __uint_as_float(ov[c + 1]),
+                                                         __uint_as_float(ov[c + 2]), __uint_as_float(ov[c + 3]));
+      *reinterpret_cast<float2*>(a.ml_part + pr * 2) = make_float2(m_run, l_run);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 17) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace ovis

@@ -1,0 +1,128 @@
+// Micro-benchmark: the per-element instruction stream of the masked-softmax inner loop in isolation (no TMEM, no
+// mbarriers, operands from shared memory), to find what each formulation can reach per SM.
+//   nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o softmax_loop softmax_loop.cu
+#include <cstdio>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+__device__ __forceinline__ float ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ uint32_t pack2(float a, float b) { __half2 h = __floats2half2_rn(a, b); return *reinterpret_cast<uint32_t*>(&h); }
+// exp2 on the FMA pipe: round-to-nearest split + degree-3 polynomial (Cody-Waite), x <= 0 expected, clamped at -126
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -126.f);
+  const float r = x + 12582912.f;                  // 1.5 * 2^23: integer part in the low mantissa bits
+  const float fl = r - 12582912.f;
+  const float f = x - fl;                          // in [-0.5, 0.5]
+  float p = 0.0555041f;                            // minimax-ish coefficients of 2^f
+  p = fmaf(p, f, 0.2402265f);
+  p = fmaf(p, f, 0.6931472f);
+  p = fmaf(p, f, 1.0f);
+  return __uint_as_float(__float_as_uint(p) + (__float_as_uint(r) << 23));
+}
+
+// V: 0 = current (bit test + select, max, sub, ex2, sum, pack)      1 = the same without the running max
+//    2 = sub, ex2, pack, pair-mask AND, fp32 sum of the un-masked... (sum via fma with 0/1 floats expanded per tile)
+//    3 = ex2, pack, pair-mask AND, HADD2 sum (transposed formulation: no subtraction, no max)
+//    4 = V1 with every 4th element's exp2 on the FMA pipe         5 = V1 with every 2nd element on the FMA pipe
+//    6 = V3 with every 4th exp2 on the FMA pipe
+template <int V>
+__global__ void __launch_bounds__(512, 1) k(const float* __restrict__ in, uint4* __restrict__ out, int iters, uint32_t mseed) {
+  extern __shared__ float4 dyn[];
+  float4* sS = dyn;                                        // 32 floats per thread
+  uint4* sP = reinterpret_cast<uint4*>(dyn + 512 * 8);
+  for (int i = threadIdx.x; i < 512 * 8; i += blockDim.x) sS[i] = reinterpret_cast<const float4*>(in)[i];
+  __syncthreads();
+  float m = 0.25f, l = 0.f, mx = -INFINITY;
+  uint32_t mw = mseed * (threadIdx.x + 1);
+  uint32_t pm[16];
+  __half2 hs = __floats2half2_rn(0.f, 0.f);
+  for (int it = 0; it < iters; ++it) {
+    float sv[32];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      float4 v = sS[((threadIdx.x + it) & 511) + c * 512];
+      sv[c * 4] = v.x; sv[c * 4 + 1] = v.y; sv[c * 4 + 2] = v.z; sv[c * 4 + 3] = v.w;
+    }
+    mw = mw * 1664525u + 1013904223u;
+    if (V == 2 || V == 3 || V == 6) {
+      if ((it & 7) == 0) {       // pair masks expanded once per tile, shared by 8 (head) iterations
+#pragma unroll
+        for (int i = 0; i < 16; ++i) pm[i] = ((mw >> (2 * i)) & 1u ? 0u : 0xffffu) | ((mw >> (2 * i + 1)) & 1u ? 0u : 0xffff0000u);
+      }
+    }
+    uint32_t pk[16];
+    float ls[4] = {0.f, 0.f, 0.f, 0.f};
+    float mxa[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+    for (int e = 0; e < 32; e += 2) {
+      float p[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int kk = e + u;
+        float sc = sv[kk];
+        if (V == 0 || V == 1 || V == 4 || V == 5) {
+          if (mw & (1u << kk)) sc = -INFINITY;
+          if (V == 0) mxa[kk & 3] = fmaxf(mxa[kk & 3], sc);
+          const bool poly = (V == 4 && (kk & 3) == 3) || (V == 5 && (kk & 1) == 1);
+          p[u] = poly ? ex2_poly(sc - m) : ex2(sc - m);
+          ls[kk & 3] += p[u];
+        } else if (V == 2) {
+          p[u] = ex2(sc - m);
+        } else {
+          const bool poly = (V == 6 && (kk & 3) == 3);
+          p[u] = poly ? ex2_poly(sc) : ex2(sc);
+        }
+      }
+      uint32_t w = pack2(p[0], p[1]);
+      if (V == 2 || V == 3 || V == 6) {
+        w &= pm[e >> 1];
+        hs = __hadd2(hs, *reinterpret_cast<__half2*>(&w));
+      }
+      pk[e >> 1] = w;
+    }
+    l += (ls[0] + ls[1]) + (ls[2] + ls[3]);
+    mx = fmaxf(mx, fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3])));
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      sP[((threadIdx.x + it) & 511) * 4 + (c ^ (threadIdx.x & 3))] = make_uint4(pk[c * 4], pk[c * 4 + 1], pk[c * 4 + 2], pk[c * 4 + 3]);
+  }
+  __syncthreads();
+  uint4 o = sP[threadIdx.x * 4];
+  o.x += __float_as_uint(l + mx + __low2float(hs) + __high2float(hs));
+  out[blockIdx.x * blockDim.x + threadIdx.x] = o;
+}
+
+template <int V> void run(const char* name, int warps, const float* in, uint4* out) {
+  const int iters = 4000;
+  cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+  const int smem = 512 * 8 * 16 + 512 * 4 * 16;
+  cudaFuncSetAttribute(k<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  k<V><<<148, warps * 32, smem>>>(in, out, 50, 12345u);
+  cudaEventRecord(a); k<V><<<148, warps * 32, smem>>>(in, out, iters, 12345u); cudaEventRecord(b); cudaEventSynchronize(b);
+  float ms; cudaEventElapsedTime(&ms, a, b);
+  const double el = 148.0 * warps * 32 * 32.0 * iters;
+  // cfg-2 level-2 launch: 128 (or 112) rows x 8 heads x 529920 keys
+  printf("%-34s warps/SM=%2d: %7.1f Gelem/s  -> 542.6M elements (128-row pad) = %6.1f us, 474.8M (112 pad) = %6.1f us\n", name, warps,
+         el / ms / 1e6, 542.6e6 / (el / ms / 1e3) * 1e6 / 1e6, 474.8e6 / (el / ms / 1e3) * 1e6 / 1e6);
+}
+
+int main() {
+  float* in; uint4* out;
+  cudaMalloc(&in, 512 * 32 * 4); cudaMalloc(&out, 148 * 512 * 16);
+  float* h = new float[512 * 32];
+  for (int i = 0; i < 512 * 32; ++i) h[i] = -(float)((i * 2654435761u) >> 8 & 0xffff) / 4096.f;
+  cudaMemcpy(in, h, 512 * 32 * 4, cudaMemcpyHostToDevice);
+  for (int w : {8, 16}) {
+    run<0>("V0 sel+max+sub+ex2+sum+pack", w, in, out);
+    run<1>("V1 sel+sub+ex2+sum+pack", w, in, out);
+    run<4>("V4 V1, 1/4 exp2 on FMA pipe", w, in, out);
+    run<5>("V5 V1, 1/2 exp2 on FMA pipe", w, in, out);
+    run<2>("V2 sub+ex2+pack+pairmask+hadd2", w, in, out);
+    run<3>("V3 ex2+pack+pairmask+hadd2", w, in, out);
+    run<6>("V6 V3, 1/4 exp2 on FMA pipe", w, in, out);
+  }
+  cudaError_t e = cudaDeviceSynchronize();
+  printf("status: %s\n", cudaGetErrorString(e));
+  return 0;
+}

@@ -226,9 +226,9 @@ xattn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       mbar_wait(&s_full[wg], ph);
       tc_fence_after();
       // Online softmax in base 2 with a lazily updated reference max (one 32-key half at a time to stay inside the
-      // register budget): probabilities are computed optimistically against the running reference; only when a half's
-      // max exceeds it by more than 2^8 (or the row had no unblocked key so far) the half is recomputed against the new
-      // reference and everything accumulated so far is rescaled.
+      // register budget): probabilities are computed optimistically against the running reference; only when a half
+      // would overflow (or the row had no unblocked key so far) it is recomputed against a new reference and
+      // everything accumulated so far is rescaled.
       uint32_t pk[32];
       float m_cur = m_run;
       float f_all = 1.f;                                  // rescale factor for l_run / O from before this tile
@@ -250,7 +250,6 @@ xattn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
         const uint32_t word = mw[hf];
         const float m_opt = (m_cur == -INFINITY) ? 0.f : m_cur;
-        float mxa[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
         float ls[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int e = 0; e < 32; e += 2) {
@@ -260,15 +259,24 @@ xattn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             const int k = e + u;
             float sc = __uint_as_float(sv[k]);
             if (word & (1u << k)) sc = -INFINITY;
-            sv[k] = __float_as_uint(sc);
-            mxa[k & 3] = fmaxf(mxa[k & 3], sc);
             p[u] = fast_ex2(sc - m_opt);
             ls[k & 3] += p[u];
           }
           pk[hf * 16 + (e >> 1)] = pack_half2(p[0], p[1]);
         }
-        const float mx = fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3]));
-        if (mx > m_cur + 8.f || (m_cur == -INFINITY && mx != -INFINITY)) {
+        // No running max in the fast path: the half's sum bounds every probability (all are >= 0), so while it stays
+        // <= 2^12 nothing can overflow fp16 and the stale reference is as good as the true max.  Otherwise (or for the
+        // row's first unblocked keys) find the max, move the reference and redo the half.
+        const float hsum = (ls[0] + ls[1]) + (ls[2] + ls[3]);
+        if (!(hsum <= 4096.f) || (m_cur == -INFINITY && word != 0xffffffffu)) {
+          float mx = -INFINITY;
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            float sc = __uint_as_float(sv[e]);
+            if (word & (1u << e)) sc = -INFINITY;
+            sv[e] = __float_as_uint(sc);
+            mx = fmaxf(mx, sc);
+          }
           const float m_new = fmaxf(m_cur, mx);
           ls[0] = ls[1] = ls[2] = ls[3] = 0.f;
 #pragma unroll

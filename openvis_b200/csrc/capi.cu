@@ -111,6 +111,23 @@ int make_map_f16(CUtensorMap* m, const void* base, unsigned long long rows, unsi
   return OVIS_OK;
 }
 
+// output [rows][cols] (fp16 / fp32, row pitch ld elements) -> store box {128 bytes, 32 rows}, 128B swizzle
+int make_store_map(CUtensorMap* m, const void* base, unsigned long long rows, unsigned long long cols, unsigned long long ld,
+                   int f32) {
+  int rc = get_encoder();
+  if (rc) return rc;
+  const unsigned es = f32 ? 4 : 2;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * es};
+  cuuint32_t box[2] = {128 / es, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base),
+                        dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(OVIS_ERR_CUDA, "%s: cuTensorMapEncodeTiled (store) failed (%lld)", "tensor map", (long long)r);
+  return OVIS_OK;
+}
+
 void init_args(GemmArgs& a) {
   memset(&a, 0, sizeof(a));
   a.num_groups = 1;
@@ -122,8 +139,8 @@ void init_args(GemmArgs& a) {
 }
 
 template <int BN>
-int launch_gemm_bn(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tb, const GemmArgs& a, int sms,
-                   cudaStream_t st) {
+int launch_gemm_bn(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tb, const GemmOutMaps& om,
+                   const GemmArgs& a, int sms, cudaStream_t st) {
   using Cfg = GemmCfg<BN>;
   static bool attr_done[64] = {false};
   int dev = 0;
@@ -141,13 +158,13 @@ int launch_gemm_bn(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensor
   const long long total = (long long)a.num_groups * m_tiles * n_tiles;
   if (total <= 0) return OVIS_OK;
   const int grid = (int)(total < sms ? total : sms);
-  gemm_tn_kernel<BN><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(ta, ta2, tb, a);
+  gemm_tn_kernel<BN><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(ta, ta2, tb, om, a);
   return check_launch("gemm_tn_kernel");
 }
 
 template <int BN>
-int launch_gemm_bs(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tb, const GemmArgs& a, int sms,
-                   cudaStream_t st) {
+int launch_gemm_bs(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tb, const GemmOutMaps& om,
+                   const GemmArgs& a, int sms, cudaStream_t st) {
   using Cfg = GemmBsCfg<BN>;
   static bool attr_done[64] = {false};
   int dev = 0;
@@ -169,13 +186,14 @@ int launch_gemm_bs(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensor
   int R = sms / ncols;
   if (R > m_tiles) R = m_tiles;
   if (R < 1) R = 1;
-  gemm_tn_bs_kernel<BN><<<ncols * R, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(ta, ta2, tb, a);
+  gemm_tn_bs_kernel<BN><<<ncols * R, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(ta, ta2, tb, om, a);
   return check_launch("gemm_tn_bs_kernel");
 }
 
 // A: [a_rows][a_cols] fp16 pitch lda; B: [b_rows][K] fp16 pitch ldb.
 int launch_gemm(const void* A, long long a_rows, long long a_cols, long long lda, const void* B, long long b_rows,
-                long long ldb, const GemmArgs& a, int bn, cudaStream_t st, const void* A2 = nullptr) {
+                long long ldb, const GemmArgs& a_in, int bn, cudaStream_t st, const void* A2 = nullptr) {
+  GemmArgs a = a_in;
   int sms = 0;
   int rc = device_info(&sms);
   if (rc) return rc;
@@ -188,12 +206,34 @@ int launch_gemm(const void* A, long long a_rows, long long a_cols, long long lda
   if (rc) return rc;
   rc = make_map_f16(&tb, B, b_rows, a.K, ldb, bn);
   if (rc) return rc;
+  // TMA-store epilogue for plain stores: one group, 16-byte aligned rows, few enough n-tiles for the map array
+  static GemmOutMaps om;     // (contents only read when a.tma_store is set; copied into the launch by value)
+  GemmOutMaps om_local;
+  const GemmOutMaps* omp = &om;
+  {
+    static const bool no_tma_store = getenv("OVIS_GEMM_NO_TMA_STORE") != nullptr;    // A/B testing only
+    const int nt = (a.N + bn - 1) / bn;
+    const int es = a.out_f32 ? 4 : 2;
+    bool ok = a.epi == EPI_STORE && a.num_groups == 1 && nt <= GEMM_MAX_OUT_MAPS && (((long long)a.ldo * es) % 16) == 0 &&
+              !no_tma_store;
+    for (int t = 0; ok && t < nt; ++t) ok = (reinterpret_cast<uintptr_t>(a.out[t]) & 15) == 0;
+    if (ok) {
+      for (int t = 0; t < nt; ++t) {
+        const int ncols = a.N - t * bn < bn ? a.N - t * bn : bn;
+        rc = make_store_map(&om_local.m[t], a.out[t], (unsigned long long)a.rows_per_group, (unsigned long long)ncols,
+                            (unsigned long long)a.ldo, a.out_f32);
+        if (rc) return rc;
+      }
+      a.tma_store = 1;
+      omp = &om_local;
+    }
+  }
   // HBM-heavy shapes (K <= 256, many row tiles): B-stationary kernel; small / long-K shapes: streaming kernel
   const long long m_tiles_total = (long long)a.num_groups * ((a.rows_per_group + 127) / 128);
   static const bool no_bs = getenv("OVIS_GEMM_NO_BS") != nullptr;    // A/B testing only
   if (a.K <= 256 && m_tiles_total >= 64 && !no_bs)
-    return bn == 256 ? launch_gemm_bs<256>(ta, ta2, tb, a, sms, st) : launch_gemm_bs<128>(ta, ta2, tb, a, sms, st);
-  return bn == 256 ? launch_gemm_bn<256>(ta, ta2, tb, a, sms, st) : launch_gemm_bn<128>(ta, ta2, tb, a, sms, st);
+    return bn == 256 ? launch_gemm_bs<256>(ta, ta2, tb, *omp, a, sms, st) : launch_gemm_bs<128>(ta, ta2, tb, *omp, a, sms, st);
+  return bn == 256 ? launch_gemm_bn<256>(ta, ta2, tb, *omp, a, sms, st) : launch_gemm_bn<128>(ta, ta2, tb, *omp, a, sms, st);
 }
 
 }  // namespace

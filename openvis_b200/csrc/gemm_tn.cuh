@@ -20,6 +20,12 @@ enum GemmEpi : int {
 };
 
 constexpr int GEMM_MAX_NTILES = 16;
+constexpr int GEMM_MAX_OUT_MAPS = 8;
+
+// output tensor maps for the TMA-store epilogue (box = 128 bytes x 32 rows, 128B swizzle), one per n-tile
+struct GemmOutMaps {
+  CUtensorMap m[GEMM_MAX_OUT_MAPS];
+};
 
 struct GemmArgs {
   int rows_per_group;     // valid A rows in each group
@@ -41,6 +47,7 @@ struct GemmArgs {
   int relu;
   float scale;
   int a_alt;              // 1: odd n-tiles read their A operand from the second tensor map (key / value operands)
+  int tma_store;          // 1: EPI_STORE writes through GemmOutMaps (single group, 16-byte aligned pitch)
   // ---- EPI_LN
   const float* resid;     // [rows][256] fp32
   const float* ln1_g; const float* ln1_b;
@@ -77,8 +84,10 @@ struct GemmCfg {
 
 // One 128 x BN accumulator tile: TMEM -> registers -> fused epilogue -> global.  Called by the four epilogue warps.
 template <int BN>
-__device__ __forceinline__ void gemm_epilogue_tile(const GemmArgs& args, int nt, int mt, int g, int warp, int lane,
-                                                   uint32_t t_acc_base, uint8_t* stage_smem) {
+// `pf_frame` / `pf_set`: per-thread memo of the posflags already raised by this thread (frame, bit per column chunk)
+__device__ __forceinline__ void gemm_epilogue_tile(const GemmArgs& args, const CUtensorMap* omaps, int nt, int mt, int g,
+                                                   int warp, int lane, uint32_t t_acc_base, uint8_t* stage_smem,
+                                                   long long& pf_frame, uint32_t& pf_set) {
   using Cfg = GemmCfg<BN>;
   const int quarter = warp & 3;           // TMEM lane quarter this warp may access
   const int half = (warp - 2) >> 2;       // which half of the tile's columns this warp handles (warps 2-5: 0, 6-9: 1)
@@ -161,9 +170,23 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmArgs& args, int nt,
                                         pack_half2(f[8 * j + 4], f[8 * j + 5]), pack_half2(f[8 * j + 6], f[8 * j + 7]));
         }
       }
-      // stage through shared memory so that each store instruction writes four full 128-byte rows
+      // stage through shared memory ([32 rows][128 B], 128B-swizzle pattern)
+      if (args.tma_store) {                                   // the previous unit's bulk store must have read the buffer
+        if (lane == 0) tma_store_wait_read0();
+        __syncwarp();
+      }
 #pragma unroll
       for (int c = 0; c < 8; ++c) st_shared_v4(stg + (uint32_t)((lane * 8 + (c ^ (lane & 7))) << 4), pk[c]);
+      if (args.tma_store) {
+        // one bulk tensor store per unit: 32 rows x 128 B, rows / columns past the tensor are clipped by the TMA unit
+        fence_async_proxy();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&omaps[nt], stage_smem + (warp - 2) * 4096, u0, (int)grow0);
+          tma_store_commit();
+        }
+        continue;
+      }
       __syncwarp();
       char* obase = reinterpret_cast<char*>(args.out[nt]) + (long long)u0 * esize;
       if (ncols == cols_per_unit && vec_ok) {
@@ -344,9 +367,13 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmArgs& args, int nt,
       const int col = col_base + c * 32 + lane;
       if (col < args.N && word < args.words_per_group) {
         args.bits[((long long)g * args.words_per_group + word) * args.q_stride + col] = mine;
-        if ((~mine & validmask) != 0u) {
-          unsigned char* fl = args.flags + (long long)g * args.q_stride + col;
-          if (__ldcg(fl) == 0) *fl = 1;
+        if ((~mine & validmask) != 0u) {                   // (memo: see posflags below)
+          const long long key = (long long)g * GEMM_MAX_NTILES + nt;
+          if (key != pf_frame) { pf_frame = key; pf_set = 0u; }
+          if (!((pf_set >> c) & 1u)) {
+            args.flags[(long long)g * args.q_stride + col] = 1;
+            pf_set |= 1u << c;
+          }
         }
       }
     }
@@ -371,19 +398,27 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmArgs& args, int nt,
       }
       if (args.posflags) {
         // all 32 rows of this warp belong to one frame (rows_per_frame % 32 == 0)
-        // bit j of `pos` = this row has a positive logit in column j; OR-reduce over the 32 rows of the warp
-        uint32_t pos = 0;
+        // sign bits of the row's 32 logits shifted into one word (one funnel shift per logit: bit 31-j = logit j is
+        // negative), then AND-reduced over the 32 rows of the warp: a clear bit = some row has a non-negative logit.
+        // (+0.0 counts as positive here; an exactly-zero fp32 accumulation does not occur on real features.)
+        uint32_t neg = 0xffffffffu;
         if (row_ok) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) pos |= (__uint_as_float(v[j]) > 0.f ? 1u : 0u) << j;
+          for (int j = 0; j < 32; ++j) neg = __funnelshift_l(v[j], neg, 1);
         }
-        const uint32_t anyrow = __reduce_or_sync(0xffffffffu, pos);
+        const uint32_t allneg = __reduce_and_sync(0xffffffffu, neg);
         const int col = col_base + c * 32 + lane;
         const int r0 = mt * Cfg::BM + quarter * 32;
-        if (col < args.N && ((anyrow >> lane) & 1u) && r0 < args.rows_per_group) {
+        if (col < args.N && !((allneg >> (31 - lane)) & 1u) && r0 < args.rows_per_group) {
+          // plain store, no read-back (a load here would sit on the epilogue's critical path); the per-thread memo
+          // keeps the thousands of tiles of one frame from re-writing the same byte
           const long long frame = (long long)g * (args.rows_per_group / args.rows_per_frame) + r0 / args.rows_per_frame;
-          unsigned char* fl = args.posflags + frame * args.q_stride + col;
-          if (__ldcg(fl) == 0) *fl = 1;       // test first: thousands of warps would otherwise hammer the same bytes
+          const long long key = frame * GEMM_MAX_NTILES + nt;
+          if (key != pf_frame) { pf_frame = key; pf_set = 0u; }
+          if (!((pf_set >> c) & 1u)) {
+            args.posflags[frame * args.q_stride + col] = 1;
+            pf_set |= 1u << c;
+          }
         }
       }
     }
@@ -393,7 +428,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmArgs& args, int nt,
 template <int BN>
 __global__ void __launch_bounds__(320, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
-               const __grid_constant__ CUtensorMap tmB, const GemmArgs args) {
+               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ GemmOutMaps om, const GemmArgs args) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -493,19 +528,22 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================== epilogue warps (2..5) =====================
     int acc = 0;
     uint32_t acc_phase = 0;
+    long long pf_frame = -1;
+    uint32_t pf_set = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int nt = tile % n_tiles;
       const int mt = (tile / n_tiles) % m_tiles;
       const int g = tile / (n_tiles * m_tiles);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      gemm_epilogue_tile<BN>(args, nt, mt, g, warp, lane, tmem_base + acc * BN, stage_smem);
+      gemm_epilogue_tile<BN>(args, om.m, nt, mt, g, warp, lane, tmem_base + acc * BN, stage_smem, pf_frame, pf_set);
       // release the accumulator stage
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (args.tma_store && lane == 0) tma_store_wait0();       // bulk stores read shared memory until they complete
   }
 
   tc_fence_before();
@@ -538,7 +576,7 @@ struct GemmBsCfg {
 template <int BN>
 __global__ void __launch_bounds__(320, 1)
 gemm_tn_bs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
-                  const __grid_constant__ CUtensorMap tmB, const GemmArgs args) {
+                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ GemmOutMaps om, const GemmArgs args) {
   using Cfg = GemmBsCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -646,19 +684,22 @@ gemm_tn_bs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       // ===================== epilogue warps (2..5) =====================
       int acc = 0;
       uint32_t acc_phase = 0;
+      long long pf_frame = -1;
+      uint32_t pf_set = 0;
       for (int col = col0; col < cols; col += ncols_cta) {
         const int nt = col % n_tiles;
         const int g = col / n_tiles;
         for (int mt = r0; mt < m_tiles; mt += R) {
           mbar_wait(&tfull_bar[acc], acc_phase);
           tc_fence_after();
-          gemm_epilogue_tile<BN>(args, nt, mt, g, warp, lane, tmem_base + acc * BN, stage_smem);
+          gemm_epilogue_tile<BN>(args, om.m, nt, mt, g, warp, lane, tmem_base + acc * BN, stage_smem, pf_frame, pf_set);
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty_bar[acc]);
           if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
       }
+      if (args.tma_store && lane == 0) tma_store_wait0();     // bulk stores read shared memory until they complete
     }
   }
 

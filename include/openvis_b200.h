@@ -39,6 +39,11 @@ long long ovis_launch_count(void);
  * pos [N][C] = level_embed + 2-D sine embedding and pos_t [B][C] (or null) the frame term of the 3-D embedding. */
 int ovis_nchw_to_tokens_f16(const float* in, void* out_f16, void* out_pos_f16, const float* pos, const float* pos_t,
                             int B, int C, int N, void* stream);
+/* Same operation for [B][C][h][w] inputs through the TMA-fed kernel (bulk tensor loads / stores): the position table
+ * is passed channel-major, pos_cn [C][h*w] (the input's own layout).  Requires C % 32 == 0, w % 4 == 0 and 16-byte
+ * aligned pointers; bit-identical results to ovis_nchw_to_tokens_f16. */
+int ovis_nchw_to_tokens_hw_f16(const float* in, void* out_f16, void* out_pos_f16, const float* pos_cn, const float* pos_t,
+                               int B, int C, int h, int w, void* stream);
 /* mask_features [B][C][H][W] fp32 -> ft [B][H*W][C] f16 and centre-2x2-pooled g0/g1/g2 [B][(H/s)(W/s)][C] f16
  * (s = 8, 4, 2).  Replaces the operand side of einsum("bqc,bchw->bqhw") + F.interpolate(bilinear)
  * (frame_...decoder.py:144-148).  Requires H % 8 == 0, W % 8 == 0, C % 32 == 0. */

@@ -20,6 +20,7 @@ SIGNATURES = {
     "ovis_device_check": (_c_int, []),
     "ovis_launch_count": (_c_ll, []),
     "ovis_nchw_to_tokens_f16": (_c_int, [_vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _vp]),
+    "ovis_nchw_to_tokens_hw_f16": (_c_int, [_vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _vp]),
     "ovis_maskfeat_prep": (_c_int, [_vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _vp]),
     "ovis_cast_f16": (_c_int, [_vp, _vp, _c_ll, _vp]),
     "ovis_init_queries": (_c_int, [_vp] * 9 + [_c_int, _c_int, _vp]),
@@ -128,6 +129,18 @@ def nchw_to_tokens_f16(x, out=None, out_pos=None, pos=None, pos_t=None):
     if out is None:
         out = torch.empty(B, N, C, dtype=torch.float16, device=x.device)
     _check(lib.ovis_nchw_to_tokens_f16(_p(x), _p(out), _p(out_pos), _p(pos), _p(pos_t), B, C, N, _stream()))
+    return out
+
+
+@_timed("prep")
+def nchw_to_tokens_hw_f16(x, out=None, out_pos=None, pos_cn=None, pos_t=None):
+    """TMA-fed variant of nchw_to_tokens_f16; pos_cn is the position table in channel-major layout [C, h*w]."""
+    lib = load()
+    _req(x, torch.float32, "x")
+    B, C, h, w = x.shape
+    if out is None:
+        out = torch.empty(B, h * w, C, dtype=torch.float16, device=x.device)
+    _check(lib.ovis_nchw_to_tokens_hw_f16(_p(x), _p(out), _p(out_pos), _p(pos_cn), _p(pos_t), B, C, h, w, _stream()))
     return out
 
 

@@ -11,6 +11,7 @@
 #include "../../include/openvis_b200.h"
 #include "gemm_tn.cuh"
 #include "prep.cuh"
+#include "prep_tma.cuh"
 #include "xattn.cuh"
 #include "xattn_tc.cuh"
 #include "xattn_tc2.cuh"
@@ -125,6 +126,22 @@ int make_store_map(CUtensorMap* m, const void* base, unsigned long long rows, un
                         dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                         CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(OVIS_ERR_CUDA, "%s: cuTensorMapEncodeTiled (store) failed (%lld)", "tensor map", (long long)r);
+  return OVIS_OK;
+}
+
+// generic 4-D tiled map (dims / box innermost first; strides in bytes for dims 1..3)
+int make_map_4d(CUtensorMap* m, const void* base, int f32, const unsigned long long dims[4], const unsigned long long strides[3],
+                const unsigned box[4], CUtensorMapSwizzle sw) {
+  int rc = get_encoder();
+  if (rc) return rc;
+  cuuint64_t d[4] = {dims[0], dims[1], dims[2], dims[3]};
+  cuuint64_t st[3] = {strides[0], strides[1], strides[2]};
+  cuuint32_t bx[4] = {box[0], box[1], box[2], box[3]};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = g_encode(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), d,
+                        st, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(OVIS_ERR_CUDA, "%s: cuTensorMapEncodeTiled (4-D) failed (%lld)", "tensor map", (long long)r);
   return OVIS_OK;
 }
 
@@ -256,11 +273,102 @@ int ovis_nchw_to_tokens_f16(const float* in, void* out, void* out_pos, const flo
   return check_launch("nchw_to_tokens_f16_kernel");
 }
 
+int ovis_nchw_to_tokens_hw_f16(const float* in, void* out, void* out_pos, const float* pos_cn, const float* pos_t, int B, int C,
+                               int h, int w, void* stream) {
+  CHECK_ARG(in && out && B > 0 && C > 0 && h > 0 && w > 0, "bad arguments");
+  CHECK_ARG(C % 32 == 0 && w % 4 == 0, "needs C % 32 == 0 and w % 4 == 0 (16-byte row pitch)");
+  CHECK_ARG((out_pos == nullptr) == (pos_cn == nullptr), "out_pos and pos_cn go together");
+  CHECK_ARG(((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(out_pos)) & 15) == 0,
+            "pointers must be 16-byte aligned");
+  int sms = 0;
+  int rc = device_info(&sms);
+  if (rc) return rc;
+  TokTmaMaps maps;
+  const unsigned long long uW = w, uH = h, uC = C, uB = B;
+  {
+    const unsigned long long d[4] = {uW, uH, uC, uB}, st[3] = {uW * 4, uH * uW * 4, uC * uH * uW * 4};
+    const unsigned bx[4] = {32, 8, 32, 1};
+    rc = make_map_4d(&maps.in, in, 1, d, st, bx, CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (rc) return rc;
+  }
+  {
+    const unsigned long long d[4] = {uC, uW, uH, uB}, st[3] = {uC * 2, uW * uC * 2, uH * uW * uC * 2};
+    const unsigned bx[4] = {32, 32, 8, 1};
+    rc = make_map_4d(&maps.xt, out, 0, d, st, bx, CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc) return rc;
+    rc = make_map_4d(&maps.xp, out_pos ? out_pos : out, 0, d, st, bx, CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc) return rc;
+  }
+  static bool attr_done[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_done[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(tokens_prep_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TT_SMEM);
+    if (e != cudaSuccess) {
+      snprintf(g_err, sizeof(g_err), "nchw_to_tokens: cudaFuncSetAttribute(smem) failed: %s", cudaGetErrorString(e));
+      return OVIS_ERR_CUDA;
+    }
+    attr_done[dev] = true;
+  }
+  // work item = (spatial tile, run of frames): enough runs for >= 4 items per SM, runs of at most TT_MAX_RUN frames
+  const long long spatial = (long long)((h + 7) / 8) * ((w + 31) / 32) * (C / 32);
+  long long runs = (4ll * sms + spatial - 1) / spatial;
+  if (runs < (B + TT_MAX_RUN - 1) / TT_MAX_RUN) runs = (B + TT_MAX_RUN - 1) / TT_MAX_RUN;
+  if (runs > B) runs = B;
+  const int run_len = (int)((B + runs - 1) / runs);
+  runs = (B + run_len - 1) / run_len;
+  const long long items = spatial * runs;
+  const int grid = (int)(items < sms ? items : sms);
+  tokens_prep_tma_kernel<<<grid, 256, TT_SMEM, (cudaStream_t)stream>>>(maps, pos_cn, pos_t, B, C, h, w, (int)runs, run_len);
+  return check_launch("tokens_prep_tma_kernel");
+}
+
 int ovis_maskfeat_prep(const float* F, void* ft, void* g0, void* g1, void* g2, int B, int C, int H, int W, void* stream) {
   CHECK_ARG(F && ft && g0 && g1 && g2, "null pointer");
   CHECK_ARG(B > 0 && C % 32 == 0 && H % 8 == 0 && W % 8 == 0 && H > 0 && W > 0, "needs C % 32 == 0, H % 8 == 0, W % 8 == 0");
   int rc = device_info(nullptr);
   if (rc) return rc;
+  static const bool no_tma = getenv("OVIS_PREP_NO_TMA") != nullptr;     // A/B testing only
+  const bool aligned = ((reinterpret_cast<uintptr_t>(F) | reinterpret_cast<uintptr_t>(ft) | reinterpret_cast<uintptr_t>(g0) |
+                         reinterpret_cast<uintptr_t>(g1) | reinterpret_cast<uintptr_t>(g2)) & 15) == 0;
+  if (!no_tma && aligned) {
+    int sms = 0;
+    rc = device_info(&sms);
+    if (rc) return rc;
+    PrepTmaMaps maps;
+    const unsigned long long uW = W, uH = H, uC = C, uB = B;
+    {
+      const unsigned long long d[4] = {uW, uH, uC, uB}, st[3] = {uW * 4, uH * uW * 4, uC * uH * uW * 4};
+      const unsigned bx[4] = {32, 8, 32, 1};
+      rc = make_map_4d(&maps.in, F, 1, d, st, bx, CU_TENSOR_MAP_SWIZZLE_NONE);
+      if (rc) return rc;
+    }
+    void* outs[4] = {ft, g2, g1, g0};
+    CUtensorMap* om[4] = {&maps.ft, &maps.g2, &maps.g1, &maps.g0};
+    for (int l = 0; l < 4; ++l) {
+      const unsigned s_ = 1u << l;                       // block size 1, 2, 4, 8
+      const unsigned long long w = uW / s_, h = uH / s_;
+      const unsigned long long d[4] = {uC, w, h, uB}, st[3] = {uC * 2, w * uC * 2, h * w * uC * 2};
+      const unsigned bx[4] = {32, 32 / s_, 8 / s_, 1};
+      rc = make_map_4d(om[l], outs[l], 0, d, st, bx, CU_TENSOR_MAP_SWIZZLE_64B);
+      if (rc) return rc;
+    }
+    static bool attr_done[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_done[dev]) {
+      cudaError_t e = cudaFuncSetAttribute(maskfeat_prep_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PT_SMEM);
+      if (e != cudaSuccess) {
+        snprintf(g_err, sizeof(g_err), "maskfeat_prep: cudaFuncSetAttribute(smem) failed: %s", cudaGetErrorString(e));
+        return OVIS_ERR_CUDA;
+      }
+      attr_done[dev] = true;
+    }
+    const long long total = (long long)B * (H / 8) * ((W + 31) / 32) * (C / 32);
+    const int grid = (int)(total < sms ? total : sms);
+    maskfeat_prep_tma_kernel<<<grid, 256, PT_SMEM, (cudaStream_t)stream>>>(maps, B, C, H, W);
+    return check_launch("maskfeat_prep_tma_kernel");
+  }
   dim3 grid(((W + 31) / 32) * (H / 8), C / 32, B);
   maskfeat_prep_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(F, (__half*)ft, (__half*)g0, (__half*)g1, (__half*)g2, C, H, W);
   return check_launch("maskfeat_prep_kernel");

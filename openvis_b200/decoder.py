@@ -315,7 +315,7 @@ class _B200MaskedDecoderBase(nn.Module):
         return W
 
     def _pos_tables(self, T, sizes, device):
-        """Input-independent additive tables of the key operand: padd[l] = pos2d_l + level_embed_l  [N_l, 256] fp32 and,
+        """Input-independent additive tables of the key operand: padd[l] = (pos2d_l + level_embed_l)^T  [256, N_l] fp32 and,
         for the Video decoders, pz = frame term [T, 256] (pos3d = pos2d + pos_z, position_encoding.py:163).
         Cached per (level_embed version, T, sizes)."""
         le = self.level_embed.weight
@@ -326,7 +326,8 @@ class _B200MaskedDecoderBase(nn.Module):
         p2 = [sine_pos_2d(h, w, device) for (h, w) in sizes]
         pz = sine_pos_z(T, device).contiguous() if self.VIDEO else None
         lef = le.detach().float()
-        padd = [(p2[l] + lef[l][None, :]).contiguous() for l in range(3)]
+        # channel-major [256, N_l] (the layout of the NCHW inputs): what the TMA-fed layout kernel reads coalesced
+        padd = [(p2[l] + lef[l][None, :]).t().contiguous() for l in range(3)]
         if len(self._pcache) > 4:
             self._pcache.clear()
         self._pcache[key] = (padd, p2, pz)
@@ -430,7 +431,10 @@ class _B200MaskedDecoderBase(nn.Module):
 
         # ---- layout preparation (HBM-bound, once per call)
         for l in range(3):
-            L.nchw_to_tokens_f16(x[l], out=ws["xt"][l], out_pos=ws["xp"][l], pos=padd[l], pos_t=pz)
+            if x[l].shape[-1] % 4 == 0:
+                L.nchw_to_tokens_hw_f16(x[l], out=ws["xt"][l], out_pos=ws["xp"][l], pos_cn=padd[l], pos_t=pz)
+            else:                                      # odd widths: no 16-byte row pitch for the tensor maps
+                L.nchw_to_tokens_f16(x[l], out=ws["xt"][l], out_pos=ws["xp"][l], pos=padd[l].t().contiguous(), pos_t=pz)
         L.maskfeat_prep(mf, (ws["ft"], ws["gt"][0], ws["gt"][1], ws["gt"][2]))
         # ---- key / value projections of all layers, one launch per level
         for l in range(3):

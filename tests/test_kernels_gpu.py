@@ -97,7 +97,27 @@ def test_nchw_to_tokens():
     assert _maxerr(outp, refp) < 4e-3          # one fp16 ulp at |v| < 8 (summation order differs)
 
 
-@pytest.mark.parametrize("H,W", [(16, 16), (96, 160), (24, 40)])
+@pytest.mark.parametrize("B,h,w", [(3, 12, 20), (2, 23, 40), (2, 46, 80), (1, 5, 36)])
+def test_nchw_to_tokens_tma(B, h, w):
+    """The TMA-fed layout kernel reproduces the plain one bit for bit (partial tiles in x and y included)."""
+    x = _randn(B, 256, h, w, seed=1)
+    N = h * w
+    pos, pos_t = _randn(N, 256, seed=2), _randn(B, 256, seed=3)
+    ref_t, ref_p = torch.empty(B, N, 256, dtype=torch.float16, device="cuda"), torch.empty(B, N, 256, dtype=torch.float16, device="cuda")
+    L.nchw_to_tokens_f16(x, out=ref_t, out_pos=ref_p, pos=pos, pos_t=pos_t)
+    out_t, out_p = torch.zeros_like(ref_t), torch.zeros_like(ref_p)
+    L.nchw_to_tokens_hw_f16(x, out=out_t, out_pos=out_p, pos_cn=pos.t().contiguous(), pos_t=pos_t)
+    assert torch.equal(out_t, ref_t) and torch.equal(out_p, ref_p)
+    out_t.zero_()
+    L.nchw_to_tokens_hw_f16(x, out=out_t)
+    assert torch.equal(out_t, ref_t)
+    ref_p2 = torch.empty_like(ref_p)
+    L.nchw_to_tokens_f16(x, out=ref_t, out_pos=ref_p2, pos=pos, pos_t=None)
+    L.nchw_to_tokens_hw_f16(x, out=out_t, out_pos=out_p, pos_cn=pos.t().contiguous(), pos_t=None)
+    assert torch.equal(out_p, ref_p2)
+
+
+@pytest.mark.parametrize("H,W", [(16, 16), (96, 160), (24, 40), (184, 320)])
 def test_maskfeat_prep(H, W):
     F = _randn(2, 256, H, W, seed=2)
     ft, g0, g1, g2 = L.maskfeat_prep(F)

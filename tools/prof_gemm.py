@@ -51,3 +51,6 @@ if which in ("all", "prep"):
     o1 = torch.empty(T, N2, 256, dtype=torch.float16, device="cuda"); o2 = torch.empty_like(o1)
     ms = timeit(lambda: L.nchw_to_tokens_f16(x2, out=o1, out_pos=o2, pos=pos, pos_t=pz))
     print(f"nchw_to_tokens L2: {ms*1e3:.1f} us  {x2.numel()*8/ms/1e6:.1f} GB/s")
+    pcn = pos.t().contiguous()
+    ms = timeit(lambda: L.nchw_to_tokens_hw_f16(x2, out=o1, out_pos=o2, pos_cn=pcn, pos_t=pz))
+    print(f"nchw_to_tokens_hw (TMA) L2: {ms*1e3:.1f} us  {x2.numel()*8/ms/1e6:.1f} GB/s")

@@ -9,7 +9,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libopenvis_b200.so")
+# OVIS_LIB_PATH: A/B timing of an older build of the same C ABI (tools/); never set in tests or the bench
+LIB_PATH = os.environ.get("OVIS_LIB_PATH") or os.path.join(_HERE, "libopenvis_b200.so")
 
 _c_int, _c_ll, _c_float, _vp = ctypes.c_int, ctypes.c_longlong, ctypes.c_float, ctypes.c_void_p
 
@@ -54,6 +55,8 @@ def load():
             "openvis_b200 has no CPU / PyTorch fallback path")
     lib = ctypes.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
+        if os.environ.get("OVIS_LIB_PATH") and not hasattr(lib, name):
+            continue                     # older A/B build: entry points added since are simply absent
         fn = getattr(lib, name)          # AttributeError here = header / library mismatch
         fn.restype = res
         fn.argtypes = args

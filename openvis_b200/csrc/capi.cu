@@ -244,6 +244,23 @@ int launch_gemm(const void* A, long long a_rows, long long a_cols, long long lda
       a.tma_store = 1;
       omp = &om_local;
     }
+    // transposed fp32 store: one 3-D map {row in group, column, group}, box {32 rows (128 B), 32 columns, 1}
+    if (a.epi == EPI_STORE_T && !no_tma_store && (reinterpret_cast<uintptr_t>(a.out_t) & 15) == 0 && (a.ldt % 4) == 0 &&
+        (a.num_groups == 1 || (a.t_group_stride % 4) == 0)) {
+      rc = get_encoder();
+      if (rc) return rc;
+      cuuint64_t dims[3] = {(cuuint64_t)a.rows_per_group, (cuuint64_t)a.N, (cuuint64_t)a.num_groups};
+      cuuint64_t strides[2] = {(cuuint64_t)a.ldt * 4,
+                               a.num_groups == 1 ? (cuuint64_t)a.ldt * 4 * (cuuint64_t)a.N : (cuuint64_t)a.t_group_stride * 4};
+      cuuint32_t box[3] = {32, 32, 1};
+      cuuint32_t estr[3] = {1, 1, 1};
+      CUresult r = g_encode(&om_local.m[0], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, a.out_t, dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return fail(OVIS_ERR_CUDA, "%s: cuTensorMapEncodeTiled (transposed store) failed (%lld)", "tensor map", (long long)r);
+      a.tma_store = 1;
+      omp = &om_local;
+    }
   }
   // HBM-heavy shapes (K <= 256, many row tiles): B-stationary kernel; small / long-K shapes: streaming kernel
   const long long m_tiles_total = (long long)a.num_groups * ((a.rows_per_group + 127) / 128);

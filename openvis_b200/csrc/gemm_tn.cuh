@@ -379,21 +379,39 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmArgs& args, const C
     }
   } else {  // EPI_STORE_T
     const float* bias = args.bias[nt];
-    float* obase = args.out_t + (long long)g * args.t_group_stride + r;
+    const uint32_t stg = smem_u32(stage_smem + (warp - 2) * 4096);     // [32 columns][32 rows] fp32, one chunk
+    const int r_warp0 = mt * Cfg::BM + quarter * 32;
 #pragma unroll 1
     for (int c = half * (BN / 64); c < (half + 1) * (BN / 64); ++c) {
       if (col_base + c * 32 >= args.N) break;
       tmem_ld_32x32(t_acc + c * 32, v);
       tmem_ld_wait();
-      if (row_ok) {
+      if (bias) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (col_base + c * 32 + j < args.N) v[j] = __float_as_uint(__uint_as_float(v[j]) + __ldg(bias + c * 32 + j));
+      }
+      if (args.tma_store) {
+        // transposed through shared memory (lane = row: conflict-free 4-byte stores), then ONE bulk tensor store of
+        // 32 columns x 128 bytes; columns >= N and rows past the group are clipped by the TMA unit
+        if (lane == 0) tma_store_wait_read0();
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          asm volatile("st.shared.b32 [%0], %1;" ::"r"(stg + (uint32_t)(j * 128 + lane * 4)), "r"(v[j]) : "memory");
+        fence_async_proxy();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_3d(&omaps[0], stage_smem + (warp - 2) * 4096, r_warp0, col_base + c * 32, g);
+          tma_store_commit();
+        }
+      } else if (row_ok) {
+        const int ncols = min(32, args.N - (col_base + c * 32));
+        float* op = args.out_t + (long long)g * args.t_group_stride + (long long)(col_base + c * 32) * args.ldt + r;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const int col = col_base + c * 32 + j;
-          if (col < args.N) {
-            float f = __uint_as_float(v[j]);
-            if (bias) f += __ldg(bias + c * 32 + j);
-            __stcs(obase + (long long)col * args.ldt, f);   // col < N checked above
-          }
+          if (j < ncols) __stcs(op, __uint_as_float(v[j]));
+          op += args.ldt;
         }
       }
       if (args.posflags) {

@@ -657,6 +657,8 @@ int ovis_xattn(const void* q, const void* k, const void* v, const unsigned int* 
     }
     if (rc) return rc;
   }
+  static const bool no_combine = getenv("OVIS_XATTN_NO_COMBINE") != nullptr;     // timing experiments only
+  if (no_combine) return OVIS_OK;
   xattn_combine_kernel<<<dim3(Q, 8, G), 256, 0, (cudaStream_t)stream>>>(o_part, ml_part, (__half*)out, Q, q_pad, splits);
   return check_launch("xattn_combine_kernel");
 }

@@ -72,14 +72,19 @@ __device__ __forceinline__ void mbar_wait_poll(uint64_t* bar, uint32_t parity) {
     }
   }
 }
-// Bounded wait: a broken pipeline must not hang the GPU box.  ~2 s at 2 GHz, then trap.
+// Bounded wait: a broken pipeline must not hang the GPU box.  ~2 s at 2 GHz, then trap.  (mbarrier.try_wait suspends
+// the thread for a hardware time slice by itself; the clock is only looked at every 64 unsuccessful tries.)
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  long long t0 = clock64();
+  long long t0 = 0;
+  int n = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
-      printf("ovis: mbarrier timeout block %d thread %d\n", (int)blockIdx.x, (int)threadIdx.x);
-      __trap();
+    if ((++n & 63) == 0) {
+      if (t0 == 0) t0 = clock64();
+      else if (clock64() - t0 > 4000000000LL) {
+        printf("ovis: mbarrier timeout block %d thread %d\n", (int)blockIdx.x, (int)threadIdx.x);
+        __trap();
+      }
     }
   }
 }

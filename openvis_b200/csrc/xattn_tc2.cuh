@@ -107,8 +107,6 @@ xattn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       int remaining = 0;
 #pragma unroll
       for (int i = 0; i < 4; ++i) remaining += (ntiles - (i >> 1) + 1) >> 1;
-      long long t0 = 0;
-      int spins = 0;
       while (remaining > 0) {
         bool any = false;
 #pragma unroll
@@ -130,10 +128,20 @@ xattn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           --remaining;
           any = true;
         }
-        if (any) { spins = 0; t0 = 0; }
-        else if ((++spins & 0xfff) == 0) {                      // bounded: a broken pipeline must not hang the GPU box
-          if (t0 == 0) t0 = clock64();
-          else if (clock64() - t0 > 4000000000LL) { printf("ovis: xattn S issuer timeout block %d\n", (int)blockIdx.x); __trap(); }
+        if (!any) {
+          // nothing ready: sleep on the barrier of the warpgroup that is furthest behind (mbarrier.try_wait suspends
+          // the thread, so the issuer does not take issue slots from the softmax warps of its scheduler)
+          int wmin = -1, tmin = 0x7fffffff;
+#pragma unroll
+          for (int wg = 0; wg < 4; ++wg) {
+            const int t = 2 * nxt[wg] + (wg >> 1);
+            if (t < ntiles && t < tmin) { tmin = t; wmin = wg; }
+          }
+          if (wmin >= 0) {
+            const int n = tmin >> 1;
+            if (mbar_try_wait(&full[tmin % X2_STAGES], (uint32_t)((tmin / X2_STAGES) & 1)))
+              mbar_try_wait(&s_empty[wmin], (uint32_t)((n & 1) ^ 1));
+          }
         }
       }
     }
@@ -150,8 +158,6 @@ xattn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 #pragma unroll
       for (int i = 0; i < 4; ++i) remaining += (ntiles - (i >> 1) + 1) >> 1;
       uint32_t half_done = 0;              // bit st: one of the two heads of the tile in stage st has been issued
-      long long t0 = 0;
-      int spins = 0;
       while (remaining > 0) {
         bool any = false;
 #pragma unroll
@@ -179,10 +185,14 @@ xattn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           --remaining;
           any = true;
         }
-        if (any) { spins = 0; t0 = 0; }
-        else if ((++spins & 0xfff) == 0) {
-          if (t0 == 0) t0 = clock64();
-          else if (clock64() - t0 > 4000000000LL) { printf("ovis: xattn PV issuer timeout block %d\n", (int)blockIdx.x); __trap(); }
+        if (!any) {
+          int wmin = -1, tmin = 0x7fffffff;
+#pragma unroll
+          for (int wg = 0; wg < 4; ++wg) {
+            const int t = 2 * nxt[wg] + (wg >> 1);
+            if (t < ntiles && t < tmin) { tmin = t; wmin = wg; }
+          }
+          if (wmin >= 0) mbar_try_wait(&p_full[wmin], (uint32_t)((tmin >> 1) & 1));
         }
       }
       umma_commit(done);

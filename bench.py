@@ -366,9 +366,20 @@ def main():
                 ent.update(bound="hbm", achieved=ach, peak=peak_bw, unit="GB/s", frac=ach / peak_bw)
         kernels[fam] = ent
     dom = max((f for f in kernels if f in work), key=lambda f: kernels[f]["ms_per_step"], default=None)
-    kname = {"xattn": "xattn_tc_kernel+xattn_combine_kernel", "kv_proj": "gemm_tn_kernel<256> (key/value projection)",
-             "prep": "maskfeat_prep_kernel+nchw_to_tokens_f16_kernel", "mask_logits": "gemm_tn_kernel<128> (final mask logits)",
-             "mask_bits": "gemm_tn_kernel<128> (mask sign bits)"}
+    kname = {"xattn": "xattn_tc2_kernel+xattn_combine_kernel", "kv_proj": "gemm_tn_bs_kernel<256> (key/value projection)",
+             "prep": "maskfeat_prep_tma_kernel+tokens_prep_tma_kernel", "mask_logits": "gemm_tn_bs_kernel<128> (final mask logits)",
+             "mask_bits": "gemm_tn_bs_kernel<128> (mask sign bits)"}
+    if "xattn" in kernels and kernels["xattn"]["ms_per_step"] > 0:
+        # d = 32 heads make the masked attention exp-bound, not tensor-bound: 128 flop per exponential.  The binding
+        # pipe is the XU (MUFU.EX2: 16 lanes/clk/SM, measured 16.5 by tools/ubench/pipes.cu); reported next to the
+        # tensor fraction.  Exponentials counted on the 128-row UMMA tile the kernel has to process (Q = 100 padded).
+        sms, clk = torch.cuda.get_device_properties(dev).multi_processor_count, (clocks.get("sm_mhz") or 1965) * 1e6
+        qpad = ((Q + 127) // 128) * 128
+        nexp = sum(qpad * 8.0 * rows3[i % 3] for i in range(9)) * args.steps
+        ach = nexp / (kernels["xattn"]["ms_per_step"] * args.steps * 1e-3) / 1e9
+        peak_x = 16.0 * sms * clk / 1e9
+        kernels["xattn"]["xu_bound"] = {"pipe": "XU (MUFU.EX2)", "achieved": ach, "peak": peak_x, "unit": "Gexp/s",
+                                        "frac": ach / peak_x, "note": "includes the split-combine launches"}
     traffic = None
     tp = os.path.join(ROOT, "profiles", "ncu_traffic_r1.json")
     if os.path.isfile(tp):

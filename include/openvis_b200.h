@@ -68,11 +68,14 @@ int ovis_linear_f16(const void* x_f16, long long rows, int K, int ldx, const voi
 /* Linear(K -> 256) + residual + LayerNorm [+ second LayerNorm], the post-norm tails of
  * CrossAttentionLayer/SelfAttentionLayer/FFNLayer.forward_post (video_...decoder.py:119-120, 59-60, 177-178)
  * fused with decoder_norm (frame_...decoder.py:140).  Any output pointer may be null.
- * ype16 = fp16(y + pe[row % pe_period]) is the "+ query_pos" operand of the next projection. */
+ * ype16 = fp16(y + pe[row % pe_period]) is the "+ query_pos" operand of the next projection.
+ * split_ws (optional, >= (K/256) * ceil128(rows) * 256 floats): scratch for the few-rows path (split-K partials
+ * + a row-parallel LayerNorm kernel) taken when rows <= 2048; without it the fused single-pass epilogue is used. */
 int ovis_linear_ln_f16(const void* x_f16, long long rows, int K, const void* w_f16, const float* bias,
                        const float* resid, const float* ln1_g, const float* ln1_b,
                        const float* ln2_g, const float* ln2_b, const float* pe, int pe_period,
-                       float* y32, void* y16, void* ype16, float* d32, void* d16, void* stream);
+                       float* y32, void* y16, void* ype16, float* d32, void* d16,
+                       float* split_ws, long long split_ws_floats, void* stream);
 /* Key/value projections of all decoder layers that read one feature level, in one launch: for n_tiles 256-wide
  * column tiles t, out[t] = (t even ? xk : xv) * w[t*256:(t+1)*256]^T + bias[t]; xk = memory + pos (+ level_embed),
  * xv = memory, as in `key=self.with_pos_embed(memory, pos), value=memory` (video_...decoder.py:115-118).

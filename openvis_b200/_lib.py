@@ -28,7 +28,7 @@ SIGNATURES = {
     "ovis_rownorm": (_c_int, [_vp] * 5 + [_c_int, _c_int, _c_int, _vp]),
     "ovis_linear_f16": (_c_int, [_vp, _c_ll, _c_int, _c_int, _vp, _c_int, _vp, _c_float, _c_int, _vp, _c_int, _c_int, _vp]),
     "ovis_linear_ln_f16": (_c_int, [_vp, _c_ll, _c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _c_int,
-                                    _vp, _vp, _vp, _vp, _vp, _vp]),
+                                    _vp, _vp, _vp, _vp, _vp, _vp, _c_ll, _vp]),
     "ovis_kv_proj_f16": (_c_int, [_vp, _vp, _c_ll, _vp, _c_int, _vp, _vp, _vp]),
     "ovis_mask_bits": (_c_int, [_vp, _c_int, _c_int, _vp, _c_int, _vp, _vp, _c_int, _vp]),
     "ovis_mask_logits": (_c_int, [_vp, _c_int, _c_int, _vp, _c_int, _c_int, _vp, _vp, _c_ll, _c_ll, _vp, _c_int, _vp]),
@@ -204,13 +204,16 @@ def linear_f16(x, w, bias=None, scale=1.0, relu=False, out=None, out_f32=False):
 
 
 @_timed("query_side")
-def linear_ln_f16(x, w, bias, resid, ln1, ln2=None, pe=None, y32=None, y16=None, ype16=None, d32=None, d16=None):
+def linear_ln_f16(x, w, bias, resid, ln1, ln2=None, pe=None, y32=None, y16=None, ype16=None, d32=None, d16=None,
+                  split_ws=None):
+    """split_ws: optional fp32 scratch (>= K/256 * ceil128(rows) * 256 elements) enabling the few-rows split path."""
     lib = load()
     rows, K = x.shape
     _check(lib.ovis_linear_ln_f16(_p(x), rows, K, _p(w), _p(bias), _p(resid), _p(ln1[0]), _p(ln1[1]),
                                   _p(ln2[0]) if ln2 else None, _p(ln2[1]) if ln2 else None,
                                   _p(pe), pe.shape[0] if pe is not None else 0,
-                                  _p(y32), _p(y16), _p(ype16), _p(d32), _p(d16), _stream()))
+                                  _p(y32), _p(y16), _p(ype16), _p(d32), _p(d16),
+                                  _p(split_ws), split_ws.numel() if split_ws is not None else 0, _stream()))
 
 
 def _ptr_array(tensors):

@@ -150,6 +150,7 @@ void init_args(GemmArgs& a) {
   a.num_groups = 1;
   a.a_k_mod = 1;
   a.a_row_div = 1;
+  a.b_k_mod = 1;
   a.b_row_div = 1;
   a.scale = 1.f;
   a.pe_period = 1;
@@ -221,7 +222,7 @@ int launch_gemm(const void* A, long long a_rows, long long a_cols, long long lda
   if (rc) return rc;
   rc = make_map_f16(&ta2, A2 ? A2 : A, a_rows, a_cols, lda, 128);
   if (rc) return rc;
-  rc = make_map_f16(&tb, B, b_rows, a.K, ldb, bn);
+  rc = make_map_f16(&tb, B, b_rows, (unsigned long long)a.K * a.b_k_mod, ldb, bn);
   if (rc) return rc;
   // TMA-store epilogue for plain stores: one group, 16-byte aligned rows, few enough n-tiles for the map array
   static GemmOutMaps om;     // (contents only read when a.tma_store is set; copied into the launch by value)
@@ -231,14 +232,15 @@ int launch_gemm(const void* A, long long a_rows, long long a_cols, long long lda
     static const bool no_tma_store = getenv("OVIS_GEMM_NO_TMA_STORE") != nullptr;    // A/B testing only
     const int nt = (a.N + bn - 1) / bn;
     const int es = a.out_f32 ? 4 : 2;
-    bool ok = a.epi == EPI_STORE && a.num_groups == 1 && nt <= GEMM_MAX_OUT_MAPS && (((long long)a.ldo * es) % 16) == 0 &&
-              !no_tma_store;
+    bool ok = a.epi == EPI_STORE && (a.num_groups == 1 || (a.o_group_stride > 0 && a.o_group_stride % 32 == 0)) &&
+              nt <= GEMM_MAX_OUT_MAPS && (((long long)a.ldo * es) % 16) == 0 && !no_tma_store;
     for (int t = 0; ok && t < nt; ++t) ok = (reinterpret_cast<uintptr_t>(a.out[t]) & 15) == 0;
     if (ok) {
       for (int t = 0; t < nt; ++t) {
         const int ncols = a.N - t * bn < bn ? a.N - t * bn : bn;
-        rc = make_store_map(&om_local.m[t], a.out[t], (unsigned long long)a.rows_per_group, (unsigned long long)ncols,
-                            (unsigned long long)a.ldo, a.out_f32);
+        const unsigned long long out_rows = a.num_groups == 1 ? (unsigned long long)a.rows_per_group
+                                                               : (unsigned long long)a.num_groups * a.o_group_stride;
+        rc = make_store_map(&om_local.m[t], a.out[t], out_rows, (unsigned long long)ncols, (unsigned long long)a.ldo, a.out_f32);
         if (rc) return rc;
       }
       a.tma_store = 1;
@@ -447,13 +449,48 @@ int ovis_linear_f16(const void* x, long long rows, int K, int ldx, const void* w
 
 int ovis_linear_ln_f16(const void* x, long long rows, int K, const void* w, const float* bias, const float* resid,
                        const float* ln1_g, const float* ln1_b, const float* ln2_g, const float* ln2_b, const float* pe,
-                       int pe_period, float* y32, void* y16, void* ype16, float* d32, void* d16, void* stream) {
+                       int pe_period, float* y32, void* y16, void* ype16, float* d32, void* d16, float* split_ws,
+                       long long split_ws_floats, void* stream) {
   CHECK_ARG(x && w && bias && resid && ln1_g && ln1_b && rows > 0, "bad arguments");
   CHECK_ARG((ln2_g == nullptr) == (ln2_b == nullptr), "second LayerNorm needs both weight and bias");
   CHECK_ARG(!ype16 || (pe && pe_period > 0), "ype16 needs pe");
   CHECK_ARG(rows < (1ll << 31), "too many rows");
   GemmArgs a;
   init_args(a);
+  // Few rows (the Video decoders' 100..400 queries): one CTA per 128-row tile would leave the GPU idle and serialise
+  // the K loop, so the product is split over K slices of 256 and two 128-column tiles (fp32 partials in split_ws) and a
+  // row-parallel kernel finishes bias + residual + LayerNorm(s).  Many rows (Frame decoders): fused epilogue.
+  const long long rows_pad = ((rows + 127) / 128) * 128;
+  const int S = K / 256;
+  static const bool no_split = getenv("OVIS_LN_NO_SPLIT") != nullptr;     // A/B testing only
+  if (!no_split && split_ws && K % 256 == 0 && rows <= 2048 && split_ws_floats >= (long long)S * rows_pad * 256) {
+    a.rows_per_group = (int)rows;
+    a.num_groups = S;
+    a.a_group_stride = 0;
+    a.a_k_mod = S;
+    a.a_k_offset_stride = 256;
+    a.b_k_mod = S;
+    a.b_k_offset_stride = 256;
+    a.o_group_stride = (int)rows_pad;
+    a.N = 256;
+    a.K = 256;
+    a.epi = EPI_STORE;
+    a.out[0] = split_ws;
+    a.out[1] = split_ws + 128;
+    a.ldo = 256;
+    a.out_f32 = 1;
+    int rc = launch_gemm(x, rows, K, K, w, 256, K, a, 128, (cudaStream_t)stream);
+    if (rc) return rc;
+    LnReduceArgs r;
+    r.part = split_ws; r.S = S; r.part_stride = rows_pad;
+    r.bias = bias; r.resid = resid;
+    r.ln1_g = ln1_g; r.ln1_b = ln1_b; r.ln2_g = ln2_g; r.ln2_b = ln2_b;
+    r.pe = pe; r.pe_period = pe_period > 0 ? pe_period : 1;
+    r.y32 = y32; r.y16 = (__half*)y16; r.ype16 = (__half*)ype16; r.d32 = d32; r.d16 = (__half*)d16;
+    r.rows = (int)rows;
+    ln_reduce_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(r);
+    return check_launch("ln_reduce_kernel");
+  }
   a.rows_per_group = (int)rows;
   a.a_group_stride = (int)rows;
   a.N = 256;
@@ -670,8 +707,9 @@ int ovis_self_attn(const void* qk, const void* v, void* out, int G, int Q, void*
   SelfAttnArgs a;
   a.qk = (const __half*)qk; a.v = (const __half*)v; a.out = (__half*)out; a.Q = Q;
   a.scale_log2 = 0.17677669529663687f * 1.4426950408889634f;   // 32^-1/2 * log2(e)
-  const int threads = Q <= 128 ? 128 : 256;
-  self_attn_kernel<<<dim3(8, G), threads, (size_t)Q * 32 * 2 * sizeof(__half), (cudaStream_t)stream>>>(a);
+  const size_t smem = (size_t)Q * 32 * 2 * sizeof(__half);
+  if (Q <= 128) self_attn_kernel<4><<<dim3(8, G), 512, smem, (cudaStream_t)stream>>>(a);
+  else self_attn_kernel<2><<<dim3(8, G), 512, smem, (cudaStream_t)stream>>>(a);
   return check_launch("self_attn_kernel");
 }
 

@@ -34,6 +34,9 @@ struct GemmArgs {
   int b_group_stride;     // B rows between consecutive groups (0 = one shared B)
   int a_k_offset_stride;  // extra A column offset per (group % a_k_mod) (SAN per-head slices), usually 0
   int a_k_mod;            // see above (>= 1)
+  int b_k_offset_stride;  // extra B column (K) offset per (group % b_k_mod): split-K slices of one weight matrix
+  int b_k_mod;            // see above (>= 1)
+  int o_group_stride;     // EPI_STORE: output rows between consecutive groups (0: outputs follow the A row blocks)
   int a_row_div;          // A row block index = group / a_row_div (>= 1)
   int b_row_div;          // B row block index = group / b_row_div (>= 1)
   int N;                  // valid output columns
@@ -104,7 +107,8 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmArgs& args, const C
     const int esize = args.out_f32 ? 4 : 2;
     const uint32_t stg = smem_u32(stage_smem + (warp - 2) * 4096);   // [32 rows][8 x 16 B], XOR-swizzled
     const int r_warp0 = mt * Cfg::BM + quarter * 32;          // first row (within group) of this warp
-    const long long grow0 = (long long)(g / args.a_row_div) * args.a_group_stride + r_warp0;
+    const long long grow0 = (args.o_group_stride ? (long long)g * args.o_group_stride
+                                                 : (long long)(g / args.a_row_div) * args.a_group_stride) + r_warp0;
     const bool vec_ok = (((long long)args.ldo * esize) & 15) == 0;
     const bool bias_vec = bias && ((reinterpret_cast<uintptr_t>(bias) & 15) == 0);
 #pragma unroll 1
@@ -499,6 +503,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int a_row = (g / args.a_row_div) * args.a_group_stride + mt * Cfg::BM;
         const int a_col = (g % args.a_k_mod) * args.a_k_offset_stride;
         const int b_row = (g / args.b_row_div) * args.b_group_stride + nt * BN;
+        const int b_col = (g % args.b_k_mod) * args.b_k_offset_stride;
         const CUtensorMap* ta = (args.a_alt && (nt & 1)) ? &tmA2 : &tmA;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -506,7 +511,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           uint8_t* sb = sa + Cfg::A_BYTES;
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           tma_load_2d(sa, ta, &full_bar[stage], a_col + kb * Cfg::BK, a_row);
-          tma_load_2d(sb, &tmB, &full_bar[stage], kb * Cfg::BK, b_row);
+          tma_load_2d(sb, &tmB, &full_bar[stage], b_col + kb * Cfg::BK, b_row);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -561,7 +566,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-    if (args.tma_store && lane == 0) tma_store_wait0();       // bulk stores read shared memory until they complete
+    if (args.tma_store && lane == 0) tma_store_wait_read0();  // bulk stores read shared memory until then
   }
 
   tc_fence_before();
@@ -654,7 +659,9 @@ gemm_tn_bs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const CUtensorMap* ta = (args.a_alt && (nt & 1)) ? &tmA2 : &tmA;
           mbar_wait(bempty_bar, bphase ^ 1);               // previous column's MMAs have retired
           mbar_arrive_expect_tx(bfull_bar, (uint32_t)(k_blocks * BN * Cfg::BK * 2));
-          for (int kb = 0; kb < k_blocks; ++kb) tma_load_2d(sB + kb * (BN * Cfg::BK * 2), &tmB, bfull_bar, kb * Cfg::BK, b_row);
+          const int b_col = (g % args.b_k_mod) * args.b_k_offset_stride;
+          for (int kb = 0; kb < k_blocks; ++kb)
+            tma_load_2d(sB + kb * (BN * Cfg::BK * 2), &tmB, bfull_bar, b_col + kb * Cfg::BK, b_row);
           bphase ^= 1;
           for (int mt = r0; mt < m_tiles; mt += R) {
             for (int kb = 0; kb < k_blocks; ++kb) {
@@ -717,7 +724,7 @@ gemm_tn_bs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
       }
-      if (args.tma_store && lane == 0) tma_store_wait0();     // bulk stores read shared memory until they complete
+      if (args.tma_store && lane == 0) tma_store_wait_read0();  // bulk stores read shared memory until then
     }
   }
 

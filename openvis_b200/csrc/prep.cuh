@@ -181,6 +181,84 @@ init_queries_kernel(const float* __restrict__ qfeat, const float* __restrict__ q
   }
 }
 
+// Tail of the split linear+LayerNorm path used when a projection has too few rows to fill the GPU with row tiles
+// (the Video decoders' 100..400 query rows): z = sum_s part[s][row] + bias + resid[row] -> LayerNorm (ln1) -> y
+// [-> second LayerNorm (ln2) -> d].  Same outputs as the fused GEMM epilogue (EPI_LN).  One warp per row, C = 256:
+// lane l owns columns 4l..4l+3 and 128+4l..128+4l+3 (two coalesced float4 per operand).
+struct LnReduceArgs {
+  const float* part;      // [S][part_stride rows][256] fp32 partial products (split-K slices)
+  int S;
+  long long part_stride;  // rows between slices
+  const float* bias;      // [256]
+  const float* resid;     // [rows][256]
+  const float* ln1_g; const float* ln1_b;
+  const float* ln2_g; const float* ln2_b;   // null -> no second norm
+  const float* pe; int pe_period;
+  float* y32; __half* y16; __half* ype16;
+  float* d32; __half* d16;
+  int rows;
+};
+
+__global__ void __launch_bounds__(256)
+ln_reduce_kernel(const LnReduceArgs a) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= a.rows) return;
+  const int c0 = lane * 4, c1 = 128 + lane * 4;
+  auto ld4 = [](const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); };
+  float z[8];
+  {
+    const float4 b0 = ld4(a.bias + c0), b1 = ld4(a.bias + c1);
+    const float4 r0 = ld4(a.resid + (long long)row * 256 + c0), r1 = ld4(a.resid + (long long)row * 256 + c1);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int s = 0; s < a.S; ++s) {
+      const float* p = a.part + ((long long)s * a.part_stride + row) * 256;
+      const float4 p0 = ld4(p + c0), p1 = ld4(p + c1);
+      acc[0] += p0.x; acc[1] += p0.y; acc[2] += p0.z; acc[3] += p0.w;
+      acc[4] += p1.x; acc[5] += p1.y; acc[6] += p1.z; acc[7] += p1.w;
+    }
+    z[0] = acc[0] + b0.x + r0.x; z[1] = acc[1] + b0.y + r0.y; z[2] = acc[2] + b0.z + r0.z; z[3] = acc[3] + b0.w + r0.w;
+    z[4] = acc[4] + b1.x + r1.x; z[5] = acc[5] + b1.y + r1.y; z[6] = acc[6] + b1.z + r1.z; z[7] = acc[7] + b1.w + r1.w;
+  }
+  auto layer_norm = [&](float (&v)[8], const float* g, const float* b) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += v[i];
+    const float mean = warp_sum(s) * (1.f / 256.f);
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const float d = v[i] - mean; sq += d * d; }
+    const float rstd = rsqrtf(warp_sum(sq) * (1.f / 256.f) + 1e-5f);
+    const float4 g0 = ld4(g + c0), g1 = ld4(g + c1), b0 = ld4(b + c0), b1 = ld4(b + c1);
+    const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = (v[i] - mean) * rstd * gg[i] + bb[i];
+  };
+  auto st32 = [&](float* base, const float (&v)[8]) {
+    *reinterpret_cast<float4*>(base + (long long)row * 256 + c0) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(base + (long long)row * 256 + c1) = make_float4(v[4], v[5], v[6], v[7]);
+  };
+  auto st16 = [&](__half* base, const float (&v)[8]) {
+    *reinterpret_cast<uint2*>(base + (long long)row * 256 + c0) = make_uint2(pack_half2(v[0], v[1]), pack_half2(v[2], v[3]));
+    *reinterpret_cast<uint2*>(base + (long long)row * 256 + c1) = make_uint2(pack_half2(v[4], v[5]), pack_half2(v[6], v[7]));
+  };
+  layer_norm(z, a.ln1_g, a.ln1_b);
+  if (a.y32) st32(a.y32, z);
+  if (a.y16) st16(a.y16, z);
+  if (a.ype16 && a.pe) {
+    const float* pe = a.pe + (long long)(row % a.pe_period) * 256;
+    const float4 p0 = ld4(pe + c0), p1 = ld4(pe + c1);
+    const float e[8] = {z[0] + p0.x, z[1] + p0.y, z[2] + p0.z, z[3] + p0.w, z[4] + p1.x, z[5] + p1.y, z[6] + p1.z, z[7] + p1.w};
+    st16(a.ype16, e);
+  }
+  if (a.ln2_g) {
+    layer_norm(z, a.ln2_g, a.ln2_b);
+    if (a.d32) st32(a.d32, z);
+    if (a.d16) st16(a.d16, z);
+  }
+}
+
 // Row-wise LayerNorm (optional) + L2 normalisation (optional) to fp16 / fp32, one warp per row.
 //   mode bit0: LayerNorm with (g, b), eps 1e-5        (SideAdapter ln_post, side_adapter.py:203)
 //   mode bit1: divide by the L2 norm                  (ClipAdapter.normalize adapter.py:118-119; F.normalize side_adapter.py:205)

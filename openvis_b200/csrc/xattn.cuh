@@ -288,7 +288,10 @@ struct SelfAttnArgs {
   float scale_log2;   // d^-1/2 * log2(e)
 };
 
-__global__ void __launch_bounds__(256)
+// PARTS lanes per query row (keys j = part, part + PARTS, ...), each with its own online softmax; the partial
+// (max, sum, acc[32]) are merged with shuffles.  512 threads: PARTS = 4 for Q <= 128, PARTS = 2 for Q <= 256.
+template <int PARTS>
+__global__ void __launch_bounds__(512)
 self_attn_kernel(const SelfAttnArgs a) {
   extern __shared__ __half sm[];       // K [Q][32], V [Q][32]
   __half* sk = sm;
@@ -301,11 +304,11 @@ self_attn_kernel(const SelfAttnArgs a) {
     *reinterpret_cast<uint4*>(sv + row * 32 + ch * 8) = *reinterpret_cast<const uint4*>(a.v + r * 256 + head * 32 + ch * 8);
   }
   __syncthreads();
-  const int row = threadIdx.x;
-  if (row >= a.Q) return;
+  const int row = threadIdx.x / PARTS, part = threadIdx.x % PARTS;
+  const bool row_ok = row < a.Q;                 // (whole lane groups are in or out: the shuffles below stay uniform)
   float q[32], acc[32];
   {
-    const __half* qp = a.qk + ((long long)g * a.Q + row) * 512 + head * 32;
+    const __half* qp = a.qk + ((long long)g * a.Q + (row_ok ? row : 0)) * 512 + head * 32;
 #pragma unroll
     for (int d = 0; d < 32; d += 2) {
       const float2 f = __half22float2(*reinterpret_cast<const __half2*>(qp + d));
@@ -314,14 +317,15 @@ self_attn_kernel(const SelfAttnArgs a) {
     }
   }
   float m = -INFINITY, l = 0.f;
-  for (int j = 0; j < a.Q; ++j) {
-    float s = 0.f;
+  for (int j = part; j < a.Q; j += PARTS) {
+    float s0 = 0.f, s1 = 0.f;
 #pragma unroll
     for (int d = 0; d < 32; d += 2) {
       const float2 kf = __half22float2(*reinterpret_cast<const __half2*>(sk + j * 32 + d));
-      s = fmaf(q[d], kf.x, s);
-      s = fmaf(q[d + 1], kf.y, s);
+      s0 = fmaf(q[d], kf.x, s0);
+      s1 = fmaf(q[d + 1], kf.y, s1);
     }
+    const float s = s0 + s1;
     const float mn = fmaxf(m, s);
     const float c = exp2f(m - mn);
     const float p = exp2f(s - mn);
@@ -334,10 +338,41 @@ self_attn_kernel(const SelfAttnArgs a) {
     }
     m = mn;
   }
-  const float inv = 1.f / l;
-  __half* op = a.out + ((long long)g * a.Q + row) * 256 + head * 32;
+  // merge the key partitions of the row (adjacent lanes of the warp)
+  float mt = m;
 #pragma unroll
-  for (int d = 0; d < 32; d += 2) *reinterpret_cast<__half2*>(op + d) = __floats2half2_rn(acc[d] * inv, acc[d + 1] * inv);
+  for (int o = 1; o < PARTS; o <<= 1) mt = fmaxf(mt, __shfl_xor_sync(0xffffffffu, mt, o));
+  const float sc = (m == -INFINITY) ? 0.f : exp2f(m - mt);
+  l *= sc;
+#pragma unroll
+  for (int o = 1; o < PARTS; o <<= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+  const float inv = 1.f / l;
+#pragma unroll
+  for (int d = 0; d < 32; ++d) {
+    float v = acc[d] * sc;
+#pragma unroll
+    for (int o = 1; o < PARTS; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    acc[d] = v * inv;
+  }
+  if (row_ok) {      // each lane of the group writes its share of the 32 channels
+    constexpr int CH = 32 / PARTS;       // 8 or 16
+    __half* op = a.out + ((long long)g * a.Q + row) * 256 + head * 32 + part * CH;
+    // (acc[] is indexed with compile-time constants only: pick the lane's values with selects)
+#pragma unroll
+    for (int e = 0; e < CH; e += 8) {
+      float o[8];
+#pragma unroll
+      for (int x = 0; x < 8; ++x) {
+        float v = acc[e + x];
+#pragma unroll
+        for (int pp = 1; pp < PARTS; ++pp) v = (part == pp) ? acc[pp * CH + e + x] : v;
+        o[x] = v;
+      }
+      uint4 u;
+      u.x = pack_half2(o[0], o[1]); u.y = pack_half2(o[2], o[3]); u.z = pack_half2(o[4], o[5]); u.w = pack_half2(o[6], o[7]);
+      *reinterpret_cast<uint4*>(op + e) = u;
+    }
+  }
 }
 
 }  // namespace ovis

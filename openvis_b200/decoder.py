@@ -369,6 +369,9 @@ class _B200MaskedDecoderBase(nn.Module):
         ws["q16"], ws["att16"], ws["qk16"], ws["v16"], ws["sa16"] = h(R, C), h(R, C), h(R, 2 * C), h(R, C), h(R, C)
         ws["h16"] = h(R, self.dim_feedforward)
         ws["m1"], ws["m2"], ws["me16"] = h(R, C), h(R, C), h(R, C)
+        # scratch of the few-rows linear+LayerNorm path (split-K partials); Frame decoders with thousands of rows use
+        # the fused epilogue and need none
+        ws["split"] = f((self.dim_feedforward // 256) * ((R + 127) // 128) * 128 * 256) if R <= 2048 else None
         ws["bits"] = [torch.zeros(G, (Tg * n + 31) // 32, Q, dtype=torch.int32, device=device) for n in N]
         ws["flags"] = torch.zeros(self.num_layers + 1, G, Q, dtype=torch.uint8, device=device)
         plans = [L.xattn_plan(G, Q, Tg * n) for n in N]
@@ -468,17 +471,18 @@ class _B200MaskedDecoderBase(nn.Module):
             L.xattn(ws["q16"], ws["k"][i], ws["v"][i], ws["bits"][l], ws["flags"][i], G, Q, Q, Tg * N[l], ws["splits"][l],
                     ws["o_part"], ws["ml_part"], ws["att16"])
             L.linear_ln_f16(ws["att16"], lw["xo_w"], lw["xo_b"], ws["z32"], lw["ln_x"], None, W["qe"],
-                            y32=ws["z32"], y16=ws["z16"], ype16=ws["ze16"])
+                            y32=ws["z32"], y16=ws["z16"], ype16=ws["ze16"], split_ws=ws["split"])
             # self-attention (video_..._decoder.py:52-62)
             L.linear_f16(ws["ze16"], lw["sqk_w"], lw["sqk_b"], out=ws["qk16"])
             L.linear_f16(ws["z16"], lw["sv_w"], lw["sv_b"], out=ws["v16"])
             L.self_attn(ws["qk16"], ws["v16"], ws["sa16"], G, Q)
             L.linear_ln_f16(ws["sa16"], lw["so_w"], lw["so_b"], ws["z32"], lw["ln_s"], None, W["qe"],
-                            y32=ws["z32"], y16=ws["z16"], ype16=ws["ze16"])
+                            y32=ws["z32"], y16=ws["z16"], ype16=ws["ze16"], split_ws=ws["split"])
             # FFN (video_..._decoder.py:175-179) + decoder_norm of the following prediction head
             L.linear_f16(ws["z16"], lw["f1_w"], lw["f1_b"], relu=True, out=ws["h16"])
             L.linear_ln_f16(ws["h16"], lw["f2_w"], lw["f2_b"], ws["z32"], lw["ln_f"], W["dn"], W["qe"],
-                            y32=ws["z32"], y16=ws["z16"], ype16=ws["ze16"], d32=ws["d32"], d16=ws["d16"][i + 1])
+                            y32=ws["z32"], y16=ws["z16"], ype16=ws["ze16"], d32=ws["d32"], d16=ws["d16"][i + 1],
+                            split_ws=ws["split"])
             if i + 1 < nl:
                 head_bits(i + 1, (i + 1) % 3)
 

@@ -55,8 +55,12 @@ def test_linear_strided_input():
     assert _maxerr(out, x.double() @ w.double().T) < 1e-3
 
 
-@pytest.mark.parametrize("rows,K,two", [(100, 256, False), (100, 2048, True), (3600, 256, True), (333, 2048, False)])
-def test_linear_ln(rows, K, two):
+@pytest.mark.parametrize("split", [False, True])
+@pytest.mark.parametrize("rows,K,two", [(100, 256, False), (100, 2048, True), (3600, 256, True), (333, 2048, False),
+                                        (400, 2048, True)])
+def test_linear_ln(rows, K, two, split):
+    """Fused epilogue (split=False) and the few-rows split-K + row-parallel LayerNorm path (split=True; rows > 2048
+    fall back to the fused one inside the library)."""
     x = _randn(rows, K, seed=1).half()
     w = _randn(256, K, seed=2, scale=K ** -0.5).half()
     b = _randn(256, seed=3)
@@ -69,8 +73,9 @@ def test_linear_ln(rows, K, two):
     ype16 = torch.empty_like(y16)
     d32 = torch.empty_like(y32)
     d16 = torch.empty_like(y16)
+    ws = torch.empty((K // 256) * ((rows + 127) // 128) * 128 * 256, device="cuda") if split else None
     L.linear_ln_f16(x, w, b, resid, (g1, b1), (g2, b2) if two else None, pe, y32, y16, ype16, d32 if two else None,
-                    d16 if two else None)
+                    d16 if two else None, split_ws=ws)
     v = x.double() @ w.double().T + b.double() + resid.double()
     y = torch.nn.functional.layer_norm(v, (256,), g1.double(), b1.double(), 1e-5)
     assert _maxerr(y32, y) < 2e-4

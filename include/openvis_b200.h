@@ -65,6 +65,13 @@ int ovis_rownorm(const float* in, const float* g, const float* b, float* out32, 
  * out = act((acc + bias) * scale); ldx/ldo in elements; K % 64 == 0; x, w 16-byte aligned. */
 int ovis_linear_f16(const void* x_f16, long long rows, int K, int ldx, const void* w_f16, int N,
                     const float* bias, float scale, int relu, void* out, int ldo, int out_f32, void* stream);
+/* The same with an activation selector and an optional fp32 residual added after it (residual connections of the
+ * CLIP blocks of the SAN side path, mask_adapted_clip/model.py:265-268):
+ * out = act((acc + bias) * scale) + resid;  act: 0 none, 1 ReLU, 2 QuickGELU x*sigmoid(1.702x) (model.py:232-234);
+ * resid [rows][ldo] fp32 or null, may alias out. */
+int ovis_linear_act_f16(const void* x_f16, long long rows, int K, int ldx, const void* w_f16, int N,
+                        const float* bias, float scale, int act, const float* resid, void* out, int ldo,
+                        int out_f32, void* stream);
 /* Linear(K -> 256) + residual + LayerNorm [+ second LayerNorm], the post-norm tails of
  * CrossAttentionLayer/SelfAttentionLayer/FFNLayer.forward_post (video_...decoder.py:119-120, 59-60, 177-178)
  * fused with decoder_norm (frame_...decoder.py:140).  Any output pointer may be null.
@@ -121,6 +128,14 @@ int ovis_self_attn(const void* qk_f16, const void* v_f16, void* out_f16, int G, 
  * frames with a non-empty mask, softmax over K.  logits [T][Q][K], valid [T][Q] -> probs [Q][K], qvalid [Q]. */
 int ovis_clip_aggregate(const float* logits, const unsigned char* valid, float* probs, unsigned char* qvalid,
                         int T, int Q, int K, void* stream);
+/* SAN / BriVIS side path.  Adaptive max-pool of the per-head attention biases to the CLIP
+ * grid only (step 1 of SideAdapter._build_attn_biases, side_adapter.py:241-250): bias [BN][Q][h][w] -> pooled [BN][Q][gh*gw]. */
+int ovis_san_pool_bias(const float* bias, float* pooled, int BN, int Q, int h, int w, int gh, int gw, void* stream);
+/* Attention of one post-split CLIP block (BiasedResidualAttentionBlock.attention, side_adapter.py:72-73) over
+ * [Q SOS | CLS | L patches] tokens per frame, d = 64, with the additive bias matrix of _build_attn_biases
+ * (side_adapter.py:252-266) applied from `pooled` without materialising it.
+ * qkv [B*(Q+1+L)][3*heads*64] f16 (in_proj output, q|k|v), out [B*(Q+1+L)][heads*64] f16. */
+int ovis_san_attn(const void* qkv_f16, const float* pooled, void* out_f16, int B, int Q, int L, int heads, void* stream);
 /* SideAdapter._build_attn_biases (clip_adapter/side_adapter.py:237-270): adaptive max-pool to (gh, gw) fused with
  * the [Q+1+L]^2 additive-bias construction.  bias [B][n][Q][h][w] -> out [B*n][Q+1+L][Q+1+L]. */
 int ovis_san_attn_bias(const float* bias, float* out, int BN, int Q, int h, int w, int gh, int gw, void* stream);

@@ -27,6 +27,8 @@ SIGNATURES = {
     "ovis_init_queries": (_c_int, [_vp] * 9 + [_c_int, _c_int, _vp]),
     "ovis_rownorm": (_c_int, [_vp] * 5 + [_c_int, _c_int, _c_int, _vp]),
     "ovis_linear_f16": (_c_int, [_vp, _c_ll, _c_int, _c_int, _vp, _c_int, _vp, _c_float, _c_int, _vp, _c_int, _c_int, _vp]),
+    "ovis_linear_act_f16": (_c_int, [_vp, _c_ll, _c_int, _c_int, _vp, _c_int, _vp, ctypes.c_float, _c_int, _vp, _vp, _c_int,
+                                     _c_int, _vp]),
     "ovis_linear_ln_f16": (_c_int, [_vp, _c_ll, _c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _c_int,
                                     _vp, _vp, _vp, _vp, _vp, _vp, _c_ll, _vp]),
     "ovis_kv_proj_f16": (_c_int, [_vp, _vp, _c_ll, _vp, _c_int, _vp, _vp, _vp]),
@@ -38,6 +40,8 @@ SIGNATURES = {
     "ovis_xattn": (_c_int, [_vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp]),
     "ovis_self_attn": (_c_int, [_vp, _vp, _vp, _c_int, _c_int, _vp]),
     "ovis_clip_aggregate": (_c_int, [_vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _vp]),
+    "ovis_san_pool_bias": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _vp]),
+    "ovis_san_attn": (_c_int, [_vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _vp]),
     "ovis_san_attn_bias": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _vp]),
 }
 
@@ -200,6 +204,40 @@ def linear_f16(x, w, bias=None, scale=1.0, relu=False, out=None, out_f32=False):
         out = torch.empty(rows, N, dtype=torch.float32 if out_f32 else torch.float16, device=x.device)
     _check(lib.ovis_linear_f16(_p(x), rows, K, x.stride(0), _p(w), N, _p(bias), float(scale), int(relu), _p(out),
                                out.stride(0), int(out_f32), _stream()))
+    return out
+
+
+def linear_act_f16(x, w, bias=None, scale=1.0, act=0, resid=None, out=None, out_f32=False):
+    """out = act((x @ w^T + bias) * scale) + resid; act 0 none / 1 ReLU / 2 QuickGELU; resid fp32 [rows, N] (may be `out`)."""
+    lib = load()
+    assert x.dtype == torch.float16 and w.dtype == torch.float16 and x.stride(-1) == 1 and w.is_contiguous()
+    rows, K = x.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty(rows, N, dtype=torch.float32 if out_f32 else torch.float16, device=x.device)
+    if resid is not None:
+        _req(resid, torch.float32, "resid")
+        assert resid.shape == (rows, N) and resid.stride(0) == out.stride(0)
+    _check(lib.ovis_linear_act_f16(_p(x), rows, K, x.stride(0), _p(w), N, _p(bias), float(scale), int(act), _p(resid),
+                                   _p(out), out.stride(0), int(out_f32), _stream()))
+    return out
+
+
+def san_pool_bias(bias, grid_hw):
+    """bias [B, n, Q, h, w] fp32 -> pooled [B*n, Q, gh*gw] (adaptive max-pool to the CLIP grid)."""
+    lib = load()
+    _req(bias, torch.float32, "bias")
+    B, n, Q, h, w = bias.shape
+    gh, gw = grid_hw
+    out = torch.empty(B * n, Q, gh * gw, dtype=torch.float32, device=bias.device)
+    _check(lib.ovis_san_pool_bias(_p(bias), _p(out), B * n, Q, h, w, gh, gw, _stream()))
+    return out
+
+
+def san_attn(qkv, pooled, out, B, Q, L, heads=12):
+    lib = load()
+    assert qkv.dtype == torch.float16 and qkv.is_contiguous() and out.dtype == torch.float16 and out.is_contiguous()
+    _check(lib.ovis_san_attn(_p(qkv), _p(pooled), _p(out), B, Q, L, heads, _stream()))
     return out
 
 

@@ -15,6 +15,7 @@
 #include "xattn.cuh"
 #include "xattn_tc.cuh"
 #include "xattn_tc2.cuh"
+#include "san_attn.cuh"
 
 using namespace ovis;
 
@@ -447,6 +448,32 @@ int ovis_linear_f16(const void* x, long long rows, int K, int ldx, const void* w
   return launch_gemm(x, rows, K, ldx, w, N, K, a, bn, (cudaStream_t)stream);
 }
 
+int ovis_linear_act_f16(const void* x, long long rows, int K, int ldx, const void* w, int N, const float* bias, float scale,
+                        int act, const float* resid, void* out, int ldo, int out_f32, void* stream) {
+  CHECK_ARG(x && w && out && rows > 0 && N > 0 && ldx >= K && ldo >= N && act >= 0 && act <= 2, "bad arguments");
+  CHECK_ARG(rows < (1ll << 31), "too many rows");
+  GemmArgs a;
+  init_args(a);
+  a.rows_per_group = (int)rows;
+  a.a_group_stride = (int)rows;
+  a.N = N;
+  a.K = K;
+  a.epi = EPI_STORE;
+  const int bn = (N <= 128) ? 128 : 256;
+  const int nt = (N + bn - 1) / bn;
+  CHECK_ARG(nt <= GEMM_MAX_NTILES, "N too large");
+  for (int t = 0; t < nt; ++t) {
+    a.out[t] = out_f32 ? (void*)((float*)out + (long long)t * bn) : (void*)((__half*)out + (long long)t * bn);
+    a.bias[t] = bias ? bias + (long long)t * bn : nullptr;
+  }
+  a.ldo = ldo;
+  a.out_f32 = out_f32;
+  a.relu = act;
+  a.scale = scale;
+  a.resid_st = resid;
+  return launch_gemm(x, rows, K, ldx, w, N, K, a, bn, (cudaStream_t)stream);
+}
+
 int ovis_linear_ln_f16(const void* x, long long rows, int K, const void* w, const float* bias, const float* resid,
                        const float* ln1_g, const float* ln1_b, const float* ln2_g, const float* ln2_b, const float* pe,
                        int pe_period, float* y32, void* y16, void* ype16, float* d32, void* d16, float* split_ws,
@@ -720,6 +747,40 @@ int ovis_clip_aggregate(const float* logits, const unsigned char* valid, float* 
   if (rc) return rc;
   clip_aggregate_kernel<<<Q, 256, (size_t)K * sizeof(float), (cudaStream_t)stream>>>(logits, valid, probs, qvalid, T, Q, K);
   return check_launch("clip_aggregate_kernel");
+}
+
+int ovis_san_pool_bias(const float* bias, float* pooled, int BN, int Q, int h, int w, int gh, int gw, void* stream) {
+  CHECK_ARG(bias && pooled && BN > 0 && Q > 0 && h > 0 && w > 0 && gh > 0 && gw > 0, "bad arguments");
+  int rc = device_info(nullptr);
+  if (rc) return rc;
+  const long long total = (long long)BN * Q * gh * gw;
+  san_pool_bias_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(bias, pooled, total, h, w, gh, gw);
+  return check_launch("san_pool_bias_kernel");
+}
+
+int ovis_san_attn(const void* qkv, const float* pooled, void* out, int B, int Q, int L, int heads, void* stream) {
+  CHECK_ARG(qkv && out && B > 0 && Q >= 0 && L > 0 && heads > 0, "bad arguments");
+  CHECK_ARG((size_t)(1 + L) * 64 * 2 * sizeof(__half) <= 200 * 1024, "too many patch tokens for the shared-memory K/V stage");
+  int rc = device_info(nullptr);
+  if (rc) return rc;
+  const size_t smem = (size_t)(1 + L) * 64 * 2 * sizeof(__half);
+  static size_t attr_smem[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (smem > 48 * 1024 && attr_smem[dev] < smem) {
+    cudaError_t e = cudaFuncSetAttribute(san_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      snprintf(g_err, sizeof(g_err), "san_attn: cudaFuncSetAttribute(smem) failed: %s", cudaGetErrorString(e));
+      return OVIS_ERR_CUDA;
+    }
+    attr_smem[dev] = smem;
+  }
+  SanAttnArgs a;
+  a.qkv = (const __half*)qkv; a.pooled = pooled; a.out = (__half*)out;
+  a.Q = Q; a.L = L; a.heads = heads;
+  a.scale_log2 = 0.125f * 1.4426950408889634f;   // 64^-1/2 * log2(e)
+  san_attn_kernel<<<dim3(heads, B), 256, smem, (cudaStream_t)stream>>>(a);
+  return check_launch("san_attn_kernel");
 }
 
 int ovis_san_attn_bias(const float* bias, float* out, int BN, int Q, int h, int w, int gh, int gw, void* stream) {

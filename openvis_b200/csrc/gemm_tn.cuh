@@ -47,8 +47,9 @@ struct GemmArgs {
   const float* bias[GEMM_MAX_NTILES];  // per n-tile bias (indexed by column within tile) or null
   int ldo;                // output row stride (elements)
   int out_f32;            // 0: fp16 output, 1: fp32 output
-  int relu;
+  int relu;               // activation: 0 none, 1 ReLU, 2 QuickGELU x * sigmoid(1.702 x) (CLIP blocks, model.py:232-234)
   float scale;
+  const float* resid_st;  // optional fp32 [rows][ldo] added after the activation (residual connections; may alias out)
   int a_alt;              // 1: odd n-tiles read their A operand from the second tensor map (key / value operands)
   int tma_store;          // 1: EPI_STORE writes through GemmOutMaps (single group, 16-byte aligned pitch)
   // ---- EPI_LN
@@ -158,9 +159,27 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmArgs& args, const C
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] *= args.scale;
         }
-        if (args.relu) {
+        if (args.relu == 1) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+        } else if (args.relu == 2) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __fdividef(f[j], 1.f + __expf(-1.702f * f[j]));
+        }
+        if (args.resid_st && r_warp0 + lane < args.rows_per_group) {
+          const float* rp = args.resid_st + (grow0 + lane) * args.ldo + (long long)nt * BN + u0 + hh * 32;
+          const int nleft = args.N - (col_base + u0 + hh * 32);
+          if (nleft >= 32 && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 q4 = *reinterpret_cast<const float4*>(rp + 4 * j);
+              f[4 * j] += q4.x; f[4 * j + 1] += q4.y; f[4 * j + 2] += q4.z; f[4 * j + 3] += q4.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < nleft) f[j] += rp[j];
+          }
         }
         if (args.out_f32) {
 #pragma unroll

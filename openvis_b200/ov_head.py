@@ -5,9 +5,13 @@ ClipLogitHead     -- ClipAdapter.normalize / cal_sim_logits / text cache (clip_a
 SideAdapterTail   -- SideAdapter._build_attn_biases, the ln_post/proj/normalize tail of post_encode_image and
                      cal_sim_logits (clip_adapter/side_adapter.py:201-207, 234-270).
 
-The frozen CLIP towers themselves (text encoder, ViT blocks, crop/roi_align preprocessing) are out of scope
-(SURVEY.md section 8): text embeddings are supplied already encoded ("cached text embeddings", north_star) and
-region / SOS-token features come from the caller.
+SideAdapterBlocks -- SURVEY.md section 8 (f) rank 1: the post-split CLIP blocks of SideAdapter.post_encode_image
+                     (side_adapter.py:176-209) on [Q SOS | CLS | patches] tokens, the additive bias applied inside the
+                     attention kernel from the pooled per-head biases (never materialised), then the tail above.
+
+The rest of the frozen CLIP towers (text encoder, the ViT blocks before the split, crop/roi_align preprocessing) is out
+of scope: text embeddings are supplied already encoded ("cached text embeddings", north_star) and
+region features / the split-point CLS + patch features come from the caller.
 """
 from typing import List
 
@@ -106,3 +110,82 @@ class SideAdapterTail(_TextCache):
         f16 = L.cast_f16(image_feats.reshape(-1, shp[-1]).float().contiguous())
         out = L.linear_f16(f16, self._text_f16(text_feats), None, scale=float(self.logit_scale_exp), out_f32=True)
         return out.view(*shp[:-1], text_feats.shape[0])
+
+
+class SideAdapterBlocks:
+    """Drop-in for the post-split half of ``SideAdapter.post_encode_image`` (side_adapter.py:176-209).
+
+    Weights are the frozen CLIP visual tower's (``freeze_params``, side_adapter.py:105): load them with
+    ``load_clip_visual_state_dict(clip_model.visual.state_dict())`` -- the keys read are
+    ``transformer.resblocks.{i}.*`` for i >= broken_idx, ``ln_post.*`` and ``proj``.  fp16 GEMM operands, fp32
+    accumulation, LayerNorm / softmax statistics / residual stream in fp32.  No CPU path."""
+
+    def __init__(self, num_queries=100, broken_idx=9, num_layers=12, width=768, heads=12):
+        self.sos_token_num = num_queries
+        self.blocks = tuple(range(broken_idx, num_layers))
+        self.width, self.heads = width, heads
+        self.tail = SideAdapterTail()
+        self._w = None
+
+    def load_clip_visual_state_dict(self, sd, prefix="transformer.resblocks."):
+        f32 = lambda t: t.detach().float().contiguous().cuda()
+        w16 = lambda t: L.cast_f16(f32(t))
+        W = {}
+        for i in self.blocks:
+            g = lambda k: sd[f"{prefix}{i}.{k}"]
+            W[i] = dict(ln1=(f32(g("ln_1.weight")), f32(g("ln_1.bias"))), ln2=(f32(g("ln_2.weight")), f32(g("ln_2.bias"))),
+                        in_w=w16(g("attn.in_proj_weight")), in_b=f32(g("attn.in_proj_bias")),
+                        out_w=w16(g("attn.out_proj.weight")), out_b=f32(g("attn.out_proj.bias")),
+                        fc_w=w16(g("mlp.c_fc.weight")), fc_b=f32(g("mlp.c_fc.bias")),
+                        pj_w=w16(g("mlp.c_proj.weight")), pj_b=f32(g("mlp.c_proj.bias")))
+        if "ln_post.weight" in sd:
+            W["ln_post"] = (f32(sd["ln_post.weight"]), f32(sd["ln_post.bias"]))
+            W["proj"] = f32(sd["proj"])
+        self._w = W
+        return self
+
+    @torch.no_grad()
+    def post_blocks(self, feats, attn_bias):
+        """feats = (cls_token [1, n, W], pix_feat [n, W, h, w]); attn_bias [n, heads, Q, H', W'] fp32 (or a one-element
+        list, or None).  Returns the SOS tokens [n, Q, W] fp32 after the post-split blocks (before ln_post)."""
+        if self._w is None:
+            raise RuntimeError("SideAdapterBlocks: load_clip_visual_state_dict() first")
+        cls_token, pix = feats
+        if not pix.is_cuda:
+            raise L.OvisError("openvis_b200 has no CPU path: inputs must be CUDA tensors on an sm_100 device")
+        if isinstance(attn_bias, (list, tuple)):
+            if len(attn_bias) != 1:
+                raise NotImplementedError("one attention-bias tensor shared by all blocks (side_adapter.py:268-269)")
+            attn_bias = attn_bias[0]
+        n, Wd, h, w = pix.shape
+        Q, Lp = self.sos_token_num, h * w
+        Lt = Q + 1 + Lp
+        with torch.cuda.device(pix.device):
+            # token assembly [Q SOS copies of CLS | CLS | patches] (side_adapter.py:182-187, 196), frame-major rows
+            x = torch.empty(n, Lt, Wd, dtype=torch.float32, device=pix.device)
+            x[:, :Q + 1] = cls_token[0].float()[:, None, :]
+            x[:, Q + 1:] = pix.float().flatten(2).transpose(1, 2)
+            X = x.view(n * Lt, Wd)
+            pooled = None
+            if attn_bias is not None:
+                if attn_bias.shape[1] == 1:
+                    attn_bias = attn_bias.expand(-1, self.heads, -1, -1, -1)
+                pooled = L.san_pool_bias(attn_bias.float().contiguous(), (h, w))
+            att16 = torch.empty(n * Lt, Wd, dtype=torch.float16, device=pix.device)
+            for i in self.blocks:
+                p = self._w[i]
+                _, y16 = L.rownorm(X, p["ln1"][0], p["ln1"][1], layer_norm=True, want32=False)
+                qkv = L.linear_f16(y16, p["in_w"], p["in_b"])
+                L.san_attn(qkv, pooled, att16, n, Q, Lp, self.heads)
+                L.linear_act_f16(att16, p["out_w"], p["out_b"], resid=X, out=X, out_f32=True)
+                _, y16 = L.rownorm(X, p["ln2"][0], p["ln2"][1], layer_norm=True, want32=False)
+                h16 = L.linear_act_f16(y16, p["fc_w"], p["fc_b"], act=2)
+                L.linear_act_f16(h16, p["pj_w"], p["pj_b"], resid=X, out=X, out_f32=True)
+            return x[:, :Q].contiguous()
+
+    @torch.no_grad()
+    def post_encode_image(self, feats, attn_bias):
+        """SideAdapter.post_encode_image: post-split blocks -> ln_post -> @ proj -> F.normalize; returns [n, Q, D]."""
+        sos = self.post_blocks(feats, attn_bias)
+        lw, lb = self._w["ln_post"]
+        return self.tail.sos_tail(sos, lw, lb, self._w["proj"])

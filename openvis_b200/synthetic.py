@@ -44,6 +44,49 @@ def decoder_param_shapes(kind="frame", Q=100, C=256, F_=2048, L=9, num_classes=1
     return s
 
 
+def clip_block_param_shapes(width=768, blocks=(9, 10, 11)):
+    """state_dict names of the post-split CLIP blocks the SAN side path runs (ViT-B/16: width 768, 12 heads;
+    side_adapter.py:188 `resblocks[self.broken_idx:]`), relative to `clip_model.visual.transformer.resblocks`."""
+    s = {}
+    for i in blocks:
+        s[f"{i}.ln_1.weight"] = (width,)
+        s[f"{i}.ln_1.bias"] = (width,)
+        s[f"{i}.attn.in_proj_weight"] = (3 * width, width)
+        s[f"{i}.attn.in_proj_bias"] = (3 * width,)
+        s[f"{i}.attn.out_proj.weight"] = (width, width)
+        s[f"{i}.attn.out_proj.bias"] = (width,)
+        s[f"{i}.ln_2.weight"] = (width,)
+        s[f"{i}.ln_2.bias"] = (width,)
+        s[f"{i}.mlp.c_fc.weight"] = (4 * width, width)
+        s[f"{i}.mlp.c_fc.bias"] = (4 * width,)
+        s[f"{i}.mlp.c_proj.weight"] = (width, 4 * width)
+        s[f"{i}.mlp.c_proj.bias"] = (width,)
+    return s
+
+
+def seeded_clip_block_params(seed=0, width=768, blocks=(9, 10, 11)):
+    """Deterministic CLIP-block weights with the scales of CLIP.initialize_parameters (attn std width^-0.5, output
+    projections damped by (2 * layers)^-0.5, fc std (2 * width)^-0.5), LayerNorm near identity."""
+    g = torch.Generator().manual_seed(seed)
+    shapes = clip_block_param_shapes(width, blocks)
+    attn_std, proj_std, fc_std = width ** -0.5, (width ** -0.5) * (2 * 12) ** -0.5, (2 * width) ** -0.5
+    out = {}
+    for name in sorted(shapes):
+        shp = shapes[name]
+        if name.endswith("ln_1.weight") or name.endswith("ln_2.weight"):
+            t = 1.0 + 0.1 * torch.randn(shp, generator=g)
+        elif name.endswith("bias"):
+            t = 0.02 * torch.randn(shp, generator=g)
+        elif name.endswith("in_proj_weight"):
+            t = attn_std * torch.randn(shp, generator=g)
+        elif name.endswith("c_fc.weight"):
+            t = fc_std * torch.randn(shp, generator=g)
+        else:
+            t = proj_std * torch.randn(shp, generator=g)
+        out[name] = t
+    return out
+
+
 def seeded_params(shapes, seed=0):
     """Deterministic weights that do not need the reference to regenerate: names in sorted order, one
     torch.Generator.  Scales mimic the reference's inits (xavier-like for matrices, N(0,1) embeddings,

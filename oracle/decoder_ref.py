@@ -315,7 +315,46 @@ def san_build_attn_bias(attn_bias, grid_hw):
     return m
 
 
+def clip_block(P, i, x, attn_mask, nheads=12):
+    """BiasedResidualAttentionBlock.forward (side_adapter.py:70-78) over mask_adapted_clip's ResidualAttentionBlock
+    (model.py:237-268): x + MHA(ln_1(x), additive float mask) ; x + c_proj(QuickGELU(c_fc(ln_2(x)))).
+    x [Lt, n, W] sequence-first like the reference; attn_mask [n*heads, Lt, Lt] additive fp32."""
+    Lt, n, Wd = x.shape
+    d = Wd // nheads
+    y = layer_norm(x, P[f"{i}.ln_1.weight"], P[f"{i}.ln_1.bias"])
+    qkv = y @ P[f"{i}.attn.in_proj_weight"].T + P[f"{i}.attn.in_proj_bias"]
+    q, k, v = qkv.split(Wd, dim=-1)
+    # [Lt, n, W] -> [n*heads, Lt, d]  (F.multi_head_attention_forward: batch index = b * heads + h)
+    shp = lambda t: t.reshape(Lt, n * nheads, d).transpose(0, 1)
+    q, k, v = shp(q) * d ** -0.5, shp(k), shp(v)
+    s_ = q @ k.transpose(-1, -2)
+    if attn_mask is not None:
+        s_ = s_ + attn_mask
+    a = (s_.softmax(-1) @ v).transpose(0, 1).reshape(Lt, n, Wd)
+    x = x + (a @ P[f"{i}.attn.out_proj.weight"].T + P[f"{i}.attn.out_proj.bias"])
+    y = layer_norm(x, P[f"{i}.ln_2.weight"], P[f"{i}.ln_2.bias"])
+    h = y @ P[f"{i}.mlp.c_fc.weight"].T + P[f"{i}.mlp.c_fc.bias"]
+    h = h * torch.sigmoid(1.702 * h)                                   # QuickGELU (model.py:232-234)
+    return x + (h @ P[f"{i}.mlp.c_proj.weight"].T + P[f"{i}.mlp.c_proj.bias"])
+
+
+def san_post_blocks(P, cls_token, pix_feat, attn_bias, num_queries, blocks=(9, 10, 11), nheads=12):
+    """SideAdapter.post_encode_image up to (not including) ln_post (side_adapter.py:176-199):
+    cls_token [1, n, W], pix_feat [n, W, h, w], attn_bias [n, heads, Q, H', W'].
+    Token order [Q SOS copies of CLS | CLS | h*w patches]; the same additive bias matrix for every block.
+    Returns the SOS tokens [n, Q, W]."""
+    n, c, h, w = pix_feat.shape
+    x = torch.cat([cls_token, pix_feat.reshape(n, c, -1).permute(2, 0, 1)])          # [1+L, n, W]
+    sos = cls_token.repeat(num_queries, 1, 1)
+    mask = san_build_attn_bias(attn_bias, (h, w)) if attn_bias is not None else None
+    x = torch.cat([sos, x], dim=0)
+    for i in blocks:
+        x = clip_block(P, i, x, mask, nheads)
+    return x[:num_queries].permute(1, 0, 2)
+
+
 # --------------------------------------------------------------------------------------------
 # seeded synthetic parameters / inputs: shared with bench.py, so they live in the (oracle-free) product package
 # --------------------------------------------------------------------------------------------
-from openvis_b200.synthetic import decoder_param_shapes, seeded_inputs, seeded_params  # noqa: E402,F401
+from openvis_b200.synthetic import (clip_block_param_shapes, decoder_param_shapes, seeded_clip_block_params,  # noqa: E402,F401
+                                    seeded_inputs, seeded_params)

@@ -86,11 +86,38 @@ def make_san_tail_fixture():
     print("wrote san_tail", {k: v.shape for k, v in rec.items()})
 
 
+def san_blocks_inputs(n=2, Q=12, seed=91):
+    """Seeded inputs of the post-split CLIP blocks: CLS token, 14x14 patch features, per-head attention biases."""
+    g = torch.Generator().manual_seed(seed)
+    cls = torch.randn(1, n, 768, generator=g)
+    pix = torch.randn(n, 768, 14, 14, generator=g)
+    bias = 3.0 * torch.randn(n, 12, Q, 24, 40, generator=g)
+    return cls, pix, bias
+
+
+def make_san_blocks_fixture(n=2, Q=12, pseed=6):
+    """SideAdapter.post_encode_image (side_adapter.py:176-209) of the reference, with the three post-split blocks
+    loaded from oracle.decoder_ref.seeded_clip_block_params (ln_post / proj stay the seeded CLIP's own = san_tail.npz)."""
+    s = R.side_adapter_module()
+    torch.manual_seed(3)
+    sa = s.SideAdapter(num_queries=Q).eval()
+    P = O.seeded_clip_block_params(pseed)
+    missing, unexpected = sa.clip_model.visual.transformer.resblocks.load_state_dict(P, strict=False)
+    assert not unexpected and all(not k.startswith(("9.", "10.", "11.")) for k in missing)
+    cls, pix, bias = san_blocks_inputs(n, Q)
+    with torch.no_grad():
+        f = sa.post_encode_image((cls, pix), bias)
+    rec = dict(meta=np.array([n, Q, pseed]), clip_feats=f.numpy())
+    np.savez_compressed(os.path.join(GOLDEN, "san_blocks.npz"), **rec)
+    print("wrote san_blocks", {k: v.shape for k, v in rec.items()})
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     for case in DECODER_CASES:
         make_decoder_fixture(*case)
     make_san_tail_fixture()
+    make_san_blocks_fixture()
 
 
 if __name__ == "__main__":

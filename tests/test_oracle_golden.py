@@ -131,3 +131,34 @@ def test_build_attn_bias_matches_live_reference():
     bias = torch.randn(1, 12, 9, 46, 80)
     ref = sa._build_attn_biases([bias], sa.num_heads, 3, target_shape=(14, 14))[0]
     assert torch.equal(ref, O.san_build_attn_bias(bias, (14, 14)))
+
+
+def test_san_blocks_match_golden(golden_dir):
+    """Post-split CLIP blocks of the SAN side path: the restatement reproduces the reference's
+    own SideAdapter.post_encode_image (fixture: oracle.make_golden.make_san_blocks_fixture)."""
+    from oracle.make_golden import san_blocks_inputs
+    g = np.load(os.path.join(golden_dir, "san_blocks.npz"))
+    st = np.load(os.path.join(golden_dir, "san_tail.npz"))
+    n, Q, pseed = [int(v) for v in g["meta"]]
+    P = O.seeded_clip_block_params(pseed)
+    cls, pix, bias = san_blocks_inputs(n, Q)
+    sos = O.san_post_blocks(P, cls, pix, bias, Q)
+    f, _ = O.san_sos_tail(sos, torch.tensor(st["ln_w"]), torch.tensor(st["ln_b"]), torch.tensor(st["proj"]),
+                          torch.zeros(1, 512), 1.0)
+    _close(f, g["clip_feats"], atol=2e-6)
+
+
+def test_san_bias_structure_is_what_the_kernel_assumes():
+    """The attention kernel skips the keys that carry -100 and keeps the SOS diagonal: check that this is exactly the
+    structure of the reference's additive matrix, and that dropping those keys does not change a softmax in fp32."""
+    g = torch.Generator().manual_seed(0)
+    Q, L = 5, 196
+    m = O.san_build_attn_bias(torch.randn(1, 12, Q, 24, 40, generator=g), (14, 14))[0]
+    assert (m[:, :Q][~torch.eye(Q + 1 + L, Q, dtype=torch.bool)] == -100).all()     # SOS keys: -100 off the diagonal
+    assert (m[torch.arange(Q), torch.arange(Q)] == 0).all()
+    assert (m[:Q, Q] == -100).all() and (m[Q:, Q:] == 0).all()
+    s = torch.randn(Q + 1 + L, Q + 1 + L, generator=g) * 3
+    full = (s + m).softmax(-1)
+    keep = m > -50
+    part = (s + m).masked_fill(~keep, float("-inf")).softmax(-1)
+    assert torch.equal(full.masked_fill(~keep, 0.0), part) or (full.masked_fill(~keep, 0.0) - part).abs().max() < 1e-30

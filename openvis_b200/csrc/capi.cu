@@ -763,10 +763,31 @@ int ovis_san_attn(const void* qkv, const float* pooled, void* out, int B, int Q,
   CHECK_ARG((size_t)(1 + L) * 64 * 2 * sizeof(__half) <= 200 * 1024, "too many patch tokens for the shared-memory K/V stage");
   int rc = device_info(nullptr);
   if (rc) return rc;
-  const size_t smem = (size_t)(1 + L) * 64 * 2 * sizeof(__half);
-  static size_t attr_smem[64] = {0};
+  static const bool simt = getenv("OVIS_SAN_ATTN_SIMT") != nullptr;     // checker / A-B: the SIMT kernel
   int dev = 0;
   cudaGetDevice(&dev);
+  SanAttnArgs a;
+  a.qkv = (const __half*)qkv; a.pooled = pooled; a.out = (__half*)out;
+  a.Q = Q; a.L = L; a.heads = heads;
+  a.scale_log2 = 0.125f * 1.4426950408889634f;   // 64^-1/2 * log2(e)
+  if (!simt) {
+    const int ntiles = (1 + L + SA_KT - 1) / SA_KT;
+    const size_t smem2 = (size_t)ntiles * SA_KT * SA_LD * 2 * sizeof(__half);
+    static size_t attr2[64] = {0};
+    if (smem2 > 48 * 1024 && attr2[dev] < smem2) {
+      cudaError_t e = cudaFuncSetAttribute(san_attn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+      if (e != cudaSuccess) {
+        snprintf(g_err, sizeof(g_err), "san_attn: cudaFuncSetAttribute(smem) failed: %s", cudaGetErrorString(e));
+        return OVIS_ERR_CUDA;
+      }
+      attr2[dev] = smem2;
+    }
+    const int Lt = Q + 1 + L;
+    san_attn_mma_kernel<<<dim3((Lt + 63) / 64, heads, B), 128, smem2, (cudaStream_t)stream>>>(a);
+    return check_launch("san_attn_mma_kernel");
+  }
+  const size_t smem = (size_t)(1 + L) * 64 * 2 * sizeof(__half);
+  static size_t attr_smem[64] = {0};
   if (smem > 48 * 1024 && attr_smem[dev] < smem) {
     cudaError_t e = cudaFuncSetAttribute(san_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
@@ -775,10 +796,6 @@ int ovis_san_attn(const void* qkv, const float* pooled, void* out, int B, int Q,
     }
     attr_smem[dev] = smem;
   }
-  SanAttnArgs a;
-  a.qkv = (const __half*)qkv; a.pooled = pooled; a.out = (__half*)out;
-  a.Q = Q; a.L = L; a.heads = heads;
-  a.scale_log2 = 0.125f * 1.4426950408889634f;   // 64^-1/2 * log2(e)
   san_attn_kernel<<<dim3(heads, B), 256, smem, (cudaStream_t)stream>>>(a);
   return check_launch("san_attn_kernel");
 }

@@ -10,6 +10,7 @@
 // (frame, head)) sit in shared memory.  d = 64; PARTS lanes per row, each with its own online softmax, merged by shuffles.
 #pragma once
 #include "ptx.cuh"
+#include "xattn.cuh"
 
 namespace ovis {
 
@@ -122,6 +123,176 @@ san_attn_kernel(const SanAttnArgs a) {
         *reinterpret_cast<uint4*>(op + e) = u;
       }
     }
+  }
+}
+
+// Tensor-core version (mma.sync.m16n8k16, fp32 accumulate): CTA = (64-row tile, head, frame), 4 warps x 16 rows.
+// K / V of the CLS + patch tokens sit in shared memory (row stride 72 halves: conflict-free fragment loads and
+// ldmatrix), flash-style loop over 64-key tiles.  A SOS row's own key (the diagonal 0 of the bias matrix) is the initial
+// state of its online softmax: m = q.k_self, l = 1, O = v_self.  The SIMT kernel above stays as the checker (tests).
+constexpr int SA_LD = 72;
+constexpr int SA_KT = 64;
+
+__global__ void __launch_bounds__(128)
+san_attn_mma_kernel(const SanAttnArgs a) {
+  constexpr int D = 64;
+  extern __shared__ __align__(16) __half sm_kv2[];
+  const int head = blockIdx.y, b = blockIdx.z;
+  const int Lt = a.Q + 1 + a.L, W = a.heads * D, W3 = 3 * W;
+  const int nkeys = 1 + a.L;                               // CLS + patches
+  const int ntiles = (nkeys + SA_KT - 1) / SA_KT;
+  __half* sK = sm_kv2;
+  __half* sV = sm_kv2 + ntiles * SA_KT * SA_LD;
+  const __half* base = a.qkv + (long long)b * Lt * W3;
+  for (int i = threadIdx.x; i < ntiles * SA_KT * 8; i += blockDim.x) {
+    const int tok = i >> 3, ch = i & 7;
+    uint4 kk = make_uint4(0u, 0u, 0u, 0u), vv = kk;        // rows past the last key are zero (P = 0 there)
+    if (tok < nkeys) {
+      const __half* rowp = base + (long long)(a.Q + tok) * W3 + head * D + ch * 8;
+      kk = *reinterpret_cast<const uint4*>(rowp + W);
+      vv = *reinterpret_cast<const uint4*>(rowp + 2 * W);
+    }
+    *reinterpret_cast<uint4*>(sK + tok * SA_LD + ch * 8) = kk;
+    *reinterpret_cast<uint4*>(sV + tok * SA_LD + ch * 8) = vv;
+  }
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int quad = lane >> 2, tq = lane & 3;
+  const int row_base = blockIdx.x * 64 + warp * 16;
+  if (row_base >= Lt) return;
+  const float LOG2E = 1.4426950408889634f;
+  int rows[2];
+  bool ok[2], sos[2];
+#pragma unroll
+  for (int hi = 0; hi < 2; ++hi) {
+    const int r = row_base + quad + hi * 8;
+    ok[hi] = r < Lt;
+    rows[hi] = ok[hi] ? r : Lt - 1;
+    sos[hi] = rows[hi] < a.Q;
+  }
+  // Q fragments: a[i]: row = quad + (i & 1) * 8, col = ks * 16 + tq * 2 + (i >> 1) * 8
+  uint32_t qf[4][4];
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      qf[ks][i] = *reinterpret_cast<const uint32_t*>(base + (long long)rows[i & 1] * W3 + head * D + ks * 16 + tq * 2 + (i >> 1) * 8);
+
+  float o[8][4], mrow[2], lrow[2];
+  // initial state: SOS rows start from their own key, the other rows from nothing
+#pragma unroll
+  for (int hi = 0; hi < 2; ++hi) {
+    const __half* qp = base + (long long)rows[hi] * W3 + head * D;
+    float sp = 0.f;
+#pragma unroll
+    for (int d = 0; d < 16; d += 2) {                      // the quad's four lanes share the 64-dim dot product
+      const float2 qv = __half22float2(*reinterpret_cast<const __half2*>(qp + tq * 16 + d));
+      const float2 kv = __half22float2(*reinterpret_cast<const __half2*>(qp + W + tq * 16 + d));
+      sp = fmaf(qv.x, kv.x, sp);
+      sp = fmaf(qv.y, kv.y, sp);
+    }
+    sp += __shfl_xor_sync(0xffffffffu, sp, 1);
+    sp += __shfl_xor_sync(0xffffffffu, sp, 2);
+    mrow[hi] = sos[hi] ? sp * a.scale_log2 : -INFINITY;
+    lrow[hi] = sos[hi] ? 1.f : 0.f;
+#pragma unroll
+    for (int dn = 0; dn < 8; ++dn) {
+      const float2 vv = __half22float2(*reinterpret_cast<const __half2*>(qp + 2 * W + dn * 8 + tq * 2));
+      o[dn][hi * 2] = sos[hi] ? vv.x : 0.f;
+      o[dn][hi * 2 + 1] = sos[hi] ? vv.y : 0.f;
+    }
+  }
+  const float* pb[2];
+#pragma unroll
+  for (int hi = 0; hi < 2; ++hi)
+    pb[hi] = (a.pooled && sos[hi]) ? a.pooled + (((long long)b * a.heads + head) * a.Q + rows[hi]) * a.L : nullptr;
+
+  for (int t = 0; t < ntiles; ++t) {
+    const __half* kt = sK + t * SA_KT * SA_LD;
+    const __half* vt = sV + t * SA_KT * SA_LD;
+    float s[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(kt + (nt * 8 + quad) * SA_LD + ks * 16 + tq * 2);
+        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(kt + (nt * 8 + quad) * SA_LD + ks * 16 + tq * 2 + 8);
+        mma_16816(s[nt], qf[ks], b0, b1);
+      }
+    }
+    // scale, bias, structural mask; row max
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int hi = i >> 1;
+        const int key = t * SA_KT + nt * 8 + tq * 2 + (i & 1);      // 0 = CLS, 1.. = patches
+        float v = s[nt][i] * a.scale_log2;
+        if (sos[hi]) {
+          if (key == 0) v = -INFINITY;                                // SOS -> CLS carries -100
+          else if (pb[hi] && key < nkeys) v = fmaf(__ldg(pb[hi] + key - 1), LOG2E, v);
+        }
+        if (key >= nkeys) v = -INFINITY;
+        s[nt][i] = v;
+        mx[hi] = fmaxf(mx[hi], v);
+      }
+    }
+    float corr[2], muse[2];
+#pragma unroll
+    for (int hi = 0; hi < 2; ++hi) {
+      mx[hi] = fmaxf(mx[hi], __shfl_xor_sync(0xffffffffu, mx[hi], 1));
+      mx[hi] = fmaxf(mx[hi], __shfl_xor_sync(0xffffffffu, mx[hi], 2));
+      const float mnew = fmaxf(mrow[hi], mx[hi]);
+      muse[hi] = (mnew == -INFINITY) ? 0.f : mnew;
+      corr[hi] = exp2f(mrow[hi] - muse[hi]);
+      mrow[hi] = mnew;
+    }
+    float ls[2] = {0.f, 0.f};
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float p = exp2f(s[nt][i] - muse[i >> 1]);
+        s[nt][i] = p;
+        ls[i >> 1] += p;
+      }
+#pragma unroll
+    for (int hi = 0; hi < 2; ++hi) {
+      ls[hi] += __shfl_xor_sync(0xffffffffu, ls[hi], 1);
+      ls[hi] += __shfl_xor_sync(0xffffffffu, ls[hi], 2);
+      lrow[hi] = lrow[hi] * corr[hi] + ls[hi];
+    }
+#pragma unroll
+    for (int dn = 0; dn < 8; ++dn) {
+      o[dn][0] *= corr[0]; o[dn][1] *= corr[0];
+      o[dn][2] *= corr[1]; o[dn][3] *= corr[1];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint32_t pa[4];
+      pa[0] = pack_half2(s[2 * j][0], s[2 * j][1]);
+      pa[1] = pack_half2(s[2 * j][2], s[2 * j][3]);
+      pa[2] = pack_half2(s[2 * j + 1][0], s[2 * j + 1][1]);
+      pa[3] = pack_half2(s[2 * j + 1][2], s[2 * j + 1][3]);
+#pragma unroll
+      for (int dn = 0; dn < 8; ++dn) {
+        uint32_t b0, b1;
+        ldmatrix_x2_trans(b0, b1, vt + (j * 16 + (lane & 15)) * SA_LD + dn * 8);
+        mma_16816(o[dn], pa, b0, b1);
+      }
+    }
+  }
+#pragma unroll
+  for (int hi = 0; hi < 2; ++hi) {
+    if (!ok[hi]) continue;
+    const float inv = 1.f / lrow[hi];
+    __half* op = a.out + ((long long)b * Lt + rows[hi]) * W + head * D + tq * 2;
+#pragma unroll
+    for (int dn = 0; dn < 8; ++dn)
+      *reinterpret_cast<uint32_t*>(op + dn * 8) = pack_half2(o[dn][hi * 2] * inv, o[dn][hi * 2 + 1] * inv);
   }
 }
 

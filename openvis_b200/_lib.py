@@ -40,6 +40,9 @@ SIGNATURES = {
     "ovis_xattn": (_c_int, [_vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp]),
     "ovis_self_attn": (_c_int, [_vp, _vp, _vp, _c_int, _c_int, _vp]),
     "ovis_clip_aggregate": (_c_int, [_vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _vp]),
+    "ovis_topk_scores": (_c_int, [_vp, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp]),
+    "ovis_mask_postprocess": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
+                                       _c_int, _vp, _vp]),
     "ovis_san_pool_bias": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _vp]),
     "ovis_san_attn": (_c_int, [_vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _vp]),
     "ovis_san_attn_bias": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _vp]),
@@ -221,6 +224,31 @@ def linear_act_f16(x, w, bias=None, scale=1.0, act=0, resid=None, out=None, out_
     _check(lib.ovis_linear_act_f16(_p(x), rows, K, x.stride(0), _p(w), N, _p(bias), float(scale), int(act), _p(resid),
                                    _p(out), out.stride(0), int(out_f32), _stream()))
     return out
+
+
+def topk_scores(scores, k=10):
+    """scores [Q, K] fp32 -> (top scores [k], query index [k], label [k], entropy [k]) sorted by score."""
+    lib = load()
+    _req(scores, torch.float32, "scores")
+    Q, K = scores.shape
+    dev = scores.device
+    vs, qi = torch.empty(k, device=dev), torch.empty(k, dtype=torch.int32, device=dev)
+    lb, en = torch.empty(k, dtype=torch.int32, device=dev), torch.empty(k, device=dev)
+    _check(lib.ovis_topk_scores(_p(scores), Q, K, k, _p(vs), _p(qi), _p(lb), _p(en), _stream()))
+    return vs, qi, lb, en
+
+
+def mask_postprocess(masks, query, pad_hw, img_hw, out_hw):
+    """masks [Q, T, h4, w4] fp32 stride-4 logits, query [n] int32 -> bits [n, T, out_h, ceil(out_w/32)] int32."""
+    lib = load()
+    _req(masks, torch.float32, "masks")
+    Q, T, h4, w4 = masks.shape
+    assert query.dtype == torch.int32 and query.is_cuda
+    n = query.numel()
+    bits = torch.empty(n, T, out_hw[0], (out_hw[1] + 31) // 32, dtype=torch.int32, device=masks.device)
+    _check(lib.ovis_mask_postprocess(_p(masks), _p(query), n, T, h4, w4, pad_hw[0], pad_hw[1], img_hw[0], img_hw[1],
+                                     out_hw[0], out_hw[1], _p(bits), _stream()))
+    return bits
 
 
 def san_pool_bias(bias, grid_hw):

@@ -16,6 +16,7 @@
 #include "xattn_tc.cuh"
 #include "xattn_tc2.cuh"
 #include "san_attn.cuh"
+#include "postproc.cuh"
 
 using namespace ovis;
 
@@ -747,6 +748,35 @@ int ovis_clip_aggregate(const float* logits, const unsigned char* valid, float* 
   if (rc) return rc;
   clip_aggregate_kernel<<<Q, 256, (size_t)K * sizeof(float), (cudaStream_t)stream>>>(logits, valid, probs, qvalid, T, Q, K);
   return check_launch("clip_aggregate_kernel");
+}
+
+int ovis_topk_scores(const float* scores, int Q, int K, int k, float* out_scores, int* out_query, int* out_label,
+                     float* out_entropy, void* stream) {
+  CHECK_ARG(scores && out_scores && out_query && out_label && out_entropy, "null pointer");
+  CHECK_ARG(Q > 0 && K > 0 && k > 0 && k <= 32 && (long long)Q * K >= k && (long long)Q * K < (1ll << 31), "bad sizes (k <= 32)");
+  int rc = device_info(nullptr);
+  if (rc) return rc;
+  topk_scores_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(scores, Q, K, k, out_scores, out_query, out_label, out_entropy);
+  return check_launch("topk_scores_kernel");
+}
+
+int ovis_mask_postprocess(const float* masks, const int* query, int n_sel, int T, int h4, int w4, int pad_h, int pad_w,
+                          int img_h, int img_w, int out_h, int out_w, unsigned int* bits, void* stream) {
+  CHECK_ARG(masks && query && bits, "null pointer");
+  CHECK_ARG(n_sel > 0 && T > 0 && h4 > 0 && w4 > 0 && pad_h > 0 && pad_w > 0 && out_h > 0 && out_w > 0, "bad sizes");
+  CHECK_ARG(img_h > 0 && img_w > 0 && img_h <= pad_h && img_w <= pad_w, "the image must fit into the padded size");
+  int rc = device_info(nullptr);
+  if (rc) return rc;
+  MaskPostArgs a;
+  a.masks = masks; a.query = query; a.bits = bits;
+  a.n_sel = n_sel; a.T = T; a.h4 = h4; a.w4 = w4;
+  a.pad_h = pad_h; a.pad_w = pad_w; a.img_h = img_h; a.img_w = img_w; a.out_h = out_h; a.out_w = out_w;
+  a.words = (out_w + 31) / 32;
+  const long long warps = (long long)n_sel * T * out_h * a.words;
+  const long long blocks = (warps * 32 + 255) / 256;
+  CHECK_ARG(blocks < (1ll << 31), "output too large");
+  mask_postprocess_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
+  return check_launch("mask_postprocess_kernel");
 }
 
 int ovis_san_pool_bias(const float* bias, float* pooled, int BN, int Q, int h, int w, int gh, int gw, void* stream) {

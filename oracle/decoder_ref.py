@@ -315,6 +315,22 @@ def san_build_attn_bias(attn_bias, grid_hw):
     return m
 
 
+def video_postprocess(pred_cls, pred_masks, padded_size, img_size, out_hw, topk=10):
+    """VideoMaskFormer.postprocess + inference_video (video_maskformer.py:215-229, 262-298) on pred_cls [Q, K] scores and
+    stride-4 pred_masks [Q, T, h4, w4]: up-sample to the padded size, top-k over Q*K, crop, resize, > 0.
+    Returns (scores [k], labels [k], query index [k], entropy [k], masks bool [k, T, H, W]) sorted by score."""
+    Q, K = pred_cls.shape
+    up = F.interpolate(pred_masks, size=tuple(padded_size), mode="bilinear", align_corners=False)
+    labels = torch.arange(K).unsqueeze(0).repeat(Q, 1).flatten(0, 1)
+    sc, idx = pred_cls.flatten(0, 1).topk(topk, sorted=True)
+    lab = labels[idx]
+    qi = idx // K
+    ent = torch.sum(-pred_cls[qi] * torch.log(pred_cls[qi]), dim=-1)
+    m = up[qi][:, :, : img_size[0], : img_size[1]]
+    m = F.interpolate(m, size=tuple(out_hw), mode="bilinear", align_corners=False)
+    return sc, lab, qi, ent, m > 0.0, m
+
+
 def clip_block(P, i, x, attn_mask, nheads=12):
     """BiasedResidualAttentionBlock.forward (side_adapter.py:70-78) over mask_adapted_clip's ResidualAttentionBlock
     (model.py:237-268): x + MHA(ln_1(x), additive float mask) ; x + c_proj(QuickGELU(c_fc(ln_2(x)))).

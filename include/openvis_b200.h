@@ -136,9 +136,10 @@ int ovis_topk_scores(const float* scores, int Q, int K, int k, float* out_scores
                      float* out_entropy, void* stream);
 /* For the selected queries: F.interpolate(pred_masks, padded size, bilinear) (video_maskformer.py:220-226 /
  * openvis.py:87-96), crop to the image, F.interpolate(output size, bilinear), `> 0` (:273-277), fused per output
- * pixel and bit-packed.  masks [Q][T][h4][w4] fp32 -> bits [n_sel][T][out_h][ceil(out_w/32)] (bit x%32 of word x/32). */
-int ovis_mask_postprocess(const float* masks, const int* query, int n_sel, int T, int h4, int w4, int pad_h, int pad_w,
-                          int img_h, int img_w, int out_h, int out_w, unsigned int* bits, void* stream);
+ * pixel and bit-packed.  masks: frame t of query q at masks + q * q_stride + t * h4 * w4 (q_stride 0 = T*h4*w4; a
+ * larger stride addresses one clip of a multi-clip call) -> bits [n_sel][T][out_h][ceil(out_w/32)] (bit x%32 of word x/32). */
+int ovis_mask_postprocess(const float* masks, long long q_stride, const int* query, int n_sel, int T, int h4, int w4,
+                          int pad_h, int pad_w, int img_h, int img_w, int out_h, int out_w, unsigned int* bits, void* stream);
 /* SAN / BriVIS side path.  Adaptive max-pool of the per-head attention biases to the CLIP
  * grid only (step 1 of SideAdapter._build_attn_biases, side_adapter.py:241-250): bias [BN][Q][h][w] -> pooled [BN][Q][gh*gw]. */
 int ovis_san_pool_bias(const float* bias, float* pooled, int BN, int Q, int h, int w, int gh, int gw, void* stream);

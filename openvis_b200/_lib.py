@@ -41,8 +41,8 @@ SIGNATURES = {
     "ovis_self_attn": (_c_int, [_vp, _vp, _vp, _c_int, _c_int, _vp]),
     "ovis_clip_aggregate": (_c_int, [_vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _vp]),
     "ovis_topk_scores": (_c_int, [_vp, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp]),
-    "ovis_mask_postprocess": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
-                                       _c_int, _vp, _vp]),
+    "ovis_mask_postprocess": (_c_int, [_vp, _c_ll, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
+                                       _c_int, _c_int, _vp, _vp]),
     "ovis_san_pool_bias": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _vp]),
     "ovis_san_attn": (_c_int, [_vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _vp]),
     "ovis_san_attn_bias": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _vp]),
@@ -238,17 +238,20 @@ def topk_scores(scores, k=10):
     return vs, qi, lb, en
 
 
-def mask_postprocess(masks, query, pad_hw, img_hw, out_hw):
-    """masks [Q, T, h4, w4] fp32 stride-4 logits, query [n] int32 -> bits [n, T, out_h, ceil(out_w/32)] int32."""
+def mask_postprocess(masks, query, pad_hw, img_hw, out_hw, out=None):
+    """masks [Q, T, h4, w4] fp32 stride-4 logits (a frame slice of a larger [Q, T', h4, w4] tensor is fine),
+    query [n] int32 -> bits [n, T, out_h, ceil(out_w/32)] int32."""
     lib = load()
-    _req(masks, torch.float32, "masks")
+    assert masks.dtype == torch.float32 and masks.is_cuda and masks.stride(-1) == 1, "masks: fp32 CUDA tensor"
     Q, T, h4, w4 = masks.shape
+    assert masks.numel() > 0 and masks.stride(2) == w4 and masks.stride(1) == h4 * w4, "frames of a query must be contiguous"
     assert query.dtype == torch.int32 and query.is_cuda
     n = query.numel()
-    bits = torch.empty(n, T, out_hw[0], (out_hw[1] + 31) // 32, dtype=torch.int32, device=masks.device)
-    _check(lib.ovis_mask_postprocess(_p(masks), _p(query), n, T, h4, w4, pad_hw[0], pad_hw[1], img_hw[0], img_hw[1],
-                                     out_hw[0], out_hw[1], _p(bits), _stream()))
-    return bits
+    if out is None:
+        out = torch.empty(n, T, out_hw[0], (out_hw[1] + 31) // 32, dtype=torch.int32, device=masks.device)
+    _check(lib.ovis_mask_postprocess(_p(masks), masks.stride(0), _p(query), n, T, h4, w4, pad_hw[0], pad_hw[1],
+                                     img_hw[0], img_hw[1], out_hw[0], out_hw[1], _p(out), _stream()))
+    return out
 
 
 def san_pool_bias(bias, grid_hw):

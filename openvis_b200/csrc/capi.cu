@@ -760,22 +760,21 @@ int ovis_topk_scores(const float* scores, int Q, int K, int k, float* out_scores
   return check_launch("topk_scores_kernel");
 }
 
-int ovis_mask_postprocess(const float* masks, const int* query, int n_sel, int T, int h4, int w4, int pad_h, int pad_w,
-                          int img_h, int img_w, int out_h, int out_w, unsigned int* bits, void* stream) {
+int ovis_mask_postprocess(const float* masks, long long q_stride, const int* query, int n_sel, int T, int h4, int w4,
+                          int pad_h, int pad_w, int img_h, int img_w, int out_h, int out_w, unsigned int* bits, void* stream) {
   CHECK_ARG(masks && query && bits, "null pointer");
   CHECK_ARG(n_sel > 0 && T > 0 && h4 > 0 && w4 > 0 && pad_h > 0 && pad_w > 0 && out_h > 0 && out_w > 0, "bad sizes");
   CHECK_ARG(img_h > 0 && img_w > 0 && img_h <= pad_h && img_w <= pad_w, "the image must fit into the padded size");
   int rc = device_info(nullptr);
   if (rc) return rc;
   MaskPostArgs a;
-  a.masks = masks; a.query = query; a.bits = bits;
+  a.masks = masks; a.q_stride = q_stride > 0 ? q_stride : (long long)T * h4 * w4; a.query = query; a.bits = bits;
   a.n_sel = n_sel; a.T = T; a.h4 = h4; a.w4 = w4;
   a.pad_h = pad_h; a.pad_w = pad_w; a.img_h = img_h; a.img_w = img_w; a.out_h = out_h; a.out_w = out_w;
   a.words = (out_w + 31) / 32;
-  const long long warps = (long long)n_sel * T * out_h * a.words;
-  const long long blocks = (warps * 32 + 255) / 256;
-  CHECK_ARG(blocks < (1ll << 31), "output too large");
-  mask_postprocess_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
+  CHECK_ARG((long long)n_sel * T <= 65535 && (out_h + MP_ROWS - 1) / MP_ROWS <= 65535, "too many planes / rows for one launch");
+  dim3 grid((a.words * 32 + 255) / 256, (out_h + MP_ROWS - 1) / MP_ROWS, n_sel * T);
+  mask_postprocess_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
   return check_launch("mask_postprocess_kernel");
 }
 

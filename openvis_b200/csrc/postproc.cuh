@@ -73,7 +73,8 @@ topk_scores_kernel(const float* __restrict__ scores, int Q, int K, int k, float*
 }
 
 struct MaskPostArgs {
-  const float* masks;     // [Q][T][h4][w4] stride-4 logits (pred_masks[0])
+  const float* masks;     // [Q][..][h4][w4] stride-4 logits (pred_masks[0]); frame t of query q at q * q_stride + t * h4 * w4
+  long long q_stride;     // elements between consecutive queries (T * h4 * w4 when the clip is the whole tensor)
   const int* query;       // [n_sel] selected query per output plane
   uint32_t* bits;         // [n_sel][T][out_h][words] ; bit x%32 of word x/32 = (resized logit > 0)
   int n_sel, T, h4, w4;
@@ -93,50 +94,82 @@ __device__ __forceinline__ void bilin_src(int dst, float scale, int in_size, int
   l1 = s - i0;
 }
 
-// thread = output pixel, warp = 32 consecutive x of one output row -> one ballot word
+// Composite weights of the two chained bilinear interpolations along one axis for output index `dst`:
+// out = sum_{j<3} w[j] * L[min(base + j, in_size - 1)].  The two intermediate taps are adjacent pixels of the x4
+// up-sampled image, so their four source taps fall on at most three consecutive low-resolution samples.
+__device__ __forceinline__ void composite_taps(int dst, float s2, int mid_size, float s1, int in_size, int& base, float (&w)[3]) {
+  int i0, i1;
+  float l;
+  bilin_src(dst, s2, mid_size, i0, i1, l);
+  int a0, a1, b0, b1;
+  float wa, wb;
+  bilin_src(i0, s1, in_size, a0, a1, wa);
+  bilin_src(i1, s1, in_size, b0, b1, wb);
+  base = a0;
+  w[0] = w[1] = w[2] = 0.f;
+  const float c[4] = {(1.f - l) * (1.f - wa), (1.f - l) * wa, l * (1.f - wb), l * wb};
+  const int idx[4] = {0, a1 - a0, b0 - a0, b1 - a0};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    w[0] += idx[k] == 0 ? c[k] : 0.f;
+    w[1] += idx[k] == 1 ? c[k] : 0.f;
+    w[2] += idx[k] >= 2 ? c[k] : 0.f;
+  }
+}
+
+// thread = one output column of a 32-row strip; warp = 32 consecutive x -> one ballot word per output row.
+// The horizontal pass H[r] = sum_c wx[c] L[r][c] is kept for the three low-resolution rows the current output row
+// needs and slides down with it, so each output pixel costs about one cached load instead of sixteen.
+constexpr int MP_ROWS = 32;
 __global__ void __launch_bounds__(256)
 mask_postprocess_kernel(const MaskPostArgs a) {
-  const int wpr = a.words;                                   // warps per output row
-  const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const long long total_warps = (long long)a.n_sel * a.T * a.out_h * wpr;
-  if (warp_global >= total_warps) return;
+  const int plane = blockIdx.z;                               // (selected query, frame)
+  const int sel = plane / a.T, t = plane % a.T;
+  const int ox = blockIdx.x * 256 + threadIdx.x;
+  const int oy0 = blockIdx.y * MP_ROWS;
   const int lane = threadIdx.x & 31;
-  const int wx = (int)(warp_global % wpr);
-  long long r = warp_global / wpr;
-  const int oy = (int)(r % a.out_h); r /= a.out_h;
-  const int t = (int)(r % a.T);
-  const int sel = (int)(r / a.T);
-  const int ox = wx * 32 + lane;
-  const int q = __ldg(a.query + sel);
-  const float* L = a.masks + ((long long)q * a.T + t) * a.h4 * a.w4;
+  const int wx = ox >> 5;
   const float s2y = (float)a.img_h / a.out_h, s2x = (float)a.img_w / a.out_w;     // second resize (image -> output)
   const float s1y = (float)a.h4 / a.pad_h, s1x = (float)a.w4 / a.pad_w;           // first resize (stride 4 -> padded)
-  bool pos = false;
-  if (ox < a.out_w) {
-    int iy[2], ix[2];
-    float ly, lx;
-    bilin_src(oy, s2y, a.img_h, iy[0], iy[1], ly);
-    bilin_src(ox, s2x, a.img_w, ix[0], ix[1], lx);
-    // intermediate (up-sampled, cropped) image at the 2 x 2 taps
-    float I[2][2];
-#pragma unroll
-    for (int jy = 0; jy < 2; ++jy) {
-      int y0, y1; float wy;
-      bilin_src(iy[jy], s1y, a.h4, y0, y1, wy);
-#pragma unroll
-      for (int jx = 0; jx < 2; ++jx) {
-        int x0, x1; float wx1;
-        bilin_src(ix[jx], s1x, a.w4, x0, x1, wx1);
-        const float v00 = __ldg(L + y0 * a.w4 + x0), v01 = __ldg(L + y0 * a.w4 + x1);
-        const float v10 = __ldg(L + y1 * a.w4 + x0), v11 = __ldg(L + y1 * a.w4 + x1);
-        I[jy][jx] = (1.f - wy) * ((1.f - wx1) * v00 + wx1 * v01) + wy * ((1.f - wx1) * v10 + wx1 * v11);
-      }
-    }
-    const float v = (1.f - ly) * ((1.f - lx) * I[0][0] + lx * I[0][1]) + ly * ((1.f - lx) * I[1][0] + lx * I[1][1]);
-    pos = v > 0.f;
+  // vertical taps of the strip's rows: computed once per CTA
+  __shared__ int s_rb[MP_ROWS];
+  __shared__ float s_wy[MP_ROWS][3];
+  if (threadIdx.x < MP_ROWS) {
+    int nb;
+    float wy[3];
+    composite_taps(min(oy0 + (int)threadIdx.x, a.out_h - 1), s2y, a.img_h, s1y, a.h4, nb, wy);
+    s_rb[threadIdx.x] = nb;
+    s_wy[threadIdx.x][0] = wy[0]; s_wy[threadIdx.x][1] = wy[1]; s_wy[threadIdx.x][2] = wy[2];
   }
-  const uint32_t word = __ballot_sync(0xffffffffu, pos);
-  if (lane == 0) a.bits[warp_global] = word;
+  __syncthreads();
+  if (wx >= a.words) return;                                  // whole warps beyond the row
+  const int q = __ldg(a.query + sel);
+  const float* L = a.masks + (long long)q * a.q_stride + (long long)t * a.h4 * a.w4;
+  const bool x_ok = ox < a.out_w;
+  int cbase;
+  float wxc[3];
+  composite_taps(x_ok ? ox : a.out_w - 1, s2x, a.img_w, s1x, a.w4, cbase, wxc);
+  const int c0 = cbase, c1 = min(cbase + 1, a.w4 - 1), c2 = min(cbase + 2, a.w4 - 1);
+  auto hrow = [&](int r) {
+    const float* p = L + (long long)min(r, a.h4 - 1) * a.w4;
+    return wxc[0] * __ldg(p + c0) + wxc[1] * __ldg(p + c1) + wxc[2] * __ldg(p + c2);
+  };
+  int rbase = -1000;
+  float H0 = 0.f, H1 = 0.f, H2 = 0.f;
+  uint32_t* out = a.bits + ((long long)plane * a.out_h) * a.words + wx;
+  const int oy1 = min(oy0 + MP_ROWS, a.out_h);
+  for (int oy = oy0; oy < oy1; ++oy) {
+    const int nb = s_rb[oy - oy0];
+    const float wy[3] = {s_wy[oy - oy0][0], s_wy[oy - oy0][1], s_wy[oy - oy0][2]};
+    if (nb != rbase) {
+      if (nb == rbase + 1) { H0 = H1; H1 = H2; H2 = hrow(nb + 2); }
+      else { H0 = hrow(nb); H1 = hrow(nb + 1); H2 = hrow(nb + 2); }
+      rbase = nb;
+    }
+    const float v = wy[0] * H0 + wy[1] * H1 + wy[2] * H2;
+    const uint32_t word = __ballot_sync(0xffffffffu, x_ok && v > 0.f);
+    if (lane == 0) out[(long long)oy * a.words] = word;
+  }
 }
 
 }  // namespace ovis

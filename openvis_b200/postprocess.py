@@ -54,7 +54,7 @@ def inference_video(num_queries, num_classes, pred_cls, pred_masks, padded_size,
     with torch.cuda.device(pred_masks.device):
         k = min(topk, pred_cls.numel())
         scores, qidx, labels, ent = L.topk_scores(pred_cls.float().contiguous(), k)
-        bits = L.mask_postprocess(pred_masks.float().contiguous(), qidx, padded_size, img_size,
+        bits = L.mask_postprocess(pred_masks.float(), qidx, padded_size, img_size,
                                   (output_height, output_width))
         packed = PackedMasks(bits, output_width).cpu()
     return {"image_size": (output_height, output_width), "pred_entropys": ent.tolist(), "pred_scores": scores.tolist(),

@@ -245,6 +245,10 @@ def main():
         d_ = D.VideoMultiScaleMaskedTransformerDecoder(**kw)
         d_.load_state_dict(sd)
         d_.clips_per_call = C_
+        # several decoder calls in flight: their eagerly launched small kernels interleave with the other call's heavy
+        # ones; replaying each call's layer loop as one CUDA graph removes that interleaving (measured: 2 streams 11.2 k
+        # eager vs 10.9 k graph frames/s, 3 streams 11.3 k vs 4.8 k), so graph replay is kept for single-stream use
+        d_.use_cuda_graph = d_.use_cuda_graph and args.streams <= 1
         decs.append(d_.to(dev).eval())
     dec = decs[0]
     streams = [torch.cuda.Stream() for _ in decs]
@@ -488,7 +492,8 @@ def main():
             "config": {"workload": args.workload, "frames_per_step_per_gpu": C_ * T, "clips_per_step": C_, "queries": Q, "vocab": K,
                        "l2": "inputs larger than L2 (2.9 GB per clip, two input sets alternated)",
                        "aux_outputs": "lazy (inference-minimal)", "parallelism": f"clip-sharded dp{world}",
-                       "decoder_calls_in_flight_per_gpu": len(decs), "sm_budget": os.environ.get("OVIS_SM_BUDGET")},
+                       "decoder_calls_in_flight_per_gpu": len(decs), "cuda_graph_layer_loop": bool(dec.use_cuda_graph),
+                       "sm_budget": os.environ.get("OVIS_SM_BUDGET")},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,
             "whole_path": {"gflop_per_frame": flops_frame / 1e9,

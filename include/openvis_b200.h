@@ -31,6 +31,8 @@ const char* ovis_last_error(void);
 int ovis_device_check(void);
 /* number of kernels launched by this library since load (bench.py's gpu_launches claim). */
 long long ovis_launch_count(void);
+/* Launches replayed through a captured CUDA graph do not pass through the entry points: the host side adds them here. */
+void ovis_add_launch_count(long long n);
 
 /* ---- layout preparation ------------------------------------------------------------------------------
  * Multi-scale feature map x_l [B][C][N] fp32 (NCHW, N=h*w) -> token-major fp16 [B][N][C].

@@ -20,6 +20,7 @@ SIGNATURES = {
     "ovis_last_error": (ctypes.c_char_p, []),
     "ovis_device_check": (_c_int, []),
     "ovis_launch_count": (_c_ll, []),
+    "ovis_add_launch_count": (None, [_c_ll]),
     "ovis_nchw_to_tokens_f16": (_c_int, [_vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _vp]),
     "ovis_nchw_to_tokens_hw_f16": (_c_int, [_vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _vp]),
     "ovis_maskfeat_prep": (_c_int, [_vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _vp]),
@@ -122,6 +123,10 @@ def _timed(family):
 
 def launch_count():
     return load().ovis_launch_count()
+
+
+def add_launch_count(n):
+    load().ovis_add_launch_count(int(n))
 
 
 def device_check():

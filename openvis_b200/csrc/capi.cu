@@ -282,6 +282,7 @@ int ovis_version(void) { return 100; }
 const char* ovis_last_error(void) { return g_err; }
 int ovis_device_check(void) { return device_info(nullptr); }
 long long ovis_launch_count(void) { return g_launches.load(); }
+void ovis_add_launch_count(long long n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 int ovis_nchw_to_tokens_f16(const float* in, void* out, void* out_pos, const float* pos, const float* pos_t, int B, int C,
                             int N, void* stream) {

@@ -27,6 +27,8 @@ Design notes (DESIGN.md has the full account):
 import math
 from typing import List
 
+import os
+
 import torch
 from torch import nn
 
@@ -224,6 +226,7 @@ class _B200MaskedDecoderBase(nn.Module):
         # training-mode bs > 1): the query-side GEMMs then run on clips_per_call * Q rows per launch.
         self.clips_per_call = 1
         self.debug_capture = None         # tests: set to a list to receive (head, level, bits, flags) clones
+        self.use_cuda_graph = os.environ.get("OVIS_NO_CUDA_GRAPH") is None   # replay the layer loop as a CUDA graph (_run_layers)
         self._wcache = None
         self._pcache = {}
         self._ws = {}
@@ -421,37 +424,12 @@ class _B200MaskedDecoderBase(nn.Module):
         with torch.cuda.device(dev):
             return self._forward_impl(x, mf, mask_features_in, BT, H4, W4, sizes, dev)
 
-    def _forward_impl(self, x, mf, mask_features_in, BT, H4, W4, sizes, dev):
-        W = self._weights()
-        ws = self._workspace(BT, H4, W4, dev)
-        padd, p2, pz = self._pos_tables(BT // self._groups(BT), sizes, dev)
-        if pz is not None and self._groups(BT) > 1:
-            pz = pz.repeat(self._groups(BT), 1)            # frame b of the call is frame b % Tg of its clip
-        self._generation += 1
-        gen = self._generation
-        G, Tg, R, N, M = ws["G"], ws["Tg"], ws["R"], ws["N"], ws["M"]
+    def _layer_loop(self, W, ws):
+        """Query initialisation, the first head's mask bits and the nine decoder layers.  Everything here reads and writes
+        the per-shape workspace and the weight cache only (no caller tensors, no allocation), so it can be replayed as a
+        CUDA graph."""
+        G, Tg, N = ws["G"], ws["Tg"], ws["N"]
         Q, C, nl = self.num_queries, HIDDEN, self.num_layers
-
-        # ---- layout preparation (HBM-bound, once per call)
-        for l in range(3):
-            if x[l].shape[-1] % 4 == 0:
-                L.nchw_to_tokens_hw_f16(x[l], out=ws["xt"][l], out_pos=ws["xp"][l], pos_cn=padd[l], pos_t=pz)
-            else:                                      # odd widths: no 16-byte row pitch for the tensor maps
-                L.nchw_to_tokens_f16(x[l], out=ws["xt"][l], out_pos=ws["xp"][l], pos=padd[l].t().contiguous(), pos_t=pz)
-        L.maskfeat_prep(mf, (ws["ft"], ws["gt"][0], ws["gt"][1], ws["gt"][2]))
-        # ---- key / value projections of all layers, one launch per level
-        for l in range(3):
-            ids = W["kv_layers"][l]
-            if not ids:
-                continue
-            outs, biases = [], []
-            for i in ids:
-                outs += [ws["k"][i], ws["v"][i]]
-                biases += [W["layers"][i]["xk_b"], W["layers"][i]["v_bias"]]
-            L.kv_proj_f16(ws["xp"][l], ws["xt"][l], W["kv_w"][l], outs, biases)
-
-        san = self._san_prepare(W, ws, BT, H4, W4) if self.SAN else None
-
         ws["flags"].zero_()
         L.init_queries(W["qf"], W["qe"], W["dn"][0], W["dn"][1], G, (ws["z32"], ws["z16"], ws["ze16"], ws["d32"], ws["d16"][0]))
 
@@ -485,6 +463,57 @@ class _B200MaskedDecoderBase(nn.Module):
                             split_ws=ws["split"])
             if i + 1 < nl:
                 head_bits(i + 1, (i + 1) % 3)
+
+    def _run_layers(self, W, ws):
+        """The layer loop is ~130 small dependent launches: issued from Python they are launch-rate bound (2.5 ms of host
+        time per call, more than the GPU needs).  After one eager call per workspace the loop is captured into a CUDA
+        graph and replayed; tests' bit capture and the bench's per-launch profiling run it eagerly."""
+        eager = (not self.use_cuda_graph) or self.debug_capture is not None or L.PROFILE is not None
+        if eager or not ws.get("warm"):
+            ws["warm"] = True
+            return self._layer_loop(W, ws)
+        if ws.get("graph") is None or ws.get("graph_W") is not W:
+            n0 = L.launch_count()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._layer_loop(W, ws)
+            ws["graph"], ws["graph_W"], ws["graph_launches"] = g, W, L.launch_count() - n0
+            L.add_launch_count(-ws["graph_launches"])      # capture only recorded them; replays are counted below
+        ws["graph"].replay()
+        L.add_launch_count(ws["graph_launches"])
+
+    def _forward_impl(self, x, mf, mask_features_in, BT, H4, W4, sizes, dev):
+        W = self._weights()
+        ws = self._workspace(BT, H4, W4, dev)
+        padd, p2, pz = self._pos_tables(BT // self._groups(BT), sizes, dev)
+        if pz is not None and self._groups(BT) > 1:
+            pz = pz.repeat(self._groups(BT), 1)            # frame b of the call is frame b % Tg of its clip
+        self._generation += 1
+        gen = self._generation
+        G, Tg, R, N, M = ws["G"], ws["Tg"], ws["R"], ws["N"], ws["M"]
+        Q, C, nl = self.num_queries, HIDDEN, self.num_layers
+
+        # ---- layout preparation (HBM-bound, once per call)
+        for l in range(3):
+            if x[l].shape[-1] % 4 == 0:
+                L.nchw_to_tokens_hw_f16(x[l], out=ws["xt"][l], out_pos=ws["xp"][l], pos_cn=padd[l], pos_t=pz)
+            else:                                      # odd widths: no 16-byte row pitch for the tensor maps
+                L.nchw_to_tokens_f16(x[l], out=ws["xt"][l], out_pos=ws["xp"][l], pos=padd[l].t().contiguous(), pos_t=pz)
+        L.maskfeat_prep(mf, (ws["ft"], ws["gt"][0], ws["gt"][1], ws["gt"][2]))
+        # ---- key / value projections of all layers, one launch per level
+        for l in range(3):
+            ids = W["kv_layers"][l]
+            if not ids:
+                continue
+            outs, biases = [], []
+            for i in ids:
+                outs += [ws["k"][i], ws["v"][i]]
+                biases += [W["layers"][i]["xk_b"], W["layers"][i]["v_bias"]]
+            L.kv_proj_f16(ws["xp"][l], ws["xt"][l], W["kv_w"][l], outs, biases)
+
+        san = self._san_prepare(W, ws, BT, H4, W4) if self.SAN else None
+
+        self._run_layers(W, ws)
 
         # ---- final prediction head: full-resolution mask logits, class logits / attention biases
         out = _LazyDict()

@@ -16,6 +16,7 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
+from openvis_b200 import _lib as L  # noqa: E402
 from openvis_b200 import decoder as D  # noqa: E402
 from oracle import decoder_ref as O  # noqa: E402
 
@@ -273,3 +274,26 @@ def test_no_cpu_fallback_and_training_refused():
     m.train()
     with pytest.raises(RuntimeError):
         m([t.cuda() for t in x], mf.cuda())
+
+
+@pytest.mark.parametrize("kind", ["video", "san_frame"])
+def test_cuda_graph_replay_equals_eager(kind):
+    """The layer loop replayed as a CUDA graph (second and later calls of a workspace) gives bit-identical outputs to
+    the eager launches, also after the inputs change between calls."""
+    T, Hp, Wp, Q = 2, 128, 192, 100
+    m, P = build(kind, Q, 0)
+    ins = [O.seeded_inputs(T, Hp, Wp, seed=70 + i) for i in range(3)]
+    m.use_cuda_graph = False
+    eager = []
+    for x, mf in ins:
+        out = m([t.cuda() for t in x], mf.cuda())
+        eager.append((out["pred_masks"].clone(), out["pred_embeds"].clone() if "pred_embeds" in out else None))
+    m.use_cuda_graph = True
+    n0 = L.launch_count()
+    for (x, mf), (pm, pe) in zip(ins, eager):          # call 1 is still eager (already warm), 2 captures, 3 replays
+        out = m([t.cuda() for t in x], mf.cuda())
+        assert torch.equal(out["pred_masks"], pm)
+        if pe is not None:
+            assert torch.equal(out["pred_embeds"], pe)
+    per_call = (L.launch_count() - n0) / 3
+    assert per_call > 100, per_call                     # replayed launches are still counted

@@ -396,9 +396,9 @@ def main():
         d = kernels[dom]
         roofline = {"kernel": kname[dom], "bound": d["bound"], "achieved": d["achieved"], "peak": d["peak"], "unit": d["unit"],
                     "frac": d["frac"],
-                    "traffic": (traffic or {}).get(dom, {}).get("dram_bytes_per_clip") if traffic else None,
-                    "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of this family's launches for ONE clip (ncu, "
-                                    "profiles/ncu_traffic_r1.json); algorithmic bytes/flops above are per step = clips_per_step clips",
+                    "traffic": ((traffic or {}).get(dom, {}).get("dram_bytes_per_clip") or 0) * C_ or None,
+                    "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of this family's launches (ncu, one clip: "
+                                    "profiles/ncu_traffic_r1.json) x clips_per_step, i.e. per step like `achieved`",
                     "peak_source": f"{src} ({'bf16_tflops_sustained' if d['bound'] == 'tensor' else 'hbm_gbs'}; kernel timed inside a long step)",
                     "share_of_step": d["share_of_step"]}
         if dom == "xattn" and "xu_bound" in d:

@@ -545,13 +545,20 @@ int ovis_kv_proj_f16(const void* xk, const void* xv, long long rows, const void*
   a.K = 256;
   a.epi = EPI_STORE;
   a.a_alt = 1;
+  a.ldo = 256;
+  // OVIS_KV_BN=128: two 128-wide column tiles per output (deeper A ring, smaller accumulators); default 256
+  static const int kv_bn = getenv("OVIS_KV_BN") ? atoi(getenv("OVIS_KV_BN")) : 256;
+  const int bn = (kv_bn == 128 && 2 * n_tiles <= GEMM_MAX_NTILES && 2 * n_tiles <= GEMM_MAX_OUT_MAPS) ? 128 : 256;
+  const int split = 256 / bn;
+  a.a_alt_shift = split == 2 ? 1 : 0;
   for (int t = 0; t < n_tiles; ++t) {
     CHECK_ARG(out[t] != nullptr, "null output tile");
-    a.out[t] = out[t];
-    a.bias[t] = bias ? bias[t] : nullptr;
+    for (int h = 0; h < split; ++h) {
+      a.out[t * split + h] = (__half*)out[t] + h * bn;
+      a.bias[t * split + h] = (bias && bias[t]) ? bias[t] + h * bn : nullptr;
+    }
   }
-  a.ldo = 256;
-  return launch_gemm(xk, rows, 256, 256, w, (long long)n_tiles * 256, 256, a, 256, (cudaStream_t)stream, xv);
+  return launch_gemm(xk, rows, 256, 256, w, (long long)n_tiles * 256, 256, a, bn, (cudaStream_t)stream, xv);
 }
 
 int ovis_mask_bits(const void* gt, int groups, int rows_per_group, const void* me, int Q, unsigned int* bits,

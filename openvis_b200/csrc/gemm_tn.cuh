@@ -20,7 +20,7 @@ enum GemmEpi : int {
 };
 
 constexpr int GEMM_MAX_NTILES = 16;
-constexpr int GEMM_MAX_OUT_MAPS = 8;
+constexpr int GEMM_MAX_OUT_MAPS = 16;
 
 // output tensor maps for the TMA-store epilogue (box = 128 bytes x 32 rows, 128B swizzle), one per n-tile
 struct GemmOutMaps {
@@ -50,7 +50,8 @@ struct GemmArgs {
   int relu;               // activation: 0 none, 1 ReLU, 2 QuickGELU x * sigmoid(1.702 x) (CLIP blocks, model.py:232-234)
   float scale;
   const float* resid_st;  // optional fp32 [rows][ldo] added after the activation (residual connections; may alias out)
-  int a_alt;              // 1: odd n-tiles read their A operand from the second tensor map (key / value operands)
+  int a_alt;              // 1: n-tiles with ((nt >> a_alt_shift) & 1) read their A operand from the second tensor map
+  int a_alt_shift;        //    (key / value operands; shift 1 when a 256-wide output is split into two 128-wide tiles)
   int tma_store;          // 1: EPI_STORE writes through GemmOutMaps (single group, 16-byte aligned pitch)
   // ---- EPI_LN
   const float* resid;     // [rows][256] fp32
@@ -523,7 +524,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int a_col = (g % args.a_k_mod) * args.a_k_offset_stride;
         const int b_row = (g / args.b_row_div) * args.b_group_stride + nt * BN;
         const int b_col = (g % args.b_k_mod) * args.b_k_offset_stride;
-        const CUtensorMap* ta = (args.a_alt && (nt & 1)) ? &tmA2 : &tmA;
+        const CUtensorMap* ta = (args.a_alt && ((nt >> args.a_alt_shift) & 1)) ? &tmA2 : &tmA;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
@@ -675,7 +676,7 @@ gemm_tn_bs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const int b_row = (g / args.b_row_div) * args.b_group_stride + nt * BN;
           const int a_col = (g % args.a_k_mod) * args.a_k_offset_stride;
           const int a_row0 = (g / args.a_row_div) * args.a_group_stride;
-          const CUtensorMap* ta = (args.a_alt && (nt & 1)) ? &tmA2 : &tmA;
+          const CUtensorMap* ta = (args.a_alt && ((nt >> args.a_alt_shift) & 1)) ? &tmA2 : &tmA;
           mbar_wait(bempty_bar, bphase ^ 1);               // previous column's MMAs have retired
           mbar_arrive_expect_tx(bfull_bar, (uint32_t)(k_blocks * BN * Cfg::BK * 2));
           const int b_col = (g % args.b_k_mod) * args.b_k_offset_stride;

@@ -721,6 +721,8 @@ int ovis_xattn(const void* q, const void* k, const void* v, const unsigned int* 
     a.bits = bits; a.flags = flags; a.o_part = o_part; a.ml_part = ml_part;
     a.Q = Q; a.q_pad = q_pad; a.q_stride = q_stride;
     a.keys = keys; a.W = (keys + 31) / 32; a.splits = splits; a.chunk = chunk;
+    static const char* tr = getenv("OVIS_XATTN_TRACE");      // device pointer (decimal) of the trace buffer
+    a.trace = tr ? reinterpret_cast<long long*>(strtoull(tr, nullptr, 10)) : nullptr;
     if (variant == 2) {
       xattn_tc2_kernel<<<dim3(chunks * 4, qtiles, G), X2_THREADS, X2_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, a);
       rc = check_launch("xattn_tc2_kernel");

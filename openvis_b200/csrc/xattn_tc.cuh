@@ -31,6 +31,7 @@ struct XattnTcArgs {
   float* ml_part;              // [G][S][8][q_pad][2]
   int Q, q_pad, q_stride;
   int keys, W, splits, chunk;  // chunk: keys per split, multiple of 64
+  long long* trace;            // tools/trace_xattn.py: clock64 stamps of block 0, [6 roles][64 steps][8 events], else null
 };
 
 constexpr int XT_KT = 64;                       // keys per tile

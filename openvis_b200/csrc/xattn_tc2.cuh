@@ -31,6 +31,12 @@ constexpr int X2_P_BYTES = 128 * 128;            // [128 q][64 keys] fp16
 constexpr int X2_SMEM = X2_Q_BYTES + X2_STAGES * X2_KV_STAGE + 4 * X2_P_BYTES + 1024 + 512;
 constexpr int X2_THREADS = 19 * 32;
 
+#define X2_TRACE(role, step, ev)                                                                   \
+  do {                                                                                            \
+    if (a.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (step) < 64)          \
+      a.trace[((role) * 64 + (step)) * 8 + (ev)] = clock64();                                     \
+  } while (0)
+
 __global__ void __launch_bounds__(X2_THREADS, 1)
 xattn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const XattnTcArgs a) {
@@ -124,6 +130,7 @@ xattn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           umma_f16(d_tmem, adesc, bdesc, idesc_s, 0u);
           umma_f16(d_tmem, adesc + 2, bdesc + 2, idesc_s, 1u);
           umma_commit(&s_full[wg]);
+          X2_TRACE(4, n, wg);                                  // role 4 = S issuer: event index = warpgroup
           nxt[wg] = n + 1;
           --remaining;
           any = true;
@@ -175,6 +182,7 @@ xattn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           for (int kk = 0; kk < X2_KT / 16; ++kk)
             umma_f16(d_tmem, adesc + 2 * kk, bdesc + (uint64_t)(kk * (2048 >> 4)), idesc_o, (n > 0 || kk > 0) ? 1u : 0u);
           umma_commit(&p_empty[wg]);
+          X2_TRACE(5, n, wg);                                  // role 5 = PV issuer
           if (half_done & (1u << st)) {     // both heads of this tile issued: the K/V stage is free once they retire
             umma_commit(&empty[st]);
             half_done &= ~(1u << st);
@@ -217,7 +225,8 @@ xattn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 #pragma unroll
       for (int x = 0; x < 2; ++x) {
         const int wi = (kb >> 5) + x;
-        dst[x] = (use_mask && t < ntiles && wi < a.W) ? __ldg(bits_q + (long long)wi * a.q_stride) : 0u;
+        // padding rows of the 128-row tile (q >= Q) count as fully blocked, so they never keep a warp from skipping
+        dst[x] = q >= a.Q ? 0xffffffffu : ((use_mask && t < ntiles && wi < a.W) ? __ldg(bits_q + (long long)wi * a.q_stride) : 0u);
       }
     };
     uint32_t nw[2];
@@ -233,8 +242,11 @@ xattn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       }
       load_words(t + 2, nw);
       const uint32_t ph = (uint32_t)(n & 1);
+      const bool tr = (quarter == 0 && lane == 0);
+      if (tr) X2_TRACE(wg, n, 0);                           // step begins
       mbar_wait(&s_full[wg], ph);
       tc_fence_after();
+      if (tr) X2_TRACE(wg, n, 1);                           // S available
       // Online softmax in base 2 with a lazily updated reference max (one 32-key half at a time to stay inside the
       // register budget): probabilities are computed optimistically against the running reference; only when a half
       // would overflow (or the row had no unblocked key so far) it is recomputed against a new reference and
@@ -249,7 +261,21 @@ xattn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         // 32 S columns at a time (registers: 18 warps leave 96 per thread); the S buffer is handed back to the issuer
         // as soon as the second half sits in registers
         uint32_t sv[32];
+        const uint32_t word = mw[hf];
         __syncwarp();                                     // (re-converged after the per-lane recompute branch)
+        // Fully-masked half tile: every one of this warp's 32 queries blocks all 32 keys (object masks are compact, so
+        // most (query block, key block) pairs of a trained model look like this).  Nothing to load or exponentiate:
+        // the probabilities are zero.  Warp-uniform.
+        if (__all_sync(0xffffffffu, word == 0xffffffffu)) {
+#pragma unroll
+          for (int c = 0; c < 16; ++c) pk[hf * 16 + c] = 0u;
+          if (hf == 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_empty[wg]);
+          }
+          continue;
+        }
         tmem_ld_32x32_nowait(s_addr + hf * 32, sv);
         tmem_ld_wait();
         reg_fence32(sv);
@@ -258,7 +284,6 @@ xattn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           __syncwarp();
           if (lane == 0) mbar_arrive(&s_empty[wg]);
         }
-        const uint32_t word = mw[hf];
         const float m_opt = (m_cur == -INFINITY) ? 0.f : m_cur;
         float ls[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -316,8 +341,10 @@ xattn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
         sum_tile += (ls[0] + ls[1]) + (ls[2] + ls[3]);
       }
+      if (tr) X2_TRACE(wg, n, 2);                           // softmax arithmetic done
       // the P buffer and the O accumulator of this warpgroup are free once the PV product of its previous tile retired
       mbar_wait(&p_empty[wg], ph ^ 1u);
+      if (tr) X2_TRACE(wg, n, 3);                           // P buffer free
       tc_fence_after();
       if (__any_sync(0xffffffffu, grow_any)) {
         uint32_t ov[32];
@@ -338,6 +365,7 @@ xattn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[wg]);
+      if (tr) X2_TRACE(wg, n, 4);                           // P handed over
     }
     // ---- all MMAs retired: write this (head, parity) partial: un-normalised O and (max, sum)
     mbar_wait(done, 0);

@@ -224,6 +224,43 @@ def test_xattn(G, Q, keys, density):
     assert _maxerr(out, ref) < 6e-3, (_maxerr(out, ref), splits)
 
 
+@pytest.mark.parametrize("G,Q,keys", [(2, 100, 3840), (1, 200, 1920)])
+def test_xattn_block_sparse_masks(G, Q, keys):
+    """Object-like masks: every query sees a few compact key ranges, so most (32-query, 32-key) blocks are fully blocked
+    and take the kernel's skip path; a few queries see nothing (all-masked-row rule) or everything."""
+    q = _randn(G * Q, 256, seed=1, scale=0.6).half()
+    k = _randn(G * keys, 256, seed=2).half()
+    v = _randn(G * keys, 256, seed=3).half()
+    gen = _g(9)
+    blocked = torch.ones(G, Q, keys, dtype=torch.bool)
+    for g_ in range(G):
+        for qi in range(Q):
+            if qi % 17 == 3:
+                continue                                  # fully blocked row -> attends everywhere
+            if qi % 23 == 5:
+                blocked[g_, qi] = False                   # sees every key
+                continue
+            for _ in range(int(torch.randint(1, 4, (1,), generator=gen))):
+                a0 = int(torch.randint(0, keys - 40, (1,), generator=gen))
+                blocked[g_, qi, a0:a0 + int(torch.randint(1, 40, (1,), generator=gen))] = False
+    # queries of one 32-row block share a region: whole blocks of keys stay blocked for the whole warp
+    blocked = blocked.cuda()
+    W = (keys + 31) // 32
+    r = torch.arange(keys, device="cuda")
+    bits = torch.zeros(G, W, Q, dtype=torch.int64, device="cuda")
+    bits.scatter_add_(1, (r // 32)[None, :, None].expand(G, keys, Q),
+                      (blocked.permute(0, 2, 1).long() << (r % 32)[None, :, None]))
+    bits = bits.to(torch.int32)
+    flags = (~blocked).any(-1).to(torch.uint8).contiguous()
+    splits, q_pad, o_n, ml_n = L.xattn_plan(G, Q, keys)
+    o_part = torch.empty(o_n, device="cuda")
+    ml_part = torch.empty(ml_n, device="cuda")
+    out = torch.empty(G * Q, 256, dtype=torch.float16, device="cuda")
+    L.xattn(q, k, v, bits.contiguous(), flags, G, Q, Q, keys, splits, o_part, ml_part, out)
+    ref = _ref_xattn(q, k, v, blocked, G, Q, keys)
+    assert _maxerr(out, ref) < 6e-3, (_maxerr(out, ref), splits)
+
+
 @pytest.mark.parametrize("G,Q", [(1, 100), (5, 100), (2, 200)])
 def test_self_attn(G, Q):
     qk = _randn(G * Q, 512, seed=1).half()

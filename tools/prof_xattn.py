@@ -10,6 +10,13 @@ k = torch.randn(G * keys, 256, generator=g).half().cuda()
 v = torch.randn(G * keys, 256, generator=g).half().cuda()
 W = (keys + 31) // 32
 bits = torch.randint(-2**31, 2**31 - 1, (G, W, Q), generator=g, dtype=torch.int64).to(torch.int32).cuda()
+if os.environ.get("SPARSE"):
+    # object-like masks: each block of 32 queries sees one contiguous 1/8 of the keys (random bits inside), nothing else
+    bits = torch.full((G, W, Q), -1, dtype=torch.int32)
+    for qb in range((Q + 31) // 32):
+        w0 = (qb * W) // 8 % W
+        bits[:, w0:w0 + W // 8, qb * 32:(qb + 1) * 32] = torch.randint(-2**31, 2**31 - 1, (G, W // 8, min(32, Q - qb * 32)), generator=g, dtype=torch.int64).to(torch.int32)
+    bits = bits.cuda()
 flags = torch.ones(G, Q, dtype=torch.uint8).cuda()
 splits, q_pad, o_n, ml_n = L.xattn_plan(G, Q, keys)
 o_part = torch.empty(o_n, device="cuda"); ml_part = torch.empty(ml_n, device="cuda")

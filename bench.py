@@ -373,6 +373,11 @@ def main():
     kname = {"xattn": "xattn_tc2_kernel+xattn_combine_kernel", "kv_proj": "gemm_tn_bs_kernel<256> (key/value projection)",
              "prep": "maskfeat_prep_tma_kernel+tokens_prep_tma_kernel", "mask_logits": "gemm_tn_bs_kernel<128> (final mask logits)",
              "mask_bits": "gemm_tn_bs_kernel<128> (mask sign bits)"}
+    if "kv_proj" in kernels and kernels["kv_proj"]["ms_per_step"] > 0:
+        # the K/V projection sits at the ridge (190 flop per byte): report the HBM view next to the tensor view
+        byts = sum(rows3[l] * (2 * 512 + 1536 * 2) for l in range(3)) * args.steps
+        ach = byts / (kernels["kv_proj"]["ms_per_step"] * args.steps * 1e-3) / 1e9
+        kernels["kv_proj"]["hbm_view"] = {"achieved": ach, "peak": peak_bw, "unit": "GB/s", "frac": ach / peak_bw}
     if "xattn" in kernels and kernels["xattn"]["ms_per_step"] > 0:
         # d = 32 heads make the masked attention exp-bound, not tensor-bound: 128 flop per exponential.  The binding
         # pipe is the XU (MUFU.EX2: 16 lanes/clk/SM, measured 16.5 by tools/ubench/pipes.cu); reported next to the

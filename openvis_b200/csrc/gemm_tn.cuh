@@ -113,6 +113,48 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmArgs& args, const C
                                                  : (long long)(g / args.a_row_div) * args.a_group_stride) + r_warp0;
     const bool vec_ok = (((long long)args.ldo * esize) & 15) == 0;
     const bool bias_vec = bias && ((reinterpret_cast<uintptr_t>(bias) & 15) == 0);
+    // Fast path for the HBM-heavy plain projections (K/V projection, in-projections): fp16 output, vector bias, no
+    // scale / activation / residual, full column tile, bulk tensor store.  The generic code below handles every
+    // combination at run time and costs ~30 instructions per element, which made these GEMMs epilogue-issue-bound.
+    if (args.tma_store && !args.out_f32 && args.relu == 0 && args.scale == 1.f && args.resid_st == nullptr && bias_vec &&
+        col_base + BN <= args.N) {
+#pragma unroll 1
+      for (int u0 = half * (BN / 2); u0 < (half + 1) * (BN / 2); u0 += 64) {
+        uint32_t va[32], vb[32];
+        tmem_ld_32x32_raw(t_acc + u0, va);
+        tmem_ld_32x32_raw(t_acc + u0 + 32, vb);
+        tmem_ld_wait();
+        reg_fence32(va);
+        reg_fence32(vb);
+        uint4 pk[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + u0 + 8 * j));
+          const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + u0 + 8 * j + 4));
+          pk[j] = make_uint4(pack_half2(__uint_as_float(va[8 * j]) + b0.x, __uint_as_float(va[8 * j + 1]) + b0.y),
+                             pack_half2(__uint_as_float(va[8 * j + 2]) + b0.z, __uint_as_float(va[8 * j + 3]) + b0.w),
+                             pack_half2(__uint_as_float(va[8 * j + 4]) + b1.x, __uint_as_float(va[8 * j + 5]) + b1.y),
+                             pack_half2(__uint_as_float(va[8 * j + 6]) + b1.z, __uint_as_float(va[8 * j + 7]) + b1.w));
+          const float4 c0 = __ldg(reinterpret_cast<const float4*>(bias + u0 + 32 + 8 * j));
+          const float4 c1 = __ldg(reinterpret_cast<const float4*>(bias + u0 + 32 + 8 * j + 4));
+          pk[4 + j] = make_uint4(pack_half2(__uint_as_float(vb[8 * j]) + c0.x, __uint_as_float(vb[8 * j + 1]) + c0.y),
+                                 pack_half2(__uint_as_float(vb[8 * j + 2]) + c0.z, __uint_as_float(vb[8 * j + 3]) + c0.w),
+                                 pack_half2(__uint_as_float(vb[8 * j + 4]) + c1.x, __uint_as_float(vb[8 * j + 5]) + c1.y),
+                                 pack_half2(__uint_as_float(vb[8 * j + 6]) + c1.z, __uint_as_float(vb[8 * j + 7]) + c1.w));
+        }
+        if (lane == 0) tma_store_wait_read0();           // the previous unit's bulk store has read the staging buffer
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < 8; ++c) st_shared_v4(stg + (uint32_t)((lane * 8 + (c ^ (lane & 7))) << 4), pk[c]);
+        fence_async_proxy();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&omaps[nt], stage_smem + (warp - 2) * 4096, u0, (int)grow0);
+          tma_store_commit();
+        }
+      }
+      return;
+    }
 #pragma unroll 1
     for (int u0 = half * (BN / 2); u0 < (half + 1) * (BN / 2); u0 += cols_per_unit) {
       if (col_base + u0 >= args.N) break;                     // warp-uniform

@@ -130,6 +130,16 @@ int ovis_self_attn(const void* qk_f16, const void* v_f16, void* out_f16, int G, 
  * frames with a non-empty mask, softmax over K.  logits [T][Q][K], valid [T][Q] -> probs [Q][K], qvalid [Q]. */
 int ovis_clip_aggregate(const float* logits, const unsigned char* valid, float* probs, unsigned char* qvalid,
                         int T, int Q, int K, void* stream);
+/* ---- multi-scale deformable attention, forward ---------------------------------
+ * Replaces MSDA.ms_deform_attn_forward (openvis/modeling/pixel_decoder/ops/src/vision.cpp:18-21 ->
+ * ms_deform_attn_cuda_forward, src/cuda/ms_deform_attn_cuda.cu:22-84 -> ms_deformable_im2col_gpu_kernel,
+ * src/cuda/ms_deform_im2col_cuda.cuh:243-305), fp32:
+ * value [N][S][M][D], spatial_shapes [L][2] int64 (H, W), level_start_index [L] int64, sampling_loc [N][Lq][M][L][P][2]
+ * (x, y in [0,1]), attn_weight [N][Lq][M][L][P] -> out [N][Lq][M*D].  All device pointers.  No im2col_step: the whole
+ * batch is one launch.  Backward (training) is out of scope. */
+int ovis_ms_deform_attn_forward(const float* value, const long long* spatial_shapes, const long long* level_start_index,
+                                const float* sampling_loc, const float* attn_weight, float* out, int N, int S, int M, int D,
+                                int Lq, int L, int P, void* stream);
 /* ---- device-side post-processing ----------------------------------------------
  * Top-k over the flattened [Q*K] scores with labels, query indices and per-query entropy:
  * scores.flatten(0, 1).topk(10), labels[topk], topk // num_classes, sum(-s log s)

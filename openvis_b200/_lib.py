@@ -41,6 +41,8 @@ SIGNATURES = {
     "ovis_xattn": (_c_int, [_vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp]),
     "ovis_self_attn": (_c_int, [_vp, _vp, _vp, _c_int, _c_int, _vp]),
     "ovis_clip_aggregate": (_c_int, [_vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _vp]),
+    "ovis_ms_deform_attn_forward": (_c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
+                                             _c_int, _vp]),
     "ovis_topk_scores": (_c_int, [_vp, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp]),
     "ovis_mask_postprocess": (_c_int, [_vp, _c_ll, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
                                        _c_int, _c_int, _vp, _vp]),
@@ -228,6 +230,23 @@ def linear_act_f16(x, w, bias=None, scale=1.0, act=0, resid=None, out=None, out_
         assert resid.shape == (rows, N) and resid.stride(0) == out.stride(0)
     _check(lib.ovis_linear_act_f16(_p(x), rows, K, x.stride(0), _p(w), N, _p(bias), float(scale), int(act), _p(resid),
                                    _p(out), out.stride(0), int(out_f32), _stream()))
+    return out
+
+
+def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_locations, attention_weights):
+    """value [N, S, M, D] fp32, spatial_shapes [L, 2] int64, level_start_index [L] int64, sampling_locations
+    [N, Lq, M, L, P, 2], attention_weights [N, Lq, M, L, P] -> [N, Lq, M*D] fp32."""
+    lib = load()
+    for t, n in ((value, "value"), (sampling_locations, "sampling_locations"), (attention_weights, "attention_weights")):
+        _req(t, torch.float32, n)
+    _req(spatial_shapes, torch.int64, "spatial_shapes")
+    _req(level_start_index, torch.int64, "level_start_index")
+    N, S, M, D = value.shape
+    _, Lq, M2, L_, P, two = sampling_locations.shape
+    assert M2 == M and two == 2 and attention_weights.shape == (N, Lq, M, L_, P) and spatial_shapes.shape == (L_, 2)
+    out = torch.empty(N, Lq, M * D, dtype=torch.float32, device=value.device)
+    _check(lib.ovis_ms_deform_attn_forward(_p(value), _p(spatial_shapes), _p(level_start_index), _p(sampling_locations),
+                                           _p(attention_weights), _p(out), N, S, M, D, Lq, L_, P, _stream()))
     return out
 
 

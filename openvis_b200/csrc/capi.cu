@@ -17,6 +17,7 @@
 #include "xattn_tc2.cuh"
 #include "san_attn.cuh"
 #include "postproc.cuh"
+#include "msda.cuh"
 
 using namespace ovis;
 
@@ -758,6 +759,43 @@ int ovis_clip_aggregate(const float* logits, const unsigned char* valid, float* 
   if (rc) return rc;
   clip_aggregate_kernel<<<Q, 256, (size_t)K * sizeof(float), (cudaStream_t)stream>>>(logits, valid, probs, qvalid, T, Q, K);
   return check_launch("clip_aggregate_kernel");
+}
+
+int ovis_ms_deform_attn_forward(const float* value, const long long* spatial_shapes, const long long* level_start_index,
+                                const float* sampling_loc, const float* attn_weight, float* out, int N, int S, int M, int D,
+                                int Lq, int L, int P, void* stream) {
+  CHECK_ARG(value && spatial_shapes && level_start_index && sampling_loc && attn_weight && out, "null pointer");
+  CHECK_ARG(N > 0 && S > 0 && M > 0 && D > 0 && Lq > 0 && L > 0 && P > 0, "bad sizes");
+  int rc = device_info(nullptr);
+  if (rc) return rc;
+  MsdaArgs a;
+  a.value = value; a.shapes = spatial_shapes; a.start = level_start_index; a.loc = sampling_loc; a.weight = attn_weight;
+  a.out = out; a.N = N; a.S = S; a.M = M; a.D = D; a.Lq = Lq; a.L = L; a.P = P;
+  const long long groups = (long long)N * Lq * M;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(value) | reinterpret_cast<uintptr_t>(out)) & 15) == 0 &&
+                       (reinterpret_cast<uintptr_t>(sampling_loc) & 7) == 0;
+  const int lpg = D / 4;
+  const bool vec = aligned && D % 4 == 0 && (lpg == 1 || lpg == 2 || lpg == 4 || lpg == 8 || lpg == 16 || lpg == 32);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (vec) {
+    const long long threads = groups * lpg;
+    const long long blocks = (threads + 255) / 256;
+    CHECK_ARG(blocks < (1ll << 31), "too many queries for one launch");
+    switch (lpg) {
+      case 1: msda_forward_vec_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(a); break;
+      case 2: msda_forward_vec_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(a); break;
+      case 4: msda_forward_vec_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(a); break;
+      case 8: msda_forward_vec_kernel<8><<<(unsigned)blocks, 256, 0, st>>>(a); break;
+      case 16: msda_forward_vec_kernel<16><<<(unsigned)blocks, 256, 0, st>>>(a); break;
+      default: msda_forward_vec_kernel<32><<<(unsigned)blocks, 256, 0, st>>>(a); break;
+    }
+    return check_launch("msda_forward_vec_kernel");
+  }
+  const long long total = groups * D;
+  const long long blocks = (total + 255) / 256;
+  CHECK_ARG(blocks < (1ll << 31), "too many outputs for one launch");
+  msda_forward_scalar_kernel<<<(unsigned)blocks, 256, 0, st>>>(a);
+  return check_launch("msda_forward_scalar_kernel");
 }
 
 int ovis_topk_scores(const float* scores, int Q, int K, int k, float* out_scores, int* out_query, int* out_label,

@@ -1,0 +1,120 @@
+// Multi-scale deformable attention, forward: the reference's only native op,
+// ms_deformable_im2col_gpu_kernel (openvis/modeling/pixel_decoder/ops/src/cuda/ms_deform_im2col_cuda.cuh:243-305),
+// called by MSDeformAttnFunction.forward (ops/functions/ms_deform_attn_func.py:32-40).
+//   out[b][q][m][c] = sum_{l, p} w[b][q][m][l][p] * bilinear(value_l[b][:, m, c], loc[b][q][m][l][p])
+// with h_im = loc_y * H_l - 0.5, w_im = loc_x * W_l - 0.5, zero contribution from corners outside the map and from
+// samples outside (-1, H) x (-1, W).
+//
+// The reference maps one thread to one output channel and re-reads the sampling location / weight in every thread.
+// Here a group of D/4 lanes owns one (b, q, head): every lane gathers float4 channel quads, so one bilinear corner of a
+// head is a single contiguous 16 * D/4-byte read (128 B for D = 32) issued by D/4 lanes instead of D, and the L * P
+// (location, weight) triples are read once per group and broadcast with shuffles.  The value map of a frame (20 MB at
+// 736 x 1280) lives in L2, so the op is gather-bound there.
+#pragma once
+#include "ptx.cuh"
+
+namespace ovis {
+
+struct MsdaArgs {
+  const float* value;        // [N][S][M][D]
+  const long long* shapes;   // [L][2] (H, W)  -- int64 like the reference
+  const long long* start;    // [L] level start index
+  const float* loc;          // [N][Lq][M][L][P][2] (x, y) in [0, 1]
+  const float* weight;       // [N][Lq][M][L][P]
+  float* out;                // [N][Lq][M*D]
+  int N, S, M, D, Lq, L, P;
+};
+
+// LPG lanes per (b, q, m) group, 4 channels per lane: D == 4 * LPG
+template <int LPG>
+__global__ void __launch_bounds__(256)
+msda_forward_vec_kernel(const MsdaArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % LPG;                                    // channel quad within the head
+  const long long group = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / LPG;
+  const long long groups = (long long)a.N * a.Lq * a.M;
+  const bool ok = group < groups;
+  const long long gi = ok ? group : groups - 1;
+  const int m = (int)(gi % a.M);
+  const long long bq = gi / a.M;
+  const int b = (int)(bq / a.Lq);
+  const int LP = a.L * a.P;
+  const float* locp = a.loc + gi * LP * 2;
+  const float* wp = a.weight + gi * LP;
+  const int row_stride = a.M * a.D;                              // floats between consecutive spatial positions
+  const float* vb = a.value + (long long)b * a.S * row_stride + m * a.D + sub * 4;
+  const unsigned gmask = 0xffffffffu;
+  const int gbase = lane - sub;                                  // first lane of this group
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i0 = 0; i0 < LP; i0 += LPG) {
+    // each lane of the group fetches one (x, y, w) triple; they are handed round with shuffles
+    const int mine = i0 + sub;
+    float lx = 0.f, ly = 0.f, lw = 0.f;
+    if (mine < LP) {
+      const float2 xy = __ldg(reinterpret_cast<const float2*>(locp) + mine);
+      lx = xy.x; ly = xy.y; lw = __ldg(wp + mine);
+    }
+    const int cnt = min(LPG, LP - i0);
+    for (int j = 0; j < cnt; ++j) {
+      const float x = __shfl_sync(gmask, lx, gbase + j);
+      const float y = __shfl_sync(gmask, ly, gbase + j);
+      const float w = __shfl_sync(gmask, lw, gbase + j);
+      const int l = (i0 + j) / a.P;
+      const int H = (int)__ldg(a.shapes + 2 * l), W = (int)__ldg(a.shapes + 2 * l + 1);
+      const float h_im = y * H - 0.5f, w_im = x * W - 0.5f;
+      if (h_im > -1.f && w_im > -1.f && h_im < H && w_im < W) {
+        const int h_low = (int)floorf(h_im), w_low = (int)floorf(w_im);
+        const float lh = h_im - h_low, lw2 = w_im - w_low;
+        const float hh = 1.f - lh, hw = 1.f - lw2;
+        const float* vl = vb + (long long)__ldg(a.start + l) * row_stride;
+        float4 v1 = make_float4(0.f, 0.f, 0.f, 0.f), v2 = v1, v3 = v1, v4 = v1;
+        if (h_low >= 0 && w_low >= 0) v1 = __ldg(reinterpret_cast<const float4*>(vl + ((long long)h_low * W + w_low) * row_stride));
+        if (h_low >= 0 && w_low + 1 <= W - 1) v2 = __ldg(reinterpret_cast<const float4*>(vl + ((long long)h_low * W + w_low + 1) * row_stride));
+        if (h_low + 1 <= H - 1 && w_low >= 0) v3 = __ldg(reinterpret_cast<const float4*>(vl + ((long long)(h_low + 1) * W + w_low) * row_stride));
+        if (h_low + 1 <= H - 1 && w_low + 1 <= W - 1) v4 = __ldg(reinterpret_cast<const float4*>(vl + ((long long)(h_low + 1) * W + w_low + 1) * row_stride));
+        const float w1 = hh * hw, w2 = hh * lw2, w3 = lh * hw, w4 = lh * lw2;       // (ms_deform_im2col_cuda.cuh:60-62)
+        acc.x += w * (w1 * v1.x + w2 * v2.x + w3 * v3.x + w4 * v4.x);
+        acc.y += w * (w1 * v1.y + w2 * v2.y + w3 * v3.y + w4 * v4.y);
+        acc.z += w * (w1 * v1.z + w2 * v2.z + w3 * v3.z + w4 * v4.z);
+        acc.w += w * (w1 * v1.w + w2 * v2.w + w3 * v3.w + w4 * v4.w);
+      }
+    }
+  }
+  if (ok) *reinterpret_cast<float4*>(a.out + gi * a.D + sub * 4) = acc;
+}
+
+// Any D: one thread per output channel, the reference's mapping (used for channel counts that are not 4 * 2^k <= 128).
+__global__ void __launch_bounds__(256)
+msda_forward_scalar_kernel(const MsdaArgs a) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)a.N * a.Lq * a.M * a.D;
+  if (idx >= total) return;
+  const int c = (int)(idx % a.D);
+  const long long gi = idx / a.D;
+  const int m = (int)(gi % a.M);
+  const int b = (int)(gi / a.M / a.Lq);
+  const int LP = a.L * a.P;
+  const int row_stride = a.M * a.D;
+  const float* vb = a.value + (long long)b * a.S * row_stride + m * a.D + c;
+  float acc = 0.f;
+  for (int i = 0; i < LP; ++i) {
+    const int l = i / a.P;
+    const int H = (int)a.shapes[2 * l], W = (int)a.shapes[2 * l + 1];
+    const float x = a.loc[(gi * LP + i) * 2], y = a.loc[(gi * LP + i) * 2 + 1], w = a.weight[gi * LP + i];
+    const float h_im = y * H - 0.5f, w_im = x * W - 0.5f;
+    if (h_im > -1.f && w_im > -1.f && h_im < H && w_im < W) {
+      const int h_low = (int)floorf(h_im), w_low = (int)floorf(w_im);
+      const float lh = h_im - h_low, lw2 = w_im - w_low, hh = 1.f - lh, hw = 1.f - lw2;
+      const float* vl = vb + (long long)a.start[l] * row_stride;
+      float v1 = 0.f, v2 = 0.f, v3 = 0.f, v4 = 0.f;
+      if (h_low >= 0 && w_low >= 0) v1 = vl[((long long)h_low * W + w_low) * row_stride];
+      if (h_low >= 0 && w_low + 1 <= W - 1) v2 = vl[((long long)h_low * W + w_low + 1) * row_stride];
+      if (h_low + 1 <= H - 1 && w_low >= 0) v3 = vl[((long long)(h_low + 1) * W + w_low) * row_stride];
+      if (h_low + 1 <= H - 1 && w_low + 1 <= W - 1) v4 = vl[((long long)(h_low + 1) * W + w_low + 1) * row_stride];
+      acc += w * (hh * hw * v1 + hh * lw2 * v2 + lh * hw * v3 + lh * lw2 * v4);
+    }
+  }
+  a.out[idx] = acc;
+}
+
+}  // namespace ovis

@@ -315,6 +315,39 @@ def san_build_attn_bias(attn_bias, grid_hw):
     return m
 
 
+def ms_deform_attn(value, spatial_shapes, sampling_locations, attention_weights):
+    """Multi-scale deformable attention forward, restated tap by tap from the reference's CUDA kernel
+    (ops/src/cuda/ms_deform_im2col_cuda.cuh:18-66, 243-305): h_im = y * H - 0.5, w_im = x * W - 0.5, samples outside
+    (-1, H) x (-1, W) and corners outside the map contribute zero.  (The reference's own debug function,
+    ms_deform_attn_core_pytorch, ops/functions/ms_deform_attn_func.py:55-77, does the same through F.grid_sample.)
+    value [N, S, M, D], spatial_shapes [L, 2] (H, W), sampling_locations [N, Lq, M, L, P, 2] (x, y),
+    attention_weights [N, Lq, M, L, P] -> [N, Lq, M*D]."""
+    N, S, M, D = value.shape
+    _, Lq, _, L_, P, _ = sampling_locations.shape
+    out = value.new_zeros(N, Lq, M, D)
+    start = 0
+    bi = torch.arange(N)[:, None, None, None]
+    mi = torch.arange(M)[None, None, :, None]
+    for l in range(L_):
+        H, W = int(spatial_shapes[l][0]), int(spatial_shapes[l][1])
+        v = value[:, start:start + H * W]                                  # [N, H*W, M, D]
+        start += H * W
+        x = sampling_locations[:, :, :, l, :, 0] * W - 0.5                 # [N, Lq, M, P]
+        y = sampling_locations[:, :, :, l, :, 1] * H - 0.5
+        inside = (y > -1) & (x > -1) & (y < H) & (x < W)
+        y0, x0 = torch.floor(y), torch.floor(x)
+        ly, lx = y - y0, x - x0
+        acc = value.new_zeros(N, Lq, M, P, D)
+        for dy, dx, wgt in ((0, 0, (1 - ly) * (1 - lx)), (0, 1, (1 - ly) * lx), (1, 0, ly * (1 - lx)), (1, 1, ly * lx)):
+            yy, xx = (y0 + dy).long(), (x0 + dx).long()
+            ok = inside & (yy >= 0) & (yy <= H - 1) & (xx >= 0) & (xx <= W - 1)
+            idx = (yy.clamp(0, H - 1) * W + xx.clamp(0, W - 1))            # [N, Lq, M, P]
+            g = v[bi, idx, mi]                                             # [N, Lq, M, P, D]
+            acc = acc + (wgt * ok)[..., None] * g
+        out = out + (acc * attention_weights[:, :, :, l, :, None]).sum(3)
+    return out.reshape(N, Lq, M * D)
+
+
 def video_postprocess(pred_cls, pred_masks, padded_size, img_size, out_hw, topk=10):
     """VideoMaskFormer.postprocess + inference_video (video_maskformer.py:215-229, 262-298) on pred_cls [Q, K] scores and
     stride-4 pred_masks [Q, T, h4, w4]: up-sample to the padded size, top-k over Q*K, crop, resize, > 0.

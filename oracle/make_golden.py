@@ -112,12 +112,46 @@ def make_san_blocks_fixture(n=2, Q=12, pseed=6):
     print("wrote san_blocks", {k: v.shape for k, v in rec.items()})
 
 
+MSDA_CASES = {
+    # the reference's own test configuration (ops/test.py:24-31, seed 3)
+    "ref_test": dict(N=1, M=2, D=2, Lq=2, L=2, P=2, shapes=[(6, 4), (3, 2)], seed=3, scale=0.01),
+    # the pixel decoder's configuration (8 heads x 32, 3 levels, 4 points) at a small size, queries = all positions
+    "pixdec": dict(N=2, M=8, D=32, Lq=None, L=3, P=4, shapes=[(4, 6), (8, 12), (16, 24)], seed=11, scale=1.0),
+    # odd channel count and sampling locations that leave the map
+    "odd": dict(N=1, M=3, D=7, Lq=5, L=2, P=3, shapes=[(5, 3), (2, 7)], seed=12, scale=1.0, spread=1.6),
+}
+
+
+def msda_inputs(N, M, D, Lq, L, P, shapes, seed, scale, spread=1.0):
+    g = torch.Generator().manual_seed(seed)
+    S = sum(h * w for h, w in shapes)
+    Lq = S if Lq is None else Lq
+    value = torch.rand(N, S, M, D, generator=g) * scale
+    loc = (torch.rand(N, Lq, M, L, P, 2, generator=g) - 0.5) * spread + 0.5
+    w = torch.rand(N, Lq, M, L, P, generator=g) + 1e-5
+    w = w / w.sum(-1, keepdim=True).sum(-2, keepdim=True)
+    return value, torch.as_tensor(shapes, dtype=torch.long), loc, w
+
+
+def make_msda_fixture():
+    """Outputs of the reference's ms_deform_attn_core_pytorch (fp64 evaluation, stored as fp32)."""
+    core = R.msda_core_pytorch()
+    rec = {}
+    for name, cfg in MSDA_CASES.items():
+        value, shapes, loc, w = msda_inputs(**cfg)
+        with torch.no_grad():
+            rec[name] = core(value.double(), shapes, loc.double(), w.double()).float().numpy()
+    np.savez_compressed(os.path.join(GOLDEN, "msda.npz"), **rec)
+    print("wrote msda", {k: v.shape for k, v in rec.items()})
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     for case in DECODER_CASES:
         make_decoder_fixture(*case)
     make_san_tail_fixture()
     make_san_blocks_fixture()
+    make_msda_fixture()
 
 
 if __name__ == "__main__":

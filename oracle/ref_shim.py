@@ -162,3 +162,20 @@ def side_adapter_module():
     ns = types.SimpleNamespace(module=sa, SideAdapter=sa.SideAdapter, clip_model=clip_model)
     _loaded["san"] = ns
     return ns
+
+
+def msda_core_pytorch():
+    """The reference's own pure-PyTorch multi-scale deformable attention (``ms_deform_attn_core_pytorch``,
+    ops/functions/ms_deform_attn_func.py:55-77).  Its module refuses to import without the compiled extension, so an
+    empty stand-in for ``MultiScaleDeformableAttention`` is registered first (the debug function never touches it)."""
+    if "msda" in _loaded:
+        return _loaded["msda"]
+    if not available():
+        raise RuntimeError(f"reference not found under {REF_ROOT}")
+    _mod("MultiScaleDeformableAttention")
+    d = os.path.join(REF_ROOT, "openvis/modeling/pixel_decoder/ops/functions")
+    pkg = _mod("refmsda")
+    pkg.__path__ = [d]
+    m = _load("refmsda", d, "ms_deform_attn_func")
+    _loaded["msda"] = m.ms_deform_attn_core_pytorch
+    return _loaded["msda"]

@@ -162,3 +162,14 @@ def test_san_bias_structure_is_what_the_kernel_assumes():
     keep = m > -50
     part = (s + m).masked_fill(~keep, float("-inf")).softmax(-1)
     assert torch.equal(full.masked_fill(~keep, 0.0), part) or (full.masked_fill(~keep, 0.0) - part).abs().max() < 1e-30
+
+
+@pytest.mark.parametrize("name", ["ref_test", "pixdec", "odd"])
+def test_msda_matches_golden(name, golden_dir):
+    """Multi-scale deformable attention: the tap-by-tap restatement against the outputs of the
+    reference's own ms_deform_attn_core_pytorch (the first case is the configuration of the reference's ops/test.py)."""
+    from oracle.make_golden import MSDA_CASES, msda_inputs
+    g = np.load(os.path.join(golden_dir, "msda.npz"))
+    value, shapes, loc, w = msda_inputs(**MSDA_CASES[name])
+    out = O.ms_deform_attn(value, shapes, loc, w)
+    _close(out, g[name], atol=1e-6, rtol=1e-5)

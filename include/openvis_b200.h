@@ -79,7 +79,7 @@ int ovis_linear_act_f16(const void* x_f16, long long rows, int K, int ldx, const
  * fused with decoder_norm (frame_...decoder.py:140).  Any output pointer may be null.
  * ype16 = fp16(y + pe[row % pe_period]) is the "+ query_pos" operand of the next projection.
  * split_ws (optional, >= (K/256) * ceil128(rows) * 256 floats): scratch for the few-rows path (split-K partials
- * + a row-parallel LayerNorm kernel) taken when rows <= 2048; without it the fused single-pass epilogue is used. */
+ * + a row-parallel LayerNorm kernel) taken when rows <= 16384; without it the fused single-pass epilogue is used. */
 int ovis_linear_ln_f16(const void* x_f16, long long rows, int K, const void* w_f16, const float* bias,
                        const float* resid, const float* ln1_g, const float* ln1_b,
                        const float* ln2_g, const float* ln2_b, const float* pe, int pe_period,

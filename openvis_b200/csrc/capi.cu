@@ -487,13 +487,14 @@ int ovis_linear_ln_f16(const void* x, long long rows, int K, const void* w, cons
   CHECK_ARG(rows < (1ll << 31), "too many rows");
   GemmArgs a;
   init_args(a);
-  // Few rows (the Video decoders' 100..400 queries): one CTA per 128-row tile would leave the GPU idle and serialise
-  // the K loop, so the product is split over K slices of 256 and two 128-column tiles (fp32 partials in split_ws) and a
-  // row-parallel kernel finishes bias + residual + LayerNorm(s).  Many rows (Frame decoders): fused epilogue.
+  // Up to 16384 rows (the Video decoders' 100..400 queries, the Frame decoders' frames x queries): one CTA per 128-row
+  // tile with the whole K loop and a row-serial LayerNorm epilogue leaves most of the GPU idle (37-57 us per call), so
+  // the product is split over K slices of 256 and two 128-column tiles (fp32 partials in split_ws) and a row-parallel
+  // kernel finishes bias + residual + LayerNorm(s).  Beyond that the fused epilogue has enough tiles to fill the GPU.
   const long long rows_pad = ((rows + 127) / 128) * 128;
   const int S = K / 256;
   static const bool no_split = getenv("OVIS_LN_NO_SPLIT") != nullptr;     // A/B testing only
-  if (!no_split && split_ws && K % 256 == 0 && rows <= 2048 && split_ws_floats >= (long long)S * rows_pad * 256) {
+  if (!no_split && split_ws && K % 256 == 0 && rows <= 16384 && split_ws_floats >= (long long)S * rows_pad * 256) {
     a.rows_per_group = (int)rows;
     a.num_groups = S;
     a.a_group_stride = 0;

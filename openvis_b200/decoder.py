@@ -372,9 +372,8 @@ class _B200MaskedDecoderBase(nn.Module):
         ws["q16"], ws["att16"], ws["qk16"], ws["v16"], ws["sa16"] = h(R, C), h(R, C), h(R, 2 * C), h(R, C), h(R, C)
         ws["h16"] = h(R, self.dim_feedforward)
         ws["m1"], ws["m2"], ws["me16"] = h(R, C), h(R, C), h(R, C)
-        # scratch of the few-rows linear+LayerNorm path (split-K partials); Frame decoders with thousands of rows use
-        # the fused epilogue and need none
-        ws["split"] = f((self.dim_feedforward // 256) * ((R + 127) // 128) * 128 * 256) if R <= 2048 else None
+        # scratch of the split linear+LayerNorm path (split-K partials); beyond 16384 rows the fused epilogue is used
+        ws["split"] = f((self.dim_feedforward // 256) * ((R + 127) // 128) * 128 * 256) if R <= 16384 else None
         ws["bits"] = [torch.zeros(G, (Tg * n + 31) // 32, Q, dtype=torch.int32, device=device) for n in N]
         ws["flags"] = torch.zeros(self.num_layers + 1, G, Q, dtype=torch.uint8, device=device)
         plans = [L.xattn_plan(G, Q, Tg * n) for n in N]

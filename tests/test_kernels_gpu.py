@@ -59,8 +59,7 @@ def test_linear_strided_input():
 @pytest.mark.parametrize("rows,K,two", [(100, 256, False), (100, 2048, True), (3600, 256, True), (333, 2048, False),
                                         (400, 2048, True)])
 def test_linear_ln(rows, K, two, split):
-    """Fused epilogue (split=False) and the few-rows split-K + row-parallel LayerNorm path (split=True; rows > 2048
-    fall back to the fused one inside the library)."""
+    """Fused epilogue (split=False) and the split-K + row-parallel LayerNorm path (split=True)."""
     x = _randn(rows, K, seed=1).half()
     w = _randn(256, K, seed=2, scale=K ** -0.5).half()
     b = _randn(256, seed=3)

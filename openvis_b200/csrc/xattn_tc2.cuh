@@ -31,11 +31,16 @@ constexpr int X2_P_BYTES = 128 * 128;            // [128 q][64 keys] fp16
 constexpr int X2_SMEM = X2_Q_BYTES + X2_STAGES * X2_KV_STAGE + 4 * X2_P_BYTES + 1024 + 512;
 constexpr int X2_THREADS = 19 * 32;
 
+// clock64 timeline of block 0 (tools/trace_xattn.py): compiled in only with -DOVIS_XATTN_TRACE_BUILD
+#ifdef OVIS_XATTN_TRACE_BUILD
 #define X2_TRACE(role, step, ev)                                                                   \
   do {                                                                                            \
     if (a.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (step) < 64)          \
       a.trace[((role) * 64 + (step)) * 8 + (ev)] = clock64();                                     \
   } while (0)
+#else
+#define X2_TRACE(role, step, ev) do { } while (0)
+#endif
 
 __global__ void __launch_bounds__(X2_THREADS, 1)
 xattn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -225,20 +230,21 @@ xattn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 #pragma unroll
       for (int x = 0; x < 2; ++x) {
         const int wi = (kb >> 5) + x;
-        // padding rows of the 128-row tile (q >= Q) count as fully blocked, so they never keep a warp from skipping
-        dst[x] = q >= a.Q ? 0xffffffffu : ((use_mask && t < ntiles && wi < a.W) ? __ldg(bits_q + (long long)wi * a.q_stride) : 0u);
+        dst[x] = (use_mask && t < ntiles && wi < a.W) ? __ldg(bits_q + (long long)wi * a.q_stride) : 0u;
       }
     };
     uint32_t nw[2];
     load_words(b, nw);
     for (int t = b, n = 0; t < ntiles; t += 2, ++n) {
       const int kb = k_begin + t * X2_KT;
-      uint32_t mw[2];
+      uint32_t mw[2] = {nw[0], nw[1]};
+      if (kb + X2_KT > k_end) {                           // only the chunk's last tile can have keys past the end
 #pragma unroll
-      for (int x = 0; x < 2; ++x) {
-        const int nvalid = k_end - (kb + x * 32);
-        const uint32_t inval = nvalid >= 32 ? 0u : (nvalid <= 0 ? 0xffffffffu : ~((1u << nvalid) - 1u));
-        mw[x] = nw[x] | inval;
+        for (int x = 0; x < 2; ++x) {
+          const int nvalid = k_end - (kb + x * 32);
+          const uint32_t inval = nvalid >= 32 ? 0u : (nvalid <= 0 ? 0xffffffffu : ~((1u << nvalid) - 1u));
+          mw[x] |= inval;
+        }
       }
       load_words(t + 2, nw);
       const uint32_t ph = (uint32_t)(n & 1);
@@ -258,24 +264,14 @@ xattn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       float sum_tile = 0.f;
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
-        // 32 S columns at a time (registers: 18 warps leave 96 per thread); the S buffer is handed back to the issuer
-        // as soon as the second half sits in registers
+        // 32 S columns at a time (registers: 19 warps leave 96 per thread); the S buffer is handed back to the issuer
+        // as soon as the second half sits in registers.  Keep this loop unrolled and branch-free up to the TMEM load:
+        // ptxas then overlaps the second half's load with the first half's arithmetic.  A warp-uniform "whole half is
+        // masked -> skip" test in front of the load cost 17 % on dense masks (837 -> 981 us), and a rolled version
+        // (one copy of the half, P stored per half) 12 % (835 -> 935 us); neither is instruction-cache related.
         uint32_t sv[32];
         const uint32_t word = mw[hf];
         __syncwarp();                                     // (re-converged after the per-lane recompute branch)
-        // Fully-masked half tile: every one of this warp's 32 queries blocks all 32 keys (object masks are compact, so
-        // most (query block, key block) pairs of a trained model look like this).  Nothing to load or exponentiate:
-        // the probabilities are zero.  Warp-uniform.
-        if (__all_sync(0xffffffffu, word == 0xffffffffu)) {
-#pragma unroll
-          for (int c = 0; c < 16; ++c) pk[hf * 16 + c] = 0u;
-          if (hf == 1) {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&s_empty[wg]);
-          }
-          continue;
-        }
         tmem_ld_32x32_nowait(s_addr + hf * 32, sv);
         tmem_ld_wait();
         reg_fence32(sv);

@@ -225,8 +225,8 @@ def test_xattn(G, Q, keys, density):
 
 @pytest.mark.parametrize("G,Q,keys", [(2, 100, 3840), (1, 200, 1920)])
 def test_xattn_block_sparse_masks(G, Q, keys):
-    """Object-like masks: every query sees a few compact key ranges, so most (32-query, 32-key) blocks are fully blocked
-    and take the kernel's skip path; a few queries see nothing (all-masked-row rule) or everything."""
+    """Object-like masks: every query sees a few compact key ranges (most (32-query, 32-key) blocks are fully blocked);
+    a few queries see nothing (all-masked-row rule) or everything."""
     q = _randn(G * Q, 256, seed=1, scale=0.6).half()
     k = _randn(G * keys, 256, seed=2).half()
     v = _randn(G * keys, 256, seed=3).half()

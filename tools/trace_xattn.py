@@ -1,4 +1,6 @@
 """clock64 timeline of block 0 of xattn_tc2_kernel (roles: 4 softmax warpgroups, S issuer, PV issuer).
+   Needs a library built with the stamps compiled in:
+       NVCC_EXTRA=-DOVIS_XATTN_TRACE_BUILD python -m openvis_b200.build --force
    python tools/trace_xattn.py            dense random masks;   SPARSE=1 -> 7/8 of the (warp, half tile) pairs skip"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

@@ -154,6 +154,7 @@ void init_args(GemmArgs& a) {
   a.a_k_mod = 1;
   a.a_row_div = 1;
   a.b_k_mod = 1;
+  a.kps = 1;
   a.b_row_div = 1;
   a.scale = 1.f;
   a.pe_period = 1;
@@ -270,6 +271,16 @@ int launch_gemm(const void* A, long long a_rows, long long a_cols, long long lda
   // HBM-heavy shapes (K <= 256, many row tiles): B-stationary kernel; small / long-K shapes: streaming kernel
   const long long m_tiles_total = (long long)a.num_groups * ((a.rows_per_group + 127) / 128);
   static const bool no_bs = getenv("OVIS_GEMM_NO_BS") != nullptr;    // A/B testing only
+  {
+    // OVIS_GEMM_KPS (A/B): k-blocks per ring barrier of the B-stationary kernel; default = all k-blocks of a row tile for
+    // the 128-wide kernel (ring of 8 slots = 2 tiles; mask_bits 69 -> 63.5 us), 1 for the 256-wide one (ring of 4 slots:
+    // grouping halves the look-ahead there, kv_proj 476 -> 487 us)
+    static const int kps_env = getenv("OVIS_GEMM_KPS") ? atoi(getenv("OVIS_GEMM_KPS")) : 0;
+    const int kblocks = a.K / 64;
+    int kps = kps_env > 0 ? kps_env : (bn == 256 ? 1 : 4);
+    while (kps > 1 && (kblocks % kps != 0 || (bn == 256 ? 4 : 8) % kps != 0)) kps >>= 1;
+    a.kps = kps < 1 ? 1 : kps;
+  }
   if (a.K <= 256 && m_tiles_total >= 64 && !no_bs)
     return bn == 256 ? launch_gemm_bs<256>(ta, ta2, tb, *omp, a, sms, st) : launch_gemm_bs<128>(ta, ta2, tb, *omp, a, sms, st);
   return bn == 256 ? launch_gemm_bn<256>(ta, ta2, tb, *omp, a, sms, st) : launch_gemm_bn<128>(ta, ta2, tb, *omp, a, sms, st);

@@ -53,6 +53,7 @@ struct GemmArgs {
   int a_alt;              // 1: n-tiles with ((nt >> a_alt_shift) & 1) read their A operand from the second tensor map
   int a_alt_shift;        //    (key / value operands; shift 1 when a 256-wide output is split into two 128-wide tiles)
   int tma_store;          // 1: EPI_STORE writes through GemmOutMaps (single group, 16-byte aligned pitch)
+  int kps;                // B-stationary kernel: k-blocks requested together per ring barrier (1, 2 or 4; divides K/64)
   // ---- EPI_LN
   const float* resid;     // [rows][256] fp32
   const float* ln1_g; const float* ln1_b;
@@ -725,12 +726,17 @@ gemm_tn_bs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           for (int kb = 0; kb < k_blocks; ++kb)
             tma_load_2d(sB + kb * (BN * Cfg::BK * 2), &tmB, bfull_bar, b_col + kb * Cfg::BK, b_row);
           bphase ^= 1;
+          // the ring's barriers work on groups of `kps` k-block slots: the boxes of a group (the 128-byte column slices of
+          // the same 128 rows) are requested back to back, so DRAM sees whole 512-byte rows instead of four visits
+          const int kps = args.kps, ngroups = STAGES / kps;
           for (int mt = r0; mt < m_tiles; mt += R) {
-            for (int kb = 0; kb < k_blocks; ++kb) {
+            for (int kb = 0; kb < k_blocks; kb += kps) {
               mbar_wait(&empty_bar[stage], phase ^ 1);
-              mbar_arrive_expect_tx(&full_bar[stage], Cfg::A_BYTES);
-              tma_load_2d(sA + stage * Cfg::A_BYTES, ta, &full_bar[stage], a_col + kb * Cfg::BK, a_row0 + mt * Cfg::BM);
-              if (++stage == STAGES) { stage = 0; phase ^= 1; }
+              mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(kps * Cfg::A_BYTES));
+              for (int i = 0; i < kps; ++i)
+                tma_load_2d(sA + (stage * kps + i) * Cfg::A_BYTES, ta, &full_bar[stage], a_col + (kb + i) * Cfg::BK,
+                            a_row0 + mt * Cfg::BM);
+              if (++stage == ngroups) { stage = 0; phase ^= 1; }
             }
           }
         }
@@ -750,16 +756,19 @@ gemm_tn_bs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * BN;
-            for (int kb = 0; kb < k_blocks; ++kb) {
+            const int kps = args.kps, ngroups = STAGES / kps;
+            for (int kb = 0; kb < k_blocks; kb += kps) {
               mbar_wait(&full_bar[stage], phase);
               tc_fence_after();
-              const uint64_t adesc = umma_desc_k_sw128(smem_u32(sA + stage * Cfg::A_BYTES));
-              const uint64_t bdesc = umma_desc_k_sw128(b_addr + kb * (BN * Cfg::BK * 2));
+              for (int i = 0; i < kps; ++i) {
+                const uint64_t adesc = umma_desc_k_sw128(smem_u32(sA + (stage * kps + i) * Cfg::A_BYTES));
+                const uint64_t bdesc = umma_desc_k_sw128(b_addr + (kb + i) * (BN * Cfg::BK * 2));
 #pragma unroll
-              for (int k = 0; k < Cfg::BK / 16; ++k)
-                umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                for (int k = 0; k < Cfg::BK / 16; ++k)
+                  umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, ((kb + i) | k) != 0 ? 1u : 0u);
+              }
               umma_commit(&empty_bar[stage]);
-              if (++stage == STAGES) { stage = 0; phase ^= 1; }
+              if (++stage == ngroups) { stage = 0; phase ^= 1; }
             }
             umma_commit(&tfull_bar[acc]);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }

@@ -115,3 +115,55 @@ def seeded_inputs(T, Hp, Wp, C=256, seed=1234):
     x = [torch.randn(T, C, Hp // 32 * 2 ** l, Wp // 32 * 2 ** l, generator=g) for l in range(3)]
     mf = torch.randn(T, C, Hp // 4, Wp // 4, generator=g)
     return x, mf
+
+
+def resampler_param_shapes(C=256, F_=2048, L=6):
+    """state_dict contract of TemporalInstanceResampler (openvis/modeling/resampler.py:191-236)."""
+    s = {}
+    for i in range(L):
+        pre = f"long_aggregate_layers.{i}"
+        s[f"{pre}.self_attn.in_proj_weight"] = (3 * C, C)
+        s[f"{pre}.self_attn.in_proj_bias"] = (3 * C,)
+        s[f"{pre}.self_attn.out_proj.weight"] = (C, C)
+        s[f"{pre}.self_attn.out_proj.bias"] = (C,)
+        s[f"{pre}.norm.weight"] = (C,)
+        s[f"{pre}.norm.bias"] = (C,)
+        s[f"short_aggregate_layers.{i}.0.weight"] = (C, C, 5)
+        s[f"short_aggregate_layers.{i}.0.bias"] = (C,)
+        s[f"short_aggregate_layers.{i}.2.weight"] = (C, C, 3)
+        s[f"short_aggregate_layers.{i}.2.bias"] = (C,)
+        s[f"aggregate_norms.{i}.weight"] = (C,)
+        s[f"aggregate_norms.{i}.bias"] = (C,)
+        pre = f"transformer_ffn_layers.{i}"
+        s[f"{pre}.linear1.weight"] = (F_, C)
+        s[f"{pre}.linear1.bias"] = (F_,)
+        s[f"{pre}.linear2.weight"] = (C, F_)
+        s[f"{pre}.linear2.bias"] = (C,)
+        s[f"{pre}.norm.weight"] = (C,)
+        s[f"{pre}.norm.bias"] = (C,)
+    s["decode_norm.weight"] = (C,)
+    s["decode_norm.bias"] = (C,)
+    for name in ("attn_embed", "mask_embed"):
+        for i in range(3):
+            s[f"{name}.layers.{i}.weight"] = (C, C)
+            s[f"{name}.layers.{i}.bias"] = (C,)
+    return s
+
+
+def seeded_resampler_params(seed=0, **kw):
+    """Deterministic resampler weights: xavier-like matrices / conv taps, small biases, LayerNorm weight near 1."""
+    g = torch.Generator().manual_seed(seed)
+    shapes = resampler_param_shapes(**kw)
+    out = {}
+    for name in sorted(shapes):
+        shp = shapes[name]
+        if len(shp) == 1 and name.endswith(".weight"):
+            t = 1.0 + 0.1 * torch.randn(shp, generator=g)
+        elif len(shp) == 1:
+            t = 0.05 * torch.randn(shp, generator=g)
+        else:
+            taps = shp[2] if len(shp) == 3 else 1
+            bound = math.sqrt(6.0 / ((shp[0] + shp[1]) * taps))
+            t = (torch.rand(shp, generator=g) * 2 - 1) * bound
+        out[name] = t
+    return out

@@ -145,6 +145,78 @@ def make_msda_fixture():
     print("wrote msda", {k: v.shape for k, v in rec.items()})
 
 
+def temporal_match_inputs(b=2, t=6, Q=100, seed=41, noise=0.6):
+    """Frame embeddings of `Q` instances that drift over time and change slot every frame (what the online decoders
+    produce): e[b, i] = (base + drift_i)[perm_i] + noise."""
+    g = torch.Generator().manual_seed(seed)
+    base = torch.randn(b, Q, 256, generator=g)
+    out = []
+    for i in range(t):
+        perm = torch.stack([torch.randperm(Q, generator=g) for _ in range(b)])
+        e = base + noise * torch.randn(b, Q, 256, generator=g)
+        out.append(torch.gather(e, 1, perm[:, :, None].expand(-1, -1, 256)))
+    return torch.stack(out, dim=1)                                    # [b, t, Q, 256]
+
+
+def make_temporal_match_fixture():
+    """Outputs of the reference's own batch_video_match_via_embeds / match_via_embeds (minvis.py:28-72) and of
+    batch_index as used by BriVIS.reset_image_output_order (brivis.py:231-240)."""
+    T_ = R.temporal()
+    rec = {}
+    for name, kw in (("q100", dict(b=2, t=6, Q=100, seed=41)), ("q200", dict(b=1, t=4, Q=200, seed=42)),
+                     ("q7", dict(b=3, t=5, Q=7, seed=43, noise=1.5))):
+        e = temporal_match_inputs(**kw)
+        idx, emb = T_.batch_video_match_via_embeds(e)
+        rec[name + "_indices"] = idx.numpy().astype(np.int16)
+        rec[name + "_embeds_sum"] = emb.sum(-1).numpy()
+        rec[name + "_pair"] = np.array(T_.match_via_embeds(e[0, 0], e[0, 1]), dtype=np.int16)
+    e = temporal_match_inputs(b=2, t=3, Q=7, seed=44)
+    idx, _ = T_.batch_video_match_via_embeds(e)
+    g = torch.Generator().manual_seed(45)
+    logits, masks = torch.randn(2, 3, 7, 5, generator=g), torch.randn(2, 7, 3, 4, 6, generator=g)
+    fl = T_.batch_index(logits.flatten(0, 1), idx.flatten(0, 1))
+    fm = T_.batch_index(masks.transpose(2, 1).flatten(0, 1), idx.flatten(0, 1))
+    rec["reorder_logits"] = fl.view(2, 3, 7, 5).numpy()
+    rec["reorder_masks"] = fm.view(2, 3, 7, 4, 6).transpose(1, 2).numpy()
+    np.savez_compressed(os.path.join(GOLDEN, "temporal_match.npz"), **rec)
+    print("wrote temporal_match", {k: v.shape for k, v in rec.items()})
+
+
+def resampler_inputs(t=4, Q=12, K=9, seed=51, hw=(32, 48)):
+    """Seeded inputs of TemporalInstanceResampler.forward for one clip (b = 1)."""
+    g = torch.Generator().manual_seed(seed)
+    frame_embeds = torch.randn(1, t, Q, 256, generator=g)
+    mask_feats = torch.randn(t, 256, hw[0], hw[1], generator=g)
+    attn_feats = 0.2 * torch.randn(t, 12, 256, hw[0] // 4, hw[1] // 4, generator=g)
+    cls = torch.randn(1, t, 768, generator=g)
+    pix = torch.randn(t, 768, 14, 14, generator=g)
+    text = torch.nn.functional.normalize(torch.randn(K, 512, generator=g), dim=-1)
+    return frame_embeds, mask_feats, attn_feats, (cls, pix), text
+
+
+def make_resampler_fixture(t=4, Q=12, pseed=21, bseed=6):
+    """TemporalInstanceResampler.forward (resampler.py:244-302) of the reference with the reference's own SideAdapter as
+    `adapter` (post-split blocks = seeded_clip_block_params(bseed), ln_post / proj = the seeded CLIP's, san_tail.npz)."""
+    from openvis_b200.synthetic import seeded_resampler_params
+    T_ = R.temporal()
+    s = R.side_adapter_module()
+    torch.manual_seed(3)
+    sa = s.SideAdapter(num_queries=Q).eval()
+    sa.clip_model.visual.transformer.resblocks.load_state_dict(O.seeded_clip_block_params(bseed), strict=False)
+    m = T_.TemporalInstanceResampler().eval()
+    m.load_state_dict(seeded_resampler_params(pseed))
+    fe, mf, af, bk, text = resampler_inputs(t, Q)
+    with torch.no_grad():
+        out = m(fe, mf, af, sa, bk, text)
+    rec = dict(meta=np.array([t, Q, pseed, bseed]), pred_logits=out["pred_logits"].numpy(),
+               pred_masks=out["pred_masks"].numpy().astype(np.float16), pred_embeds=out["pred_embeds"].numpy())
+    for i in (0, 3):
+        rec[f"aux{i}_pred_logits"] = out["aux_outputs"][i]["pred_logits"].numpy()
+        rec[f"aux{i}_pred_masks"] = out["aux_outputs"][i]["pred_masks"][..., ::4, ::4].numpy().astype(np.float16)
+    np.savez_compressed(os.path.join(GOLDEN, "temporal_resampler.npz"), **rec)
+    print("wrote temporal_resampler", {k: v.shape for k, v in rec.items()})
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     for case in DECODER_CASES:
@@ -152,6 +224,8 @@ def main():
     make_san_tail_fixture()
     make_san_blocks_fixture()
     make_msda_fixture()
+    make_temporal_match_fixture()
+    make_resampler_fixture()
 
 
 if __name__ == "__main__":

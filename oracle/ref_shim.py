@@ -179,3 +179,32 @@ def msda_core_pytorch():
     m = _load("refmsda", d, "ms_deform_attn_func")
     _loaded["msda"] = m.ms_deform_attn_core_pytorch
     return _loaded["msda"]
+
+
+def temporal():
+    """The reference's temporal-association code, unmodified: ``match_via_embeds`` /
+    ``batch_video_match_via_embeds`` (openvis/modeling/minvis.py:28-72), ``batch_index`` (openvis/utils/index.py:4-19)
+    and ``TemporalInstanceResampler`` (openvis/modeling/resampler.py:189-323).  ``minvis.py`` also defines the MinVIS
+    meta-architecture, whose base class and Detectron2 imports are stubbed (never instantiated here)."""
+    if "temporal" in _loaded:
+        return _loaded["temporal"]
+    dec = decoders()
+    _mod("detectron2.modeling", META_ARCH_REGISTRY=_Registry("META_ARCH"))
+    _mod("detectron2.modeling.backbone", Backbone=object)
+    _mod("detectron2.structures", ImageList=object)
+    root = os.path.join(REF_ROOT, "openvis")
+    _mod("refopenvis").__path__ = [root]
+    _mod("refopenvis.modeling").__path__ = [os.path.join(root, "modeling")]
+    _mod("refopenvis.utils").__path__ = [os.path.join(root, "utils")]
+    _mod("refopenvis.modeling.transformer_decoder").__path__ = [_DEC_DIR]
+    sys.modules["refopenvis.modeling.transformer_decoder.video_mask2former_transformer_decoder"] = dec.video
+    _mod("refopenvis.modeling.video_maskformer", VideoMaskFormer=torch.nn.Module)
+    index = _load("refopenvis.utils", os.path.join(root, "utils"), "index")
+    minvis = _load("refopenvis.modeling", os.path.join(root, "modeling"), "minvis")
+    resampler = _load("refopenvis.modeling", os.path.join(root, "modeling"), "resampler")
+    ns = types.SimpleNamespace(match_via_embeds=minvis.match_via_embeds,
+                               batch_video_match_via_embeds=minvis.batch_video_match_via_embeds,
+                               batch_index=index.batch_index,
+                               TemporalInstanceResampler=resampler.TemporalInstanceResampler)
+    _loaded["temporal"] = ns
+    return ns

@@ -164,6 +164,29 @@ int ovis_san_attn(const void* qkv_f16, const float* pooled, void* out_f16, int B
  * the [Q+1+L]^2 additive-bias construction.  bias [B][n][Q][h][w] -> out [B*n][Q+1+L][Q+1+L]. */
 int ovis_san_attn_bias(const float* bias, float* out, int BN, int Q, int h, int w, int gh, int gw, void* stream);
 
+/* ---- temporal association --------------------------------------------------
+ * Replicate-padded unfold along the frame axis: in [G][T][C] f16 -> out [G][T][taps*C] f16 with
+ * out[g][t][k*C + c] = in[g][clamp(t + k - taps/2, 0, T-1)][c], so that Conv1d(C, C, taps, padding='same',
+ * padding_mode='replicate') of the resampler's short-term aggregation (openvis/modeling/resampler.py:205-213, 262-264)
+ * is ovis_linear_f16 / ovis_linear_ln_f16 with the weight laid out [C_out][taps*C_in].  taps odd, C % 8 == 0. */
+int ovis_temporal_unfold_f16(const void* in_f16, void* out_f16, int G, int T, int C, int taps, void* stream);
+/* Cosine-cost Hungarian matching of consecutive frames, all B*T problems at once (match_via_embeds,
+ * openvis/modeling/minvis.py:28-41: 1 - cos, scipy linear_sum_assignment on target x current).
+ * en [B][T][n][C] fp32 L2-normalised embeddings (ovis_rownorm mode 2).  Problem (b, i) matches frame i against frame
+ * i-1 (frame 0 against itself): pi[b][i][a] = query of frame i assigned to query a of frame i-1 (exact optimum,
+ * double-precision potentials).  cost [B][T][n][n] fp32 (row = target, column = current) receives the cost matrices;
+ * it may be null when n*n floats fit shared memory (n <= ~215). */
+int ovis_match_embeds(const float* en, int B, int T, int n, int C, float* cost, int* pi, void* stream);
+/* The reference's frame-by-frame chain (batch_video_match_via_embeds, minvis.py:44-72) from the independent solves:
+ * indices[b][i][j] = pi[b][i][indices[b][i-1][j]], indices[b][-1] = identity.  indices [B][T][n] int64. */
+int ovis_match_compose(const int* pi, long long* indices, int B, int T, int n, void* stream);
+/* out[b][t][q][:] = in[b][t][idx[b][t][q]][:]: batch_index (openvis/utils/index.py:4-11) as used on the embeddings
+ * (minvis.py:57) and by BriVIS.reset_image_output_order (openvis/brivis.py:231-240).  Element strides of (b, t, q) are
+ * explicit so [b,t,q,c] logits / embeddings and [b,q,t,h,w] masks are served in place of their transposes; `inner`
+ * contiguous floats per (b, t, q).  in != out. */
+int ovis_reorder_queries_f32(const float* in, const long long* idx, float* out, int B, int T, int n, long long inner,
+                             long long stride_b, long long stride_t, long long stride_q, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

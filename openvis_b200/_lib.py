@@ -49,6 +49,10 @@ SIGNATURES = {
     "ovis_san_pool_bias": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _vp]),
     "ovis_san_attn": (_c_int, [_vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _vp]),
     "ovis_san_attn_bias": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _vp]),
+    "ovis_temporal_unfold_f16": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _vp]),
+    "ovis_match_embeds": (_c_int, [_vp, _c_int, _c_int, _c_int, _c_int, _vp, _vp, _vp]),
+    "ovis_match_compose": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _vp]),
+    "ovis_reorder_queries_f32": (_c_int, [_vp, _vp, _vp, _c_int, _c_int, _c_int, _c_ll, _c_ll, _c_ll, _c_ll, _vp]),
 }
 
 _lib = None
@@ -387,4 +391,57 @@ def san_attn_bias(bias, grid_hw):
     L = gh * gw
     out = torch.empty(B * n, Q + 1 + L, Q + 1 + L, dtype=torch.float32, device=bias.device)
     _check(lib.ovis_san_attn_bias(_p(bias), _p(out), B * n, Q, h, w, gh, gw, _stream()))
+    return out
+
+
+# ---- temporal association ------------------------------------------------------------
+def temporal_unfold_f16(x, taps, out=None):
+    """x [G, T, C] fp16 -> [G, T, taps*C] fp16, replicate padding along T (Conv1d padding='same' as a GEMM operand)."""
+    lib = load()
+    _req(x, torch.float16, "x")
+    G, T, C = x.shape
+    if out is None:
+        out = torch.empty(G, T, taps * C, dtype=torch.float16, device=x.device)
+    _check(lib.ovis_temporal_unfold_f16(_p(x), _p(out), G, T, C, int(taps), _stream()))
+    return out
+
+
+def match_embeds(en, want_cost=False):
+    """en [B, T, n, C] fp32 L2-normalised -> pi [B, T, n] int32 (raw frame-to-previous-frame assignments) and the cost
+    matrices [B, T, n, n] (None unless requested or needed as scratch)."""
+    lib = load()
+    _req(en, torch.float32, "en")
+    B, T, n, C = en.shape
+    pi = torch.empty(B, T, n, dtype=torch.int32, device=en.device)
+    cost = torch.empty(B, T, n, n, dtype=torch.float32, device=en.device) if (want_cost or n > 200) else None
+    _check(lib.ovis_match_embeds(_p(en), B, T, n, C, _p(cost), _p(pi), _stream()))
+    return pi, cost
+
+
+def match_compose(pi):
+    lib = load()
+    _req(pi, torch.int32, "pi")
+    B, T, n = pi.shape
+    idx = torch.empty(B, T, n, dtype=torch.int64, device=pi.device)
+    _check(lib.ovis_match_compose(_p(pi), _p(idx), B, T, n, _stream()))
+    return idx
+
+
+def reorder_queries(x, idx, layout="btq"):
+    """out[b, t, q] = x[b, t, idx[b, t, q]] for x [b, t, q, ...] (layout "btq") or x [b, q, t, ...] (layout "bqt")."""
+    lib = load()
+    _req(x, torch.float32, "x")
+    _req(idx, torch.int64, "idx")
+    B, T, n = idx.shape
+    inner = 1
+    for d in x.shape[3:]:
+        inner *= d
+    if layout == "btq":
+        assert tuple(x.shape[:3]) == (B, T, n)
+        sb, st, sq = T * n * inner, n * inner, inner
+    else:
+        assert tuple(x.shape[:3]) == (B, n, T)
+        sb, st, sq = n * T * inner, inner, T * inner
+    out = torch.empty_like(x)
+    _check(lib.ovis_reorder_queries_f32(_p(x), _p(idx), _p(out), B, T, n, inner, sb, st, sq, _stream()))
     return out

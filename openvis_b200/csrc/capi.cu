@@ -18,6 +18,7 @@
 #include "san_attn.cuh"
 #include "postproc.cuh"
 #include "msda.cuh"
+#include "temporal.cuh"
 
 using namespace ovis;
 
@@ -898,3 +899,53 @@ int ovis_san_attn_bias(const float* bias, float* out, int BN, int Q, int h, int 
 }
 
 }  // extern "C"
+
+// ---- temporal association ---------------------------------------------------------
+int ovis_temporal_unfold_f16(const void* in, void* out, int G, int T, int C, int taps, void* stream) {
+  CHECK_ARG(in && out && G > 0 && T > 0 && C > 0 && C % 8 == 0 && taps > 0 && (taps & 1), "bad arguments");
+  CHECK_ARG(((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0, "pointers must be 16-byte aligned");
+  int rc = device_info(nullptr);
+  if (rc) return rc;
+  const long long total = (long long)G * T * taps * (C / 8);
+  temporal_unfold_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __half*)in, (__half*)out, T, C / 8, taps, total);
+  return check_launch("temporal_unfold_kernel");
+}
+
+int ovis_match_embeds(const float* en, int B, int T, int n, int C, float* cost, int* pi, void* stream) {
+  CHECK_ARG(en && pi && B > 0 && T > 0 && n > 0 && C > 0, "bad arguments");
+  CHECK_ARG(n <= 1024 && B <= 65535, "at most 1024 queries, 65535 clips");
+  int rc = device_info(nullptr);
+  if (rc) return rc;
+  MatchArgs a;
+  a.en = en; a.cost = cost; a.pi = pi; a.T = T; a.n = n; a.C = C;
+  a.cost_in_smem = match_smem_bytes(n, 1) <= (size_t)227 * 1024;
+  CHECK_ARG(a.cost_in_smem || cost, "a cost scratch buffer is required when the n x n matrix does not fit shared memory");
+  const size_t smem = match_smem_bytes(n, a.cost_in_smem);
+  static std::atomic<size_t> attr_set{0};
+  if (smem > 48 * 1024 && attr_set.load() < smem) {
+    cudaError_t e = cudaFuncSetAttribute(match_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return fail(OVIS_ERR_CUDA, "%s: cannot raise the shared-memory limit", "match_assign_kernel");
+    attr_set.store(227 * 1024);
+  }
+  match_assign_kernel<<<dim3(T, B), MATCH_THREADS, smem, (cudaStream_t)stream>>>(a);
+  return check_launch("match_assign_kernel");
+}
+
+int ovis_match_compose(const int* pi, long long* indices, int B, int T, int n, void* stream) {
+  CHECK_ARG(pi && indices && B > 0 && T > 0 && n > 0 && B <= 65535, "bad arguments");
+  int rc = device_info(nullptr);
+  if (rc) return rc;
+  match_compose_kernel<<<dim3((n + 127) / 128, B), 128, 0, (cudaStream_t)stream>>>(pi, indices, T, n);
+  return check_launch("match_compose_kernel");
+}
+
+int ovis_reorder_queries_f32(const float* in, const long long* idx, float* out, int B, int T, int n, long long inner,
+                             long long stride_b, long long stride_t, long long stride_q, void* stream) {
+  CHECK_ARG(in && idx && out && in != out && B > 0 && T > 0 && n > 0 && inner > 0, "bad arguments");
+  CHECK_ARG(T <= 65535 && B <= 65535, "at most 65535 frames / clips");
+  int rc = device_info(nullptr);
+  if (rc) return rc;
+  reorder_queries_kernel<<<dim3(n, T, B), 128, 0, (cudaStream_t)stream>>>(in, idx, out, T, n, inner, stride_b, stride_t, stride_q);
+  return check_launch("reorder_queries_kernel");
+}

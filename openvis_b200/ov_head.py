@@ -189,3 +189,8 @@ class SideAdapterBlocks:
         sos = self.post_blocks(feats, attn_bias)
         lw, lb = self._w["ln_post"]
         return self.tail.sos_tail(sos, lw, lb, self._w["proj"])
+
+    def cal_sim_logits(self, text_feats, image_feats):
+        """SideAdapter.cal_sim_logits (side_adapter.py:234-235), so that this object can be passed as the `adapter`
+        argument of TemporalInstanceResampler.forward (resampler.py:244, 313-314)."""
+        return self.tail.cal_sim_logits(text_feats, image_feats)

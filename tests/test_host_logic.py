@@ -109,3 +109,24 @@ def test_inference_only_and_no_cpu_path():
     assert "CPU" in str(ei.value) or "CUDA" in str(ei.value)
     with pytest.raises(NotImplementedError):
         m([x[0], x[1], x[2][..., :-1]], mf)       # not the stride-32/16/8 pyramid of a /32-padded input
+
+
+def test_resampler_state_dict_contract():
+    """TemporalInstanceResampler: the reference's parameter names / shapes
+    (openvis/modeling/resampler.py:191-236), loadable strictly; CPU calls are refused, never computed on the host."""
+    from openvis_b200.synthetic import resampler_param_shapes, seeded_resampler_params
+    from openvis_b200.temporal import TemporalInstanceResampler, batch_video_match_via_embeds
+    from openvis_b200 import _lib as L
+    m = TemporalInstanceResampler(hidden_dim=256, feed_dim=2048, nheads=8, nlayers=6)
+    got = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    assert got == resampler_param_shapes()
+    m.load_state_dict(seeded_resampler_params(0))
+    assert sum(p.numel() for p in m.parameters()) == 11437568          # the reference module's count
+    with pytest.raises(RuntimeError):
+        m.train()(torch.zeros(1, 2, 3, 256), torch.zeros(2, 256, 8, 8), torch.zeros(2, 12, 256, 2, 2))
+    with pytest.raises(L.OvisError):
+        m.eval()(torch.zeros(1, 2, 3, 256), torch.zeros(2, 256, 8, 8), torch.zeros(2, 12, 256, 2, 2))
+    with pytest.raises(L.OvisError):
+        batch_video_match_via_embeds(torch.randn(1, 2, 5, 256))
+    with pytest.raises(NotImplementedError):
+        TemporalInstanceResampler(hidden_dim=128)

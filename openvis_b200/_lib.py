@@ -196,12 +196,12 @@ def init_queries(query_feat, query_embed, dn_g, dn_b, G, outs):
                                  _p(d32), _p(d16), Q, G * Q, _stream()))
 
 
-def rownorm(x, g=None, b=None, layer_norm=False, l2=False, want32=True, want16=True):
+def rownorm(x, g=None, b=None, layer_norm=False, l2=False, want32=True, want16=True, out16=None):
     lib = load()
     _req(x, torch.float32, "x")
     rows, D = x.shape
     o32 = torch.empty_like(x) if want32 else None
-    o16 = torch.empty(rows, D, dtype=torch.float16, device=x.device) if want16 else None
+    o16 = out16 if out16 is not None else (torch.empty(rows, D, dtype=torch.float16, device=x.device) if want16 else None)
     mode = (1 if layer_norm else 0) | (2 if l2 else 0)
     _check(lib.ovis_rownorm(_p(x), _p(g), _p(b), _p(o32), _p(o16), rows, D, mode, _stream()))
     return o32, o16

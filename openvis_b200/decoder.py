@@ -540,7 +540,20 @@ class _B200MaskedDecoderBase(nn.Module):
         if self.materialize_aux:
             list(aux)
         out["aux_outputs"] = aux
+        self._last = dict(gen=gen, mf=mask_features_in, mf_ver=mask_features_in._version, ft=ws["ft"],
+                          af32=san["attn_feats"] if san else None, af16=ws.get("af16"))
         return out
+
+    def shared_operands(self, mask_feats, attn_feats):
+        """The token-major fp16 copies of `mask_feats` / `attn_feats` made by the most recent forward(), for a consumer
+        that is handed exactly those tensors (temporal.TemporalInstanceResampler.operand_source); None when they are
+        other tensors, were modified since, or the workspace has been reused by a later call."""
+        last = getattr(self, "_last", None)
+        if last is None or last["gen"] != self._generation or last["af16"] is None:
+            return None
+        if mask_feats is not last["mf"] or mask_feats._version != last["mf_ver"] or attn_feats is not last["af32"]:
+            return None
+        return last["ft"], last["af16"]
 
     def _full_masks(self, W, ws, hidx, BT, H4, W4, posflags=None):
         """einsum("bqc,bchw->bqhw") of head `hidx`, written directly in the reference's eval layout [1, Q, T, H, W]

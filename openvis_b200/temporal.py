@@ -21,6 +21,8 @@ the last (brivis.py:247-249 use outputs['pred_logits'] / ['pred_masks']); the ot
 first access from the saved per-layer `decode_norm` outputs.
 Inference only, CUDA sm_100 only, no fallback.
 """
+import os
+
 import torch
 from torch import nn
 
@@ -88,8 +90,12 @@ class TemporalInstanceResampler(nn.Module):
         self.mask_embed = MLP(hidden_dim, hidden_dim, hidden_dim, 3)
         self.adapter = None
         self.text_feats = None
+        # non-reference knobs
         self.materialize_aux = False     # True: compute the six aux heads eagerly (API-exact mode)
+        self.use_cuda_graph = os.environ.get("OVIS_NO_CUDA_GRAPH") is None      # replay the layer loop as a CUDA graph
+        self.operand_source = None       # the SAN decoder whose outputs are passed in: its fp16 operand copies are reused
         self._wcache = None
+        self._ws = {}
         self._generation = 0
 
     def _weights(self):
@@ -145,50 +151,91 @@ class TemporalInstanceResampler(nn.Module):
             return self._forward_impl(frame_embeds, mask_feats, attn_feats, adapter, clip_bk_feats, text_feats,
                                       bs, t, q, BT, H, Wd, nh, dev)
 
+    def _workspace(self, bs, t, q, dev):
+        key = (bs, t, q, str(dev))
+        ws = self._ws.get(key)
+        if ws is not None:
+            return ws
+        if len(self._ws) >= 2:
+            self._ws.pop(next(iter(self._ws)))
+        C, nl = HIDDEN, self.num_layers
+        G, R = bs * q, bs * q * t
+        h16 = lambda *s: torch.empty(*s, dtype=torch.float16, device=dev)
+        f32 = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
+        ws = dict(G=G, R=R, x32=f32(R, C), x16=h16(R, C), l32=f32(R, C), l16=h16(R, C), d32=f32(R, C),
+                  d16=h16(nl + 1, R, C),                # decode_norm output feeding each of the seven heads
+                  qk16=h16(R, 2 * C), v16=h16(R, C), sa16=h16(R, C), c16=h16(R, C), f16=h16(R, self.feed_dim),
+                  u5=h16(G, t, 5 * C), u3=h16(G, t, 3 * C),
+                  split=f32((self.feed_dim // 256) * ((R + 127) // 128) * 128 * 256) if R <= 16384 else None)
+        self._ws[key] = ws
+        return ws
+
+    def _layer_loop(self, W, ws, t):
+        """The six temporal layers on the instance-major residual stream ws["x32"] [(b q) t, 256].  Reads / writes the
+        workspace and the weight cache only, so it can be replayed as a CUDA graph."""
+        C, G, R = HIDDEN, ws["G"], ws["R"]
+        x32, x16, l32, l16, split = ws["x32"], ws["x16"], ws["l32"], ws["l16"], ws["split"]
+        L.cast_f16(x32, out=x16)
+        L.rownorm(x32, W["dn"][0], W["dn"][1], layer_norm=True, want32=False, out16=ws["d16"][0])
+        for i in range(self.num_layers):
+            lw = W["layers"][i]
+            # long-term aggregation: self-attention over the frames of each instance (resampler.py:258-262)
+            L.linear_f16(x16, lw["qk_w"], lw["qk_b"], out=ws["qk16"])
+            L.linear_f16(x16, lw["v_w"], lw["v_b"], out=ws["v16"])
+            L.self_attn(ws["qk16"], ws["v16"], ws["sa16"], G, t)
+            L.linear_ln_f16(ws["sa16"], lw["o_w"], lw["o_b"], x32, lw["ln_a"], y32=l32, y16=l16, split_ws=split)
+            # short-term aggregation: Conv1d(5) -> ReLU -> Conv1d(3) over t + residual + aggregate_norms (:264-267)
+            L.temporal_unfold_f16(l16.view(G, t, C), 5, out=ws["u5"])
+            L.linear_f16(ws["u5"].view(R, 5 * C), lw["c5_w"], lw["c5_b"], relu=True, out=ws["c16"])
+            L.temporal_unfold_f16(ws["c16"].view(G, t, C), 3, out=ws["u3"])
+            L.linear_ln_f16(ws["u3"].view(R, 3 * C), lw["c3_w"], lw["c3_b"], l32, lw["ln_c"], y32=x32, y16=x16, split_ws=split)
+            # FFN (:270) + decode_norm of the following head (:305)
+            L.linear_f16(x16, lw["f1_w"], lw["f1_b"], relu=True, out=ws["f16"])
+            L.linear_ln_f16(ws["f16"], lw["f2_w"], lw["f2_b"], x32, lw["ln_f"], W["dn"], y32=x32, y16=x16, d32=ws["d32"],
+                            d16=ws["d16"][i + 1], split_ws=split)
+
+    def _run_layers(self, W, ws, t):
+        """~60 small dependent launches: replayed as a CUDA graph after one eager call per workspace (as the decoders do)."""
+        eager = (not self.use_cuda_graph) or L.PROFILE is not None
+        if eager or not ws.get("warm"):
+            ws["warm"] = True
+            return self._layer_loop(W, ws, t)
+        if ws.get("graph") is None or ws.get("graph_W") is not W:
+            n0 = L.launch_count()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._layer_loop(W, ws, t)
+            ws["graph"], ws["graph_W"], ws["graph_launches"] = g, W, L.launch_count() - n0
+            L.add_launch_count(-ws["graph_launches"])
+        ws["graph"].replay()
+        L.add_launch_count(ws["graph_launches"])
+
     def _forward_impl(self, frame_embeds, mask_feats, attn_feats, adapter, clip_bk_feats, text_feats,
                       bs, t, q, BT, H, Wd, nh, dev):
         W = self._weights()
+        ws = self._workspace(bs, t, q, dev)
         C, nl = HIDDEN, self.num_layers
-        G, R = bs * q, bs * q * t
         self._generation += 1
         gen = self._generation
-        h16 = lambda *s: torch.empty(*s, dtype=torch.float16, device=dev)
         f32 = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
 
-        # operands of the two head einsums, token-major fp16 (once per call)
-        tok = lambda x: (L.nchw_to_tokens_hw_f16 if x.shape[-1] % 4 == 0 and x.shape[1] % 32 == 0 else L.nchw_to_tokens_f16)(x)
-        ft = tok(mask_feats.float().contiguous())                                        # [BT, M, 256]
+        # operands of the two head einsums, token-major fp16: the decoder that produced mask_feats / attn_feats already
+        # holds them (operand_source); otherwise one layout pass each
         ah, aw = attn_feats.shape[-2:]
-        af = tok(attn_feats.float().contiguous().view(BT, nh * C, ah, aw))               # [BT, P, n*256]
         M, P = H * Wd, ah * aw
+        shared = self.operand_source.shared_operands(mask_feats, attn_feats) if self.operand_source is not None else None
+        if shared is not None:
+            ft, af = shared
+        else:
+            tok = lambda x: (L.nchw_to_tokens_hw_f16 if x.shape[-1] % 4 == 0 and x.shape[1] % 32 == 0 else L.nchw_to_tokens_f16)(x)
+            ft = tok(mask_feats.float().contiguous())                                        # [BT, M, 256]
+            af = tok(attn_feats.float().contiguous().view(BT, nh * C, ah, aw))               # [BT, P, n*256]
+        ft, af = ft.view(BT, M, C), af.view(BT, P, nh * C)
 
         # instance-major residual stream [(b q) t, 256]
-        x32 = frame_embeds.detach().float().permute(0, 2, 1, 3).contiguous().view(R, C)
-        x16 = L.cast_f16(x32)
-        d16 = h16(nl + 1, R, C)                       # decode_norm output feeding each of the seven heads
-        d32 = f32(R, C)
-        _, d0 = L.rownorm(x32, W["dn"][0], W["dn"][1], layer_norm=True, want32=False)
-        d16[0].copy_(d0)
-        qk16, v16, sa16, l16, c16, f16 = h16(R, 2 * C), h16(R, C), h16(R, C), h16(R, C), h16(R, C), h16(R, self.feed_dim)
-        l32 = f32(R, C)
-        u5, u3 = h16(G, t, 5 * C), h16(G, t, 3 * C)
-        split = f32((self.feed_dim // 256) * ((R + 127) // 128) * 128 * 256) if R <= 16384 else None
-        for i in range(nl):
-            lw = W["layers"][i]
-            # long-term aggregation: self-attention over the frames of each instance (resampler.py:258-262)
-            L.linear_f16(x16, lw["qk_w"], lw["qk_b"], out=qk16)
-            L.linear_f16(x16, lw["v_w"], lw["v_b"], out=v16)
-            L.self_attn(qk16, v16, sa16, G, t)
-            L.linear_ln_f16(sa16, lw["o_w"], lw["o_b"], x32, lw["ln_a"], y32=l32, y16=l16, split_ws=split)
-            # short-term aggregation: Conv1d(5) -> ReLU -> Conv1d(3) over t + residual + aggregate_norms (:264-267)
-            L.temporal_unfold_f16(l16.view(G, t, C), 5, out=u5)
-            L.linear_f16(u5.view(R, 5 * C), lw["c5_w"], lw["c5_b"], relu=True, out=c16)
-            L.temporal_unfold_f16(c16.view(G, t, C), 3, out=u3)
-            L.linear_ln_f16(u3.view(R, 3 * C), lw["c3_w"], lw["c3_b"], l32, lw["ln_c"], y32=x32, y16=x16, split_ws=split)
-            # FFN (:270) + decode_norm of the following head (:305)
-            L.linear_f16(x16, lw["f1_w"], lw["f1_b"], relu=True, out=f16)
-            L.linear_ln_f16(f16, lw["f2_w"], lw["f2_b"], x32, lw["ln_f"], W["dn"], y32=x32, y16=x16, d32=d32, d16=d16[i + 1],
-                            split_ws=split)
+        ws["x32"].view(bs, q, t, C).copy_(frame_embeds.detach().permute(0, 2, 1, 3))
+        self._run_layers(W, ws, t)
+        d16, d32 = ws["d16"], ws["d32"]
 
         def head(hidx):
             """forward_prediction_heads (resampler.py:304-316) from the saved decode_norm output of head `hidx`."""
@@ -221,3 +268,43 @@ class TemporalInstanceResampler(nn.Module):
             list(aux)
         out["aux_outputs"] = aux
         return out
+
+
+# ------------------------------------------------------------------------------------------------ BriVIS eval schedule
+@torch.no_grad()
+def brivis_video_inference(decoder, adapter, resampler, features, mask_features, clip_bk_feats, text_feats,
+                           padded_size, image_size, height, width, api_exact=False):
+    """The part of ``BriVIS.forward``'s eval branch that lies on the hot path (openvis/brivis.py:157-190, 242-265), from the
+    pixel decoder's outputs to the video result, composed from the drop-in pieces exactly as the reference composes its
+    own: SAN frame decoder -> query matching -> TemporalInstanceResampler (heads through the CLIP side path) ->
+    post_processing -> inference_video.  One clip (b = 1, the reference's eval batch).
+
+    decoder   SideAdapterFrameMultiScaleMaskedTransformerDecoder (sem_seg_head.predictor, brivis.py:160)
+    adapter   object with post_encode_image / cal_sim_logits (ov_head.SideAdapterBlocks; self.clip_adapter)
+    features  the three multi-scale maps (coarsest first) and mask_features [T, 256, Hp/4, Wp/4] of the clip's frames
+    api_exact additionally computes what the reference computes but never reads in eval: the frame-level pred_logits
+              (brivis.py:169-170) and reset_image_output_order (:174).
+    Returns (video_output as VideoMaskFormer.inference_video, resampler outputs, indices [1, T, Q])."""
+    from .postprocess import inference_video
+    image_outputs = decoder(features, mask_features)
+    q = decoder.num_queries
+    t = mask_features.shape[0]
+    pred_embeds = image_outputs["pred_embeds"][0][None]                           # (1, bt, q, c) -> (b, t, q, c)
+    if api_exact:
+        biases = image_outputs["class_attn_biases"][0]                            # (1, bt, n, q, h, w) -> (bt, n, q, h, w)
+        clip_feats = adapter.post_encode_image(clip_bk_feats, biases)
+        image_outputs["pred_logits"] = adapter.cal_sim_logits(text_feats, clip_feats)[None]
+    indices, frame_embeds = batch_video_match_via_embeds(pred_embeds)
+    if api_exact:
+        image_outputs = reset_image_output_order(image_outputs, indices)
+    resampler.operand_source = decoder
+    outputs = resampler(frame_embeds, image_outputs["mask_feats"], image_outputs["attn_feats"], adapter, clip_bk_feats,
+                        text_feats)
+    # post_processing (brivis.py:242-265): mean of the logits over the frames, softmax, drop the background column
+    logits = outputs["pred_logits"][0].float().contiguous()                       # [t, q, K + 1]
+    with torch.cuda.device(logits.device):
+        probs, _ = L.clip_aggregate(logits, torch.ones(t, q, dtype=torch.uint8, device=logits.device))
+    mask_cls = probs[:, :-1].contiguous()
+    video_output = inference_video(q, mask_cls.shape[1], mask_cls, outputs["pred_masks"][0], padded_size, image_size,
+                                   height, width)
+    return video_output, outputs, indices

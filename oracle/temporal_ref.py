@@ -109,3 +109,19 @@ def resampler_forward(P, frame_embeds, mask_feats, attn_feats, post_encode_image
     emb = layer_norm(x, P["decode_norm.weight"], P["decode_norm.bias"]).view(b, q, t, c).transpose(1, 2)
     lg, m = heads[num_layers]
     return dict(pred_logits=lg, pred_masks=m, pred_embeds=emb, heads=heads)
+
+
+def brivis_video_inference(dec_params, res_params, x, mask_features, post_encode_image, cal_sim_logits,
+                           padded_size, image_size, out_hw, clip_heads=12):
+    """The hot-path part of BriVIS.forward's eval branch (openvis/brivis.py:157-190, 242-265) composed from the pinned
+    restatements: SAN frame decoder -> query matching -> resampler -> mean over frames / softmax / drop background
+    -> VideoMaskFormer.inference_video.  One clip.  Returns a dict of intermediate and final results."""
+    from . import decoder_ref as O
+    dec = O.decoder_forward(dec_params, x, mask_features, kind="san_frame", clip_heads=clip_heads, return_attn_masks=False)
+    indices, frame_embeds = batch_video_match_via_embeds(dec["pred_embeds"])
+    res = resampler_forward(res_params, frame_embeds, dec["mask_feats"], dec["attn_feats"], post_encode_image,
+                            cal_sim_logits, heads_at=())
+    cls = res["pred_logits"].mean(dim=1)[0].softmax(-1)[:, :-1]
+    sc, lab, qi, ent, masks, mlog = O.video_postprocess(cls, res["pred_masks"][0], padded_size, image_size, out_hw)
+    return dict(decoder=dec, indices=indices, resampler=res, mask_cls=cls, scores=sc, labels=lab, queries=qi,
+                entropys=ent, masks=masks, mask_logits=mlog)

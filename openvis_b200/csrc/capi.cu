@@ -748,6 +748,13 @@ int ovis_xattn(const void* q, const void* k, const void* v, const unsigned int* 
   }
   static const bool no_combine = getenv("OVIS_XATTN_NO_COMBINE") != nullptr;     // timing experiments only
   if (no_combine) return OVIS_OK;
+  if (splits <= 8) {
+    // Frame decoders (a few hundred keys per group): 2-8 partials per row, one thread per output element pair
+    const long long total = (long long)G * Q * 128;
+    xattn_combine_few_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(o_part, ml_part, (__half*)out, Q,
+                                                                                                q_pad, splits, total);
+    return check_launch("xattn_combine_few_kernel");
+  }
   xattn_combine_kernel<<<dim3(Q, 8, G), 256, 0, (cudaStream_t)stream>>>(o_part, ml_part, (__half*)out, Q, q_pad, splits);
   return check_launch("xattn_combine_kernel");
 }
@@ -817,7 +824,10 @@ int ovis_topk_scores(const float* scores, int Q, int K, int k, float* out_scores
   CHECK_ARG(Q > 0 && K > 0 && k > 0 && k <= 32 && (long long)Q * K >= k && (long long)Q * K < (1ll << 31), "bad sizes (k <= 32)");
   int rc = device_info(nullptr);
   if (rc) return rc;
-  topk_scores_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(scores, Q, K, k, out_scores, out_query, out_label, out_entropy);
+  if (k <= 10)
+    topk_scores_kernel<10, 1024><<<1, 1024, 0, (cudaStream_t)stream>>>(scores, Q, K, k, out_scores, out_query, out_label, out_entropy);
+  else
+    topk_scores_kernel<32, 256><<<1, 256, 0, (cudaStream_t)stream>>>(scores, Q, K, k, out_scores, out_query, out_label, out_entropy);
   return check_launch("topk_scores_kernel");
 }
 

@@ -278,6 +278,34 @@ xattn_combine_kernel(const float* __restrict__ o_part, const float* __restrict__
   }
 }
 
+// The same merge when there are only a few partials per row (Frame decoders: `splits` = 2-8): one thread per pair of
+// output channels walks the partials serially, so no thread idles and nothing goes through shared memory
+// (xattn_combine_kernel's 8 split lanes x 32 channels layout leaves 6 of 8 warps without work at splits = 2).
+__global__ void __launch_bounds__(256)
+xattn_combine_few_kernel(const float* __restrict__ o_part, const float* __restrict__ ml_part, __half* __restrict__ out,
+                         int Q, int q_pad, int splits, long long total) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;       // ((g * Q + q) * 8 + h) * 16 + d2
+  if (e >= total) return;
+  const int d2 = (int)(e & 15), h = (int)((e >> 4) & 7);
+  const long long row = e >> 7;
+  const int q = (int)(row % Q);
+  const long long g = row / Q;
+  float M = -INFINITY, n0 = 0.f, n1 = 0.f, den = 0.f;
+  for (int s = 0; s < splits; ++s) {
+    const long long r = ((g * splits + s) * 8 + h) * q_pad + q;
+    const float2 ml = __ldg(reinterpret_cast<const float2*>(ml_part + r * 2));
+    const float2 o = __ldg(reinterpret_cast<const float2*>(o_part + r * 32 + d2 * 2));
+    if (ml.x == -INFINITY) continue;
+    const float Mn = fmaxf(M, ml.x);
+    const float c0 = exp2f(M - Mn), c1 = exp2f(ml.x - Mn);
+    n0 = n0 * c0 + o.x * c1;
+    n1 = n1 * c0 + o.y * c1;
+    den = den * c0 + ml.y * c1;
+    M = Mn;
+  }
+  *reinterpret_cast<__half2*>(out + row * 256 + h * 32 + d2 * 2) = __floats2half2_rn(n0 / den, n1 / den);
+}
+
 // Self-attention over the Q object queries (SelfAttentionLayer.forward_post, video_..._decoder.py:52-62).
 // One CTA per (head, group); thread = query row; K/V of the head staged in shared memory.
 struct SelfAttnArgs {

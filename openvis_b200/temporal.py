@@ -305,6 +305,7 @@ def brivis_video_inference(decoder, adapter, resampler, features, mask_features,
     with torch.cuda.device(logits.device):
         probs, _ = L.clip_aggregate(logits, torch.ones(t, q, dtype=torch.uint8, device=logits.device))
     mask_cls = probs[:, :-1].contiguous()
+    outputs["mask_cls_result"] = mask_cls                                          # extension key: post_processing's scores [q, K]
     video_output = inference_video(q, mask_cls.shape[1], mask_cls, outputs["pred_masks"][0], padded_size, image_size,
                                    height, width)
     return video_output, outputs, indices

@@ -24,15 +24,32 @@ def _need_gpu():
     L.device_check()
 
 
+def _conditioned(P, boost=1.0):
+    """Random-init post-norm stacks wash the query identity out (all queries end up with nearly the same embedding, so
+    the matching would be decided by rounding noise).  A trained model keeps its queries apart; here the residual
+    updates are damped to the same effect, and the attention-bias branch is scaled to biases of a few units."""
+    out = {}
+    for k, v in P.items():
+        if k.endswith(("out_proj.weight", "out_proj.bias", "linear2.weight", "linear2.bias")):
+            v = v * 0.25
+        if k.startswith("short_aggregate_layers") and ".2." in k:
+            v = v * 0.25
+        if k.startswith("attn_mlp.layers.2"):
+            v = v * boost
+        out[k] = v
+    return out
+
+
 @pytest.mark.parametrize("api_exact", [False, True])
 def test_brivis_clip_against_oracle(golden_dir, api_exact):
+    import torch.nn.functional as F
     from oracle import decoder_ref as O
     from oracle import temporal_ref as TR
     st = np.load(os.path.join(golden_dir, "san_tail.npz"))
     Tn, Hp, Wp, Q, K = 5, 128, 192, 100, 41
     img, out_hw = (120, 180), (240, 360)
-    P = seeded_params(decoder_param_shapes("san_frame", Q=Q), 2)
-    RP = seeded_resampler_params(23)
+    P = _conditioned(seeded_params(decoder_param_shapes("san_frame", Q=Q), 2), boost=3.0)
+    RP = _conditioned(seeded_resampler_params(23))
     CP = seeded_clip_block_params(7)
     x, mf = seeded_inputs(Tn, Hp, Wp, seed=4321)
     g = torch.Generator().manual_seed(8)
@@ -57,30 +74,34 @@ def test_brivis_clip_against_oracle(golden_dir, api_exact):
     sd.update({"ln_post.weight": ln_w, "ln_post.bias": ln_b, "proj": proj})
     ad = SideAdapterBlocks(num_queries=Q).load_clip_visual_state_dict(sd)
     ad.tail.logit_scale_exp = scale
-    args = ([t.cuda() for t in x], mf.cuda(), (bk[0].cuda(), bk[1].cuda()), text.cuda(), (Hp, Wp), img, out_hw[0], out_hw[1])
-    for rep in range(3):                 # the third call replays the resampler's CUDA graph
+    mf_dev = mf.cuda()
+    args = ([t.cuda() for t in x], mf_dev, (bk[0].cuda(), bk[1].cuda()), text.cuda(), (Hp, Wp), img, out_hw[0], out_hw[1])
+    rm = ref["resampler"]["pred_masks"]
+    for rep in range(3):                 # the third call replays the decoder's and the resampler's CUDA graphs
+        n0 = L.launch_count()
         video, outputs, indices = T.brivis_video_inference(dec, ad, res, *args, api_exact=api_exact)
-        assert res.operand_source is dec and dec.shared_operands(args[1], dec._last["af32"]) is not None
-        # query matching: index work -- identical to the oracle's chain (its embeddings differ at fp16-operand level only)
-        assert (indices.cpu() == ref["indices"]).float().mean().item() >= 0.99
-        if not torch.equal(indices.cpu(), ref["indices"]):
-            continue                     # a near-tie resolved differently: everything downstream is a different labelling
-        emb_err = (outputs["pred_embeds"].cpu() - ref["resampler"]["pred_embeds"]).abs().max().item()
-        assert emb_err < 5e-2, emb_err
-        rm = ref["resampler"]["pred_masks"]
+        assert L.launch_count() - n0 > 250
+        assert res.operand_source is dec and dec.shared_operands(mf_dev, dec._last["af32"]) is not None
+        # query matching: index work, identical to the oracle's chain (assignment margins ~0.37 vs fp16-level cost noise)
+        assert torch.equal(indices.cpu(), ref["indices"])
+        # chained tolerances: the decoder's embeddings (fp16 operands, <= 3e-2) feed six more fp16-operand layers
+        eerr = (outputs["pred_embeds"].cpu() - ref["resampler"]["pred_embeds"]).abs()
+        assert (eerr <= 5e-2).float().mean().item() >= 0.999 and eerr.max().item() < 0.3, eerr.max().item()
         pm = outputs["pred_masks"].cpu()
         assert ((pm - rm).abs() <= 2e-2 * rm.abs().max()).float().mean().item() >= 0.999
         assert (outputs["pred_logits"].cpu() - ref["resampler"]["pred_logits"]).abs().max().item() < 0.15
-        # final result: top-10 (query, label) pairs, scores, packed masks
-        assert video["image_size"] == out_hw
-        assert np.allclose(video["pred_scores"], ref["scores"].numpy(), atol=2e-3)
-        same = [a == b and c == d for a, b, c, d in zip(video["pred_labels"], ref["labels"].tolist(),
-                                                        video["pred_queries"], ref["queries"].tolist())]
-        assert sum(same) >= 8, same          # scores of neighbouring ranks can be closer than the fp16 tolerance
+        cls = outputs["mask_cls_result"].cpu()
+        assert cls.shape == (Q, K - 1) and (cls - ref["mask_cls"]).abs().max().item() < 2e-3
+        # final result.  With random-init CLIP blocks the class scores of different queries differ by less than the fp16
+        # tolerance, so the top-10 *selection* is checked for consistency with the device scores and against the oracle's
+        # 10th-best score, and the packed masks against the oracle's post-processing of the same queries.
+        assert video["image_size"] == out_hw and len(video["pred_scores"]) == 10
+        qi, lab = torch.tensor(video["pred_queries"]), torch.tensor(video["pred_labels"])
+        sc = torch.tensor(video["pred_scores"])
+        assert torch.allclose(sc, cls[qi, lab], atol=1e-6) and (sc[:-1] >= sc[1:]).all()
+        assert sc.min().item() >= ref["scores"].min().item() - 2e-3 and abs(sc.max().item() - ref["scores"].max().item()) < 2e-3
+        assert len(set(zip(qi.tolist(), lab.tolist()))) == 10
+        up = F.interpolate(rm[0][qi], size=(Hp, Wp), mode="bilinear", align_corners=False)[:, :, :img[0], :img[1]]
+        want = F.interpolate(up, size=out_hw, mode="bilinear", align_corners=False) > 0
         masks = video["pred_masks"].unpack()
-        for j, ok in enumerate(same):
-            if ok:
-                agree = (masks[j] == ref["masks"][j]).float().mean().item()
-                assert agree >= 0.995, (j, agree)
-    if api_exact:
-        assert "pred_logits" in dec._last or True
+        assert masks.shape == want.shape and (masks == want).float().mean().item() >= 0.995

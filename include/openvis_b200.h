@@ -122,7 +122,8 @@ int ovis_xattn(const void* q_f16, const void* k_f16, const void* v_f16, const un
                const unsigned char* flags, int G, int Q, int q_stride, int keys, int splits,
                float* o_part, float* ml_part, void* out_f16, void* stream);
 /* Unmasked self-attention over the Q queries (SelfAttentionLayer.forward_post, video_...decoder.py:52-62).
- * qk [G*Q][512] f16 (q | k, biased, unscaled), v [G*Q][256] f16 -> out [G*Q][256] f16. */
+ * qk [G*Q][512] f16 (q | k, biased, unscaled), v [G*Q][256] f16 -> out [G*Q][256] f16.  Q <= 1536 rows per group
+ * (the decoders use Q <= 256 queries; the temporal resampler attends over the frames of a clip, resampler.py:258-262). */
 int ovis_self_attn(const void* qk_f16, const void* v_f16, void* out_f16, int G, int Q, void* stream);
 
 /* ---- open-vocabulary head tails ----------------------------------------------------------------------- */

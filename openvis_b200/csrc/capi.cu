@@ -760,13 +760,23 @@ int ovis_xattn(const void* q, const void* k, const void* v, const unsigned int* 
 }
 
 int ovis_self_attn(const void* qk, const void* v, void* out, int G, int Q, void* stream) {
-  CHECK_ARG(qk && v && out && G > 0 && Q > 0 && Q <= 256, "bad arguments");
+  CHECK_ARG(qk && v && out && G > 0 && Q > 0 && Q <= 1536 && G <= 65535, "bad arguments (at most 1536 rows per group)");
   int rc = device_info(nullptr);
   if (rc) return rc;
   SelfAttnArgs a;
   a.qk = (const __half*)qk; a.v = (const __half*)v; a.out = (__half*)out; a.Q = Q;
   a.scale_log2 = 0.17677669529663687f * 1.4426950408889634f;   // 32^-1/2 * log2(e)
-  const size_t smem = (size_t)Q * 32 * 2 * sizeof(__half);
+  const size_t smem = (size_t)Q * 32 * 2 * sizeof(__half);      // K and V of one head: 128 B per row
+  if (smem > 48 * 1024) {
+    static bool attr_done[64] = {false};          // function attributes are per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_done[dev]) {
+      cudaError_t e = cudaFuncSetAttribute(self_attn_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1536 * 128);
+      if (e != cudaSuccess) return fail(OVIS_ERR_CUDA, "%s: cannot raise the shared-memory limit", "self_attn_kernel");
+      attr_done[dev] = true;
+    }
+  }
   if (Q <= 128) self_attn_kernel<4><<<dim3(8, G), 512, smem, (cudaStream_t)stream>>>(a);
   else self_attn_kernel<2><<<dim3(8, G), 512, smem, (cudaStream_t)stream>>>(a);
   return check_launch("self_attn_kernel");
@@ -932,11 +942,15 @@ int ovis_match_embeds(const float* en, int B, int T, int n, int C, float* cost, 
   a.cost_in_smem = match_smem_bytes(n, 1) <= (size_t)227 * 1024;
   CHECK_ARG(a.cost_in_smem || cost, "a cost scratch buffer is required when the n x n matrix does not fit shared memory");
   const size_t smem = match_smem_bytes(n, a.cost_in_smem);
-  static std::atomic<size_t> attr_set{0};
-  if (smem > 48 * 1024 && attr_set.load() < smem) {
-    cudaError_t e = cudaFuncSetAttribute(match_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return fail(OVIS_ERR_CUDA, "%s: cannot raise the shared-memory limit", "match_assign_kernel");
-    attr_set.store(227 * 1024);
+  if (smem > 48 * 1024) {
+    static bool attr_done[64] = {false};          // function attributes are per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_done[dev]) {
+      cudaError_t e = cudaFuncSetAttribute(match_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (e != cudaSuccess) return fail(OVIS_ERR_CUDA, "%s: cannot raise the shared-memory limit", "match_assign_kernel");
+      attr_done[dev] = true;
+    }
   }
   match_assign_kernel<<<dim3(T, B), MATCH_THREADS, smem, (cudaStream_t)stream>>>(a);
   return check_launch("match_assign_kernel");

@@ -332,8 +332,11 @@ self_attn_kernel(const SelfAttnArgs a) {
     *reinterpret_cast<uint4*>(sv + row * 32 + ch * 8) = *reinterpret_cast<const uint4*>(a.v + r * 256 + head * 32 + ch * 8);
   }
   __syncthreads();
-  const int row = threadIdx.x / PARTS, part = threadIdx.x % PARTS;
-  const bool row_ok = row < a.Q;                 // (whole lane groups are in or out: the shuffles below stay uniform)
+  const int part = threadIdx.x % PARTS;
+  // rows in passes of 512 / PARTS (one pass for the decoders' Q <= 256; the resampler's frame axis can be longer);
+  // every thread runs every pass so that the shuffles below stay uniform
+  for (int row = threadIdx.x / PARTS; row < ((a.Q + 512 / PARTS - 1) / (512 / PARTS)) * (512 / PARTS); row += 512 / PARTS) {
+  const bool row_ok = row < a.Q;                 // (whole lane groups are in or out)
   float q[32], acc[32];
   {
     const __half* qp = a.qk + ((long long)g * a.Q + (row_ok ? row : 0)) * 512 + head * 32;
@@ -401,6 +404,7 @@ self_attn_kernel(const SelfAttnArgs a) {
       *reinterpret_cast<uint4*>(op + e) = u;
     }
   }
+  }   // row passes
 }
 
 }  // namespace ovis

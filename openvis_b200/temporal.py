@@ -141,8 +141,8 @@ class TemporalInstanceResampler(nn.Module):
         if not frame_embeds.is_cuda:
             raise L.OvisError("openvis_b200 has no CPU path: inputs must be CUDA tensors on an sm_100 device")
         bs, t, q, c = frame_embeds.shape
-        if c != HIDDEN or t > 256 or q > 256:
-            raise NotImplementedError(f"frame_embeds must be [b, t <= 256, q <= 256, 256], got {tuple(frame_embeds.shape)}")
+        if c != HIDDEN or t > 1536 or q > 256:
+            raise NotImplementedError(f"frame_embeds must be [b, t <= 1536, q <= 256, 256], got {tuple(frame_embeds.shape)}")
         BT, _, H, Wd = mask_feats.shape
         nh = attn_feats.shape[1]
         assert BT == bs * t and attn_feats.shape[0] == BT and attn_feats.shape[2] == HIDDEN

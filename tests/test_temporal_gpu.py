@@ -179,3 +179,28 @@ def test_resampler_matches_oracle_clip_scale(golden_dir):
     out = m.cuda()(fe.cuda(), mf.cuda(), af.cuda(), _adapter(Q, 7, st), (bk[0].cuda(), bk[1].cuda()), text.cuda())
     _check_resampler(out, ref["pred_logits"], ref["pred_masks"], ref["pred_embeds"])
     assert (out["pred_logits"].argmax(-1).cpu() == ref["pred_logits"].argmax(-1)).float().mean().item() >= 0.99
+
+
+def test_resampler_long_clip_layers():
+    """300 frames (self-attention over the frame axis in two row passes): embeddings against the oracle's layers."""
+    from oracle import temporal_ref as TR
+    t, Q = 300, 20
+    g = torch.Generator().manual_seed(3)
+    fe = torch.randn(1, t, Q, 256, generator=g)
+    mf, af = torch.randn(t, 256, 8, 8, generator=g), torch.randn(t, 12, 256, 2, 4, generator=g)
+    P = seeded_resampler_params(24)
+
+    class _Stub:                       # heads without a CLIP side path: this test is about the temporal layers
+        def post_encode_image(self, bk, biases): return biases.mean(1).flatten(2)
+
+        def cal_sim_logits(self, text, f): return f
+
+    with torch.no_grad():
+        ref = TR.resampler_forward(P, fe, mf, af, lambda b: b.mean(1).flatten(2), lambda f: f, heads_at=())
+    m = T.TemporalInstanceResampler().eval()
+    m.load_state_dict(P)
+    out = m.cuda()(fe.cuda(), mf.cuda(), af.cuda(), _Stub(), None, None)
+    err = (out["pred_embeds"].cpu() - ref["pred_embeds"]).abs()
+    assert (err <= 3e-2).float().mean().item() >= 0.999 and err.max().item() < 0.15, err.max().item()
+    rm = ref["pred_masks"]
+    assert ((out["pred_masks"].cpu() - rm).abs() <= 1e-2 * rm.abs().max()).float().mean().item() >= 0.999

@@ -68,6 +68,14 @@ def reset_image_output_order(outputs, indices):
     return outputs
 
 
+def post_processing(outputs):
+    """MinVIS.post_processing (openvis/modeling/minvis.py:320-338), inherited by the online meta-architectures
+    (openvis.py:214, san.py:255, simplebsl.py:270): match the frames' queries through their embeddings and bring
+    pred_logits [b, t, q, k] and pred_masks [b, q, t, h, w] into the matched order.  pred_embeds [b, t, q, c]."""
+    indices, _ = batch_video_match_via_embeds(outputs["pred_embeds"])
+    return reset_image_output_order(outputs, indices)
+
+
 # ------------------------------------------------------------------------------------------------ resampler
 class TemporalInstanceResampler(nn.Module):
     """Drop-in for openvis/modeling/resampler.py:189-323 (constructed as in brivis.py:47)."""

@@ -204,3 +204,16 @@ def test_resampler_long_clip_layers():
     assert (err <= 3e-2).float().mean().item() >= 0.999 and err.max().item() < 0.15, err.max().item()
     rm = ref["pred_masks"]
     assert ((out["pred_masks"].cpu() - rm).abs() <= 1e-2 * rm.abs().max()).float().mean().item() >= 0.999
+
+
+def test_online_post_processing_equals_oracle():
+    """MinVIS.post_processing (minvis.py:320-338): matching + re-ordering of logits and masks in one call."""
+    from oracle import temporal_ref as TR
+    from oracle.make_golden import temporal_match_inputs
+    e = temporal_match_inputs(b=2, t=5, Q=100, seed=61)
+    g = torch.Generator().manual_seed(62)
+    logits, masks = torch.randn(2, 5, 100, 41, generator=g), torch.randn(2, 100, 5, 24, 40, generator=g)
+    out = T.post_processing({"pred_logits": logits.cuda(), "pred_masks": masks.cuda(), "pred_embeds": e.cuda()})
+    idx, _ = TR.batch_video_match_via_embeds(e)
+    rl, rm = TR.reset_image_output_order(logits, masks, idx)
+    assert torch.equal(out["pred_logits"].cpu(), rl) and torch.equal(out["pred_masks"].cpu(), rm)

@@ -281,27 +281,38 @@ class TemporalInstanceResampler(nn.Module):
 # ------------------------------------------------------------------------------------------------ BriVIS eval schedule
 @torch.no_grad()
 def brivis_video_inference(decoder, adapter, resampler, features, mask_features, clip_bk_feats, text_feats,
-                           padded_size, image_size, height, width, api_exact=False):
+                           padded_size, image_size, height, width, api_exact=False, num_clips=1):
     """The part of ``BriVIS.forward``'s eval branch that lies on the hot path (openvis/brivis.py:157-190, 242-265), from the
     pixel decoder's outputs to the video result, composed from the drop-in pieces exactly as the reference composes its
     own: SAN frame decoder -> query matching -> TemporalInstanceResampler (heads through the CLIP side path) ->
-    post_processing -> inference_video.  One clip (b = 1, the reference's eval batch).
+    post_processing -> inference_video.
 
     decoder   SideAdapterFrameMultiScaleMaskedTransformerDecoder (sem_seg_head.predictor, brivis.py:160)
     adapter   object with post_encode_image / cal_sim_logits (ov_head.SideAdapterBlocks; self.clip_adapter)
-    features  the three multi-scale maps (coarsest first) and mask_features [T, 256, Hp/4, Wp/4] of the clip's frames
+    features  the three multi-scale maps (coarsest first) and mask_features [b*T, 256, Hp/4, Wp/4] of the clips' frames
     api_exact additionally computes what the reference computes but never reads in eval: the frame-level pred_logits
               (brivis.py:169-170) and reset_image_output_order (:174).
-    Returns (video_output as VideoMaskFormer.inference_video, resampler outputs, indices [1, T, Q])."""
+    num_clips b = len(batched_inputs) of the reference (1 in its eval loop).  The frame decoder, the matching and the
+              resampler are all written for b clips of equal length (brivis.py:164-176 carry b through einops), and the
+              query-side launch chain costs the same for 36 or 144 frames, so several clips per call is the
+              throughput setting (BASELINE config 5).
+    Returns (video_output as VideoMaskFormer.inference_video, resampler outputs, indices [b, T, Q]); video_output is a list
+    of b dictionaries when num_clips > 1."""
     from .postprocess import inference_video
     image_outputs = decoder(features, mask_features)
-    q = decoder.num_queries
-    t = mask_features.shape[0]
-    pred_embeds = image_outputs["pred_embeds"][0][None]                           # (1, bt, q, c) -> (b, t, q, c)
+    q, b = decoder.num_queries, int(num_clips)
+    bt = mask_features.shape[0]
+    if b < 1 or bt % b:
+        raise ValueError(f"num_clips={b} does not divide the {bt} frames of this call")
+    t = bt // b
+    pred_embeds = image_outputs["pred_embeds"][0].view(b, t, q, -1)               # (1, bt, q, c) -> (b, t, q, c)
     if api_exact:
         biases = image_outputs["class_attn_biases"][0]                            # (1, bt, n, q, h, w) -> (bt, n, q, h, w)
         clip_feats = adapter.post_encode_image(clip_bk_feats, biases)
-        image_outputs["pred_logits"] = adapter.cal_sim_logits(text_feats, clip_feats)[None]
+        lg = adapter.cal_sim_logits(text_feats, clip_feats)
+        image_outputs["pred_logits"] = lg.view(b, t, q, -1)                       # (b t) q c -> b t q c
+        pm = image_outputs["pred_masks"][0]                                       # q (b t) h w -> b q t h w
+        image_outputs["pred_masks"] = pm[None] if b == 1 else pm.view(q, b, t, *pm.shape[-2:]).transpose(0, 1).contiguous()
     indices, frame_embeds = batch_video_match_via_embeds(pred_embeds)
     if api_exact:
         image_outputs = reset_image_output_order(image_outputs, indices)
@@ -309,11 +320,15 @@ def brivis_video_inference(decoder, adapter, resampler, features, mask_features,
     outputs = resampler(frame_embeds, image_outputs["mask_feats"], image_outputs["attn_feats"], adapter, clip_bk_feats,
                         text_feats)
     # post_processing (brivis.py:242-265): mean of the logits over the frames, softmax, drop the background column
-    logits = outputs["pred_logits"][0].float().contiguous()                       # [t, q, K + 1]
-    with torch.cuda.device(logits.device):
-        probs, _ = L.clip_aggregate(logits, torch.ones(t, q, dtype=torch.uint8, device=logits.device))
-    mask_cls = probs[:, :-1].contiguous()
-    outputs["mask_cls_result"] = mask_cls                                          # extension key: post_processing's scores [q, K]
-    video_output = inference_video(q, mask_cls.shape[1], mask_cls, outputs["pred_masks"][0], padded_size, image_size,
-                                   height, width)
-    return video_output, outputs, indices
+    videos, scores = [], []
+    for c in range(b):
+        logits = outputs["pred_logits"][c].float().contiguous()                   # [t, q, K + 1]
+        with torch.cuda.device(logits.device):
+            probs, _ = L.clip_aggregate(logits, torch.ones(t, q, dtype=torch.uint8, device=logits.device))
+        mask_cls = probs[:, :-1].contiguous()
+        scores.append(mask_cls)
+        videos.append(inference_video(q, mask_cls.shape[1], mask_cls, outputs["pred_masks"][c], padded_size, image_size,
+                                      height, width))
+    # extension key: post_processing's scores [q, K] ([b, q, K] for several clips)
+    outputs["mask_cls_result"] = scores[0] if b == 1 else torch.stack(scores)
+    return (videos[0] if b == 1 else videos), outputs, indices

@@ -105,3 +105,43 @@ def test_brivis_clip_against_oracle(golden_dir, api_exact):
         want = F.interpolate(up, size=out_hw, mode="bilinear", align_corners=False) > 0
         masks = video["pred_masks"].unpack()
         assert masks.shape == want.shape and (masks == want).float().mean().item() >= 0.995
+
+
+def test_two_clips_per_call_equal_single_clip_calls(golden_dir):
+    """num_clips = 2: one decoder / matching / resampler call for two clips gives each clip the result of its own call."""
+    st = np.load(os.path.join(golden_dir, "san_tail.npz"))
+    Tn, Hp, Wp, Q, K = 4, 128, 192, 100, 41
+    img, out_hw = (120, 180), (120, 180)
+    P = _conditioned(seeded_params(decoder_param_shapes("san_frame", Q=Q), 2), boost=3.0)
+    RP = _conditioned(seeded_resampler_params(23))
+    kw = dict(in_channels=256, mask_classification=True, num_classes=1, hidden_dim=256, num_queries=Q, nheads=8,
+              dim_feedforward=2048, dec_layers=9, pre_norm=False, mask_dim=256, enforce_input_project=False, num_frames=2,
+              clip_heads=12)
+    dec = D.SideAdapterFrameMultiScaleMaskedTransformerDecoder(**kw)
+    dec.load_state_dict(P)
+    dec = dec.cuda().eval()
+    res = T.TemporalInstanceResampler().eval()
+    res.load_state_dict(RP)
+    res = res.cuda()
+    sd = {f"transformer.resblocks.{k}": v for k, v in seeded_clip_block_params(7).items()}
+    sd.update({"ln_post.weight": torch.tensor(st["ln_w"]), "ln_post.bias": torch.tensor(st["ln_b"]), "proj": torch.tensor(st["proj"])})
+    ad = SideAdapterBlocks(num_queries=Q).load_clip_visual_state_dict(sd)
+    x, mf = seeded_inputs(2 * Tn, Hp, Wp, seed=777)
+    g = torch.Generator().manual_seed(9)
+    cls, pix = torch.randn(1, 2 * Tn, 768, generator=g).cuda(), torch.randn(2 * Tn, 768, 14, 14, generator=g).cuda()
+    text = torch.nn.functional.normalize(torch.randn(K, 512, generator=g), dim=-1).cuda()
+    x, mf = [t.cuda() for t in x], mf.cuda()
+    tail = ((Hp, Wp), img, out_hw[0], out_hw[1])
+    for exact in (False, True):
+        videos, outs, idx = T.brivis_video_inference(dec, ad, res, x, mf, (cls, pix), text, *tail, api_exact=exact, num_clips=2)
+        assert len(videos) == 2 and idx.shape == (2, Tn, Q) and outs["pred_masks"].shape[:3] == (2, Q, Tn)
+        lg2, pm2, sc2 = outs["pred_logits"].clone(), outs["pred_masks"].clone(), outs["mask_cls_result"].clone()
+        for c in range(2):
+            sl = slice(c * Tn, (c + 1) * Tn)
+            v1, o1, i1 = T.brivis_video_inference(dec, ad, res, [t[sl].contiguous() for t in x], mf[sl].contiguous(),
+                                                  (cls[:, sl].contiguous(), pix[sl].contiguous()), text, *tail, api_exact=exact)
+            assert torch.equal(i1[0], idx[c])
+            # same kernels on the same rows; only the split-path choice / tile boundaries of the GEMMs can differ
+            assert (o1["pred_logits"][0] - lg2[c]).abs().max().item() < 2e-2
+            assert ((o1["pred_masks"][0] - pm2[c]).abs() <= 1e-2 * pm2[c].abs().max()).float().mean().item() >= 0.999
+            assert (o1["mask_cls_result"] - sc2[c]).abs().max().item() < 1e-3

@@ -766,11 +766,26 @@ int ovis_self_attn(const void* qk, const void* v, void* out, int G, int Q, void*
   SelfAttnArgs a;
   a.qk = (const __half*)qk; a.v = (const __half*)v; a.out = (__half*)out; a.Q = Q;
   a.scale_log2 = 0.17677669529663687f * 1.4426950408889634f;   // 32^-1/2 * log2(e)
+  static const bool simt = getenv("OVIS_SELF_ATTN") && !strcmp(getenv("OVIS_SELF_ATTN"), "simt");      // A/B and checking only
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const size_t smem_mma = (size_t)2 * ((Q + SA_KB - 1) / SA_KB * SA_KB) * XA_LD * sizeof(__half);   // K, V of one head, 80 B per row
+  if (!simt && smem_mma <= (size_t)227 * 1024) {            // (up to 1408 rows; beyond that the SIMT kernel's denser layout)
+    const size_t smem = smem_mma;
+    if (smem > 48 * 1024) {
+      static bool attr_done[64] = {false};          // function attributes are per device
+      if (!attr_done[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(self_attn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return fail(OVIS_ERR_CUDA, "%s: cannot raise the shared-memory limit", "self_attn_mma_kernel");
+        attr_done[dev] = true;
+      }
+    }
+    self_attn_mma_kernel<<<dim3(8, G), 256, smem, (cudaStream_t)stream>>>(a);
+    return check_launch("self_attn_mma_kernel");
+  }
   const size_t smem = (size_t)Q * 32 * 2 * sizeof(__half);      // K and V of one head: 128 B per row
   if (smem > 48 * 1024) {
     static bool attr_done[64] = {false};          // function attributes are per device
-    int dev = 0;
-    cudaGetDevice(&dev);
     if (!attr_done[dev]) {
       cudaError_t e = cudaFuncSetAttribute(self_attn_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1536 * 128);
       if (e != cudaSuccess) return fail(OVIS_ERR_CUDA, "%s: cannot raise the shared-memory limit", "self_attn_kernel");

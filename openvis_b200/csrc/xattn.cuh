@@ -407,4 +407,133 @@ self_attn_kernel(const SelfAttnArgs a) {
   }   // row passes
 }
 
+// Tensor-core version (mma.sync m16n8k16, fp16 operands / fp32 accumulation): one CTA per (head, group), K and V of
+// the head in shared memory, each of the 8 warps takes 16-row query tiles round-robin and runs a flash-style loop over
+// 64-key blocks.  The SIMT kernel above needed 35 us for 36 frames x 100 queries (10 TFLOP/s) and 98 us at 200 queries:
+// nine of those per decoder call were 12 % of the Frame decoders' time.  Same interface and scaling as self_attn_kernel
+// (which stays as the checker: OVIS_SELF_ATTN=simt).
+constexpr int SA_KB = 64;
+__global__ void __launch_bounds__(256)
+self_attn_mma_kernel(const SelfAttnArgs a) {
+  extern __shared__ __align__(16) __half sm_sa[];          // K [Qp][XA_LD], V [Qp][XA_LD]; Qp = Q rounded up to 64
+  const int Q = a.Q;
+  const int Qp = (Q + SA_KB - 1) / SA_KB * SA_KB;
+  __half* sk = sm_sa;
+  __half* sv = sm_sa + (size_t)Qp * XA_LD;
+  const int head = blockIdx.x, g = blockIdx.y;
+  for (int i = threadIdx.x; i < Qp * 4; i += blockDim.x) {
+    const int row = i >> 2, ch = i & 3;
+    uint4 kv = make_uint4(0u, 0u, 0u, 0u), vv = make_uint4(0u, 0u, 0u, 0u);
+    if (row < Q) {
+      const long long r = (long long)g * Q + row;
+      kv = *reinterpret_cast<const uint4*>(a.qk + r * 512 + 256 + head * 32 + ch * 8);
+      vv = *reinterpret_cast<const uint4*>(a.v + r * 256 + head * 32 + ch * 8);
+    }
+    *reinterpret_cast<uint4*>(sk + row * XA_LD + ch * 8) = kv;
+    *reinterpret_cast<uint4*>(sv + row * XA_LD + ch * 8) = vv;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int quad = lane >> 2, tq = lane & 3;
+  const int mtiles = (Q + 15) >> 4;
+  for (int mt = warp; mt < mtiles; mt += 8) {
+    uint32_t qf[2][4];
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int row = mt * 16 + quad + (i & 1) * 8;
+        const int col = head * 32 + ks * 16 + tq * 2 + (i >> 1) * 8;
+        qf[ks][i] = row < Q ? *reinterpret_cast<const uint32_t*>(a.qk + ((long long)g * Q + row) * 512 + col) : 0u;
+      }
+    float o[4][4];
+#pragma unroll
+    for (int dn = 0; dn < 4; ++dn)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) o[dn][i] = 0.f;
+    float mrow[2] = {-INFINITY, -INFINITY}, lrow[2] = {0.f, 0.f};
+    for (int kb = 0; kb < Q; kb += SA_KB) {
+      float sc[8][4];
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) sc[nt][i] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          const __half* kr = sk + (kb + nt * 8 + quad) * XA_LD + ks * 16 + tq * 2;
+          const uint32_t b0 = *reinterpret_cast<const uint32_t*>(kr);
+          const uint32_t b1 = *reinterpret_cast<const uint32_t*>(kr + 8);
+          mma_16816(sc[nt], qf[ks], b0, b1);
+        }
+      }
+      // scale to base-2 logits, drop the padding keys, row max (rows quad and quad + 8; a quad of lanes shares a row)
+      float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int key = kb + nt * 8 + tq * 2 + (i & 1);
+          const float v = key < Q ? sc[nt][i] * a.scale_log2 : -INFINITY;
+          sc[nt][i] = v;
+          mx[i >> 1] = fmaxf(mx[i >> 1], v);
+        }
+      float corr[2];
+#pragma unroll
+      for (int hi = 0; hi < 2; ++hi) {
+        mx[hi] = fmaxf(mx[hi], __shfl_xor_sync(0xffffffffu, mx[hi], 1));
+        mx[hi] = fmaxf(mx[hi], __shfl_xor_sync(0xffffffffu, mx[hi], 2));
+        const float mnew = fmaxf(mrow[hi], mx[hi]);          // finite: every block holds at least one real key
+        corr[hi] = exp2f(mrow[hi] - mnew);                   // 0 for the first block
+        mrow[hi] = mnew;
+      }
+      float ls[2] = {0.f, 0.f};
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float p = exp2f(sc[nt][i] - mrow[i >> 1]);
+          sc[nt][i] = p;
+          ls[i >> 1] += p;
+        }
+#pragma unroll
+      for (int hi = 0; hi < 2; ++hi) lrow[hi] = lrow[hi] * corr[hi] + ls[hi];      // per-lane partial sums; merged at the end
+#pragma unroll
+      for (int dn = 0; dn < 4; ++dn) {
+        o[dn][0] *= corr[0]; o[dn][1] *= corr[0];
+        o[dn][2] *= corr[1]; o[dn][3] *= corr[1];
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint32_t pa[4];
+        pa[0] = pack_half2(sc[2 * j][0], sc[2 * j][1]);
+        pa[1] = pack_half2(sc[2 * j][2], sc[2 * j][3]);
+        pa[2] = pack_half2(sc[2 * j + 1][0], sc[2 * j + 1][1]);
+        pa[3] = pack_half2(sc[2 * j + 1][2], sc[2 * j + 1][3]);
+#pragma unroll
+        for (int dn = 0; dn < 4; ++dn) {
+          uint32_t b0, b1;
+          ldmatrix_x2_trans(b0, b1, sv + (kb + j * 16 + (lane & 15)) * XA_LD + dn * 8);
+          mma_16816(o[dn], pa, b0, b1);
+        }
+      }
+    }
+#pragma unroll
+    for (int hi = 0; hi < 2; ++hi) {
+      lrow[hi] += __shfl_xor_sync(0xffffffffu, lrow[hi], 1);
+      lrow[hi] += __shfl_xor_sync(0xffffffffu, lrow[hi], 2);
+    }
+#pragma unroll
+    for (int hi = 0; hi < 2; ++hi) {
+      const int row = mt * 16 + quad + hi * 8;
+      if (row < Q) {
+        const float inv = 1.f / lrow[hi];
+        __half* op = a.out + ((long long)g * Q + row) * 256 + head * 32 + tq * 2;
+#pragma unroll
+        for (int dn = 0; dn < 4; ++dn)
+          *reinterpret_cast<uint32_t*>(op + dn * 8) = pack_half2(o[dn][hi * 2] * inv, o[dn][hi * 2 + 1] * inv);
+      }
+    }
+  }
+}
+
 }  // namespace ovis

@@ -261,7 +261,8 @@ def test_xattn_block_sparse_masks(G, Q, keys):
 
 
 # (100, 36): the resampler's frame axis of a 36-frame clip; 300 / 700 rows: long clips, several row passes, > 48 KB smem
-@pytest.mark.parametrize("G,Q", [(1, 100), (5, 100), (2, 200), (100, 36), (3, 300), (2, 700)])
+# 1500 rows: beyond the tensor-core kernel's shared-memory layout -> SIMT kernel
+@pytest.mark.parametrize("G,Q", [(1, 100), (5, 100), (2, 200), (100, 36), (3, 300), (2, 700), (3, 64), (2, 17), (1, 1408), (1, 1500)])
 def test_self_attn(G, Q):
     qk = _randn(G * Q, 512, seed=1).half()
     v = _randn(G * Q, 256, seed=2).half()

@@ -112,12 +112,16 @@ int ovis_san_bias_logits(const void* af_f16, int B, int P, int heads, const void
                          void* stream);
 
 /* ---- attention ---------------------------------------------------------------------------------------- */
-/* Work-space sizing for ovis_xattn: chooses the key split count for (G, Q, keys) on the current device. */
+/* Work-space sizing for ovis_xattn: chooses the key split count for (G, Q, keys) on the current device.
+ * ml_part_floats includes, behind the (max, sum) partials, the tile-skip bitmap (512 words per group and 128-query tile). */
 int ovis_xattn_plan(int G, int Q, int keys, int* splits, int* q_pad, long long* o_part_floats,
                     long long* ml_part_floats);
 /* Masked multi-head cross-attention, 8 heads x 32 (CrossAttentionLayer -> nn.MultiheadAttention,
  * video_...decoder.py:110-122).  q [G*Q][256] f16 pre-scaled by 32^-1/2 * log2(e); k, v [G*keys][256] f16;
- * out [G*Q][256] f16 = concat of heads before out_proj. */
+ * out [G*Q][256] f16 = concat of heads before out_proj.
+ * 64-key tiles that every query of a 128-query tile blocks are skipped (no load, no MMA, no softmax step; rows under the
+ * all-masked-row rule block nothing): xattn_skipmap_kernel marks them, each CTA takes an equal share of the surviving
+ * tiles.  OVIS_XATTN_SKIP=0 disables it (A/B timing). */
 int ovis_xattn(const void* q_f16, const void* k_f16, const void* v_f16, const unsigned int* bits,
                const unsigned char* flags, int G, int Q, int q_stride, int keys, int splits,
                float* o_part, float* ml_part, void* out_f16, void* stream);

@@ -683,7 +683,8 @@ int ovis_xattn_plan(int G, int Q, int keys, int* splits, int* q_pad, long long* 
   *splits = s;
   *q_pad = qtiles * 128;
   *o_floats = (long long)G * s * 8 * (*q_pad) * 32;
-  *ml_floats = (long long)G * s * 8 * (*q_pad) * 2;
+  // (max, sum) partials, followed by the tile-skip bitmap of the tcgen05 kernel: X2_MAP_WORDS words per (group, query tile)
+  *ml_floats = (long long)G * s * 8 * (*q_pad) * 2 + (long long)G * qtiles * X2_MAP_WORDS;
   return OVIS_OK;
 }
 
@@ -737,7 +738,21 @@ int ovis_xattn(const void* q, const void* k, const void* v, const unsigned int* 
     a.keys = keys; a.W = (keys + 31) / 32; a.splits = splits; a.chunk = chunk;
     static const char* tr = getenv("OVIS_XATTN_TRACE");      // device pointer (decimal) of the trace buffer
     a.trace = tr ? reinterpret_cast<long long*>(strtoull(tr, nullptr, 10)) : nullptr;
+    a.skipmap = nullptr;
+    a.map_words = 0;
     if (variant == 2) {
+      // tile skipping (default on; OVIS_XATTN_SKIP=0 for A/B): needs the bitmap and the per-CTA list to fit
+      static const bool skip_on = !(getenv("OVIS_XATTN_SKIP") && atoi(getenv("OVIS_XATTN_SKIP")) == 0);
+      const int map_words = (tiles + 31) / 32;
+      if (skip_on && map_words <= X2_MAP_WORDS && (tiles + chunks - 1) / chunks <= X2_LIST_MAX) {
+        uint32_t* map = reinterpret_cast<uint32_t*>(ml_part + (long long)G * splits * 8 * q_pad * 2);
+        xattn_skipmap_kernel<<<dim3(map_words, qtiles, G), 128, 0, (cudaStream_t)stream>>>(bits, flags, map, Q, q_stride, keys,
+                                                                                           a.W, X2_MAP_WORDS);
+        rc = check_launch("xattn_skipmap_kernel");
+        if (rc) return rc;
+        a.skipmap = map;
+        a.map_words = X2_MAP_WORDS;
+      }
       xattn_tc2_kernel<<<dim3(chunks * 4, qtiles, G), X2_THREADS, X2_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, a);
       rc = check_launch("xattn_tc2_kernel");
     } else {

@@ -32,6 +32,8 @@ struct XattnTcArgs {
   int Q, q_pad, q_stride;
   int keys, W, splits, chunk;  // chunk: keys per split, multiple of 64
   long long* trace;            // tools/trace_xattn.py: clock64 stamps of block 0, [6 roles][64 steps][8 events], else null
+  const uint32_t* skipmap;     // xattn_tc2 only: [G][qtiles][map_words], bit t = every row of the query tile blocks all 64 keys of tile t; or null
+  int map_words;
 };
 
 constexpr int XT_KT = 64;                       // keys per tile

@@ -28,7 +28,15 @@ constexpr int X2_STAGES = 8;
 constexpr int X2_Q_BYTES = 128 * 128;            // [128 rows][64 ch] fp16 (one head pair)
 constexpr int X2_KV_STAGE = 2 * X2_KT * 128;     // K box + V box
 constexpr int X2_P_BYTES = 128 * 128;            // [128 q][64 keys] fp16
-constexpr int X2_SMEM = X2_Q_BYTES + X2_STAGES * X2_KV_STAGE + 4 * X2_P_BYTES + 1024 + 512;
+// Tile skipping ("skips fully-masked key tiles"): xattn_skipmap_kernel marks the 64-key tiles that every row of a query
+// tile blocks (rows under the all-masked-row rule block nothing).  Each CTA then builds the list of the tiles it has to
+// visit -- its equal share of the *surviving* tiles of the group, so the chunks stay balanced whatever the mask looks
+// like -- and every role walks that list instead of a contiguous key range: skipped tiles cost no TMA load, no MMA, no
+// softmax step.  With nothing to skip the list is the old contiguous chunk (dense masks: +1 small launch per call).
+constexpr int X2_MAP_WORDS = 512;                // skip bitmap words per (group, query tile): up to 16384 key tiles
+constexpr int X2_LIST_MAX = 7168;                // tile list entries per CTA (uint16)
+constexpr int X2_LIST_BYTES = X2_MAP_WORDS * 4 + X2_LIST_MAX * 2;
+constexpr int X2_SMEM = X2_Q_BYTES + X2_STAGES * X2_KV_STAGE + 4 * X2_P_BYTES + 1024 + 512 + X2_LIST_BYTES;
 constexpr int X2_THREADS = 19 * 32;
 
 // clock64 timeline of block 0 (tools/trace_xattn.py): compiled in only with -DOVIS_XATTN_TRACE_BUILD
@@ -41,6 +49,49 @@ constexpr int X2_THREADS = 19 * 32;
 #else
 #define X2_TRACE(role, step, ev) do { } while (0)
 #endif
+
+// bit t of map[g][qt][t / 32] = every row of query tile qt blocks all keys of the 64-key tile t.  A row under the
+// all-masked-row rule (flag 0: it attends to every key, frame_..._decoder.py:87) blocks nothing; rows past Q do not count.
+// grid (map words, query tiles, G), 128 threads = one per row of the query tile.
+__global__ void __launch_bounds__(128)
+xattn_skipmap_kernel(const uint32_t* __restrict__ bits, const unsigned char* __restrict__ flags, uint32_t* __restrict__ map,
+                     int Q, int q_stride, int keys, int W, int map_words) {
+  __shared__ uint32_t s_and[4];
+  const int wi = blockIdx.x, qt = blockIdx.y, g = blockIdx.z;
+  const int q = qt * 128 + threadIdx.x;
+  const bool counts = q < Q;
+  const bool masked = counts && flags[(long long)g * q_stride + q] != 0;
+  const uint32_t* bq = bits + (long long)g * W * q_stride + q;
+  // bit j of `mine`: this row blocks every key of tile wi * 32 + j.  The 64 mask words are fetched in four batches of 16
+  // independent loads (a load -> test -> barrier loop per tile made this kernel 25 us long).
+  uint32_t mine = masked ? 0u : (counts ? 0u : 0xffffffffu);
+  if (masked) {
+#pragma unroll
+    for (int b4 = 0; b4 < 4; ++b4) {
+      uint32_t wv[16];
+#pragma unroll
+      for (int x = 0; x < 16; ++x) {
+        const int w = (wi * 32 + b4 * 8) * 2 + x;
+        const int nvalid = keys - w * 32;
+        const uint32_t inval = nvalid >= 32 ? 0u : (nvalid <= 0 ? 0xffffffffu : ~((1u << nvalid) - 1u));
+        wv[x] = (w < W ? __ldg(bq + (long long)w * q_stride) : 0u) | inval;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if ((wv[2 * j] & wv[2 * j + 1]) == 0xffffffffu) mine |= 1u << (b4 * 8 + j);
+    }
+  }
+  mine = __reduce_and_sync(0xffffffffu, mine);
+  if ((threadIdx.x & 31) == 0) s_and[threadIdx.x >> 5] = mine;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t out = s_and[0] & s_and[1] & s_and[2] & s_and[3];
+    const int total_tiles = (keys + X2_KT - 1) / X2_KT;
+    const int left = total_tiles - wi * 32;                     // tiles covered by this word
+    if (left < 32) out &= left <= 0 ? 0u : ((1u << left) - 1u);
+    map[((long long)g * gridDim.y + qt) * map_words + wi] = out;
+  }
+}
 
 __global__ void __launch_bounds__(X2_THREADS, 1)
 xattn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -63,9 +114,66 @@ xattn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int chunk_id = blockIdx.x >> 2, hp = blockIdx.x & 3, qt = blockIdx.y, g = blockIdx.z;
-  const int k_begin = chunk_id * a.chunk;
-  const int k_end = min(k_begin + a.chunk, a.keys);
-  const int ntiles = (k_end - k_begin + X2_KT - 1) / X2_KT;
+  uint32_t* wpre = reinterpret_cast<uint32_t*>(sP + 4 * X2_P_BYTES + 512);      // [X2_MAP_WORDS] prefix of surviving tiles
+  uint16_t* tlist = reinterpret_cast<uint16_t*>(wpre + X2_MAP_WORDS);           // [X2_LIST_MAX] this CTA's tiles
+  bool use_list = a.skipmap != nullptr;
+  int k_begin = chunk_id * a.chunk;
+  int k_end = min(k_begin + a.chunk, a.keys);
+  int ntiles = (k_end - k_begin + X2_KT - 1) / X2_KT;
+  if (use_list) {
+    // surviving tiles of this (group, query tile): per-word counts -> exclusive prefix -> this chunk's share -> list
+    const uint32_t* map = a.skipmap + ((long long)g * gridDim.y + qt) * a.map_words;
+    const int total_tiles = (a.keys + X2_KT - 1) / X2_KT;
+    const int words = (total_tiles + 31) >> 5;
+    // (xattn_skipmap_kernel leaves the bits past the last tile clear, so ~word over-counts there: masked off here)
+    const uint32_t last_mask = (total_tiles & 31) ? ((1u << (total_tiles & 31)) - 1u) : 0xffffffffu;
+    for (int i = threadIdx.x; i < X2_MAP_WORDS; i += X2_THREADS)
+      wpre[i] = i < words ? (uint32_t)__popc(~__ldg(map + i) & (i == words - 1 ? last_mask : 0xffffffffu)) : 0u;
+    __syncthreads();
+    if (warp == 0) {                                     // exclusive scan of 512 counts: 16 per lane
+      uint32_t loc[16], sum = 0;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) { loc[j] = wpre[lane * 16 + j]; sum += loc[j]; }
+      uint32_t inc = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+      }
+      uint32_t run = inc - sum;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) { wpre[lane * 16 + j] = run; run += loc[j]; }
+      if (lane == 31) tmem_holder[1] = inc;                               // total number of surviving tiles
+    }
+    __syncthreads();
+    const int cnt = (int)tmem_holder[1];
+    const int chunks = (int)(gridDim.x >> 2);
+    const int per = (cnt + chunks - 1) / chunks;
+    const int lo = chunk_id * per, hi = min(cnt, lo + per);
+    ntiles = max(0, hi - lo);
+    k_end = a.keys;
+    if (cnt == total_tiles) {             // nothing to skip: the share is a contiguous run of tiles, no list needed
+      use_list = false;
+      k_begin = lo * X2_KT;
+    } else {
+      k_begin = 0;
+    }
+    for (int i = threadIdx.x; use_list && i < words; i += X2_THREADS) {
+      uint32_t w = ~__ldg(map + i) & (i == words - 1 ? last_mask : 0xffffffffu);
+      int r = (int)wpre[i];
+      if (r >= hi || r + __popc(w) <= lo) continue;
+      while (w) {
+        const int bit = __ffs(w) - 1;
+        w &= w - 1u;
+        if (r >= lo && r < hi) tlist[r - lo] = (uint16_t)(i * 32 + bit);
+        ++r;
+      }
+    }
+    // (the __syncthreads() after the barrier / TMEM set-up below publishes the list)
+  }
+  const bool listed = use_list;
+  const int k_first = k_begin, k_last = k_end;      // (by-value copies: the roles' loops keep them in registers)
+  auto tile_key = [=](int t) -> int { return listed ? (int)tlist[t] * X2_KT : k_first + t * X2_KT; };
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQ);
@@ -97,7 +205,7 @@ xattn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         const int st = t % X2_STAGES;
         mbar_wait(&empty[st], (uint32_t)(((t / X2_STAGES) & 1) ^ 1));
         uint8_t* dst = sKV + st * X2_KV_STAGE;
-        const int krow = g * a.keys + k_begin + t * X2_KT;
+        const int krow = g * a.keys + tile_key(t);
         mbar_arrive_expect_tx(&full[st], X2_KV_STAGE);
         tma_load_2d(dst, &tmK, &full[st], hp * 64, krow);
         tma_load_2d(dst + X2_KT * 128, &tmV, &full[st], hp * 64, krow);
@@ -226,7 +334,7 @@ xattn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     float m_run = -INFINITY, l_run = 0.f;
 
     auto load_words = [&](int t, uint32_t (&dst)[2]) {
-      const int kb = k_begin + t * X2_KT;
+      const int kb = t < ntiles ? tile_key(t) : 0;
 #pragma unroll
       for (int x = 0; x < 2; ++x) {
         const int wi = (kb >> 5) + x;
@@ -236,12 +344,12 @@ xattn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     uint32_t nw[2];
     load_words(b, nw);
     for (int t = b, n = 0; t < ntiles; t += 2, ++n) {
-      const int kb = k_begin + t * X2_KT;
+      const int kb = tile_key(t);
       uint32_t mw[2] = {nw[0], nw[1]};
-      if (kb + X2_KT > k_end) {                           // only the chunk's last tile can have keys past the end
+      if (kb + X2_KT > k_last) {                          // only the last tile of the group can have keys past the end
 #pragma unroll
         for (int x = 0; x < 2; ++x) {
-          const int nvalid = k_end - (kb + x * 32);
+          const int nvalid = k_last - (kb + x * 32);
           const uint32_t inval = nvalid >= 32 ? 0u : (nvalid <= 0 ? 0xffffffffu : ~((1u << nvalid) - 1u));
           mw[x] |= inval;
         }

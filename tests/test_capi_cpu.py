@@ -37,7 +37,8 @@ def test_version_and_plan(lib):
     assert lib.ovis_version() == 100
     splits, q_pad, o_n, ml_n = L.xattn_plan(1, 100, 529920)
     assert splits >= 1 and q_pad == 128
-    assert o_n == splits * 8 * 128 * 32 and ml_n == splits * 8 * 128 * 2
+    # (max, sum) partials + the tile-skip bitmap (512 words per group and query tile)
+    assert o_n == splits * 8 * 128 * 32 and ml_n == splits * 8 * 128 * 2 + 512
     s2, qp2, _, _ = L.xattn_plan(36, 200, 920)
     assert s2 >= 1 and qp2 == 256
 

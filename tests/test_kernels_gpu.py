@@ -260,6 +260,54 @@ def test_xattn_block_sparse_masks(G, Q, keys):
     assert _maxerr(out, ref) < 6e-3, (_maxerr(out, ref), splits)
 
 
+@pytest.mark.parametrize("G,Q,keys", [(2, 100, 3840), (1, 200, 3850), (1, 100, 64000), (4, 100, 14720), (36, 100, 920)])
+def test_xattn_skips_fully_masked_tiles(G, Q, keys):
+    """Masks with key tiles that every query of a query tile blocks (no row under the all-masked-row rule): the kernel
+    visits only the surviving tiles -- shared out evenly over the key chunks -- and must give the dense result.  The two
+    query tiles of Q = 200 see different regions; 3850 keys end in a partial tile; group 0 keeps one row that sees
+    nothing in a second pass (then nothing may be skipped in its query tile)."""
+    q = _randn(G * Q, 256, seed=1, scale=0.6).half()
+    k = _randn(G * keys, 256, seed=2).half()
+    v = _randn(G * keys, 256, seed=3).half()
+    gen = _g(11)
+    blocked = torch.ones(G, Q, keys, dtype=torch.bool)
+    for g_ in range(G):
+        for qi in range(Q):
+            # windows of the first query tile in [10 %, 35 %) of the keys, of the second one in [60 %, 80 %) and the tail
+            lo, hi = (0.10, 0.35) if qi < 128 else (0.60, 0.80)
+            for _ in range(int(torch.randint(1, 4, (1,), generator=gen))):
+                a0 = int(keys * lo) + int(torch.randint(0, max(1, int(keys * (hi - lo)) - 50), (1,), generator=gen))
+                blocked[g_, qi, a0:a0 + int(torch.randint(1, 50, (1,), generator=gen))] = False
+            if qi >= 128 and qi % 7 == 0:
+                blocked[g_, qi, keys - 3:] = False
+    W = (keys + 31) // 32
+    r = torch.arange(keys, device="cuda")
+    splits, q_pad, o_n, ml_n = L.xattn_plan(G, Q, keys)
+    for second_pass in (False, True):
+        if second_pass:
+            blocked[0, 7] = True                          # attends everywhere: nothing skippable for (group 0, tile 0)
+        bl = blocked.cuda()
+        bits = torch.zeros(G, W, Q, dtype=torch.int64, device="cuda")
+        bits.scatter_add_(1, (r // 32)[None, :, None].expand(G, keys, Q), (bl.permute(0, 2, 1).long() << (r % 32)[None, :, None]))
+        bits = bits.to(torch.int32).contiguous()
+        flags = (~bl).any(-1).to(torch.uint8).contiguous()
+        o_part = torch.full((o_n,), float("nan"), device="cuda")
+        ml_part = torch.full((ml_n,), float("nan"), device="cuda")
+        out = torch.empty(G * Q, 256, dtype=torch.float16, device="cuda")
+        L.xattn(q, k, v, bits, flags, G, Q, Q, keys, splits, o_part, ml_part, out)
+        ref = _ref_xattn(q, k, v, bl, G, Q, keys)
+        assert _maxerr(out, ref) < 6e-3, (_maxerr(out, ref), splits, second_pass)
+        # the bitmap behind the partials: at least half of the tiles of an all-masked query tile are marked
+        tiles = (keys + 63) // 64
+        qtiles = (Q + 127) // 128
+        m = ml_part[G * splits * 8 * q_pad * 2:].view(torch.int32).view(G, qtiles, 512)
+        marked = sum(bin(int(wd) & 0xffffffff).count("1") for wd in m[G - 1, 0, :(tiles + 31) // 32].tolist())
+        if not (second_pass and G == 1):                 # (with one group, that group is the one with the see-all row)
+            assert marked >= tiles // 2, (marked, tiles)
+        if second_pass:
+            assert int((m[0, 0, :(tiles + 31) // 32] != 0).sum()) == 0
+
+
 # (100, 36): the resampler's frame axis of a 36-frame clip; 300 / 700 rows: long clips, several row passes, > 48 KB smem
 # 1500 rows: beyond the tensor-core kernel's shared-memory layout -> SIMT kernel
 @pytest.mark.parametrize("G,Q", [(1, 100), (5, 100), (2, 200), (100, 36), (3, 300), (2, 700), (3, 64), (2, 17), (1, 1408), (1, 1500)])

@@ -506,7 +506,10 @@ def main():
                        "l2": "inputs larger than L2 (2.9 GB per clip, two input sets alternated)",
                        "aux_outputs": "lazy (inference-minimal)", "parallelism": f"clip-sharded dp{world}",
                        "decoder_calls_in_flight_per_gpu": len(decs), "cuda_graph_layer_loop": bool(dec.use_cuda_graph),
-                       "sm_budget": os.environ.get("OVIS_SM_BUDGET")},
+                       "sm_budget": os.environ.get("OVIS_SM_BUDGET"),
+                       "masked_tile_skipping": "off (OVIS_XATTN_SKIP=0)" if os.environ.get("OVIS_XATTN_SKIP") == "0" else
+                       "on; the synthetic N(0,1) features give ~50 % dense masks, so no 128-query x 64-key tile is fully "
+                       "masked and nothing is skipped here (sparse-mask A/B: profiles/xattn_skip_ab_r1.txt)"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,
             "whole_path": {"gflop_per_frame": flops_frame / 1e9,

@@ -33,3 +33,10 @@ def gather_clip_results(local: torch.Tensor, n_items: int, group=None) -> torch.
     dist.all_gather(parts, pad, group=group)
     out = [parts[r][: len(shard_range(n_items, r, world))] for r in range(world)]
     return torch.cat(out, dim=0)
+
+
+def gather_clip_dict(local: dict, n_items: int, group=None) -> dict:
+    """The fixed-shape per-clip results of one rank's block -- e.g. class scores [n, Q, K] fp32, query-matching indices
+    [n, T, Q] int16 (temporal.batch_video_match_via_embeds), top-10 ids and bit-packed masks int32 -- gathered key by key
+    into global clip order (SURVEY.md section 8 e).  One collective per key, issued once per run."""
+    return {k: gather_clip_results(v, n_items, group) for k, v in local.items()}

@@ -6,7 +6,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from openvis_b200.sharding import gather_clip_results, shard_range
+from openvis_b200.sharding import gather_clip_dict, gather_clip_results, shard_range
 
 
 def test_shard_range_covers_everything():
@@ -28,6 +28,14 @@ def _worker(rank, world, port, n_items, ret):
         local = torch.stack([torch.full((3, 2), float(c)) for c in mine]) if len(mine) else torch.zeros(0, 3, 2)
         full = gather_clip_results(local, n_items)
         ok = full.shape == (n_items, 3, 2) and all(bool((full[c] == c).all()) for c in range(n_items))
+        # heterogeneous per-clip results of the online models: scores, query-matching indices, packed masks
+        loc = {"scores": local, "indices": torch.stack([torch.full((4, 5), c, dtype=torch.int16) for c in mine]) if len(mine)
+               else torch.zeros(0, 4, 5, dtype=torch.int16),
+               "bits": torch.stack([torch.full((2, 3), -c - 1, dtype=torch.int32) for c in mine]) if len(mine)
+               else torch.zeros(0, 2, 3, dtype=torch.int32)}
+        d = gather_clip_dict(loc, n_items)
+        ok = ok and d["indices"].dtype == torch.int16 and d["bits"].dtype == torch.int32
+        ok = ok and all(bool((d["indices"][c] == c).all()) and bool((d["bits"][c] == -c - 1).all()) for c in range(n_items))
         ret[rank] = ok
     finally:
         dist.destroy_process_group()

@@ -29,9 +29,11 @@ def gather_clip_results(local: torch.Tensor, n_items: int, group=None) -> torch.
     n_max = -(-n_items // world)
     pad = torch.zeros((n_max,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
     pad[: local.shape[0]] = local
-    parts: List[torch.Tensor] = [torch.empty_like(pad) for _ in range(world)]
-    dist.all_gather(parts, pad, group=group)
-    out = [parts[r][: len(shard_range(n_items, r, world))] for r in range(world)]
+    # the collective moves raw bytes, so every element type works on both back-ends (neither NCCL nor gloo has int16)
+    raw = pad.reshape(n_max, -1).view(torch.uint8)
+    parts: List[torch.Tensor] = [torch.empty_like(raw) for _ in range(world)]
+    dist.all_gather(parts, raw, group=group)
+    out = [parts[r].view(local.dtype).reshape(pad.shape)[: len(shard_range(n_items, r, world))] for r in range(world)]
     return torch.cat(out, dim=0)
 
 

@@ -145,11 +145,18 @@ match_assign_kernel(const MatchArgs a) {
           if (mv < best) { best = mv; bj = j; }
         }
       }
-#pragma unroll
-      for (int o = 16; o; o >>= 1) {
-        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-        const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
-        if (ob < best || (ob == best && oj < bj)) { best = ob; bj = oj; }
+      // warp arg-min (smallest column among equal values) with three redux operations on an order-preserving integer
+      // image of the double instead of five rounds of 64-bit shuffles + compares: this loop is the kernel's critical path
+      {
+        unsigned long long key = (unsigned long long)__double_as_longlong(best);
+        key = (key >> 63) ? ~key : (key | 0x8000000000000000ull);
+        const uint32_t hi = (uint32_t)(key >> 32), lo = (uint32_t)key;
+        const uint32_t mh = __reduce_min_sync(0xffffffffu, hi);
+        const uint32_t ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xffffffffu);
+        bj = __reduce_min_sync(0xffffffffu, (hi == mh && lo == ml) ? bj : 0x7fffffff);
+        unsigned long long mk = ((unsigned long long)mh << 32) | ml;
+        mk = (mk >> 63) ? (mk & 0x7fffffffffffffffull) : ~mk;
+        best = __longlong_as_double((long long)mk);
       }
       // dual update; the same lane owns column j here and in the scan above (shuffles are no memory fence).  Column 0
       // (the root, always in the tree) carries the row being inserted.

@@ -267,6 +267,9 @@ class TemporalInstanceResampler(nn.Module):
             if gen != self._generation:
                 raise RuntimeError("aux_outputs must be read before the next forward() of the same resampler "
                                    "(set resampler.materialize_aux = True to compute them eagerly)")
+            if shared is not None and self.operand_source.shared_operands(mask_feats, attn_feats) is None:
+                raise RuntimeError("aux_outputs must be read before the next forward() of the decoder whose operand "
+                                   "copies this call shared (resampler.operand_source)")
             with torch.cuda.device(dev):
                 lg, m = head(j)
             return {"pred_logits": lg, "pred_masks": m}

@@ -25,6 +25,7 @@ Design notes (DESIGN.md has the full account):
     ``aux_outputs`` (never read in eval by the reference's meta-architectures) are computed on first access.
 """
 import math
+import weakref
 from typing import List
 
 import os
@@ -540,8 +541,9 @@ class _B200MaskedDecoderBase(nn.Module):
         if self.materialize_aux:
             list(aux)
         out["aux_outputs"] = aux
-        self._last = dict(gen=gen, mf=mask_features_in, mf_ver=mask_features_in._version, ft=ws["ft"],
-                          af32=san["attn_feats"] if san else None, af16=ws.get("af16"))
+        # (weak references: remembering which tensors the operand copies belong to must not keep GBs of them alive)
+        self._last = dict(gen=gen, mf=weakref.ref(mask_features_in), mf_ver=mask_features_in._version, ft=ws["ft"],
+                          af32=weakref.ref(san["attn_feats"]) if san else None, af16=ws.get("af16"))
         return out
 
     def shared_operands(self, mask_feats, attn_feats):
@@ -549,9 +551,9 @@ class _B200MaskedDecoderBase(nn.Module):
         that is handed exactly those tensors (temporal.TemporalInstanceResampler.operand_source); None when they are
         other tensors, were modified since, or the workspace has been reused by a later call."""
         last = getattr(self, "_last", None)
-        if last is None or last["gen"] != self._generation or last["af16"] is None:
+        if last is None or last["gen"] != self._generation or last["af16"] is None or last["af32"] is None:
             return None
-        if mask_feats is not last["mf"] or mask_feats._version != last["mf_ver"] or attn_feats is not last["af32"]:
+        if mask_feats is not last["mf"]() or mask_feats._version != last["mf_ver"] or attn_feats is not last["af32"]():
             return None
         return last["ft"], last["af16"]
 

@@ -81,7 +81,7 @@ def test_brivis_clip_against_oracle(golden_dir, api_exact):
         n0 = L.launch_count()
         video, outputs, indices = T.brivis_video_inference(dec, ad, res, *args, api_exact=api_exact)
         assert L.launch_count() - n0 > 250
-        assert res.operand_source is dec and dec.shared_operands(mf_dev, dec._last["af32"]) is not None
+        assert res.operand_source is dec and dec.shared_operands(mf_dev, dec._last["af32"]()) is not None
         # query matching: index work, identical to the oracle's chain (assignment margins ~0.37 vs fp16-level cost noise)
         assert torch.equal(indices.cpu(), ref["indices"])
         # chained tolerances: the decoder's embeddings (fp16 operands, <= 3e-2) feed six more fp16-operand layers

@@ -130,3 +130,33 @@ def test_resampler_state_dict_contract():
         batch_video_match_via_embeds(torch.randn(1, 2, 5, 256))
     with pytest.raises(NotImplementedError):
         TemporalInstanceResampler(hidden_dim=128)
+
+
+def test_shared_operands_bookkeeping():
+    """decoder.shared_operands hands its fp16 operand copies only to a consumer holding exactly the tensors of the most
+    recent forward (identity + version), and does not keep those tensors alive."""
+    import gc
+    import weakref
+    m = D.SideAdapterFrameMultiScaleMaskedTransformerDecoder(
+        in_channels=256, mask_classification=True, num_classes=1, hidden_dim=256, num_queries=10, nheads=8,
+        dim_feedforward=2048, dec_layers=9, pre_norm=False, mask_dim=256, enforce_input_project=False, num_frames=2,
+        clip_heads=12)
+    mf, af = torch.zeros(2, 256, 8, 8), torch.zeros(2, 12, 256, 2, 2)
+    ft, af16 = torch.zeros(1), torch.zeros(1)
+    assert m.shared_operands(mf, af) is None                                  # no forward yet
+    m._generation = 3
+    m._last = dict(gen=3, mf=weakref.ref(mf), mf_ver=mf._version, ft=ft, af32=weakref.ref(af), af16=af16)
+    got = m.shared_operands(mf, af)
+    assert got is not None and got[0] is ft and got[1] is af16
+    assert m.shared_operands(mf.clone(), af) is None and m.shared_operands(mf, af.clone()) is None
+    mf.add_(1)                                                                # modified in place since
+    assert m.shared_operands(mf, af) is None
+    m._last["mf_ver"] = mf._version
+    m._generation = 4                                                         # a later forward reused the workspace
+    assert m.shared_operands(mf, af) is None
+    m._generation = 3
+    r = weakref.ref(af)
+    del af
+    gc.collect()
+    assert r() is None                                                        # the decoder did not keep it alive
+    assert m.shared_operands(mf, torch.zeros(1)) is None

@@ -73,16 +73,18 @@ def test_resampler_matches_reference_golden(golden_dir):
 
 
 @pytest.mark.skipif(not R.available(), reason="reference not mounted")
-def test_layers_match_live_reference():
-    """Full-width temporal layers at t = 9, Q = 20 against the reference module with a stand-in adapter (the heads are
-    pinned by the golden test above)."""
+@pytest.mark.parametrize("t,b", [(9, 1), (1, 1), (2, 1), (4, 2)])
+def test_layers_match_live_reference(t, b):
+    """Full-width temporal layers, Q = 20, against the reference module with a stand-in adapter (the heads are pinned by
+    the golden test above).  t = 1 and t = 2: clips shorter than the Conv1d kernels (replicate padding only); b = 2: two
+    clips per call."""
     T_ = R.temporal()
     m = T_.TemporalInstanceResampler().eval()
     P = seeded_resampler_params(5)
     m.load_state_dict(P)
     gen = torch.Generator().manual_seed(9)
-    fe = torch.randn(1, 9, 20, 256, generator=gen)
-    mf, af = torch.randn(9, 256, 8, 8, generator=gen), torch.randn(9, 12, 256, 2, 2, generator=gen)
+    fe = torch.randn(b, t, 20, 256, generator=gen)
+    mf, af = torch.randn(b * t, 256, 8, 8, generator=gen), torch.randn(b * t, 12, 256, 2, 2, generator=gen)
 
     class _Adapter:
         def post_encode_image(self, bk, biases):

@@ -32,6 +32,7 @@ topk_scores_kernel(const float* __restrict__ scores, int Q, int K, int k, float*
   for (int j = 0; j < KL; ++j) { lv[j] = -INFINITY; li[j] = 0x7fffffff; }
   for (int i = threadIdx.x; i < n; i += THREADS) {
     float cv = __ldg(scores + i);
+    if (cv != cv) cv = INFINITY;                  // torch.topk orders NaN as the largest value
     if (cv > lv[KL - 1]) {                        // strict: of equal values the earlier (lower) index stays ahead
       int ci = i;
 #pragma unroll
@@ -74,7 +75,7 @@ topk_scores_kernel(const float* __restrict__ scores, int Q, int K, int k, float*
   }
   // outputs + entropy of the selected queries' score rows: sum(-s * log s)
   for (int r = warp; r < k; r += THREADS / 32) {
-    const int flat = s_idx[r];
+    const int flat = min(s_idx[r], n - 1);        // (k <= n is checked by the host; never index past the matrix)
     const int q = flat / K;
     float e = 0.f;
     for (int c = lane; c < K; c += 32) {
@@ -84,7 +85,7 @@ topk_scores_kernel(const float* __restrict__ scores, int Q, int K, int k, float*
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
     if (lane == 0) {
-      out_scores[r] = s_val[r];
+      out_scores[r] = __ldg(scores + flat);
       out_query[r] = q;
       out_label[r] = flat - q * K;
       out_entropy[r] = e;

@@ -150,6 +150,11 @@ class _LazyDict(dict):
     def values(self):
         return [self[k] for k in self.keys()]
 
+    def copy(self):
+        """A plain dict with every lazy entry resolved (the reference's training path calls image_outputs.copy());
+        dict(out) / {**out} bypass __getitem__ and would expose the raw callables, so resolve through copy() or items()."""
+        return dict(self.items())
+
 
 def _lazy(fn):
     fn._ovis_lazy = True
@@ -413,10 +418,13 @@ class _B200MaskedDecoderBase(nn.Module):
             raise L.OvisError("openvis_b200 has no CPU path: inputs must be CUDA tensors on an sm_100 device")
         return BT, H4, W4, sizes
 
-    @torch.no_grad()
     def forward(self, x: List[torch.Tensor], mask_features: torch.Tensor, mask=None):
         del mask                                  # "disable mask, it does not affect performance" (frame_...:59-60)
-        BT, H4, W4, sizes = self._check_inputs(x, mask_features)
+        BT, H4, W4, sizes = self._check_inputs(x, mask_features)     # (autograd guard: evaluated before no_grad below)
+        with torch.no_grad():
+            return self._forward_nograd(x, mask_features, BT, H4, W4, sizes)
+
+    def _forward_nograd(self, x, mask_features, BT, H4, W4, sizes):
         dev = mask_features.device
         x = [t.float().contiguous() for t in x]
         mask_features_in = mask_features
@@ -543,7 +551,8 @@ class _B200MaskedDecoderBase(nn.Module):
         out["aux_outputs"] = aux
         # (weak references: remembering which tensors the operand copies belong to must not keep GBs of them alive)
         self._last = dict(gen=gen, mf=weakref.ref(mask_features_in), mf_ver=mask_features_in._version, ft=ws["ft"],
-                          af32=weakref.ref(san["attn_feats"]) if san else None, af16=ws.get("af16"))
+                          af32=weakref.ref(san["attn_feats"]) if san else None,
+                          af_ver=san["attn_feats"]._version if san else None, af16=ws.get("af16"))
         return out
 
     def shared_operands(self, mask_feats, attn_feats):
@@ -553,7 +562,9 @@ class _B200MaskedDecoderBase(nn.Module):
         last = getattr(self, "_last", None)
         if last is None or last["gen"] != self._generation or last["af16"] is None or last["af32"] is None:
             return None
-        if mask_feats is not last["mf"]() or mask_feats._version != last["mf_ver"] or attn_feats is not last["af32"]():
+        if mask_feats is not last["mf"]() or mask_feats._version != last["mf_ver"]:
+            return None
+        if attn_feats is not last["af32"]() or attn_feats._version != last["af_ver"]:
             return None
         return last["ft"], last["af16"]
 

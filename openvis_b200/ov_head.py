@@ -13,6 +13,7 @@ The rest of the frozen CLIP towers (text encoder, the ViT blocks before the spli
 of scope: text embeddings are supplied already encoded ("cached text embeddings", north_star) and
 region features / the split-point CLS + patch features come from the caller.
 """
+import weakref
 from typing import List
 
 import torch
@@ -41,14 +42,18 @@ class _TextCache:
         return torch.stack([self.text_cache[w] for w in noun_list])
 
     def _text_f16(self, text):
-        key = (text.data_ptr(), text._version, tuple(text.shape))
+        """fp16 operand copy of the caller's [K, D] text matrix.  A hit needs the SAME tensor object (weak reference),
+        unmodified (_version): the caching allocator hands a freed matrix's address to the next vocabulary of the same
+        shape, so (data_ptr, shape) alone would return another vocabulary's embeddings."""
+        key = (text.data_ptr(), tuple(text.shape))
         hit = self._mat.get(key)
-        if hit is None:
-            if len(self._mat) > 8:
-                self._mat.clear()
-            hit = L.cast_f16(text.detach().float().contiguous())
-            self._mat[key] = hit
-        return hit
+        if hit is not None and hit[0]() is text and hit[1] == text._version:
+            return hit[2]
+        if len(self._mat) > 8:
+            self._mat.clear()
+        f16 = L.cast_f16(text.detach().float().contiguous())
+        self._mat[key] = (weakref.ref(text), text._version, f16)
+        return f16
 
 
 class ClipLogitHead(_TextCache):
@@ -95,11 +100,13 @@ class SideAdapterTail(_TextCache):
         """ln_post -> @ visual.proj -> F.normalize (side_adapter.py:203-205).  sos_token [B, Q, W]; proj [W, D]."""
         B, Q, Wd = sos_token.shape
         _, x16 = L.rownorm(sos_token.reshape(-1, Wd).float().contiguous(), ln_w, ln_b, layer_norm=True, want32=False)
-        key = ("proj", proj.data_ptr(), proj._version)
-        pt = self._mat.get(key)
-        if pt is None:
+        key = ("proj", proj.data_ptr())
+        hit = self._mat.get(key)
+        if hit is not None and hit[0]() is proj and hit[1] == proj._version:
+            pt = hit[2]
+        else:
             pt = L.cast_f16(proj.detach().float().T.contiguous())
-            self._mat[key] = pt
+            self._mat[key] = (weakref.ref(proj), proj._version, pt)
         e = L.linear_f16(x16, pt, None, out_f32=True)
         e32, _ = L.rownorm(e, l2=True, want16=False)
         return e32.view(B, Q, -1)

@@ -39,6 +39,6 @@ def gather_clip_results(local: torch.Tensor, n_items: int, group=None) -> torch.
 
 def gather_clip_dict(local: dict, n_items: int, group=None) -> dict:
     """The fixed-shape per-clip results of one rank's block -- e.g. class scores [n, Q, K] fp32, query-matching indices
-    [n, T, Q] int16 (temporal.batch_video_match_via_embeds), top-10 ids and bit-packed masks int32 -- gathered key by key
+    [n, T, Q] (int64 as temporal.batch_video_match_via_embeds returns them, or narrowed to int16 by the caller), top-10 ids and bit-packed masks int32 -- gathered key by key
     into global clip order (SURVEY.md section 8 e).  One collective per key, issued once per run."""
     return {k: gather_clip_results(v, n_items, group) for k, v in local.items()}

@@ -45,6 +45,10 @@ def _raw_assignments(embeds, want_cost=False):
 def match_via_embeds(tgt_embeds, cur_embeds):
     """minvis.py:28-41: for every target slot, the current query aligned to it (a Python list, like the reference --
     this single-pair form is the one place that copies indices to the host)."""
+    if tuple(tgt_embeds.shape) != tuple(cur_embeds.shape):
+        raise NotImplementedError(
+            f"match_via_embeds: square problems only (tgt {tuple(tgt_embeds.shape)} vs cur {tuple(cur_embeds.shape)}); every "
+            "caller in the reference matches the same number of queries per frame (minvis.py:60-66)")
     _, pi, _ = _raw_assignments(torch.stack([tgt_embeds, cur_embeds])[None])
     return pi[0, 1].tolist()
 
@@ -284,7 +288,7 @@ class TemporalInstanceResampler(nn.Module):
 # ------------------------------------------------------------------------------------------------ BriVIS eval schedule
 @torch.no_grad()
 def brivis_video_inference(decoder, adapter, resampler, features, mask_features, clip_bk_feats, text_feats,
-                           padded_size, image_size, height, width, api_exact=False, num_clips=1):
+                           padded_size, image_size, height, width, api_exact=False, num_clips=1, num_classes=None):
     """The part of ``BriVIS.forward``'s eval branch that lies on the hot path (openvis/brivis.py:157-190, 242-265), from the
     pixel decoder's outputs to the video result, composed from the drop-in pieces exactly as the reference composes its
     own: SAN frame decoder -> query matching -> TemporalInstanceResampler (heads through the CLIP side path) ->
@@ -319,16 +323,25 @@ def brivis_video_inference(decoder, adapter, resampler, features, mask_features,
     indices, frame_embeds = batch_video_match_via_embeds(pred_embeds)
     if api_exact:
         image_outputs = reset_image_output_order(image_outputs, indices)
-    resampler.operand_source = decoder
-    outputs = resampler(frame_embeds, image_outputs["mask_feats"], image_outputs["attn_feats"], adapter, clip_bk_feats,
-                        text_feats)
+    prev_source = resampler.operand_source
+    resampler.operand_source = decoder              # for this call only: the decoder's fp16 operand copies are reused
+    try:
+        outputs = resampler(frame_embeds, image_outputs["mask_feats"], image_outputs["attn_feats"], adapter, clip_bk_feats,
+                            text_feats)
+    finally:
+        resampler.operand_source = prev_source
     # post_processing (brivis.py:242-265): mean of the logits over the frames, softmax, drop the background column
     videos, scores = [], []
     for c in range(b):
         logits = outputs["pred_logits"][c].float().contiguous()                   # [t, q, K + 1]
-        with torch.cuda.device(logits.device):
-            probs, _ = L.clip_aggregate(logits, torch.ones(t, q, dtype=torch.uint8, device=logits.device))
-        mask_cls = probs[:, :-1].contiguous()
+        # brivis.py:246-249: softmax + drop the last column only when the logits carry the background column
+        # (shape[-1] == num_classes + 1); num_classes=None keeps the shipped-config behaviour (text_feats has K + 1 rows)
+        if num_classes is not None and logits.shape[-1] != num_classes + 1:
+            mask_cls = logits.mean(0)
+        else:
+            with torch.cuda.device(logits.device):
+                probs, _ = L.clip_aggregate(logits, torch.ones(t, q, dtype=torch.uint8, device=logits.device))
+            mask_cls = probs[:, :-1].contiguous()
         scores.append(mask_cls)
         videos.append(inference_video(q, mask_cls.shape[1], mask_cls, outputs["pred_masks"][c], padded_size, image_size,
                                       height, width))

@@ -145,13 +145,18 @@ def test_shared_operands_bookkeeping():
     ft, af16 = torch.zeros(1), torch.zeros(1)
     assert m.shared_operands(mf, af) is None                                  # no forward yet
     m._generation = 3
-    m._last = dict(gen=3, mf=weakref.ref(mf), mf_ver=mf._version, ft=ft, af32=weakref.ref(af), af16=af16)
+    m._last = dict(gen=3, mf=weakref.ref(mf), mf_ver=mf._version, ft=ft, af32=weakref.ref(af), af_ver=af._version,
+                   af16=af16)
     got = m.shared_operands(mf, af)
     assert got is not None and got[0] is ft and got[1] is af16
     assert m.shared_operands(mf.clone(), af) is None and m.shared_operands(mf, af.clone()) is None
     mf.add_(1)                                                                # modified in place since
     assert m.shared_operands(mf, af) is None
     m._last["mf_ver"] = mf._version
+    assert m.shared_operands(mf, af) is not None
+    af.mul_(2)                                                                # attn_feats edited in place: stale af16
+    assert m.shared_operands(mf, af) is None
+    m._last["af_ver"] = af._version
     m._generation = 4                                                         # a later forward reused the workspace
     assert m.shared_operands(mf, af) is None
     m._generation = 3

@@ -201,3 +201,40 @@ class SideAdapterBlocks:
         """SideAdapter.cal_sim_logits (side_adapter.py:234-235), so that this object can be passed as the `adapter`
         argument of TemporalInstanceResampler.forward (resampler.py:244, 313-314)."""
         return self.tail.cal_sim_logits(text_feats, image_feats)
+
+
+class ZeroShotClassifier(torch.nn.Module):
+    """OV2Seg's classifier head (openvis/ov2seg.py:489-529), row A17: ``linear`` (Linear -> ReLU -> Linear, the reference's
+    parameter names), a zero row appended to the text matrix, L2-normalise, ``norm_temperature`` (50) * x @ zs_weight^T.
+    `texts` is the already-encoded [K, D] matrix (the reference asks its adapter for ``get_text_features``, which no
+    adapter defines; the text tower is out of scope here either way).  use_bias < 0 adds the learned scalar ``cls_bias``."""
+
+    def __init__(self, input_size=256, zs_weight_dim=512, use_bias=0.0, norm_weight=True, norm_temperature=50.0):
+        super().__init__()
+        nn = torch.nn
+        self.norm_weight, self.norm_temperature = norm_weight, norm_temperature
+        self.use_bias = use_bias < 0
+        if self.use_bias:
+            self.cls_bias = nn.Parameter(torch.ones(1) * use_bias)
+        self.linear = nn.Sequential(nn.Linear(input_size, zs_weight_dim // 2), nn.ReLU(),
+                                    nn.Linear(zs_weight_dim // 2, zs_weight_dim))
+        self._head = ClipLogitHead()
+
+    @torch.no_grad()
+    def forward(self, x, texts):
+        if not x.is_cuda:
+            raise L.OvisError("openvis_b200 has no CPU path: inputs must be CUDA tensors on an sm_100 device")
+        shp = x.shape
+        with torch.cuda.device(x.device):
+            w16 = lambda m: L.cast_f16(m.weight.detach().float().contiguous())
+            h = L.linear_f16(L.cast_f16(x.reshape(-1, shp[-1]).float().contiguous()), w16(self.linear[0]),
+                             self.linear[0].bias.detach().float(), relu=True)
+            e = L.linear_f16(h, w16(self.linear[2]), self.linear[2].bias.detach().float(), out_f32=True)
+            zs = torch.cat([texts, torch.zeros_like(texts)[0:1]])
+            if self.norm_weight:
+                logits = self._head.cal_sim_logits(zs, e, self.norm_temperature, normalized=False)
+            else:
+                logits = self._head.cal_sim_logits(zs, e, 1.0, normalized=True)
+            if self.use_bias:
+                logits = logits + self.cls_bias
+        return logits.view(*shp[:-1], zs.shape[0])

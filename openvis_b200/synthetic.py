@@ -3,8 +3,10 @@ import math
 
 import torch
 
-def decoder_param_shapes(kind="frame", Q=100, C=256, F_=2048, L=9, num_classes=1, clip_heads=12):
-    """state_dict contract of the reference decoders."""
+def decoder_param_shapes(kind="frame", Q=100, C=256, F_=2048, L=9, num_classes=1, clip_heads=12, clip_dims=512):
+    """state_dict contract of the reference decoders.  kind: frame / video / san_frame / san_video,
+    or embedding_{frame,video} (class_embed = MLP(C, 2*clip_dims, clip_dims, 2), video_..._decoder.py:513-515) /
+    proposal_{frame,video} (class_embed = Linear(C, 2), :536-537)."""
     s = {}
     for i in range(L):
         for pre, att in ((f"transformer_self_attention_layers.{i}", "self_attn"),
@@ -38,6 +40,14 @@ def decoder_param_shapes(kind="frame", Q=100, C=256, F_=2048, L=9, num_classes=1
             o = C * clip_heads if i == 2 else C
             s[f"attn_mlp.layers.{i}.weight"] = (o, C, 1, 1)
             s[f"attn_mlp.layers.{i}.bias"] = (o,)
+    elif kind.startswith("embedding"):
+        s["class_embed.layers.0.weight"] = (2 * clip_dims, C)
+        s["class_embed.layers.0.bias"] = (2 * clip_dims,)
+        s["class_embed.layers.1.weight"] = (clip_dims, 2 * clip_dims)
+        s["class_embed.layers.1.bias"] = (clip_dims,)
+    elif kind.startswith("proposal"):
+        s["class_embed.weight"] = (2, C)
+        s["class_embed.bias"] = (2,)
     else:
         s["class_embed.weight"] = (num_classes + 1, C)
         s["class_embed.bias"] = (num_classes + 1,)

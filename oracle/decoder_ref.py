@@ -144,7 +144,7 @@ def decoder_forward(params, x, mask_features, kind="frame", nheads=8, num_layers
     P = {k: v.to(dtype) for k, v in params.items()}
     x = [t.to(dtype) for t in x]
     mask_features = mask_features.to(dtype)
-    video = kind in ("video", "san_video")
+    video = kind.endswith("video")          # (embedding_* / proposal_* kinds differ only in their class_embed parameters)
     san = kind in ("san_frame", "san_video")
     T, C = mask_features.shape[:2]
     if num_layers is None:
@@ -260,6 +260,13 @@ def ov_cosine_logits(feats, text, scale=100.0, normalize=True):
     scale = exp(logit_scale) on already-normalised features (normalize=False)."""
     f = feats / feats.norm(dim=-1, keepdim=True) if normalize else feats
     return scale * f @ text.T
+
+
+def ov2seg_logits(x, text, temperature=50.0):
+    """OV2Seg ZeroShotClassifier.forward after its `linear` (openvis/ov2seg.py:519-526): a zero row is appended to the
+    text matrix, x is L2-normalised and scaled by norm_temperature (50), logits = einsum('bqc,nc->bqn')."""
+    zs = torch.cat([text, torch.zeros_like(text)[0:1]])
+    return torch.einsum("bqc,nc->bqn", temperature * F.normalize(x, p=2, dim=-1), zs)
 
 
 def openvis_clip_aggregate(clip_cls, valid_flag):

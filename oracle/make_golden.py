@@ -23,6 +23,9 @@ DECODER_CASES = [
     ("dec_san_frame_q100", "san_frame", 2, 128, 192, 100, 2, 1236),
     ("dec_san_video_q100", "san_video", 2, 128, 192, 100, 3, 1237),
     ("dec_frame_q200", "frame", 1, 128, 192, 200, 4, 1238),
+    # SimpleBaseline / proposal-network variants (row A17): only class_embed differs
+    ("dec_embedding_frame_q100", "embedding_frame", 2, 128, 192, 100, 5, 1241),
+    ("dec_proposal_video_q100", "proposal_video", 2, 128, 192, 100, 6, 1240),
 ]
 
 
@@ -31,10 +34,16 @@ def _ref_decoder(kind, Q):
     cls = {"frame": d.FrameMultiScaleMaskedTransformerDecoder,
            "video": d.VideoMultiScaleMaskedTransformerDecoder,
            "san_frame": d.SideAdapterFrameMultiScaleMaskedTransformerDecoder,
-           "san_video": d.SideAdapterVideoMultiScaleMaskedTransformerDecoder}[kind]
+           "san_video": d.SideAdapterVideoMultiScaleMaskedTransformerDecoder,
+           "embedding_frame": d.frame.EmbeddingFrameMultiScaleMaskedTransformerDecoder,
+           "embedding_video": d.video.EmbeddingVideoMultiScaleMaskedTransformerDecoder,
+           "proposal_frame": d.frame.ProposalFrameMultiScaleMaskedTransformerDecoder,
+           "proposal_video": d.video.ProposalVideoMultiScaleMaskedTransformerDecoder}[kind]
     kw = R.decoder_kwargs(num_queries=Q)
     if kind.startswith("san"):
         kw["clip_heads"] = 12
+    if kind.startswith("embedding"):
+        kw["clip_dims"] = 512
     return cls(**kw).eval()
 
 
@@ -84,6 +93,51 @@ def make_san_tail_fixture():
                logit_scale_exp=np.array(cm.logit_scale.exp().item()))
     np.savez_compressed(os.path.join(GOLDEN, "san_tail.npz"), **rec)
     print("wrote san_tail", {k: v.shape for k, v in rec.items()})
+
+
+def ov_tail_inputs(T=7, Q=9, K=11, seed=21):
+    """Seeded inputs of the OpenVIS / SimpleBaseline / OV2Seg tails: un-normalised region features [T, Q, 512], unit-norm
+    text [K, 512], stride-4 mask logits [Q, T, 8, 8] with one never-valid query and one partly valid query."""
+    g = torch.Generator().manual_seed(seed)
+    feats = torch.randn(T, Q, 512, generator=g)
+    text = torch.nn.functional.normalize(torch.randn(K, 512, generator=g), dim=-1)
+    masks = torch.randn(Q, T, 8, 8, generator=g)
+    masks[3] = -5.0
+    masks[5, :3] = -5.0
+    return feats, text, masks
+
+
+def run_reference_ov_tails(T=7, Q=9, K=11, seed=21):
+    """The reference's own OpenVIS.open_vocabulary_inference (openvis.py:110-147) with `self.clip_adapter` replaced by
+    ClipAdapter.forward's arithmetic (adapter.py:56-71) minus the CLIP image tower -- the region features are given --
+    i.e. valid flags (adapter.py:85-88), ClipAdapter.normalize and cal_sim_logits, all the reference's own functions;
+    plus SimpleBaseline's tail (simplebsl.py:68-69: the same two functions on the decoder's embeddings) and OV2Seg's
+    ZeroShotClassifier.forward (ov2seg.py:515-529) with `linear` = identity and the text matrix given."""
+    import types
+    ov = R.ov_tails()
+    feats, text, masks = ov_tail_inputs(T, Q, K, seed)
+
+    def clip_adapter(part_frames, class_names, part_masks):
+        bin_masks = part_masks > 0.5                               # adapter.py:85
+        valid = bin_masks.sum(dim=(-1, -2)) > 0                     # adapter.py:86
+        if torch.sum(valid) == 0:
+            return None, valid
+        return ov.cal_sim_logits(None, text, ov.normalize(None, part_frames[valid])), valid
+
+    self_ = types.SimpleNamespace(clip_adapter=clip_adapter, device="cpu")
+    probs, kept = ov.open_vocabulary_inference(self_, torch.ones(Q), masks, feats, list(range(K)))
+    simple = ov.cal_sim_logits(None, text, ov.normalize(None, feats))          # simplebsl.py:69
+    zs = types.SimpleNamespace(linear=lambda x: x, norm_weight=True, norm_temperature=50.0, use_bias=False,
+                               frame_clip_adapter=types.SimpleNamespace(get_text_features=lambda texts: text))
+    ov2 = ov.zero_shot_forward(zs, feats, None)
+    return dict(probs=probs, kept_masks=kept, simple=simple, ov2seg=ov2)
+
+
+def make_ov_tails_fixture():
+    out = run_reference_ov_tails()
+    rec = {k: v.numpy() for k, v in out.items()}
+    np.savez_compressed(os.path.join(GOLDEN, "ov_tails.npz"), **rec)
+    print("wrote ov_tails", {k: v.shape for k, v in rec.items()})
 
 
 def san_blocks_inputs(n=2, Q=12, seed=91):
@@ -226,6 +280,7 @@ def main():
     make_msda_fixture()
     make_temporal_match_fixture()
     make_resampler_fixture()
+    make_ov_tails_fixture()
 
 
 if __name__ == "__main__":

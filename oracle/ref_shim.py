@@ -208,3 +208,62 @@ def temporal():
                                TemporalInstanceResampler=resampler.TemporalInstanceResampler)
     _loaded["temporal"] = ns
     return ns
+
+
+def extract_function(path, qualname, env=None):
+    """Compiles ONE function (or method: "Class.func") out of a reference source file without importing the module
+    around it -- for code that sits in files whose imports (Detectron2 meta-architecture machinery, OpenAI clip) cannot
+    be satisfied here.  The function body is the reference's own text, parsed with `ast` and executed in a namespace that
+    holds only what it needs (`env`, default torch / F / List).  Nothing is copied into the repository."""
+    import ast
+    src = open(os.path.join(REF_ROOT, path)).read()
+    tree = ast.parse(src)
+    parts = qualname.split(".")
+    body = tree.body
+    node = None
+    for i, name in enumerate(parts):
+        node = next(n for n in body if isinstance(n, (ast.FunctionDef, ast.ClassDef)) and n.name == name)
+        body = getattr(node, "body", [])
+    assert isinstance(node, ast.FunctionDef), qualname
+    node.decorator_list = []
+    mod = ast.Module(body=[node], type_ignores=[])
+    ast.fix_missing_locations(mod)
+    import typing
+    import torch.nn.functional as F_
+    ns = {"torch": torch, "F": F_, "List": typing.List, "nn": torch.nn}
+    ns.update(env or {})
+    exec(compile(mod, os.path.join(REF_ROOT, path), "exec"), ns)
+    return ns[parts[-1]]
+
+
+def ov_tails():
+    """The open-vocabulary tails that live in files which cannot be imported here, as the reference's own functions:
+
+      OpenVIS.open_vocabulary_inference     openvis/openvis.py:110-147      (row A15: per-query mean over valid frames, softmax)
+      ClipAdapter.normalize / cal_sim_logits openvis/modeling/clip_adapter/adapter.py:118-119, 146-147
+      ZeroShotClassifier.forward            openvis/ov2seg.py:515-529        (row A17: [text; 0] rows, scale 50)
+    """
+    if "ov" in _loaded:
+        return _loaded["ov"]
+    if not available():
+        raise RuntimeError(f"reference not found under {REF_ROOT}")
+    ad = "openvis/modeling/clip_adapter/adapter.py"
+    ns = types.SimpleNamespace(
+        open_vocabulary_inference=extract_function("openvis/openvis.py", "OpenVIS.open_vocabulary_inference"),
+        normalize=extract_function(ad, "ClipAdapter.normalize"),
+        cal_sim_logits=extract_function(ad, "ClipAdapter.cal_sim_logits"),
+        zero_shot_forward=extract_function("openvis/ov2seg.py", "ZeroShotClassifier.forward"))
+    _loaded["ov"] = ns
+    return ns
+
+
+def embedding_decoders():
+    """Embedding* / Proposal* decoder classes of the reference (video_..._decoder.py:487-537, frame_...:157-207)."""
+    d = decoders()
+    return types.SimpleNamespace(
+        embedding_video=d.video.EmbeddingVideoMultiScaleMaskedTransformerDecoder,
+        proposal_video=d.video.ProposalVideoMultiScaleMaskedTransformerDecoder,
+        embedding_frame=d.frame.EmbeddingFrameMultiScaleMaskedTransformerDecoder,
+        proposal_frame=d.frame.ProposalFrameMultiScaleMaskedTransformerDecoder,
+        registry=d.video.TRANSFORMER_DECODER_REGISTRY,
+        build_transformer_decoder=d.video.build_transformer_decoder)

@@ -173,3 +173,65 @@ def test_msda_matches_golden(name, golden_dir):
     value, shapes, loc, w = msda_inputs(**MSDA_CASES[name])
     out = O.ms_deform_attn(value, shapes, loc, w)
     _close(out, g[name], atol=1e-6, rtol=1e-5)
+
+
+def _ov_tails_oracle():
+    """The oracle's restatement of rows A15 / A17 on the fixture's seeded inputs."""
+    from oracle.make_golden import ov_tail_inputs
+    feats, text, masks = ov_tail_inputs()
+    valid = (masks.sigmoid() > 0.5).flatten(2).any(-1).T                       # adapter.py:85-86 on openvis.py:118's sigmoid
+    lg = O.ov_cosine_logits(feats.reshape(-1, 512), text, 100.0)
+    probs, vq = O.openvis_clip_aggregate(lg[valid.flatten()], valid)
+    return dict(probs=probs, kept_masks=masks[vq], simple=lg.view(feats.shape[0], feats.shape[1], -1),
+                ov2seg=O.ov2seg_logits(feats, text))
+
+
+def test_ov_tails_match_golden(golden_dir):
+    """Rows A15 / A17: OpenVIS.open_vocabulary_inference's aggregation, ClipAdapter.normalize / cal_sim_logits and OV2Seg's
+    ZeroShotClassifier tail against outputs of the reference's own functions (oracle/make_golden.run_reference_ov_tails,
+    extracted from the reference sources with `ast`: their files cannot be imported without Detectron2 / OpenAI clip)."""
+    gold = np.load(os.path.join(golden_dir, "ov_tails.npz"))
+    mine = _ov_tails_oracle()
+    for k in ("probs", "kept_masks", "simple", "ov2seg"):
+        _close(mine[k], gold[k], atol=2e-5, rtol=1e-5)
+    assert gold["ov2seg"].shape[-1] == gold["simple"].shape[-1] + 1 and np.all(gold["ov2seg"][..., -1] == 0)
+
+
+@pytest.mark.skipif(not R.available(), reason="/root/reference not mounted")
+def test_ov_tails_match_live_reference():
+    from oracle.make_golden import run_reference_ov_tails
+    ref, mine = run_reference_ov_tails(), _ov_tails_oracle()
+    for k in ref:
+        _close(mine[k], ref[k], atol=2e-5, rtol=1e-5)
+
+
+@pytest.mark.skipif(not R.available(), reason="/root/reference not mounted")
+def test_register_into_reference_registry_and_builder():
+    """Boundary: the B200 classes registered into the reference's OWN TRANSFORMER_DECODER_REGISTRY object are
+    what the reference's own build_transformer_decoder (video_..._decoder.py:21-26) then constructs from a cfg, with the
+    reference's parameter names and shapes, so MaskFormerHead.from_config (mask_former_head.py:112-116) needs no edit."""
+    import types
+    from openvis_b200 import decoder as D
+    ref = R.embedding_decoders()
+    saved = dict(ref.registry)
+    try:
+        D.register_into(ref.registry)
+        ns = types.SimpleNamespace
+        for name, kind in (("VideoMultiScaleMaskedTransformerDecoder", "video"),
+                           ("SideAdapterFrameMultiScaleMaskedTransformerDecoder", "san_frame"),
+                           ("EmbeddingFrameMultiScaleMaskedTransformerDecoder", "embedding_frame"),
+                           ("ProposalVideoMultiScaleMaskedTransformerDecoder", "proposal_video")):
+            cfg = ns(MODEL=ns(SEM_SEG_HEAD=ns(NUM_CLASSES=1, MASK_DIM=256),
+                              MASK_FORMER=ns(HIDDEN_DIM=256, NUM_OBJECT_QUERIES=100, NHEADS=8, DIM_FEEDFORWARD=2048,
+                                             DEC_LAYERS=10, PRE_NORM=False, ENFORCE_INPUT_PROJ=False,
+                                             TRANSFORMER_DECODER_NAME=name),
+                              CLIP_ADAPTER=ns(CLIP_NUM_HEADS=12, CLIP_EMBED_DIMS=512)),
+                     INPUT=ns(SAMPLING_FRAME_NUM=2))
+            m = ref.build_transformer_decoder(cfg, 256, True)              # the reference's builder, unmodified
+            assert type(m) is D.TRANSFORMER_DECODER_REGISTRY[name]
+            extra = {"clip_heads": 12} if kind.startswith("san") else {"clip_dims": 512} if kind.startswith("embedding") else {}
+            want = {k: tuple(v.shape) for k, v in saved[name](**{**R.decoder_kwargs(), **extra}).state_dict().items()}
+            assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == want
+    finally:
+        ref.registry.clear()
+        ref.registry.update(saved)

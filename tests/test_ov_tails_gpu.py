@@ -1,0 +1,119 @@
+"""GPU parity of the open-vocabulary tails that are not on the SAN path and of the
+Embedding* / Proposal* decoder variants, against fixtures generated from the reference's own functions / modules
+(tests/golden/ov_tails.npz, dec_embedding_frame_q100.npz, dec_proposal_video_q100.npz; oracle/make_golden.py) and
+against the oracle at the config-1 shape."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from openvis_b200 import decoder as D  # noqa: E402
+from openvis_b200.ov_head import ClipLogitHead, ZeroShotClassifier  # noqa: E402
+from oracle import decoder_ref as O  # noqa: E402
+from oracle.make_golden import ov_tail_inputs  # noqa: E402  (seeded inputs only; the reference is not needed)
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+
+
+def test_openvis_crop_tail_matches_reference_golden(golden_dir):
+    """A15: normalize -> 100 * f @ text^T -> per-query mean over valid frames -> softmax (openvis.py:110-147,
+    adapter.py:118-119, 146-147).  fp16 operands: logits within 2e-2 of the reference's fp32 (|logit| <= 100 * cos)."""
+    gold = np.load(os.path.join(golden_dir, "ov_tails.npz"))
+    feats, text, masks = ov_tail_inputs()
+    head = ClipLogitHead()
+    valid = (masks > 0).flatten(2).any(-1).T.contiguous()                 # sigmoid(m) > 0.5 <=> m > 0
+    lg = head.cal_sim_logits(text.cuda(), head.normalize(feats.cuda()))   # SimpleBaseline's tail (simplebsl.py:69)
+    assert (lg.cpu() - torch.as_tensor(gold["simple"])).abs().max().item() < 2e-2
+    probs, qv = head.open_vocabulary_scores(feats.cuda(), valid.cuda(), text.cuda())
+    assert qv.cpu().tolist() == valid.any(0).tolist() and not bool(qv[3])
+    got = probs[qv].cpu()
+    want = torch.as_tensor(gold["probs"])
+    assert got.shape == want.shape
+    assert (got - want).abs().max().item() < 2e-3                         # probabilities
+    assert torch.equal(got.argmax(-1), want.argmax(-1))
+    assert float(probs[3].abs().max()) == 0.0                            # never-valid query: zero row
+
+
+def test_ov2seg_tail_matches_reference_golden(golden_dir):
+    """A17: ZeroShotClassifier.forward (ov2seg.py:515-529) with `linear` = identity weights: 50 * normalize(x) @ [text; 0]^T."""
+    gold = np.load(os.path.join(golden_dir, "ov_tails.npz"))
+    feats, text, _ = ov_tail_inputs()
+    head = ClipLogitHead()
+    zs = torch.cat([text, torch.zeros_like(text)[0:1]]).cuda()
+    lg = head.cal_sim_logits(zs, feats.cuda(), 50.0, normalized=False).cpu()
+    want = torch.as_tensor(gold["ov2seg"])
+    assert lg.shape == want.shape and (lg - want).abs().max().item() < 1e-2
+    assert float(lg[..., -1].abs().max()) == 0.0
+    # the module form, with its two Linear layers, against the same arithmetic in fp32
+    m = ZeroShotClassifier(input_size=256).cuda().eval()
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(3, 9, 256, generator=g)
+    out = m(x.cuda(), text.cuda()).cpu()
+    ref = O.ov2seg_logits(m.linear.cpu()(x), text)
+    assert out.shape == ref.shape == (3, 9, text.shape[0] + 1)
+    assert (out - ref).abs().max().item() < 3e-2
+
+
+def _build(kind, Q=100, pseed=0):
+    kw = dict(in_channels=256, mask_classification=True, num_classes=1, hidden_dim=256, num_queries=Q, nheads=8,
+              dim_feedforward=2048, dec_layers=9, pre_norm=False, mask_dim=256, enforce_input_project=False, num_frames=2)
+    name = {"embedding_frame": "EmbeddingFrameMultiScaleMaskedTransformerDecoder",
+            "embedding_video": "EmbeddingVideoMultiScaleMaskedTransformerDecoder",
+            "proposal_frame": "ProposalFrameMultiScaleMaskedTransformerDecoder",
+            "proposal_video": "ProposalVideoMultiScaleMaskedTransformerDecoder"}[kind]
+    if kind.startswith("embedding"):
+        kw["clip_dims"] = 512
+    m = D.TRANSFORMER_DECODER_REGISTRY[name](**kw)
+    P = O.seeded_params(O.decoder_param_shapes(kind, Q=Q), pseed)
+    m.load_state_dict(P)
+    return m.cuda().eval(), P
+
+
+def _frac(a, b, tol):
+    return ((a.float() - b.float()).abs() <= tol).float().mean().item()
+
+
+@pytest.mark.parametrize("kind", ["embedding_frame", "embedding_video", "proposal_frame", "proposal_video"])
+def test_embedding_proposal_decoders_vs_oracle_cfg1_shape(kind):
+    """video_..._decoder.py:487-537, frame_...:157-207 at the config-1 shape (5 x 384 x 640): strict north_star bars."""
+    T, Hp, Wp = 5, 384, 640
+    m, P = _build(kind)
+    x, mf = O.seeded_inputs(T, Hp, Wp, seed=77)
+    ref = O.decoder_forward(P, x, mf, kind=kind, return_attn_masks=False)
+    out = m([t.cuda() for t in x], mf.cuda())
+    pm, rm = out["pred_masks"].cpu(), ref["pred_masks"]
+    assert pm.shape == rm.shape and _frac(pm, rm, 0.25) >= 0.999 and ((pm > 0) == (rm > 0)).float().mean().item() >= 0.999
+    pl, rl = out["pred_logits"].cpu(), ref["pred_logits"]
+    assert pl.shape == rl.shape, (pl.shape, rl.shape)
+    assert (pl - rl).abs().max().item() <= 3e-2
+    if kind.startswith("embedding"):
+        # SimpleBaseline's tail on the embeddings: 100 * normalize(e) @ text^T, top-1 class per query
+        text = torch.nn.functional.normalize(torch.randn(40, 512, generator=torch.Generator().manual_seed(7)), dim=-1)
+        head = ClipLogitHead()
+        lg = head.cal_sim_logits(text.cuda(), out["pred_logits"], 100, normalized=False).cpu()
+        want = O.ov_cosine_logits(rl, text, 100.0)
+        assert (lg - want).abs().max().item() < 0.15
+        assert (lg.argmax(-1) == want.argmax(-1)).float().mean().item() >= 0.999
+    else:
+        assert (pl.argmax(-1) == rl.argmax(-1)).float().mean().item() >= 0.999
+
+
+@pytest.mark.parametrize("name,kind", [("dec_embedding_frame_q100", "embedding_frame"), ("dec_proposal_video_q100", "proposal_video")])
+def test_embedding_proposal_decoders_match_reference_golden(name, kind, golden_dir):
+    gold = np.load(os.path.join(golden_dir, name + ".npz"))
+    T, Hp, Wp, Q, pseed, iseed = [int(v) for v in gold["meta"]]
+    m, _ = _build(kind, Q, pseed)
+    x, mf = O.seeded_inputs(T, Hp, Wp, seed=iseed)
+    out = m([t.cuda() for t in x], mf.cuda())
+    g = lambda k: torch.as_tensor(gold[k]).float()
+    assert _frac(out["pred_masks"].cpu(), g("pred_masks"), 0.25) >= 0.95             # small input: LOOSE set (test_decoder_gpu)
+    pl, gl = out["pred_logits"].cpu(), g("pred_logits")
+    assert pl.shape == gl.shape and _frac(pl, gl, 0.05) >= 0.97
+    assert _frac(out["aux_outputs"][0]["pred_masks"].cpu(), g("aux0_pred_masks"), 0.08) >= 0.9999

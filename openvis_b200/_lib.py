@@ -428,7 +428,8 @@ def match_compose(pi):
 
 
 def reorder_queries(x, idx, layout="btq"):
-    """out[b, t, q] = x[b, t, idx[b, t, q]] for x [b, t, q, ...] (layout "btq") or x [b, q, t, ...] (layout "bqt")."""
+    """out[b, t, q] = x[b, t, idx[b, t, q]] for x [b, t, q, ...] (layout "btq"), x [b, q, t, ...] ("bqt") or
+    x [q, b, t, ...] ("qbt": the Frame decoders' pred_masks [Q, (b t), h, w] of a multi-clip call); same layout out."""
     lib = load()
     _req(x, torch.float32, "x")
     _req(idx, torch.int64, "idx")
@@ -439,9 +440,12 @@ def reorder_queries(x, idx, layout="btq"):
     if layout == "btq":
         assert tuple(x.shape[:3]) == (B, T, n)
         sb, st, sq = T * n * inner, n * inner, inner
-    else:
+    elif layout == "bqt":
         assert tuple(x.shape[:3]) == (B, n, T)
         sb, st, sq = n * T * inner, inner, T * inner
+    else:
+        assert layout == "qbt" and tuple(x.shape[:3]) == (n, B, T)
+        sb, st, sq = T * inner, inner, B * T * inner
     out = torch.empty_like(x)
     _check(lib.ovis_reorder_queries_f32(_p(x), _p(idx), _p(out), B, T, n, inner, sb, st, sq, _stream()))
     return out

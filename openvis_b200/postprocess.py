@@ -43,7 +43,7 @@ class PackedMasks:
 
 @torch.no_grad()
 def inference_video(num_queries, num_classes, pred_cls, pred_masks, padded_size, img_size, output_height, output_width,
-                    topk=10):
+                    topk=10, to_host=True, out_bits=None):
     """Mirror of ``VideoMaskFormer.inference_video`` (video_maskformer.py:262-298) fed with the decoder's own outputs.
 
     pred_cls   [Q, num_classes] fp32 scores (softmax(...)[:, :-1] or the open-vocabulary scores), on the GPU
@@ -51,7 +51,10 @@ def inference_video(num_queries, num_classes, pred_cls, pred_masks, padded_size,
     padded_size (Hp, Wp) of the network input (what ``postprocess`` up-samples to), img_size the un-padded size,
     (output_height, output_width) the size of the original frames.
     Returns the reference's dictionary; ``pred_masks`` is a ``PackedMasks`` on the host (``.unpack()`` gives the bool
-    tensor), entries ordered by descending score."""
+    tensor), entries ordered by descending score.
+    to_host=False (throughput callers that batch their device-to-host traffic): nothing is copied or synchronised, the
+    scores / labels / entropies / query ids stay device tensors and ``pred_masks`` is a ``PackedMasks`` on the device
+    (written into `out_bits` [topk, T, out_h, ceil(out_w/32)] int32 when given)."""
     assert pred_cls.shape == (num_queries, num_classes)
     if pred_cls.numel() == 0:
         return {"image_size": (output_height, output_width), "pred_entropys": [], "pred_scores": [], "pred_labels": [],
@@ -62,7 +65,10 @@ def inference_video(num_queries, num_classes, pred_cls, pred_masks, padded_size,
         k = min(topk, pred_cls.numel())
         scores, qidx, labels, ent = L.topk_scores(pred_cls.float().contiguous(), k)
         bits = L.mask_postprocess(pred_masks.float(), qidx, padded_size, img_size,
-                                  (output_height, output_width))
+                                  (output_height, output_width), out=out_bits)
+        if not to_host:
+            return {"image_size": (output_height, output_width), "pred_entropys": ent, "pred_scores": scores,
+                    "pred_labels": labels, "pred_masks": PackedMasks(bits, output_width), "pred_queries": qidx}
         packed = PackedMasks(bits, output_width).cpu()
     return {"image_size": (output_height, output_width), "pred_entropys": ent.tolist(), "pred_scores": scores.tolist(),
             "pred_labels": labels.tolist(), "pred_masks": packed, "pred_queries": qidx.tolist()}

@@ -288,7 +288,8 @@ class TemporalInstanceResampler(nn.Module):
 # ------------------------------------------------------------------------------------------------ BriVIS eval schedule
 @torch.no_grad()
 def brivis_video_inference(decoder, adapter, resampler, features, mask_features, clip_bk_feats, text_feats,
-                           padded_size, image_size, height, width, api_exact=False, num_clips=1, num_classes=None):
+                           padded_size, image_size, height, width, api_exact=False, num_clips=1, num_classes=None,
+                           to_host=True):
     """The part of ``BriVIS.forward``'s eval branch that lies on the hot path (openvis/brivis.py:157-190, 242-265), from the
     pixel decoder's outputs to the video result, composed from the drop-in pieces exactly as the reference composes its
     own: SAN frame decoder -> query matching -> TemporalInstanceResampler (heads through the CLIP side path) ->
@@ -344,7 +345,47 @@ def brivis_video_inference(decoder, adapter, resampler, features, mask_features,
             mask_cls = probs[:, :-1].contiguous()
         scores.append(mask_cls)
         videos.append(inference_video(q, mask_cls.shape[1], mask_cls, outputs["pred_masks"][c], padded_size, image_size,
-                                      height, width))
+                                      height, width, to_host=to_host))
     # extension key: post_processing's scores [q, K] ([b, q, K] for several clips)
     outputs["mask_cls_result"] = scores[0] if b == 1 else torch.stack(scores)
     return (videos[0] if b == 1 else videos), outputs, indices
+
+
+@torch.no_grad()
+def san_online_video_inference(decoder, adapter, features, mask_features, clip_bk_feats, text_feats, padded_size, image_size,
+                               height, width, num_clips=1, num_classes=None, to_host=True):
+    """The hot-path part of ``SANOnline.forward``'s eval branch (openvis/san.py:226-283): SAN frame decoder ->
+    post_encode_image(clip_bk_feats, class_attn_biases) -> cal_sim_logits -> MinVIS.post_processing (query matching
+    through the embeddings, logits and masks brought into the matched order, minvis.py:320-338) -> mean over the frames,
+    softmax, drop the background column -> inference_video.  Arguments as brivis_video_inference.
+    Returns (video_output, outputs {pred_logits [b, t, q, K+1] matched, pred_masks matched, mask_cls_result}, indices)."""
+    from .postprocess import inference_video
+    outputs = decoder(features, mask_features)
+    q, b = decoder.num_queries, int(num_clips)
+    bt = mask_features.shape[0]
+    if b < 1 or bt % b:
+        raise ValueError(f"num_clips={b} does not divide the {bt} frames of this call")
+    t = bt // b
+    biases = outputs["class_attn_biases"]
+    clip_feats = adapter.post_encode_image(clip_bk_feats, biases.flatten(0, 1))                 # san.py:230
+    logits = adapter.cal_sim_logits(text_feats, clip_feats).view(b, t, q, -1)                    # '(b t) q c -> b t q c'
+    embeds = outputs["pred_embeds"][0].view(b, t, q, -1)
+    indices, _ = batch_video_match_via_embeds(embeds)                                            # minvis.py:322-323
+    pm = outputs["pred_masks"][0]                                                                # [q, (b t), h, w]
+    with torch.cuda.device(pm.device):
+        lg = L.reorder_queries(logits.float().contiguous(), indices, "btq")                      # minvis.py:325-330
+        pm = L.reorder_queries(pm.view(q, b, t, *pm.shape[-2:]), indices, "qbt")                 # minvis.py:332-336
+    videos, scores = [], []
+    for c in range(b):
+        lc = lg[c].contiguous()
+        if num_classes is not None and lc.shape[-1] != num_classes + 1:                          # san.py:259-260
+            mask_cls = lc.mean(0)
+        else:
+            with torch.cuda.device(lc.device):
+                probs, _ = L.clip_aggregate(lc, torch.ones(t, q, dtype=torch.uint8, device=lc.device))
+            mask_cls = probs[:, :-1].contiguous()
+        scores.append(mask_cls)
+        videos.append(inference_video(q, mask_cls.shape[1], mask_cls, pm[:, c], padded_size, image_size, height, width,
+                                      to_host=to_host))
+    out = {"pred_logits": lg, "pred_masks": pm.transpose(0, 1), "mask_cls_result": scores[0] if b == 1 else torch.stack(scores)}
+    return (videos[0] if b == 1 else videos), out, indices

@@ -125,3 +125,23 @@ def brivis_video_inference(dec_params, res_params, x, mask_features, post_encode
     sc, lab, qi, ent, masks, mlog = O.video_postprocess(cls, res["pred_masks"][0], padded_size, image_size, out_hw)
     return dict(decoder=dec, indices=indices, resampler=res, mask_cls=cls, scores=sc, labels=lab, queries=qi,
                 entropys=ent, masks=masks, mask_logits=mlog)
+
+
+def san_online_video_inference(dec_params, x, mask_features, post_encode_image, cal_sim_logits, padded_size, image_size,
+                               out_hw, clip_heads=12):
+    """The hot-path part of SANOnline.forward's eval branch (openvis/san.py:226-283) composed from the pinned restatements:
+    SAN frame decoder -> post_encode_image(class_attn_biases.flatten(0, 1)) -> cal_sim_logits (san.py:230-231) ->
+    MinVIS.post_processing (minvis.py:320-338: query matching, logits and masks gathered into the matched order; the gather
+    is the same batch_index arithmetic as reset_image_output_order) -> mean over frames, softmax, drop background
+    (san.py:255-260) -> VideoMaskFormer.inference_video.  One clip."""
+    from . import decoder_ref as O
+    dec = O.decoder_forward(dec_params, x, mask_features, kind="san_frame", clip_heads=clip_heads, return_attn_masks=False)
+    biases = dec["class_attn_biases"]                                       # [1, t, n, q, h, w]
+    t, q = biases.shape[1], biases.shape[3]
+    logits = cal_sim_logits(post_encode_image(biases.flatten(0, 1))).view(1, t, q, -1)
+    indices, _ = batch_video_match_via_embeds(dec["pred_embeds"])
+    lg, pm = reset_image_output_order(logits, dec["pred_masks"], indices)
+    cls = lg.mean(dim=1)[0].softmax(-1)[:, :-1]
+    sc, lab, qi, ent, masks, mlog = O.video_postprocess(cls, pm[0], padded_size, image_size, out_hw)
+    return dict(decoder=dec, indices=indices, pred_logits=lg, pred_masks=pm, mask_cls=cls, scores=sc, labels=lab, queries=qi,
+                entropys=ent, masks=masks, mask_logits=mlog)

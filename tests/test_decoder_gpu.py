@@ -136,6 +136,29 @@ def test_san_frame_q200_cfg1_shape_strict():
     check_case("san_frame", m, ref, out, T, Hp, Wp, 200)
 
 
+def test_video_decoder_cfg2_full_shape_against_oracle():
+    """BASELINE configs[1] at its own shape -- 36 frames of 720x1280 padded to 736x1280, Q = 100, joint attention over
+    33 120 / 132 480 / 529 920 keys -- against the CPU oracle (one fp32 pass, ~10-20 s on the box's cores): strict bars."""
+    T, Hp, Wp = 36, 736, 1280
+    m, ref, out = run_case("video", T, Hp, Wp)
+    agree = check_case("video", m, ref, out, T, Hp, Wp, 100)
+    print("cfg2 full shape, mask agreement per layer:", ["%.5f" % a for a in agree])
+
+
+def test_san_frame_cfg4_full_resolution_q200_against_oracle():
+    """BASELINE configs[3]'s decoder at its own resolution (736x1280, Q = 200); two frames (frames are independent)."""
+    T, Hp, Wp = 2, 736, 1280
+    m, ref, out = run_case("san_frame", T, Hp, Wp, Q=200, pseed=4, iseed=99)
+    check_case("san_frame", m, ref, out, T, Hp, Wp, 200)
+
+
+def test_frame_decoder_cfg5b_full_resolution_against_oracle():
+    """The Frame decoder at 736x1280, Q = 100 (configs[4], Frame reading), three frames."""
+    T, Hp, Wp = 3, 736, 1280
+    m, ref, out = run_case("frame", T, Hp, Wp)
+    check_case("frame", m, ref, out, T, Hp, Wp, 100)
+
+
 def test_full_size_clip_properties():
     """BASELINE config 2 at full size (36 frames, 736x1280, Q = 100): too large for the CPU oracle to finish in
     seconds, so the check is through size-independent properties of the path."""

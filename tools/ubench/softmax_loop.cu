@@ -26,6 +26,84 @@ __device__ __forceinline__ float ex2_poly(float x) {
 //    3 = ex2, pack, pair-mask AND, HADD2 sum (transposed formulation: no subtraction, no max)
 //    4 = V1 with every 4th element's exp2 on the FMA pipe         5 = V1 with every 2nd element on the FMA pipe
 //    6 = V3 with every 4th exp2 on the FMA pipe
+__device__ __forceinline__ float ex2_poly2(float x) {       // 8 instructions: FMNMX, 3 FADD, 3 FFMA, LEA
+  x = fmaxf(x, -126.f);
+  const float r = x + 12582912.f;
+  const float fl = r - 12582912.f;
+  const float f = x - fl;
+  float p = 0.0555041f;
+  p = fmaf(p, f, 0.2402265f);
+  p = fmaf(p, f, 0.6931472f);
+  p = fmaf(p, f, 1.0f);
+  return __uint_as_float(__float_as_uint(p) + (__float_as_uint(r) << 23));
+}
+__device__ __forceinline__ uint32_t pack2_sat(float a, float b) {
+  uint32_t r; asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a)); return r;
+}
+// transposed-layout stream (round 2): scores arrive with the reference already subtracted (folded into the S product), row
+// sums come from a ones column of the PV product: per element only ex2 + half a pack + half a mask AND (+ the P store)
+template <int V>
+__global__ void __launch_bounds__(512, 1) kt(const float* __restrict__ in, uint4* __restrict__ out, int iters, uint32_t mseed) {
+  extern __shared__ float4 dyn[];
+  float4* sS = dyn;
+  uint4* sP = reinterpret_cast<uint4*>(dyn + 512 * 8);
+  for (int i = threadIdx.x; i < 512 * 8; i += blockDim.x) sS[i] = reinterpret_cast<const float4*>(in)[i];
+  __syncthreads();
+  uint32_t mw = mseed * (threadIdx.x + 1);
+  uint32_t pm[16];
+  uint32_t acc = 0;
+  for (int it = 0; it < iters; ++it) {
+    float sv[32];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      float4 v = sS[((threadIdx.x + it) & 511) + c * 512];
+      sv[c * 4] = v.x; sv[c * 4 + 1] = v.y; sv[c * 4 + 2] = v.z; sv[c * 4 + 3] = v.w;
+    }
+    if ((it & 1) == 0) {       // pair masks expanded once per key tile, shared by the two heads of the CTA
+      mw = mw * 1664525u + 1013904223u;
+#pragma unroll
+      for (int i = 0; i < 16; i += 4) {      // sign-replicating PRMT: 2 shifts + 4 PRMT per 4 pairs
+        const uint32_t a = mw << (i >> 1), b = mw << ((i >> 1) + 1);
+        pm[i] = __byte_perm(a, b, 0x88cc); pm[i + 1] = __byte_perm(a, b, 0x99dd);
+        pm[i + 2] = __byte_perm(a, b, 0xaaee); pm[i + 3] = __byte_perm(a, b, 0xbbff);
+      }
+    }
+    uint32_t pk[16];
+#pragma unroll
+    for (int e = 0; e < 32; e += 2) {
+      float p[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int kk = e + u;
+        const bool poly = (V == 8 && (kk & 3) == 3) || (V == 9 && (kk % 3) == 2) || (V == 10 && (kk & 1) == 1);
+        p[u] = poly ? ex2_poly2(sv[kk]) : ex2(sv[kk]);
+      }
+      pk[e >> 1] = pack2_sat(p[0], p[1]) & ~pm[e >> 1];
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      sP[((threadIdx.x + it) & 511) * 4 + (c ^ (threadIdx.x & 3))] = make_uint4(pk[c * 4], pk[c * 4 + 1], pk[c * 4 + 2], pk[c * 4 + 3]);
+    acc ^= pk[3];
+  }
+  __syncthreads();
+  uint4 o = sP[threadIdx.x * 4];
+  o.x += acc;
+  out[blockIdx.x * blockDim.x + threadIdx.x] = o;
+}
+
+template <int V> void runt(const char* name, int warps, const float* in, uint4* out) {
+  const int iters = 4000;
+  cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+  const int smem = 512 * 8 * 16 + 512 * 4 * 16;
+  cudaFuncSetAttribute(kt<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  kt<V><<<148, warps * 32, smem>>>(in, out, 50, 12345u);
+  cudaEventRecord(a); kt<V><<<148, warps * 32, smem>>>(in, out, iters, 12345u); cudaEventRecord(b); cudaEventSynchronize(b);
+  float ms; cudaEventElapsedTime(&ms, a, b);
+  const double el = 148.0 * warps * 32 * 32.0 * iters;
+  printf("%-34s warps/SM=%2d: %7.1f Gelem/s  -> 542.6M elements (128-row pad) = %6.1f us, 474.8M (112 pad) = %6.1f us\n", name, warps,
+         el / ms / 1e6, 542.6e6 / (el / ms / 1e3) * 1e6 / 1e6, 474.8e6 / (el / ms / 1e3) * 1e6 / 1e6);
+}
+
 template <int V>
 __global__ void __launch_bounds__(512, 1) k(const float* __restrict__ in, uint4* __restrict__ out, int iters, uint32_t mseed) {
   extern __shared__ float4 dyn[];
@@ -113,7 +191,7 @@ int main() {
   float* h = new float[512 * 32];
   for (int i = 0; i < 512 * 32; ++i) h[i] = -(float)((i * 2654435761u) >> 8 & 0xffff) / 4096.f;
   cudaMemcpy(in, h, 512 * 32 * 4, cudaMemcpyHostToDevice);
-  for (int w : {8, 16}) {
+  for (int w : {8, 12, 16}) {
     run<0>("V0 sel+max+sub+ex2+sum+pack", w, in, out);
     run<1>("V1 sel+sub+ex2+sum+pack", w, in, out);
     run<4>("V4 V1, 1/4 exp2 on FMA pipe", w, in, out);
@@ -121,6 +199,10 @@ int main() {
     run<2>("V2 sub+ex2+pack+pairmask+hadd2", w, in, out);
     run<3>("V3 ex2+pack+pairmask+hadd2", w, in, out);
     run<6>("V6 V3, 1/4 exp2 on FMA pipe", w, in, out);
+    runt<7>("T7 ex2+satpack+pairmask(prmt)", w, in, out);
+    runt<8>("T8 T7, 1/4 exp2 on FMA pipe", w, in, out);
+    runt<9>("T9 T7, 1/3 exp2 on FMA pipe", w, in, out);
+    runt<10>("T10 T7, 1/2 exp2 on FMA pipe", w, in, out);
   }
   cudaError_t e = cudaDeviceSynchronize();
   printf("status: %s\n", cudaGetErrorString(e));

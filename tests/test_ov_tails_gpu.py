@@ -100,7 +100,12 @@ def test_embedding_proposal_decoders_vs_oracle_cfg1_shape(kind):
         lg = head.cal_sim_logits(text.cuda(), out["pred_logits"], 100, normalized=False).cpu()
         want = O.ov_cosine_logits(rl, text, 100.0)
         assert (lg - want).abs().max().item() < 0.15
-        assert (lg.argmax(-1) == want.argmax(-1)).float().mean().item() >= 0.999
+        # top-1 class per query: 500 (frame, query) samples, so one near-tie flip already reads 99.8 %; a disagreement is
+        # accepted only where the oracle's own top-2 margin is inside the logit tolerance (a tie at fp16-operand precision)
+        top2 = want.topk(2, dim=-1).values
+        tie = (top2[..., 0] - top2[..., 1]) < 0.3
+        agree = lg.argmax(-1) == want.argmax(-1)
+        assert bool((agree | tie).all()) and agree.float().mean().item() >= 0.99
     else:
         assert (pl.argmax(-1) == rl.argmax(-1)).float().mean().item() >= 0.999
 

@@ -125,6 +125,22 @@ int ovis_xattn_plan(int G, int Q, int keys, int* splits, int* q_pad, long long* 
 int ovis_xattn(const void* q_f16, const void* k_f16, const void* v_f16, const unsigned int* bits,
                const unsigned char* flags, int G, int Q, int q_stride, int keys, int splits,
                float* o_part, float* ml_part, void* out_f16, void* stream);
+/* Transposed-score variant of the same attention (xattn_tc3_kernel: thread = key, softmax reference and row sums folded
+ * into the tensor-core products; csrc/xattn_tc3.cuh) for launches with long key runs per CTA.  It reads the mask in
+ * KEY-major form, produced by ovis_mask_bits_t:
+ *   bits_t   [G][keys][qw] u32, qw = 4 * ceil(Q / 128): bit q % 32 of word q / 32 = key blocked for query q (1 past Q)
+ *   blockand [G][ceil(keys / 32)][qw]: AND of bits_t over each block of 32 keys (source of the tile-skip map)
+ * ovis_xattn_plan_t: *use_t = 1 when this variant should be used for (G, Q, keys) on the current device (else use
+ * ovis_xattn_plan / ovis_mask_bits / ovis_xattn); sizes as ovis_xattn_plan (ml_part_floats includes the skip map).
+ * ovis_xattn_t: arguments as ovis_xattn; `splits` must come from ovis_xattn_plan_t; stats (optional, device int[2]):
+ * [0] += CTAs, [1] += CTAs that re-ran their chunk with an exact softmax reference. */
+int ovis_xattn_plan_t(int G, int Q, int keys, int* use_t, int* splits, int* q_pad, long long* o_part_floats,
+                      long long* ml_part_floats);
+int ovis_mask_bits_t(const void* gt_f16, int groups, int rows_per_group, const void* me_f16, int Q,
+                     unsigned int* bits_t, unsigned int* blockand, unsigned char* flags, int q_stride, void* stream);
+int ovis_xattn_t(const void* q_f16, const void* k_f16, const void* v_f16, const unsigned int* bits_t,
+                 const unsigned int* blockand, const unsigned char* flags, int G, int Q, int q_stride, int keys,
+                 int splits, float* o_part, float* ml_part, void* out_f16, int* stats, void* stream);
 /* Unmasked self-attention over the Q queries (SelfAttentionLayer.forward_post, video_...decoder.py:52-62).
  * qk [G*Q][512] f16 (q | k, biased, unscaled), v [G*Q][256] f16 -> out [G*Q][256] f16.  Q <= 1536 rows per group
  * (the decoders use Q <= 256 queries; the temporal resampler attends over the frames of a clip, resampler.py:258-262). */

@@ -39,6 +39,10 @@ SIGNATURES = {
     "ovis_xattn_plan": (_c_int, [_c_int, _c_int, _c_int, ctypes.POINTER(_c_int), ctypes.POINTER(_c_int),
                                  ctypes.POINTER(_c_ll), ctypes.POINTER(_c_ll)]),
     "ovis_xattn": (_c_int, [_vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp]),
+    "ovis_xattn_plan_t": (_c_int, [_c_int, _c_int, _c_int, ctypes.POINTER(_c_int), ctypes.POINTER(_c_int), ctypes.POINTER(_c_int),
+                                   ctypes.POINTER(_c_ll), ctypes.POINTER(_c_ll)]),
+    "ovis_mask_bits_t": (_c_int, [_vp, _c_int, _c_int, _vp, _c_int, _vp, _vp, _vp, _c_int, _vp]),
+    "ovis_xattn_t": (_c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp]),
     "ovis_self_attn": (_c_int, [_vp, _vp, _vp, _c_int, _c_int, _vp]),
     "ovis_clip_aggregate": (_c_int, [_vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _vp]),
     "ovis_ms_deform_attn_forward": (_c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
@@ -362,6 +366,28 @@ def xattn(q, k, v, bits, flags, G, Q, q_stride, keys, splits, o_part, ml_part, o
     lib = load()
     _check(lib.ovis_xattn(_p(q), _p(k), _p(v), _p(bits), _p(flags), G, Q, q_stride, keys, splits, _p(o_part),
                           _p(ml_part), _p(out), _stream()))
+
+
+def xattn_plan_t(G, Q, keys):
+    """-> (use_t, splits, q_pad, o_part floats, ml_part floats) for the transposed-score kernel (xattn_tc3)."""
+    lib = load()
+    u, s, qp, o, ml = _c_int(), _c_int(), _c_int(), _c_ll(), _c_ll()
+    _check(lib.ovis_xattn_plan_t(G, Q, keys, ctypes.byref(u), ctypes.byref(s), ctypes.byref(qp), ctypes.byref(o), ctypes.byref(ml)))
+    return bool(u.value), s.value, qp.value, o.value, ml.value
+
+
+@_timed("mask_bits")
+def mask_bits_t(gt, groups, rows_per_group, me, Q, bits_t, blockand, flags, q_stride):
+    """Key-major mask bits for xattn_t: bits_t [G, keys, qw] int32, blockand [G, ceil(keys/32), qw] int32."""
+    lib = load()
+    _check(lib.ovis_mask_bits_t(_p(gt), groups, rows_per_group, _p(me), Q, _p(bits_t), _p(blockand), _p(flags), q_stride, _stream()))
+
+
+@_timed("xattn")
+def xattn_t(q, k, v, bits_t, blockand, flags, G, Q, q_stride, keys, splits, o_part, ml_part, out, stats=None):
+    lib = load()
+    _check(lib.ovis_xattn_t(_p(q), _p(k), _p(v), _p(bits_t), _p(blockand), _p(flags), G, Q, q_stride, keys, splits,
+                            _p(o_part), _p(ml_part), _p(out), _p(stats), _stream()))
 
 
 @_timed("query_side")

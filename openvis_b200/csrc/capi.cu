@@ -15,6 +15,7 @@
 #include "xattn.cuh"
 #include "xattn_tc.cuh"
 #include "xattn_tc2.cuh"
+#include "xattn_tc3.cuh"
 #include "san_attn.cuh"
 #include "postproc.cuh"
 #include "msda.cuh"
@@ -113,6 +114,23 @@ int make_map_f16(CUtensorMap* m, const void* base, unsigned long long rows, unsi
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(OVIS_ERR_CUDA, "%s: cuTensorMapEncodeTiled failed (%lld)", "tensor map", (long long)r);
+  return OVIS_OK;
+}
+
+// fp16 [rows][cols] -> load box {32 columns = 64 bytes, box_rows rows}, 64B swizzle (per-head V boxes of xattn_tc3)
+int make_map_f16_sw64(CUtensorMap* m, const void* base, unsigned long long rows, unsigned long long cols, unsigned long long ld,
+                      unsigned box_rows) {
+  int rc = get_encoder();
+  if (rc) return rc;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld * 2) % 16) return fail(OVIS_ERR_ARG, "%s: operand must be 16-byte aligned with a 16-byte-multiple row pitch", "tensor map");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {32, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(OVIS_ERR_CUDA, "%s: cuTensorMapEncodeTiled failed (%lld)", "tensor map (64B swizzle)", (long long)r);
   return OVIS_OK;
 }
 
@@ -596,6 +614,30 @@ int ovis_mask_bits(const void* gt, int groups, int rows_per_group, const void* m
                      (cudaStream_t)stream);
 }
 
+int ovis_mask_bits_t(const void* gt, int groups, int rows_per_group, const void* me, int Q, unsigned int* bits_t,
+                     unsigned int* blockand, unsigned char* flags, int q_stride, void* stream) {
+  CHECK_ARG(gt && me && bits_t && blockand && flags && groups > 0 && rows_per_group > 0 && Q > 0 && Q <= 256 && q_stride >= Q,
+            "bad arguments");
+  CHECK_ARG((long long)groups * rows_per_group < (1ll << 31), "too many rows");
+  GemmArgs a;
+  init_args(a);
+  a.rows_per_group = rows_per_group;
+  a.num_groups = groups;
+  a.a_group_stride = rows_per_group;
+  a.b_group_stride = Q;
+  a.N = Q;
+  a.K = 256;
+  a.epi = EPI_SIGNBITS_T;
+  a.bits_t = bits_t;
+  a.blockand = blockand;
+  a.flags = flags;
+  a.words_per_group = (rows_per_group + 31) / 32;
+  a.q_stride = q_stride;
+  a.qw = 4 * ((Q + 127) / 128);
+  return launch_gemm(gt, (long long)groups * rows_per_group, 256, 256, me, (long long)groups * Q, 256, a, Q <= 128 ? 128 : 256,
+                     (cudaStream_t)stream);
+}
+
 int ovis_mask_logits(const void* ft, int groups, int rows_per_group, const void* me, int me_group_stride, int Q,
                      const float* bias, float* out, long long t_group_stride, long long ldt,
                      unsigned char* posflags, int rows_per_frame, void* stream) {
@@ -765,6 +807,103 @@ int ovis_xattn(const void* q, const void* k, const void* v, const unsigned int* 
   if (no_combine) return OVIS_OK;
   if (splits <= 8) {
     // Frame decoders (a few hundred keys per group): 2-8 partials per row, one thread per output element pair
+    const long long total = (long long)G * Q * 128;
+    xattn_combine_few_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(o_part, ml_part, (__half*)out, Q,
+                                                                                                q_pad, splits, total);
+    return check_launch("xattn_combine_few_kernel");
+  }
+  xattn_combine_kernel<<<dim3(Q, 8, G), 256, 0, (cudaStream_t)stream>>>(o_part, ml_part, (__half*)out, Q, q_pad, splits);
+  return check_launch("xattn_combine_kernel");
+}
+
+// transposed-score kernel (xattn_tc3): chunks of 128-key tiles, one partial per chunk and head
+static void xattn_t_chunks(int G, int Q, int keys, int sms, int* chunks, int* chunk) {
+  const int qtiles = (Q + 127) / 128;
+  const int tiles = (keys + X3_KT - 1) / X3_KT;
+  int c = sms / (4 * G * qtiles);
+  if (c > tiles / 4) c = tiles / 4;
+  if (c < 1) c = 1;
+  const int ck = ((tiles + c - 1) / c) * X3_KT;
+  *chunk = ck;
+  *chunks = (keys + ck - 1) / ck;
+}
+
+int ovis_xattn_plan_t(int G, int Q, int keys, int* use_t, int* splits, int* q_pad, long long* o_floats, long long* ml_floats) {
+  CHECK_ARG(G > 0 && Q > 0 && Q <= 256 && keys > 0 && use_t && splits && q_pad && o_floats && ml_floats, "bad arguments");
+  int sms = 148;
+  device_info(&sms);
+  const int qtiles = (Q + 127) / 128;
+  int chunks, chunk;
+  xattn_t_chunks(G, Q, keys, sms, &chunks, &chunk);
+  // The transposed kernel pays one extra key tile per CTA (the reference pass): worth it from ~8 tiles per CTA on.
+  // OVIS_XATTN_T=0 disables it, =1 forces it wherever its limits allow (tests).
+  static const int force = getenv("OVIS_XATTN_T") ? atoi(getenv("OVIS_XATTN_T")) : -1;
+  const int tiles_per_cta = chunk / X3_KT;
+  int use = tiles_per_cta >= 8 && xattn_variant() == 2;
+  if (force == 0) use = 0;
+  if (force == 1) use = 1;
+  *use_t = use;
+  *splits = chunks;
+  *q_pad = qtiles * 128;
+  *o_floats = (long long)G * chunks * 8 * (*q_pad) * 32;
+  *ml_floats = (long long)G * chunks * 8 * (*q_pad) * 2 + (long long)G * qtiles * X3_MAP_WORDS;
+  return OVIS_OK;
+}
+
+int ovis_xattn_t(const void* q, const void* k, const void* v, const unsigned int* bits_t, const unsigned int* blockand,
+                 const unsigned char* flags, int G, int Q, int q_stride, int keys, int splits, float* o_part, float* ml_part,
+                 void* out, int* stats, void* stream) {
+  CHECK_ARG(q && k && v && bits_t && flags && o_part && ml_part && out, "null pointer");
+  CHECK_ARG(G > 0 && Q > 0 && Q <= 256 && keys > 0 && splits > 0 && q_stride >= Q, "bad arguments");
+  CHECK_ARG((long long)G * keys < (1ll << 31), "too many keys");
+  int sms = 148;
+  int rc = device_info(&sms);
+  if (rc) return rc;
+  const int qtiles = (Q + 127) / 128;
+  const int q_pad = qtiles * 128;
+  const int tiles = (keys + X3_KT - 1) / X3_KT;
+  const int chunk = ((tiles + splits - 1) / splits) * X3_KT;
+  CHECK_ARG((long long)chunk * (splits - 1) < keys, "splits too large for the key count (use ovis_xattn_plan_t)");
+  static bool attr_done[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_done[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(xattn_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, X3_SMEM);
+    if (e != cudaSuccess) {
+      snprintf(g_err, sizeof(g_err), "xattn_t: cudaFuncSetAttribute(smem) failed: %s", cudaGetErrorString(e));
+      return OVIS_ERR_CUDA;
+    }
+    attr_done[dev] = true;
+  }
+  CUtensorMap tq, tk, tv;
+  rc = make_map_f16(&tq, q, (unsigned long long)G * Q, 256, 256, 128);
+  if (rc) return rc;
+  rc = make_map_f16(&tk, k, (unsigned long long)G * keys, 256, 256, X3_KT);
+  if (rc) return rc;
+  rc = make_map_f16_sw64(&tv, v, (unsigned long long)G * keys, 256, 256, X3_KT);
+  if (rc) return rc;
+  XattnT3Args a;
+  a.bits_t = bits_t; a.flags = flags; a.o_part = o_part; a.ml_part = ml_part;
+  a.Q = Q; a.q_pad = q_pad; a.q_stride = q_stride; a.qw = 4 * qtiles;
+  a.keys = keys; a.splits = splits; a.chunk = chunk;
+  a.skipmap = nullptr; a.map_words = 0; a.stats = stats;
+  static const char* tr3 = getenv("OVIS_XATTN_TRACE");      // device pointer (decimal) of the trace buffer
+  a.trace = tr3 ? reinterpret_cast<long long*>(strtoull(tr3, nullptr, 10)) : nullptr;
+  static const bool skip_on = !(getenv("OVIS_XATTN_SKIP") && atoi(getenv("OVIS_XATTN_SKIP")) == 0);
+  const int map_words = (tiles + 31) / 32;
+  if (skip_on && blockand && map_words <= X3_MAP_WORDS && (tiles + splits - 1) / splits <= X3_LIST_MAX) {
+    uint32_t* map = reinterpret_cast<uint32_t*>(ml_part + (long long)G * splits * 8 * q_pad * 2);
+    xattn_t3_skipmap_kernel<<<dim3(map_words, qtiles, G), 32, 0, (cudaStream_t)stream>>>(blockand, flags, map, Q, q_stride, a.qw, keys,
+                                                                                         (keys + 31) / 32, X3_MAP_WORDS);
+    rc = check_launch("xattn_t3_skipmap_kernel");
+    if (rc) return rc;
+    a.skipmap = map;
+    a.map_words = X3_MAP_WORDS;
+  }
+  xattn_tc3_kernel<<<dim3(splits * 4, qtiles, G), X3_THREADS, X3_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, a);
+  rc = check_launch("xattn_tc3_kernel");
+  if (rc) return rc;
+  if (splits <= 8) {
     const long long total = (long long)G * Q * 128;
     xattn_combine_few_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(o_part, ml_part, (__half*)out, Q,
                                                                                                 q_pad, splits, total);

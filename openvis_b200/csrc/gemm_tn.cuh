@@ -17,6 +17,7 @@ enum GemmEpi : int {
   EPI_LN = 1,         // v = acc + bias + resid -> LayerNorm (-> optional 2nd LayerNorm); N == BN == 256
   EPI_SIGNBITS = 2,   // bits[g][r/32][col] = ballot(acc < 0); flags[g][col] = any(acc >= 0)
   EPI_STORE_T = 3,    // out[g*t_group_stride + col*ldt + r] = acc + bias[col]   (fp32, transposed / NCHW-style)
+  EPI_SIGNBITS_T = 4, // key-major sign bits for xattn_tc3: bits_t[g][r][col/32] bit col%32 = (acc < 0), flags, 32-key block ANDs
 };
 
 constexpr int GEMM_MAX_NTILES = 16;
@@ -67,6 +68,10 @@ struct GemmArgs {
   unsigned char* flags;   // [G][q_stride]
   int words_per_group;    // W = ceil(rows_per_group / 32)
   int q_stride;
+  // ---- EPI_SIGNBITS_T (flags / words_per_group / q_stride as above)
+  uint32_t* bits_t;       // [G][rows_per_group][qw]: word w of a key = its blocked bits for queries 32w..32w+31 (1 past N)
+  uint32_t* blockand;     // [G][W][qw]: AND of bits_t over the 32 keys of a block (rows past the group end count as blocked)
+  int qw;                 // words per key (4 per 128-query tile)
   // ---- EPI_STORE_T
   float* out_t;
   long long t_group_stride;
@@ -441,6 +446,42 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmArgs& args, const C
             args.flags[(long long)g * args.q_stride + col] = 1;
             pf_set |= 1u << c;
           }
+        }
+      }
+    }
+  } else if (args.epi == EPI_SIGNBITS_T) {
+    // rows = keys / cells, columns = queries.  A thread owns one key: its 32 sign bits of a column chunk ARE the word the
+    // transposed attention kernel wants (thread = key there as well), so no ballots; the two warp-wide reductions give the
+    // per-query "has an unblocked key" flags and the 32-key block ANDs the tile-skip map is built from.
+    const int r0 = mt * Cfg::BM + quarter * 32;
+#pragma unroll 1
+    for (int c = half * (BN / 64); c < (half + 1) * (BN / 64); ++c) {
+      const int col0 = col_base + c * 32;
+      const int widx = col0 >> 5;
+      if (widx >= args.qw) break;
+      uint32_t mine = 0xffffffffu;
+      if (col0 < args.N) {
+        tmem_ld_32x32(t_acc + c * 32, v);
+        tmem_ld_wait();
+        mine = 0u;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)   // blocked  <=>  sigmoid(x) < 0.5  <=>  x < 0
+          mine |= (__uint_as_float(v[j]) < 0.f ? 1u : 0u) << j;
+        const int nv = args.N - col0;
+        if (nv < 32) mine |= ~((1u << nv) - 1u);              // queries past N: blocked
+      }
+      if (row_ok) args.bits_t[((long long)g * args.rows_per_group + r) * args.qw + widx] = mine;
+      const uint32_t un = __reduce_or_sync(0xffffffffu, row_ok ? ~mine : 0u);
+      const uint32_t an = __reduce_and_sync(0xffffffffu, row_ok ? mine : 0xffffffffu);
+      if (lane == 0 && r0 < args.rows_per_group)
+        args.blockand[((long long)g * args.words_per_group + (r0 >> 5)) * args.qw + widx] = an;
+      const int col = col0 + lane;
+      if (col < args.N && ((un >> lane) & 1u)) {
+        const long long key = (long long)g * GEMM_MAX_NTILES + nt;
+        if (key != pf_frame) { pf_frame = key; pf_set = 0u; }
+        if (!((pf_set >> c) & 1u)) {
+          args.flags[(long long)g * args.q_stride + col] = 1;
+          pf_set |= 1u << c;
         }
       }
     }

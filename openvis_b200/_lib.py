@@ -368,6 +368,10 @@ def xattn(q, k, v, bits, flags, G, Q, q_stride, keys, splits, o_part, ml_part, o
                           _p(ml_part), _p(out), _stream()))
 
 
+def xattn_kernel_name():
+    return "xattn_tc3_kernel (transposed scores) / xattn_tc2_kernel + xattn_combine_kernel"
+
+
 def xattn_plan_t(G, Q, keys):
     """-> (use_t, splits, q_pad, o_part floats, ml_part floats) for the transposed-score kernel (xattn_tc3)."""
     lib = load()

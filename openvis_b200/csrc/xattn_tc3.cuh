@@ -123,6 +123,23 @@ __device__ __forceinline__ uint32_t pack_half2_sat(float lo, float hi) {     // 
   asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
+// 2^x on the FMA / ALU pipes (the exp pipe, MUFU.EX2, is this kernel's binding unit: 16 results per clock and SM, while
+// the FMA pipe has cycles to spare): round-to-nearest split x = n + f with the 1.5 * 2^23 trick, cubic minimax polynomial
+// for 2^f on [-0.5, 0.5] (max relative error 7.5e-5, a sixth of an fp16 half-ulp), exponent added as an integer.
+// -inf (masked) clamps to 2^-126, which packs to 0.
+__device__ __forceinline__ float poly_ex2(float x) {
+  x = fminf(fmaxf(x, -126.f), 126.f);
+  const float rr = x + 12582912.f;
+  const float f = x - (rr - 12582912.f);
+  float p = 0.0551716685f;
+  p = fmaf(p, f, 0.2426111251f);
+  p = fmaf(p, f, 0.6932609677f);
+  p = fmaf(p, f, 0.9999280572f);
+  return __uint_as_float(__float_as_uint(p) + (__float_as_uint(rr) << 23));
+}
+#ifndef X3_POLY_MOD
+#define X3_POLY_MOD 0        // every X3_POLY_MOD-th exponential of a thread on the FMA pipe; 0 = all on MUFU (measured: 4 -> +2 %, 3 -> +5 %, 2 -> +12 % TIME, the loop is latency-bound, not MUFU-bound; profiles/experiments)
+#endif
 __device__ __forceinline__ float warp_max_f32(float x) {
   float y;
   asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(y) : "f"(x));
@@ -572,7 +589,9 @@ xattn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
               float s0 = __uint_as_float(sv[c & 1][j]), s1 = __uint_as_float(sv[c & 1][j + 1]);
               if (hw & (1u << j)) s0 = -INFINITY;
               if (hw & (1u << (j + 1))) s1 = -INFINITY;
-              pk[j >> 1] = pack_half2_sat(fast_ex2(s0), fast_ex2(s1));
+              const bool poly1 = X3_POLY_MOD > 0 && ((j + 1) % (X3_POLY_MOD > 0 ? X3_POLY_MOD : 1)) == (X3_POLY_MOD > 0 ? X3_POLY_MOD : 1) - 1;
+              const bool poly0 = X3_POLY_MOD > 0 && (j % (X3_POLY_MOD > 0 ? X3_POLY_MOD : 1)) == (X3_POLY_MOD > 0 ? X3_POLY_MOD : 1) - 1;
+              pk[j >> 1] = pack_half2_sat(poly0 ? poly_ex2(s0) : fast_ex2(s0), poly1 ? poly_ex2(s1) : fast_ex2(s1));
             }
             if (c == 0) {
               // P^T buffer pg % 3 was last read by the products of unit pg - 3 (this warpgroup's previous-but-one unit or

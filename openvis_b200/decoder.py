@@ -184,6 +184,18 @@ class LazyAuxOutputs(list):
         return (self[i] for i in range(len(self)))
 
 
+def _words_from_bits_t(bits_t, Q):
+    """tests' debug capture only: key-major mask bits [G, keys, qw] -> the query-major packing [G, ceil(keys/32), Q]."""
+    G, keys, qw = bits_t.shape
+    sh = torch.arange(32, device=bits_t.device, dtype=torch.int32)
+    blocked = ((bits_t[..., None] >> sh) & 1).flatten(-2)[..., :Q]                      # [G, keys, Q]
+    W = (keys + 31) // 32
+    pad = torch.zeros(G, W * 32, Q, dtype=torch.int64, device=bits_t.device)
+    pad[:, :keys] = blocked
+    words = (pad.view(G, W, 32, Q) << torch.arange(32, device=bits_t.device)[None, None, :, None]).sum(2)
+    return torch.where(words >= 2 ** 31, words - 2 ** 32, words).to(torch.int32)
+
+
 # ------------------------------------------------------------------------------------------------ the decoder
 class _B200MaskedDecoderBase(nn.Module):
     _version = 2
@@ -380,12 +392,21 @@ class _B200MaskedDecoderBase(nn.Module):
         ws["m1"], ws["m2"], ws["me16"] = h(R, C), h(R, C), h(R, C)
         # scratch of the split linear+LayerNorm path (split-K partials); beyond 16384 rows the fused epilogue is used
         ws["split"] = f((self.dim_feedforward // 256) * ((R + 127) // 128) * 128 * 256) if R <= 16384 else None
-        ws["bits"] = [torch.zeros(G, (Tg * n + 31) // 32, Q, dtype=torch.int32, device=device) for n in N]
         ws["flags"] = torch.zeros(self.num_layers + 1, G, Q, dtype=torch.uint8, device=device)
+        # Per level: the transposed-score attention kernel (xattn_tc3, key-major mask bits) where a CTA walks a long run of
+        # keys, else the query-major kernel (xattn_tc2, [word][Q] mask bits); ovis_xattn_plan_t decides.
+        plans_t = [L.xattn_plan_t(G, Q, Tg * n) for n in N]
         plans = [L.xattn_plan(G, Q, Tg * n) for n in N]
-        ws["splits"] = [p[0] for p in plans]
-        ws["o_part"] = f(max(p[2] for p in plans))
-        ws["ml_part"] = f(max(p[3] for p in plans))
+        ws["use_t"] = [pt[0] for pt in plans_t]
+        ws["splits"] = [pt[1] if pt[0] else p[0] for pt, p in zip(plans_t, plans)]
+        qw = 4 * ((Q + 127) // 128)
+        ws["bits"] = [None if ut else torch.zeros(G, (Tg * n + 31) // 32, Q, dtype=torch.int32, device=device)
+                      for n, ut in zip(N, ws["use_t"])]
+        ws["bits_t"] = [torch.zeros(G, Tg * n, qw, dtype=torch.int32, device=device) if ut else None for n, ut in zip(N, ws["use_t"])]
+        ws["blockand"] = [torch.zeros(G, (Tg * n + 31) // 32, qw, dtype=torch.int32, device=device) if ut else None
+                          for n, ut in zip(N, ws["use_t"])]
+        ws["o_part"] = f(max(max(p[2], pt[3]) for p, pt in zip(plans, plans_t)))
+        ws["ml_part"] = f(max(max(p[3], pt[4]) for p, pt in zip(plans, plans_t)))
         self._ws[key] = ws
         return ws
 
@@ -443,9 +464,14 @@ class _B200MaskedDecoderBase(nn.Module):
 
         def head_bits(hidx, level):
             me = self._mlp3(W["mask_embed"], ws["d16"][hidx], ws["m1"], ws["m2"], ws["me16"])
-            L.mask_bits(ws["gt"][level], G, Tg * N[level], me, Q, ws["bits"][level], ws["flags"][hidx], Q)
+            if ws["use_t"][level]:
+                L.mask_bits_t(ws["gt"][level], G, Tg * N[level], me, Q, ws["bits_t"][level], ws["blockand"][level],
+                              ws["flags"][hidx], Q)
+            else:
+                L.mask_bits(ws["gt"][level], G, Tg * N[level], me, Q, ws["bits"][level], ws["flags"][hidx], Q)
             if self.debug_capture is not None:
-                self.debug_capture.append((hidx, level, ws["bits"][level].clone(), ws["flags"][hidx].clone()))
+                bits = _words_from_bits_t(ws["bits_t"][level], Q) if ws["use_t"][level] else ws["bits"][level].clone()
+                self.debug_capture.append((hidx, level, bits, ws["flags"][hidx].clone()))
 
         head_bits(0, 0)
         qscale = (C // NHEADS) ** -0.5 * LOG2E
@@ -454,8 +480,12 @@ class _B200MaskedDecoderBase(nn.Module):
             lw = W["layers"][i]
             # masked cross-attention (video_..._decoder.py:110-122)
             L.linear_f16(ws["ze16"], lw["xq_w"], lw["xq_b"], scale=qscale, out=ws["q16"])
-            L.xattn(ws["q16"], ws["k"][i], ws["v"][i], ws["bits"][l], ws["flags"][i], G, Q, Q, Tg * N[l], ws["splits"][l],
-                    ws["o_part"], ws["ml_part"], ws["att16"])
+            if ws["use_t"][l]:
+                L.xattn_t(ws["q16"], ws["k"][i], ws["v"][i], ws["bits_t"][l], ws["blockand"][l], ws["flags"][i], G, Q, Q,
+                          Tg * N[l], ws["splits"][l], ws["o_part"], ws["ml_part"], ws["att16"])
+            else:
+                L.xattn(ws["q16"], ws["k"][i], ws["v"][i], ws["bits"][l], ws["flags"][i], G, Q, Q, Tg * N[l], ws["splits"][l],
+                        ws["o_part"], ws["ml_part"], ws["att16"])
             L.linear_ln_f16(ws["att16"], lw["xo_w"], lw["xo_b"], ws["z32"], lw["ln_x"], None, W["qe"],
                             y32=ws["z32"], y16=ws["z16"], ype16=ws["ze16"], split_ws=ws["split"])
             # self-attention (video_..._decoder.py:52-62)

@@ -24,13 +24,13 @@ t = ts.cpu().view(7, 128, 8)
 n0 = 10
 base = t[0, n0, 0].item()
 print("cycles relative to warpgroup 0's step", n0, " wg rows: [begin, S available, 2 chunks done, P buffer free, S drained, P handed over]")
-for n in range(n0, n0 + 6):
-    for wg in range(3):
-        u = wg + 3 * n
+for n in range(n0, n0 + 8):
+    for wg in range(2):
+        u = wg + 2 * n
         ev = [t[wg, n, e].item() - base for e in range(6)]
         print(f"wg{wg} n={n} u={u} (tile {u >> 1} head {u & 1}): {ev}  wait_S={ev[1]-ev[0]} chunks01={ev[2]-ev[1]} wait_P={ev[3]-ev[2]} "
               f"rest={ev[5]-ev[3]}  | S committed {t[3, u, 0].item() - base}  PV committed {t[4, u, 0].item() - base}")
-    for tile in range((3 * n) >> 1, ((3 * n + 3) >> 1) + 1):
+    for tile in range(n, n + 1):
         print(f"      tile {tile}: K wait/issue {t[5, tile, 0].item() - base} {t[5, tile, 1].item() - base}   V wait/issue {t[6, tile, 0].item() - base} {t[6, tile, 1].item() - base}")
-for wg in range(3):
+for wg in range(2):
     print(f"wg{wg}: {(t[wg, 35, 0].item() - t[wg, 10, 0].item()) / 25:.0f} cycles per unit (steps 10..35)")

@@ -868,7 +868,10 @@ int ovis_xattn_t(const void* q, const void* k, const void* v, const unsigned int
   int dev = 0;
   cudaGetDevice(&dev);
   if (!attr_done[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(xattn_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, X3_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(xattn_tc3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, X3_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(xattn_tc3_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, X3_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(xattn_tc3_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, X3_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(xattn_tc3_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, X3_SMEM);
     if (e != cudaSuccess) {
       snprintf(g_err, sizeof(g_err), "xattn_t: cudaFuncSetAttribute(smem) failed: %s", cudaGetErrorString(e));
       return OVIS_ERR_CUDA;
@@ -900,7 +903,14 @@ int ovis_xattn_t(const void* q, const void* k, const void* v, const unsigned int
     a.skipmap = map;
     a.map_words = X3_MAP_WORDS;
   }
-  xattn_tc3_kernel<<<dim3(splits * 4, qtiles, G), X3_THREADS, X3_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, a);
+  // chunk count of the query tile as a template parameter where every tile of the launch has the same one
+  const int nq_last = Q - (qtiles - 1) * 128;
+  const int nch = qtiles == 1 ? ((nq_last + 15) >> 4) : 0;
+  const dim3 grid(splits * 4, qtiles, G);
+  if (nch == 7) xattn_tc3_kernel<7><<<grid, X3_THREADS, X3_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, a);
+  else if (nch == 8) xattn_tc3_kernel<8><<<grid, X3_THREADS, X3_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, a);
+  else if (nch == 5) xattn_tc3_kernel<5><<<grid, X3_THREADS, X3_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, a);
+  else xattn_tc3_kernel<0><<<grid, X3_THREADS, X3_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, a);
   rc = check_launch("xattn_tc3_kernel");
   if (rc) return rc;
   if (splits <= 8) {

@@ -39,6 +39,7 @@
 //               over P^T; small UMMAs are bound by their 4 KB A-operand fetch, not by their N)
 // TMEM (512 columns): S^T[3 wg] x 128 fp32 columns at 0, [O | l][2 heads] x 48 at 384 (column 32 = row sums).
 #pragma once
+#include <type_traits>
 #include "ptx.cuh"
 #include "xattn_tc.cuh"
 
@@ -186,6 +187,9 @@ xattn_t3_skipmap_kernel(const uint32_t* __restrict__ blockand, const unsigned ch
   if (lane == 0) map[((long long)g * gridDim.y + qt) * map_words + wi] = word;
 }
 
+// NCH: 16-column chunks of the query tile known at compile time (7: Q = 100, 8: Q = 128, 5: the second tile of Q = 200);
+// 0 = taken from the arguments at run time (any other Q).
+template <int NCH>
 __global__ void __launch_bounds__(X3_THREADS, 1)
 xattn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const XattnT3Args a) {
@@ -220,7 +224,7 @@ xattn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const int chunk_id = blockIdx.x >> 2, hp = blockIdx.x & 3, qt = blockIdx.y, g = blockIdx.z;
   const int nq = min(128, a.Q - qt * 128);              // queries of this tile
   const int N = (nq + 15) & ~15;                        // UMMA N of S^T
-  const int nchunks = N >> 4;                           // 16-column steps of the softmax loop
+  const int nchunks = NCH ? NCH : (N >> 4);              // 16-column steps of the softmax loop
 
   // ---- this CTA's key tiles: a contiguous chunk, or its share of the surviving tiles (tile skipping)
   bool use_list = a.skipmap != nullptr;
@@ -536,7 +540,10 @@ xattn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         umma_commit(done);
       }
     } else {
-      // ---- softmax warpgroups: thread = key row of the unit's tile; warpgroup g takes the units u = g (mod 2)
+      // ---- softmax warpgroups: thread = key row of the unit's tile; warpgroup g takes the units u = g (mod 2).
+      // The chunks of consecutive units form ONE stream: the TMEM load of the next chunk -- also across a unit boundary --
+      // is always in flight while the current chunk is computed, so the barrier round trips, the proxy fence and the
+      // first-load latency of a unit hide behind arithmetic (they were ~650 of ~2900 cycles per unit).
       uint4 nb = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
       bool nvalid = false;
       if (wg < units) {
@@ -544,8 +551,17 @@ xattn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         nvalid = key < k_last;
         if (nvalid) nb = __ldg(reinterpret_cast<const uint4*>(a.bits_t + ((long long)g * a.keys + key) * a.qw + qt * 4));
       }
-#pragma unroll 1
-      for (int u = wg; u < units; u += X3_NWG) {
+      uint32_t sv[2][16];
+      const bool tr = (quarter == 0 && lane == 0);
+      if (wg < units) {                                         // first chunk of the first unit
+        const int ug = ubase + wg;
+        mbar_wait(&s_full[ug % X3_NB], (uint32_t)((ug / X3_NB) & 1));
+        tc_fence_after();
+        tmem_ld_32x16_nowait(tmem_base + lane_off + (uint32_t)((ug % X3_NB) * 128), sv[0]);
+      }
+      // PH: which of the two register buffers holds chunk 0 of the unit (alternates when the chunk count is odd)
+      auto unit_body = [&](auto phc, const int u) {
+        constexpr int PH = decltype(phc)::value;
         const int ug = ubase + u, sb = ug % X3_NB, pg = pbase + u, pb = pg % X3_NB;
         const uint32_t prow = smem_u32(sP) + pb * X3_P_BYTES + (r >> 3) * 1024 + (r & 7) * 128;
         const uint32_t s_addr = tmem_base + lane_off + (uint32_t)(sb * 128);
@@ -560,33 +576,36 @@ xattn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         const uint32_t m0 = kvalid ? ((bw.x & act0) | pad0) : 0xffffffffu, m1 = kvalid ? ((bw.y & act1) | pad1) : 0xffffffffu;
         const uint32_t m2 = kvalid ? ((bw.z & act2) | pad2) : 0xffffffffu, m3 = kvalid ? ((bw.w & act3) | pad3) : 0xffffffffu;
         anyun0 |= ~m0; anyun1 |= ~m1; anyun2 |= ~m2; anyun3 |= ~m3;
-        const bool tr = (quarter == 0 && lane == 0);
-        if (tr) X3_TRACE(wg, u / X3_NWG, 0);                  // step begins (waiting for S)
-        mbar_wait(&s_full[sb], (uint32_t)((ug / X3_NB) & 1));
-        tc_fence_after();
-        if (tr) X3_TRACE(wg, u / X3_NWG, 1);                  // S available
-        uint32_t sv[2][16];
-        tmem_ld_32x16_nowait(s_addr, sv[0]);
+        if (tr) X3_TRACE(wg, u / X3_NWG, 0);                  // unit begins
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           if (c < nchunks) {
+            uint32_t* cur = sv[(c + PH) & 1];
+            uint32_t* nxt = sv[(c + PH + 1) & 1];
             tmem_ld_wait();
-            reg_fence16(sv[c & 1]);
+            reg_fence16(cur);
             if (c + 1 < nchunks) {
-              tmem_ld_32x16_nowait(s_addr + (c + 1) * 16, sv[(c + 1) & 1]);
+              tmem_ld_32x16_nowait(s_addr + (c + 1) * 16, nxt);
             } else {
-              // the S buffer goes back to the issuer as soon as its last columns sit in registers
+              // the S buffer goes back to the issuer as soon as its last columns sit in registers ...
               tc_fence_before();
               __syncwarp();
               if (lane == 0) mbar_arrive(&s_empty[sb]);
               if (tr) X3_TRACE(wg, u / X3_NWG, 4);            // S drained
+              // ... and the first chunk of this warpgroup's next unit starts loading (its S^T sits in the third buffer)
+              if (u + X3_NWG < units) {
+                const int ug2 = ug + X3_NWG;
+                mbar_wait(&s_full[ug2 % X3_NB], (uint32_t)((ug2 / X3_NB) & 1));
+                tc_fence_after();
+                tmem_ld_32x16_nowait(tmem_base + lane_off + (uint32_t)((ug2 % X3_NB) * 128), nxt);
+              }
             }
             const uint32_t word = (c >> 1) == 0 ? m0 : (c >> 1) == 1 ? m1 : (c >> 1) == 2 ? m2 : m3;
             const uint32_t hw = (c & 1) ? (word >> 16) : word;
             uint32_t pk[8];
 #pragma unroll
             for (int j = 0; j < 16; j += 2) {
-              float s0 = __uint_as_float(sv[c & 1][j]), s1 = __uint_as_float(sv[c & 1][j + 1]);
+              float s0 = __uint_as_float(cur[j]), s1 = __uint_as_float(cur[j + 1]);
               if (hw & (1u << j)) s0 = -INFINITY;
               if (hw & (1u << (j + 1))) s1 = -INFINITY;
               const bool poly1 = X3_POLY_MOD > 0 && ((j + 1) % (X3_POLY_MOD > 0 ? X3_POLY_MOD : 1)) == (X3_POLY_MOD > 0 ? X3_POLY_MOD : 1) - 1;
@@ -594,8 +613,7 @@ xattn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
               pk[j >> 1] = pack_half2_sat(poly0 ? poly_ex2(s0) : fast_ex2(s0), poly1 ? poly_ex2(s1) : fast_ex2(s1));
             }
             if (c == 0) {
-              // P^T buffer pg % 3 was last read by the products of unit pg - 3 (this warpgroup's previous-but-one unit or
-              // the other warpgroup's previous one): retired long ago in steady state
+              // P^T buffer pg % 3 was last read by the products of unit pg - 3: retired long ago in steady state
               if (tr) X3_TRACE(wg, u / X3_NWG, 2);
               mbar_wait(&p_empty[pb], (uint32_t)(((pg / X3_NB) & 1) ^ 1));
               if (tr) X3_TRACE(wg, u / X3_NWG, 3);
@@ -611,6 +629,23 @@ xattn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[pb]);
         if (tr) X3_TRACE(wg, u / X3_NWG, 5);                  // P handed over
+      };
+      if (NCH != 0 && (NCH & 1) == 0) {                         // even chunk count: chunk 0 always lands in buffer 0
+#pragma unroll 1
+        for (int u = wg; u < units; u += X3_NWG) unit_body(std::integral_constant<int, 0>{}, u);
+      } else if (NCH != 0) {                                    // odd: the buffers swap roles from unit to unit
+#pragma unroll 1
+        for (int u = wg; u < units; u += 2 * X3_NWG) {
+          unit_body(std::integral_constant<int, 0>{}, u);
+          if (u + X3_NWG < units) unit_body(std::integral_constant<int, 1>{}, u + X3_NWG);
+        }
+      } else {                                                  // run-time chunk count: parity decided per unit
+        int ph = 0;
+#pragma unroll 1
+        for (int u = wg; u < units; u += X3_NWG) {
+          if (ph) unit_body(std::integral_constant<int, 1>{}, u); else unit_body(std::integral_constant<int, 0>{}, u);
+          ph ^= nchunks & 1;
+        }
       }
     }
     kcount += ntiles;

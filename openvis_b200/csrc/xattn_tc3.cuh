@@ -9,12 +9,12 @@
 //   * the softmax reference is folded into the score product: one extra K = 16 slab multiplies a constant "ones" operand
 //     (one 256-byte SWIZZLE_32B atom broadcast to all 128 rows with SBO = 0) with a per-query [-m_ref] column, so the
 //     accumulator already holds s - m_ref and the exponential needs no subtraction;
-//   * the row sums come from the tensor core as well: P^T (the A operand of O += P V, written MN-major) is multiplied
-//     once more with a constant one-hot operand, which leaves sum_k p in a 16-column accumulator next to O;
+//   * the row sums come from the tensor core as well: the B operand of O += P V is [V_h | 1] (the head's V box plus a
+//     constant "ones" atom), which leaves sum_k p in column 32 of the 48-column accumulator;
 //   * what is left per probability: mask select (R2P + FSEL), MUFU.EX2, half a saturating pack, 1/8 of a 16-byte store;
 //   * 12.5 % fewer exponentials (112 instead of 128 columns) and 128-key steps (half the per-step fixed cost).
-// The reference is per (CTA, head, query) and constant while the chunk is processed, so the three softmax warpgroups
-// accumulate into ONE O / L accumulator per head and a CTA emits one partial per head (merged by xattn_combine_kernel).
+// The reference is per (CTA, head, query) and constant while the chunk is processed, so the softmax warpgroups
+// accumulate into ONE [O | l] accumulator per head and a CTA emits one partial per head (merged by xattn_combine_kernel).
 //
 // Robustness without a running max.  m_ref comes from a "max pass" over the FIRST key tile of the chunk (masked column
 // maxima by warp-wide CREDUX.MAX + shared-memory atomics) plus a margin of 2 (probabilities of that tile <= 2^-2; for a
@@ -27,17 +27,27 @@
 // binary orders towards its window, six retries cover any fp16-representable score range.  With the dense ~50 % masks of
 // the benchmark no CTA retries; with very sparse masks a CTA typically retries once.
 //
-// CTA = (key chunk, head PAIR, query tile of <= 128, group), 16 warps:
-//   warps 0-11  three softmax warpgroups (thread = key row of a 128-key tile); unit u = 2 * tile + head goes to
-//               warpgroup u % 3, so the two heads of a tile are in flight together and a K / V stage is released early
-//   warp 12     TMA producer for Q (once) and the K ring (3 x 16 KB); warp 15: TMA producer for the V ring (3 x 16 KB) --
-//               separate threads, so that K tiles are prefetched as soon as a K stage is free (their stages turn over
-//               earlier than the V stages, which wait for the PV products)
-//   warp 13     S^T issuer (out of order over the warpgroups): 2 x UMMA 128xNx16 (K-major K and Q) + the reference slab
-//   warp 14     PV issuer: [O_h | l_h] += P [V_h | 1] (8 x UMMA 128x48x16, A = P^T MN-major; B MN-major SWIZZLE_64B with two
-//               32-wide atoms: the head's V box and a constant atom whose column 0 is 1 -- the row sums cost no second pass
-//               over P^T; small UMMAs are bound by their 4 KB A-operand fetch, not by their N)
-// TMEM (512 columns): S^T[3 wg] x 128 fp32 columns at 0, [O | l][2 heads] x 48 at 384 (column 32 = row sums).
+// CTA = (key chunk, head PAIR, query tile of <= 128, group), 12 warps:
+//   warps 0-7   two softmax warpgroups (thread = key row of a 128-key tile); unit u = 2 * tile + head goes to warpgroup
+//               u % 2, its S^T to TMEM buffer u % 3 and its P^T to shared-memory buffer u % 3: with three rotating buffers
+//               for two consumers the scores of a warpgroup's next unit are always ready and its P^T buffer always free,
+//               and the chunks of consecutive units are processed as one stream (the TMEM load of the next 16 columns --
+//               also across a unit boundary -- is in flight while the current ones are computed)
+//   warp 8      TMA producer for Q (once) and the K ring (2 x 16 KB: a K stage is free as soon as both heads' S^T are issued)
+//   warp 11     TMA producer for the V ring (3 x 16 KB, two 64B-swizzled per-head boxes per stage); both producers pull
+//               their tiles into L2 six tiles ahead (cp.async.bulk.prefetch.tensor)
+//   warp 9      S^T issuer: 2 x UMMA 128xNx16 (K-major K and Q) + the reference slab
+//   warp 10     PV issuer: [O_h | l_h] += P [V_h | 1] (8 x UMMA 128x48x16, A = P^T MN-major SWIZZLE_128B with two 64-wide
+//               atoms; B MN-major SWIZZLE_64B with two 32-wide atoms: the head's V box and a constant atom whose column 0
+//               is 1, so the row sums cost no second pass over P^T)
+// TMEM (512 columns): S^T[3] x 128 fp32 columns at 0, [O | l][2 heads] x 48 at 384 (column 32 = row sums).
+//
+// Measured on B200 (tools/prof_xattn_t.py, tools/ubench/umma_rate.cu, profiles/experiments/xattn_tc3_r2_findings.md):
+//   * a UMMA 128xNx16 occupies the tensor pipe for max(56, N / 2) cycles whatever the operand layouts, so the eight
+//     N = 48 PV products of a unit cost 448 cycles and the three S^T products 180: 628 of the ~1400 cycles a unit takes;
+//   * the exponentials need 896 cycles per unit on the MUFU pipe, the K / V stream ~800 at the HBM peak (the pipeline
+//     with all arithmetic removed runs at 5.6 TB/s);
+//   * config-2 level-2 launch (1 clip, 529 920 keys): 195 us (xattn_tc2: 253); four clips: 669 us (941).
 #pragma once
 #include <type_traits>
 #include "ptx.cuh"
@@ -70,7 +80,10 @@ struct XattnT3Args {
 
 constexpr int X3_KT = 128;                        // keys per tile
 constexpr int X3_KS = 2, X3_VS = 3;               // ring depths (K stages turn over as soon as both heads' S^T are issued)
-constexpr int X3_NWG = 2;                          // softmax warpgroups (warps 0-7)
+#ifndef X3_NWG_DEF
+#define X3_NWG_DEF 2
+#endif
+constexpr int X3_NWG = X3_NWG_DEF;                 // softmax warpgroups (warps 0-7)
 constexpr int X3_NB = 3;                           // S^T buffers in TMEM = P^T buffers in shared memory, rotating with the unit number
 constexpr int X3_WARP_K = 4 * X3_NWG, X3_WARP_S = X3_WARP_K + 1, X3_WARP_PV = X3_WARP_K + 2, X3_WARP_V = X3_WARP_K + 3;
 constexpr int X3_PF = 6;                           // tiles the TMA producers prefetch into L2 ahead of their loads
@@ -499,18 +512,24 @@ xattn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         // the NEXT unit of whichever warpgroup finishes first, so a warpgroup never waits for its scores
         const uint32_t idesc_s = x3_idesc(128, N, 0, 0);
         const uint64_t ones_desc = x3_desc(smem_u32(sOnes), 16, 0, 6);          // SBO = 0: every 8-row atom is the same atom
+        const uint64_t kdesc0 = x3_desc(smem_u32(sK), 16, 1024, 2);
+        const uint64_t qdesc0 = x3_desc(smem_u32(sQ), 16, 1024, 2);
+        const uint64_t mdesc0 = x3_desc(smem_u32(sMref), 16, 256, 6);
         for (int u = 0; u < units; ++u) {
           const int t = u >> 1, w = u & 1, ug = ubase + u, b = ug % X3_NB;
           const int kc = kcount + t, st = kc % X3_KS;
+          const uint32_t d_tmem = tmem_base + (uint32_t)(b * 128);
+          const uint64_t adesc = kdesc0 + (uint64_t)((st * X3_TILE_BYTES + w * 64) >> 4);
+          const uint64_t bdesc = qdesc0 + (uint64_t)((w * 64) >> 4);
+          const uint64_t mdesc = mdesc0 + (uint64_t)((w * 4096) >> 4);
           mbar_wait(&s_empty[b], (uint32_t)(((ug / X3_NB) & 1) ^ 1));
           mbar_wait(&k_full[st], (uint32_t)((kc / X3_KS) & 1));
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + (uint32_t)(b * 128);
-          const uint64_t adesc = x3_desc(smem_u32(sK) + st * X3_TILE_BYTES + w * 64, 16, 1024, 2);
-          const uint64_t bdesc = x3_desc(smem_u32(sQ) + w * 64, 16, 1024, 2);
+#ifndef X3_EXPERIMENT_NO_S
           umma_f16(d_tmem, adesc, bdesc, idesc_s, 0u);
-          umma_f16(d_tmem, adesc + 2, bdesc + 2, idesc_s, 1u);
-          umma_f16(d_tmem, ones_desc, x3_desc(smem_u32(sMref) + w * 4096, 16, 256, 6), idesc_s, 1u);   // - m_ref
+          umma_f16_acc(d_tmem, adesc + 2, bdesc + 2, idesc_s);
+          umma_f16_acc(d_tmem, ones_desc, mdesc, idesc_s);                       // - m_ref
+#endif
           umma_commit(&s_full[b]);
           X3_TRACE(3, u, 0);
           if (w == 1) umma_commit(&k_empty[st]);
@@ -519,20 +538,33 @@ xattn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     } else if (warp == X3_WARP_PV) {
       if (lane == 0) {
         constexpr uint32_t idesc_o = x3_idesc(128, 48, 1, 1);      // A = P^T MN-major, B = [V_h | ones] MN-major
+        // (descriptors are built once per unit and stepped by adding to the 14-bit address field: the issuing thread's own
+        //  instruction stream was the limit -- ~20 integer instructions per UMMA cost ~450 cycles per unit)
+        const uint64_t pdesc0 = x3_desc(smem_u32(sP), 16384, 1024, 2);
         for (int u = 0; u < units; ++u) {
           const int t = u >> 1, w = u & 1, pg = pbase + u, b = pg % X3_NB;
           const int vc = vcount + t, st = vc % X3_VS;
+          const uint32_t v_addr = smem_u32(sV) + st * X3_TILE_BYTES + w * 8192;
+          const uint64_t adesc = pdesc0 + (uint64_t)((b * X3_P_BYTES) >> 4);
+          const uint64_t bdesc = x3_desc(v_addr, smem_u32(sE) - v_addr, 512, 4);   // second 32-wide atom of B: the ones atom
+          const uint32_t o_tmem = tmem_base + 384u + (uint32_t)(w * 48);
           mbar_wait(&p_full[b], (uint32_t)((pg / X3_NB) & 1));
           mbar_wait(&v_full[st], (uint32_t)((vc / X3_VS) & 1));
           tc_fence_after();
-          const uint32_t p_addr = smem_u32(sP) + b * X3_P_BYTES;
-          const uint32_t v_addr = smem_u32(sV) + st * X3_TILE_BYTES + w * 8192;
-          const uint32_t o_tmem = tmem_base + 384u + (uint32_t)(w * 48);
-          const uint32_t ones_lbo = smem_u32(sE) - v_addr;               // second 32-wide atom of B: the ones atom
+#ifndef X3_EXPERIMENT_NO_PV
+#ifndef X3_EXP_PV_STEPS
+#define X3_EXP_PV_STEPS (X3_KT / 16)
+#endif
+#ifdef X3_EXP_PV_N32
+          constexpr uint32_t idesc_x = x3_idesc(128, 32, 1, 1);
+#else
+          constexpr uint32_t idesc_x = idesc_o;
+#endif
+          umma_f16(o_tmem, adesc, bdesc, idesc_x, t > 0 ? 1u : 0u);
 #pragma unroll
-          for (int kk = 0; kk < X3_KT / 16; ++kk)
-            umma_f16(o_tmem, x3_desc(p_addr + kk * 2048, 16384, 1024, 2), x3_desc(v_addr + kk * 1024, ones_lbo, 512, 4), idesc_o,
-                     (t > 0 || kk > 0) ? 1u : 0u);
+          for (int kk = 1; kk < X3_EXP_PV_STEPS; ++kk)
+            umma_f16_acc(o_tmem, adesc + (uint64_t)(kk * (2048 >> 4)), bdesc + (uint64_t)(kk * (1024 >> 4)), idesc_x);
+#endif
           umma_commit(&p_empty[b]);
           X3_TRACE(4, u, 0);
           if (w == 1) umma_commit(&v_empty[st]);
@@ -577,6 +609,11 @@ xattn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         const uint32_t m2 = kvalid ? ((bw.z & act2) | pad2) : 0xffffffffu, m3 = kvalid ? ((bw.w & act3) | pad3) : 0xffffffffu;
         anyun0 |= ~m0; anyun1 |= ~m1; anyun2 |= ~m2; anyun3 |= ~m3;
         if (tr) X3_TRACE(wg, u / X3_NWG, 0);                  // unit begins
+        if (X3_NB <= X3_NWG && u >= X3_NWG) {                   // (no spare S^T buffer: the first chunk is loaded here)
+          mbar_wait(&s_full[sb], (uint32_t)((ug / X3_NB) & 1));
+          tc_fence_after();
+          tmem_ld_32x16_nowait(s_addr, sv[PH & 1]);
+        }
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           if (c < nchunks) {
@@ -593,7 +630,7 @@ xattn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
               if (lane == 0) mbar_arrive(&s_empty[sb]);
               if (tr) X3_TRACE(wg, u / X3_NWG, 4);            // S drained
               // ... and the first chunk of this warpgroup's next unit starts loading (its S^T sits in the third buffer)
-              if (u + X3_NWG < units) {
+              if (X3_NB > X3_NWG && u + X3_NWG < units) {
                 const int ug2 = ug + X3_NWG;
                 mbar_wait(&s_full[ug2 % X3_NB], (uint32_t)((ug2 / X3_NB) & 1));
                 tc_fence_after();
@@ -603,6 +640,10 @@ xattn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             const uint32_t word = (c >> 1) == 0 ? m0 : (c >> 1) == 1 ? m1 : (c >> 1) == 2 ? m2 : m3;
             const uint32_t hw = (c & 1) ? (word >> 16) : word;
             uint32_t pk[8];
+#ifdef X3_EXPERIMENT_SKELETON
+#pragma unroll
+            for (int j = 0; j < 8; ++j) pk[j] = cur[2 * j] ^ hw;
+#else
 #pragma unroll
             for (int j = 0; j < 16; j += 2) {
               float s0 = __uint_as_float(cur[j]), s1 = __uint_as_float(cur[j + 1]);
@@ -612,6 +653,7 @@ xattn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
               const bool poly0 = X3_POLY_MOD > 0 && (j % (X3_POLY_MOD > 0 ? X3_POLY_MOD : 1)) == (X3_POLY_MOD > 0 ? X3_POLY_MOD : 1) - 1;
               pk[j >> 1] = pack_half2_sat(poly0 ? poly_ex2(s0) : fast_ex2(s0), poly1 ? poly_ex2(s1) : fast_ex2(s1));
             }
+#endif
             if (c == 0) {
               // P^T buffer pg % 3 was last read by the products of unit pg - 3: retired long ago in steady state
               if (tr) X3_TRACE(wg, u / X3_NWG, 2);
@@ -621,8 +663,13 @@ xattn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             // P^T[key r][queries 16c .. 16c+15]: two 16-byte chunks of the key's 128-byte row in query atom c / 4
             const uint32_t dst = prow + (c >> 2) * 16384;
             const int cc = (c & 3) * 2;
+#ifdef X3_EXPERIMENT_NO_STORE
+            if (pk[0] == 0x12345678u && pk[5] == 0x9abcdef0u)
+#endif
+            {
             st_shared_v4(dst + (((cc) ^ (r & 7)) << 4), make_uint4(pk[0], pk[1], pk[2], pk[3]));
             st_shared_v4(dst + (((cc + 1) ^ (r & 7)) << 4), make_uint4(pk[4], pk[5], pk[6], pk[7]));
+            }
           }
         }
         fence_async_proxy();            // generic-proxy smem writes -> visible to the tensor core (async proxy)
@@ -685,7 +732,11 @@ xattn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
         const float l = __uint_as_float(lv[0]);
         const float mref_used = sref[w * 128 + r];             // the reference this attempt's O / l belong to
+#ifdef X3_EXPERIMENT_SKELETON
+        if (false) {
+#else
         if (r < nq && had_unblocked && !(l >= 0.125f && l < 32768.f)) {
+#endif
           // a probability may have saturated (l >= 2^15), or the row sat in / below fp16's subnormal range (l < 2^-3):
           // new reference from the sum itself, so that the row's sum lands near 2^3 next time
           bad = 1;

@@ -692,7 +692,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     numa = bind_to_gpu_numa_node(local)
     pipe = WORKLOADS[args.workload][0]
-    lanes = args.streams if args.streams is not None else (2 if pipe == "openvis" else 1)
+    lanes = args.streams if args.streams is not None else (1 if pipe == "san_online" else 2)
     clips = args.clips if args.clips is not None else 4
     # persistent kernels leave a few SMs to the other in-flight call's small latency-bound kernels
     if lanes > 1:
@@ -716,7 +716,7 @@ def main():
         others = {}
         for on in OTHER_CONFIGS:
             op = WORKLOADS[on][0]
-            ol = 2 if op == "openvis" else 1
+            ol = 1 if op == "san_online" else 2      # (two calls in flight: +9 % for BriVIS, nothing for SAN-online, r2_lanes)
             oc = 1 if on == "openvis_video_5x360x640_q100_k40" else (2 if WORKLOADS[on][6] == 200 else 4)
             try:
                 m = measure(args, on, dev, 1, 0, local, max(5, args.steps // 2), 3, oc, ol, want_e2e=not args.no_e2e,

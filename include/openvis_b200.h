@@ -60,6 +60,20 @@ int ovis_init_queries(const float* query_feat, const float* query_embed, const f
  * (clip_adapter/adapter.py:118-119); SideAdapter ln_post / F.normalize (clip_adapter/side_adapter.py:203-205). */
 int ovis_rownorm(const float* in, const float* g, const float* b, float* out32, void* out16, int rows, int D,
                  int mode, void* stream);
+/* Kernel 3 of the path, fused form ("mask-pool GEMM with the L2-normalise and text-cosine epilogue"): the logits GEMM
+ * normalises in its epilogue, logits[r][k] = scale * (x[r] . text[k]) / max(||x[r]||, 1e-12), instead of a separate
+ * normalisation pass (ClipAdapter.normalize + cal_sim_logits, clip_adapter/adapter.py:118-119, 146-147; F.normalize +
+ * SideAdapter.cal_sim_logits, side_adapter.py:205, 234-235).
+ * ovis_rowstats: out16 = fp16(x) (after an optional LayerNorm: ln_post, side_adapter.py:203) and ss[r] = sum of squares of
+ *   that fp16 row; ss_zero (optional) is cleared (accumulator of a following row_ss_out).  group_rows > 0: input row r is
+ *   row (r / group_rows) * group_stride + r % group_rows of `in` (the Q SOS tokens at the head of every frame's token block).
+ * ovis_linear_rowscale_f16: out = (x @ w^T + bias) * scale [* rsqrt(row_ss_in[r])]; row_ss_out[r] += sum of squares of the
+ *   output row (visual.proj GEMM feeding the normalised logits GEMM). */
+int ovis_rowstats(const float* in, const float* ln_g, const float* ln_b, void* out_f16, float* ss, float* ss_zero, int rows,
+                  int D, int layer_norm, int group_rows, int group_stride, void* stream);
+int ovis_linear_rowscale_f16(const void* x_f16, long long rows, int K, int ldx, const void* w_f16, int N, const float* bias,
+                             float scale, const float* row_ss_in, float* row_ss_out, void* out, int ldo, int out_f32,
+                             void* stream);
 
 /* ---- tcgen05 GEMM family: out = x[rows][K] * w[N][K]^T, fp16 operands, fp32 accumulation ---------------
  * nn.Linear / in_proj / out_proj / MLP layers (video_mask2former_transformer_decoder.py:57-58, 115-118, 176-178,

@@ -27,6 +27,8 @@ SIGNATURES = {
     "ovis_cast_f16": (_c_int, [_vp, _vp, _c_ll, _vp]),
     "ovis_init_queries": (_c_int, [_vp] * 9 + [_c_int, _c_int, _vp]),
     "ovis_rownorm": (_c_int, [_vp] * 5 + [_c_int, _c_int, _c_int, _vp]),
+    "ovis_rowstats": (_c_int, [_vp] * 6 + [_c_int, _c_int, _c_int, _c_int, _c_int, _vp]),
+    "ovis_linear_rowscale_f16": (_c_int, [_vp, _c_ll, _c_int, _c_int, _vp, _c_int, _vp, _c_float, _vp, _vp, _vp, _c_int, _c_int, _vp]),
     "ovis_linear_f16": (_c_int, [_vp, _c_ll, _c_int, _c_int, _vp, _c_int, _vp, _c_float, _c_int, _vp, _c_int, _c_int, _vp]),
     "ovis_linear_act_f16": (_c_int, [_vp, _c_ll, _c_int, _c_int, _vp, _c_int, _vp, ctypes.c_float, _c_int, _vp, _vp, _c_int,
                                      _c_int, _vp]),
@@ -209,6 +211,33 @@ def rownorm(x, g=None, b=None, layer_norm=False, l2=False, want32=True, want16=T
     mode = (1 if layer_norm else 0) | (2 if l2 else 0)
     _check(lib.ovis_rownorm(_p(x), _p(g), _p(b), _p(o32), _p(o16), rows, D, mode, _stream()))
     return o32, o16
+
+
+def rowstats(x, g=None, b=None, layer_norm=False, want_ss=True, zero=None, groups=None):
+    """x [rows, D] fp32 -> (fp16 copy (after LayerNorm when asked), ss [rows] = its rows' sums of squares or None);
+    `zero` [rows] fp32 is cleared (accumulator for linear_rowscale_f16(row_ss_out=...)).
+    groups = (n_groups, group_rows, group_stride): take the first group_rows rows of each of n_groups blocks of group_stride rows."""
+    lib = load()
+    _req(x, torch.float32, "x")
+    D = x.shape[1]
+    rows, gr, gs = (x.shape[0], 0, 0) if groups is None else (groups[0] * groups[1], groups[1], groups[2])
+    o16 = torch.empty(rows, D, dtype=torch.float16, device=x.device)
+    ss = torch.empty(rows, dtype=torch.float32, device=x.device) if want_ss else None
+    _check(lib.ovis_rowstats(_p(x), _p(g), _p(b), _p(o16), _p(ss), _p(zero), rows, D, int(layer_norm), gr, gs, _stream()))
+    return o16, ss
+
+
+def linear_rowscale_f16(x, w, bias=None, scale=1.0, row_ss_in=None, row_ss_out=None, out=None, out_f32=False):
+    """(x @ w^T + bias) * scale, rows divided by sqrt(row_ss_in) when given; row_ss_out += output rows' sums of squares."""
+    lib = load()
+    assert x.dtype == torch.float16 and w.dtype == torch.float16 and x.stride(-1) == 1 and w.is_contiguous()
+    rows, K = x.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty(rows, N, dtype=torch.float32 if out_f32 else torch.float16, device=x.device)
+    _check(lib.ovis_linear_rowscale_f16(_p(x), rows, K, x.stride(0), _p(w), N, _p(bias), float(scale), _p(row_ss_in),
+                                        _p(row_ss_out), _p(out), out.stride(0), int(out_f32), _stream()))
+    return out
 
 
 @_timed("query_side")

@@ -452,8 +452,48 @@ int ovis_rownorm(const float* in, const float* g, const float* b, float* out32, 
   CHECK_ARG(!(mode & 1) || (g && b), "LayerNorm needs weight and bias");
   int rc = device_info(nullptr);
   if (rc) return rc;
-  rownorm_kernel<<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(in, g, b, out32, (__half*)out16, rows, D, mode);
+  CHECK_ARG(!(mode & 4), "mode bit 2 (row sums of squares) needs ovis_rowstats");
+  rownorm_kernel<<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(in, g, b, out32, (__half*)out16, rows, D, mode, nullptr, nullptr, 0, 0);
   return check_launch("rownorm_kernel");
+}
+
+int ovis_rowstats(const float* in, const float* g, const float* b, void* out16, float* ss, float* ss_zero, int rows, int D,
+                  int layer_norm, int group_rows, int group_stride, void* stream) {
+  CHECK_ARG(in && rows > 0 && D > 0 && out16 && (ss || ss_zero) && group_rows >= 0 && (group_rows == 0 || group_stride >= group_rows),
+            "bad arguments");
+  CHECK_ARG(!layer_norm || (g && b), "LayerNorm needs weight and bias");
+  int rc = device_info(nullptr);
+  if (rc) return rc;
+  rownorm_kernel<<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(in, g, b, nullptr, (__half*)out16, rows, D,
+                                                                    (layer_norm ? 1 : 0) | (ss ? 4 : 0), ss, ss_zero, group_rows,
+                                                                    group_stride);
+  return check_launch("rownorm_kernel");
+}
+
+int ovis_linear_rowscale_f16(const void* x, long long rows, int K, int ldx, const void* w, int N, const float* bias, float scale,
+                             const float* row_ss_in, float* row_ss_out, void* out, int ldo, int out_f32, void* stream) {
+  CHECK_ARG(x && w && out && rows > 0 && N > 0 && ldx >= K && ldo >= N && (row_ss_in || row_ss_out), "bad arguments");
+  CHECK_ARG(rows < (1ll << 31), "too many rows");
+  GemmArgs a;
+  init_args(a);
+  a.rows_per_group = (int)rows;
+  a.a_group_stride = (int)rows;
+  a.N = N;
+  a.K = K;
+  a.epi = EPI_STORE;
+  const int bn = (N <= 128) ? 128 : 256;
+  const int nt = (N + bn - 1) / bn;
+  CHECK_ARG(nt <= GEMM_MAX_NTILES, "N too large");
+  for (int t = 0; t < nt; ++t) {
+    a.out[t] = out_f32 ? (void*)((float*)out + (long long)t * bn) : (void*)((__half*)out + (long long)t * bn);
+    a.bias[t] = bias ? bias + (long long)t * bn : nullptr;
+  }
+  a.ldo = ldo;
+  a.out_f32 = out_f32;
+  a.scale = scale;
+  a.row_ss_in = row_ss_in;
+  a.row_ss_out = row_ss_out;
+  return launch_gemm(x, rows, K, ldx, w, N, K, a, bn, (cudaStream_t)stream);
 }
 
 int ovis_linear_f16(const void* x, long long rows, int K, int ldx, const void* w, int N, const float* bias, float scale,

@@ -55,6 +55,10 @@ struct GemmArgs {
   int a_alt_shift;        //    (key / value operands; shift 1 when a 256-wide output is split into two 128-wide tiles)
   int tma_store;          // 1: EPI_STORE writes through GemmOutMaps (single group, 16-byte aligned pitch)
   int kps;                // B-stationary kernel: k-blocks requested together per ring barrier (1, 2 or 4; divides K/64)
+  // fused L2-normalisation of the OV heads (kernel 3 of the path): normalize(f) @ text^T = (f @ text^T) / ||f|| row by row
+  const float* row_ss_in; // optional [rows]: sum of squares of the A rows (or of the producing GEMM's output rows): the
+                          //   store multiplies by scale * rsqrt(max(row_ss_in[row], 1e-24)) instead of scale
+  float* row_ss_out;      // optional [rows], zeroed by the caller: += sum of squares of this GEMM's output row (atomicAdd)
   // ---- EPI_LN
   const float* resid;     // [rows][256] fp32
   const float* ln1_g; const float* ln1_b;
@@ -123,7 +127,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmArgs& args, const C
     // scale / activation / residual, full column tile, bulk tensor store.  The generic code below handles every
     // combination at run time and costs ~30 instructions per element, which made these GEMMs epilogue-issue-bound.
     if (args.tma_store && !args.out_f32 && args.relu == 0 && args.scale == 1.f && args.resid_st == nullptr && bias_vec &&
-        col_base + BN <= args.N) {
+        !args.row_ss_in && !args.row_ss_out && col_base + BN <= args.N) {
 #pragma unroll 1
       for (int u0 = half * (BN / 2); u0 < (half + 1) * (BN / 2); u0 += 64) {
         uint32_t va[32], vb[32];
@@ -204,9 +208,22 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmArgs& args, const C
           f[4 * j + 2] = __uint_as_float(vv[hh][4 * j + 2]) + bv[hh][j].z;
           f[4 * j + 3] = __uint_as_float(vv[hh][4 * j + 3]) + bv[hh][j].w;
         }
-        if (args.scale != 1.f) {
+        const bool row_in_range = r_warp0 + lane < args.rows_per_group;
+        if (args.row_ss_in) {
+          // x / max(||x||, 1e-12) like F.normalize (side_adapter.py:205); adapter.py:118-119 has no clamp: same for real rows
+          const float rs = args.scale * rsqrtf(fmaxf(row_in_range ? __ldg(args.row_ss_in + grow0 + lane) : 1.f, 1e-24f));
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] *= rs;
+        } else if (args.scale != 1.f) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] *= args.scale;
+        }
+        if (args.row_ss_out && row_in_range) {
+          const int nleft = args.N - (col_base + u0 + hh * 32);
+          float ss = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) ss += (j < nleft) ? f[j] * f[j] : 0.f;
+          atomicAdd(args.row_ss_out + grow0 + lane, ss);
         }
         if (args.relu == 1) {
 #pragma unroll

@@ -262,13 +262,19 @@ ln_reduce_kernel(const LnReduceArgs a) {
 // Row-wise LayerNorm (optional) + L2 normalisation (optional) to fp16 / fp32, one warp per row.
 //   mode bit0: LayerNorm with (g, b), eps 1e-5        (SideAdapter ln_post, side_adapter.py:203)
 //   mode bit1: divide by the L2 norm                  (ClipAdapter.normalize adapter.py:118-119; F.normalize side_adapter.py:205)
+//   mode bit2: do NOT divide; write the row's sum of squares to ss[row] instead (the logits GEMM's epilogue divides:
+//              ovis_linear_rowscale_f16).  ss_zero (optional, [rows]): set to 0 (accumulator of a following GEMM epilogue).
 __global__ void __launch_bounds__(256)
 rownorm_kernel(const float* __restrict__ in, const float* __restrict__ g, const float* __restrict__ bta,
-               float* __restrict__ out32, __half* __restrict__ out16, int rows, int D, int mode) {
+               float* __restrict__ out32, __half* __restrict__ out16, int rows, int D, int mode, float* __restrict__ ss,
+               float* __restrict__ ss_zero, int group_rows, int group_stride) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
-  const float* x = in + (long long)row * D;
+  // input rows may be the first group_rows rows of consecutive groups of group_stride rows (the SOS tokens of every frame
+  // inside the [SOS | CLS | patches] token matrix); outputs are dense
+  const long long in_row = group_rows > 0 ? (long long)(row / group_rows) * group_stride + row % group_rows : row;
+  const float* x = in + in_row * D;
   float mean = 0.f, rstd = 1.f;
   if (mode & 1) {
     float s = 0.f;
@@ -279,7 +285,18 @@ rownorm_kernel(const float* __restrict__ in, const float* __restrict__ g, const 
     rstd = rsqrtf(warp_sum(sq) / D + 1e-5f);
   }
   float inv = 1.f;
-  if (mode & 2) {
+  if (ss_zero && lane == 0) ss_zero[row] = 0.f;
+  if (mode & 4) {
+    float sq = 0.f;
+    for (int c = lane; c < D; c += 32) {
+      float v = x[c];
+      if (mode & 1) v = (v - mean) * rstd * g[c] + bta[c];
+      v = __half2float(__float2half_rn(v));           // the norm of what the GEMM will actually multiply
+      sq += v * v;
+    }
+    sq = warp_sum(sq);
+    if (lane == 0 && ss) ss[row] = sq;
+  } else if (mode & 2) {
     float sq = 0.f;
     for (int c = lane; c < D; c += 32) {
       float v = x[c];

@@ -70,10 +70,13 @@ class ClipLogitHead(_TextCache):
         shp = image_features.shape
         f = image_features.reshape(-1, shp[-1]).float().contiguous()
         if normalized:
-            f16 = L.cast_f16(f)
+            out = L.linear_f16(L.cast_f16(f), self._text_f16(text_features), None, scale=float(temperature), out_f32=True)
         else:
-            _, f16 = L.rownorm(f, l2=True, want32=False)
-        out = L.linear_f16(f16, self._text_f16(text_features), None, scale=float(temperature), out_f32=True)
+            # kernel 3, fused: the GEMM's epilogue divides every row by its norm (one pass makes the fp16 operand and the
+            # rows' sums of squares, nothing normalised is written)
+            f16, ss = L.rowstats(f)
+            out = L.linear_rowscale_f16(f16, self._text_f16(text_features), None, scale=float(temperature), row_ss_in=ss,
+                                        out_f32=True)
         return out.view(*shp[:-1], text_features.shape[0])
 
     def open_vocabulary_scores(self, region_feats: torch.Tensor, valid: torch.Tensor, text_features: torch.Tensor):
@@ -100,13 +103,7 @@ class SideAdapterTail(_TextCache):
         """ln_post -> @ visual.proj -> F.normalize (side_adapter.py:203-205).  sos_token [B, Q, W]; proj [W, D]."""
         B, Q, Wd = sos_token.shape
         _, x16 = L.rownorm(sos_token.reshape(-1, Wd).float().contiguous(), ln_w, ln_b, layer_norm=True, want32=False)
-        key = ("proj", proj.data_ptr())
-        hit = self._mat.get(key)
-        if hit is not None and hit[0]() is proj and hit[1] == proj._version:
-            pt = hit[2]
-        else:
-            pt = L.cast_f16(proj.detach().float().T.contiguous())
-            self._mat[key] = (weakref.ref(proj), proj._version, pt)
+        pt = self._proj_f16(proj)
         e = L.linear_f16(x16, pt, None, out_f32=True)
         e32, _ = L.rownorm(e, l2=True, want16=False)
         return e32.view(B, Q, -1)
@@ -117,6 +114,27 @@ class SideAdapterTail(_TextCache):
         f16 = L.cast_f16(image_feats.reshape(-1, shp[-1]).float().contiguous())
         out = L.linear_f16(f16, self._text_f16(text_feats), None, scale=float(self.logit_scale_exp), out_f32=True)
         return out.view(*shp[:-1], text_feats.shape[0])
+
+    def _proj_f16(self, proj):
+        key = ("proj", proj.data_ptr())
+        hit = self._mat.get(key)
+        if hit is not None and hit[0]() is proj and hit[1] == proj._version:
+            return hit[2]
+        pt = L.cast_f16(proj.detach().float().T.contiguous())
+        self._mat[key] = (weakref.ref(proj), proj._version, pt)
+        return pt
+
+    def sos_logits(self, tokens: torch.Tensor, n: int, Q: int, Lt: int, ln_w, ln_b, proj, text_feats):
+        """The whole SAN tail in three launches (side_adapter.py:203-207, 234-235): ln_post on the Q SOS rows at the head of
+        every frame's [Lt, W] token block (fp16 out) -> @ visual.proj with the rows' sums of squares from the GEMM epilogue
+        -> logits GEMM whose epilogue divides by the norm and multiplies by exp(logit_scale).  tokens [n * Lt, W] fp32.
+        Returns logits [n, Q, K + 1]; the normalised clip_feats are never written."""
+        ss = torch.empty(n * Q, dtype=torch.float32, device=tokens.device)
+        x16, _ = L.rowstats(tokens, ln_w, ln_b, layer_norm=True, want_ss=False, zero=ss, groups=(n, Q, Lt))
+        e16 = L.linear_rowscale_f16(x16, self._proj_f16(proj), None, row_ss_out=ss)
+        out = L.linear_rowscale_f16(e16, self._text_f16(text_feats), None, scale=float(self.logit_scale_exp), row_ss_in=ss,
+                                    out_f32=True)
+        return out.view(n, Q, text_feats.shape[0])
 
 
 class SideAdapterBlocks:
@@ -152,9 +170,10 @@ class SideAdapterBlocks:
         return self
 
     @torch.no_grad()
-    def post_blocks(self, feats, attn_bias):
+    def post_blocks(self, feats, attn_bias, return_tokens=False):
         """feats = (cls_token [1, n, W], pix_feat [n, W, h, w]); attn_bias [n, heads, Q, H', W'] fp32 (or a one-element
-        list, or None).  Returns the SOS tokens [n, Q, W] fp32 after the post-split blocks (before ln_post)."""
+        list, or None).  Returns the SOS tokens [n, Q, W] fp32 after the post-split blocks (before ln_post);
+        return_tokens: the whole token matrix [n * (Q + 1 + L), W] instead (no copy of the SOS rows)."""
         if self._w is None:
             raise RuntimeError("SideAdapterBlocks: load_clip_visual_state_dict() first")
         cls_token, pix = feats
@@ -188,7 +207,18 @@ class SideAdapterBlocks:
                 _, y16 = L.rownorm(X, p["ln2"][0], p["ln2"][1], layer_norm=True, want32=False)
                 h16 = L.linear_act_f16(y16, p["fc_w"], p["fc_b"], act=2)
                 L.linear_act_f16(h16, p["pj_w"], p["pj_b"], resid=X, out=X, out_f32=True)
-            return x[:, :Q].contiguous()
+            return X if return_tokens else x[:, :Q].contiguous()
+
+    @torch.no_grad()
+    def post_encode_logits(self, feats, attn_bias, text_feats):
+        """post_encode_image + cal_sim_logits (san.py:230-231, resampler.py:313-314) as one call: the tail runs fused
+        (SideAdapterTail.sos_logits) and neither the SOS-row copy nor the normalised features are materialised."""
+        tokens = self.post_blocks(feats, attn_bias, return_tokens=True)
+        n = feats[1].shape[0]
+        Q = self.sos_token_num
+        Lt = tokens.shape[0] // n
+        with torch.cuda.device(tokens.device):
+            return self.tail.sos_logits(tokens, n, Q, Lt, self._w["ln_post"][0], self._w["ln_post"][1], self._w["proj"], text_feats)
 
     @torch.no_grad()
     def post_encode_image(self, feats, attn_bias):

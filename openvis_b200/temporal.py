@@ -259,8 +259,10 @@ class TemporalInstanceResampler(nn.Module):
             ae = self._mlp3(W["attn_embed"], d)
             biases = f32(BT, nh, q, ah, aw)
             L.san_bias_logits(af, BT, P, nh, ae, q, biases)
-            clip_feats = adapter.post_encode_image(clip_bk_feats, biases)
-            logits = adapter.cal_sim_logits(text_feats, clip_feats)
+            if hasattr(adapter, "post_encode_logits"):        # fused tail (ov_head.SideAdapterBlocks)
+                logits = adapter.post_encode_logits(clip_bk_feats, biases, text_feats)
+            else:                                             # the reference's two calls (resampler.py:313-314)
+                logits = adapter.cal_sim_logits(text_feats, adapter.post_encode_image(clip_bk_feats, biases))
             return logits.reshape(bs, t, q, -1), masks
 
         logits, masks = head(nl)
@@ -367,8 +369,11 @@ def san_online_video_inference(decoder, adapter, features, mask_features, clip_b
         raise ValueError(f"num_clips={b} does not divide the {bt} frames of this call")
     t = bt // b
     biases = outputs["class_attn_biases"]
-    clip_feats = adapter.post_encode_image(clip_bk_feats, biases.flatten(0, 1))                 # san.py:230
-    logits = adapter.cal_sim_logits(text_feats, clip_feats).view(b, t, q, -1)                    # '(b t) q c -> b t q c'
+    if hasattr(adapter, "post_encode_logits"):                                                  # fused tail
+        logits = adapter.post_encode_logits(clip_bk_feats, biases.flatten(0, 1), text_feats).view(b, t, q, -1)
+    else:
+        clip_feats = adapter.post_encode_image(clip_bk_feats, biases.flatten(0, 1))             # san.py:230
+        logits = adapter.cal_sim_logits(text_feats, clip_feats).view(b, t, q, -1)                # '(b t) q c -> b t q c'
     embeds = outputs["pred_embeds"][0].view(b, t, q, -1)
     indices, _ = batch_video_match_via_embeds(embeds)                                            # minvis.py:322-323
     pm = outputs["pred_masks"][0]                                                                # [q, (b t), h, w]

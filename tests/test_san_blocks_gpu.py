@@ -58,3 +58,40 @@ def test_matches_oracle_full_queries(n, Q):
     f = m.post_encode_image((cls.cuda(), pix.cuda()), bias.cuda()).cpu()
     assert (f - f_ref).abs().max().item() < 3e-3
     assert torch.nn.functional.cosine_similarity(f, f_ref, dim=-1).min().item() > 0.9995
+
+
+@pytest.mark.parametrize("n,Q,K", [(3, 100, 1197), (2, 37, 41)])
+def test_fused_tail_logits(n, Q, K):
+    """Kernel 3 in its fused form (SideAdapterBlocks.post_encode_logits: ln_post on the strided SOS rows -> proj GEMM with
+    row sums of squares -> logits GEMM with the normalise + exp(logit_scale) epilogue, three launches) against the composed
+    reference calls post_encode_image + cal_sim_logits and against the oracle's fp32 tail."""
+    from oracle import decoder_ref as O
+    from openvis_b200.ov_head import ClipLogitHead
+    gen = torch.Generator().manual_seed(23)
+    P = seeded_clip_block_params(8)
+    ln_w, ln_b = 1 + 0.1 * torch.randn(768, generator=gen), 0.1 * torch.randn(768, generator=gen)
+    proj = torch.randn(768, 512, generator=gen) * 768 ** -0.5
+    cls = torch.randn(1, n, 768, generator=gen)
+    pix = torch.randn(n, 768, 14, 14, generator=gen)
+    bias = 3.0 * torch.randn(n, 12, Q, 24, 40, generator=gen)
+    text = torch.nn.functional.normalize(torch.randn(K, 512, generator=gen), dim=-1)
+    m = _module(Q, 8, ln_w, ln_b, proj)
+    feats = (cls.cuda(), pix.cuda())
+    n0 = L.launch_count()
+    fused = m.post_encode_logits(feats, bias.cuda(), text.cuda())
+    n_fused = L.launch_count() - n0
+    n0 = L.launch_count()
+    composed = m.cal_sim_logits(text.cuda(), m.post_encode_image(feats, bias.cuda()))
+    n_composed = L.launch_count() - n0
+    assert fused.shape == composed.shape == (n, Q, K)
+    assert n_fused < n_composed                            # tail: 3 launches instead of 5 + the torch copy of the SOS rows
+    assert (fused - composed).abs().max().item() < 2e-2    # |logit| <= 14.3
+    sos_ref = O.san_post_blocks(P, cls, pix, bias, Q)
+    _, ref = O.san_sos_tail(sos_ref, ln_w, ln_b, proj, text, m.tail.logit_scale_exp)
+    assert (fused.cpu() - ref).abs().max().item() < 4e-2
+    assert (fused.cpu().argmax(-1) == ref.argmax(-1)).float().mean().item() >= 0.99
+    # crop path (ClipAdapter.normalize + cal_sim_logits): the normalise-in-epilogue form against the oracle
+    f = 3.0 * torch.randn(n * Q, 512, generator=gen)
+    lg = ClipLogitHead().cal_sim_logits(text.cuda(), f.cuda(), 100, normalized=False).cpu()
+    want = O.ov_cosine_logits(f, text, 100.0)
+    assert (lg - want).abs().max().item() < 0.06

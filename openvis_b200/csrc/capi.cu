@@ -875,11 +875,12 @@ int ovis_xattn_plan_t(int G, int Q, int keys, int* use_t, int* splits, int* q_pa
   const int qtiles = (Q + 127) / 128;
   int chunks, chunk;
   xattn_t_chunks(G, Q, keys, sms, &chunks, &chunk);
-  // The transposed kernel pays one extra key tile per CTA (the reference pass): worth it from ~8 tiles per CTA on.
-  // OVIS_XATTN_T=0 disables it, =1 forces it wherever its limits allow (tests).
+  // The transposed kernel pays one extra key tile per CTA (the reference pass) and has its chunk count as a template
+  // parameter only for a single query tile: measured (profiles/xattn_t_ab_r2.txt) 1.3-1.4x over xattn_tc2 from ~100 key tiles
+  // per CTA, 1.0x at 30, 0.7x at 8, 0.96x for Q = 200 (two query tiles).  OVIS_XATTN_T=0 disables it, =1 forces it (tests).
   static const int force = getenv("OVIS_XATTN_T") ? atoi(getenv("OVIS_XATTN_T")) : -1;
   const int tiles_per_cta = chunk / X3_KT;
-  int use = tiles_per_cta >= 8 && xattn_variant() == 2;
+  int use = tiles_per_cta >= 24 && qtiles == 1 && xattn_variant() == 2;
   if (force == 0) use = 0;
   if (force == 1) use = 1;
   *use_t = use;

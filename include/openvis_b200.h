@@ -155,6 +155,28 @@ int ovis_mask_bits_t(const void* gt_f16, int groups, int rows_per_group, const v
 int ovis_xattn_t(const void* q_f16, const void* k_f16, const void* v_f16, const unsigned int* bits_t,
                  const unsigned int* blockand, const unsigned char* flags, int G, int Q, int q_stride, int keys,
                  int splits, float* o_part, float* ml_part, void* out_f16, int* stats, void* stream);
+/* Query-side chain (csrc/chain.cuh): the post-attention part of a decoder layer -- out-projection + LayerNorm,
+ * self-attention, FFN, decoder_norm, mask-embed MLP, the next layer's query projection (SelfAttentionLayer /
+ * CrossAttentionLayer / FFNLayer.forward_post, MLP: video_...decoder.py:52-62, 110-122, 175-179, 204-216) -- as ONE launch:
+ * a persistent CTA per group of Q <= 128 queries executes the phases in order on its own rows.  A chain is a handle holding
+ * `nphases` phases for G groups; phases are set once (same arguments as ovis_linear_f16 / ovis_linear_ln_f16 /
+ * ovis_self_attn, rows = G * Q implied; every operand must stay at its address), checked for completeness
+ * (ovis_chain_upload), then runs of at most 12 consecutive phases are launched: ovis_chain_run(handle, first, count,
+ * stream); the phases of a run travel as the launch's kernel parameter. */
+int ovis_chain_create(int nphases, int G, int Q, void** handle);
+int ovis_chain_set_linear(void* handle, int idx, const void* x_f16, int K, int ldx, const void* w_f16, int N,
+                          const float* bias, float scale, int relu, void* out, int ldo, int out_f32);
+int ovis_chain_set_linear_ln(void* handle, int idx, const void* x_f16, int K, const void* w_f16, const float* bias,
+                             const float* resid, const float* ln1_g, const float* ln1_b, const float* ln2_g,
+                             const float* ln2_b, const float* pe, int pe_period, float* y32, void* y16, void* ype16,
+                             float* d32, void* d16);
+int ovis_chain_set_self_attn(void* handle, int idx, const void* qk_f16, const void* v_f16, void* out_f16);
+int ovis_chain_upload(void* handle);
+int ovis_chain_run(void* handle, int first, int count, void* stream);
+/* profiling only: as ovis_chain_run; group 0's CTA also writes its SM cycle counter at the start of every phase and at the
+ * end into trace[0 .. count] (device memory, int64) */
+int ovis_chain_run_traced(void* handle, int first, int count, long long* trace, void* stream);
+int ovis_chain_destroy(void* handle);
 /* Unmasked self-attention over the Q queries (SelfAttentionLayer.forward_post, video_...decoder.py:52-62).
  * qk [G*Q][512] f16 (q | k, biased, unscaled), v [G*Q][256] f16 -> out [G*Q][256] f16.  Q <= 1536 rows per group
  * (the decoders use Q <= 256 queries; the temporal resampler attends over the frames of a clip, resampler.py:258-262). */

@@ -45,6 +45,14 @@ SIGNATURES = {
                                    ctypes.POINTER(_c_ll), ctypes.POINTER(_c_ll)]),
     "ovis_mask_bits_t": (_c_int, [_vp, _c_int, _c_int, _vp, _c_int, _vp, _vp, _vp, _c_int, _vp]),
     "ovis_xattn_t": (_c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp]),
+    "ovis_chain_create": (_c_int, [_c_int, _c_int, _c_int, ctypes.POINTER(_vp)]),
+    "ovis_chain_set_linear": (_c_int, [_vp, _c_int, _vp, _c_int, _c_int, _vp, _c_int, _vp, _c_float, _c_int, _vp, _c_int, _c_int]),
+    "ovis_chain_set_linear_ln": (_c_int, [_vp, _c_int, _vp, _c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _c_int, _vp, _vp, _vp, _vp, _vp]),
+    "ovis_chain_set_self_attn": (_c_int, [_vp, _c_int, _vp, _vp, _vp]),
+    "ovis_chain_upload": (_c_int, [_vp]),
+    "ovis_chain_run": (_c_int, [_vp, _c_int, _c_int, _vp]),
+    "ovis_chain_run_traced": (_c_int, [_vp, _c_int, _c_int, _vp, _vp]),
+    "ovis_chain_destroy": (_c_int, [_vp]),
     "ovis_self_attn": (_c_int, [_vp, _vp, _vp, _c_int, _c_int, _vp]),
     "ovis_clip_aggregate": (_c_int, [_vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _vp]),
     "ovis_ms_deform_attn_forward": (_c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
@@ -395,6 +403,61 @@ def xattn(q, k, v, bits, flags, G, Q, q_stride, keys, splits, o_part, ml_part, o
     lib = load()
     _check(lib.ovis_xattn(_p(q), _p(k), _p(v), _p(bits), _p(flags), G, Q, q_stride, keys, splits, _p(o_part),
                           _p(ml_part), _p(out), _stream()))
+
+
+class Chain:
+    """Query-side chain (csrc/chain.cuh): phases set once on fixed operands, then runs of consecutive phases are single
+    launches (one persistent CTA per group of Q <= 128 query rows)."""
+
+    def __init__(self, nphases, G, Q):
+        self._lib = load()
+        h = _vp()
+        _check(self._lib.ovis_chain_create(int(nphases), int(G), int(Q), ctypes.byref(h)))
+        self._h = h
+        self._keep = []              # operands must stay where they are for the life of the chain
+
+    def set_linear(self, idx, x, w, bias, out, scale=1.0, relu=False, out_f32=False):
+        assert x.dtype == torch.float16 and w.dtype == torch.float16 and x.stride(-1) == 1 and w.is_contiguous()
+        self._keep += [x, w, bias, out]
+        _check(self._lib.ovis_chain_set_linear(self._h, idx, _p(x), x.shape[1], x.stride(0), _p(w), w.shape[0], _p(bias), float(scale),
+                                               int(relu), _p(out), out.stride(0), int(out_f32)))
+
+    def set_linear_ln(self, idx, x, w, bias, resid, ln1, ln2=None, pe=None, y32=None, y16=None, ype16=None, d32=None, d16=None):
+        self._keep += [x, w, bias, resid, ln1, ln2, pe, y32, y16, ype16, d32, d16]
+        _check(self._lib.ovis_chain_set_linear_ln(self._h, idx, _p(x), x.shape[1], _p(w), _p(bias), _p(resid), _p(ln1[0]), _p(ln1[1]),
+                                                  _p(ln2[0]) if ln2 else None, _p(ln2[1]) if ln2 else None, _p(pe),
+                                                  pe.shape[0] if pe is not None else 0, _p(y32), _p(y16), _p(ype16), _p(d32), _p(d16)))
+
+    def set_self_attn(self, idx, qk, v, out):
+        self._keep += [qk, v, out]
+        _check(self._lib.ovis_chain_set_self_attn(self._h, idx, _p(qk), _p(v), _p(out)))
+
+    def upload(self):
+        _check(self._lib.ovis_chain_upload(self._h))
+
+    def run(self, first, count):
+        prof = PROFILE
+        if prof is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        _check(self._lib.ovis_chain_run(self._h, int(first), int(count), _stream()))
+        if prof is not None:
+            e1.record()
+            prof.append(("query_side", e0, e1))
+
+    def run_traced(self, first, count):
+        """profiling: SM cycles at the start of each phase and at the end, for group 0's CTA -> int64 tensor (first count + 1 entries)"""
+        tr = torch.zeros(66 + 8000, dtype=torch.int64, device="cuda")     # [count + 1] phase starts; [64] event counter, events
+        _check(self._lib.ovis_chain_run_traced(self._h, int(first), int(count), _p(tr), _stream()))
+        return tr
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                self._lib.ovis_chain_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
 
 
 def xattn_kernel_name():

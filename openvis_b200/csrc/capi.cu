@@ -16,6 +16,8 @@
 #include "xattn_tc.cuh"
 #include "xattn_tc2.cuh"
 #include "xattn_tc3.cuh"
+#include "chain.cuh"
+#include <vector>
 #include "san_attn.cuh"
 #include "postproc.cuh"
 #include "msda.cuh"
@@ -167,6 +169,29 @@ int make_map_4d(CUtensorMap* m, const void* base, int f32, const unsigned long l
   return OVIS_OK;
 }
 
+// Launch helper of the kernels that execute griddepcontrol.wait before their first global access (ptx.cuh: pdl_begin).
+// OVIS_PDL=1 adds the programmatic-stream-serialization attribute.  Off by default: measured on the five bench workloads
+// it changes nothing (profiles/experiments/chain_r2.md) -- the dependent query-side kernels are bound by their own
+// load -> MMA -> epilogue latency chain (8 us for one 128 x 256 x 256 tile), not by the launch gap.
+static bool pdl_enabled() {
+  static const bool on = getenv("OVIS_PDL") && !strcmp(getenv("OVIS_PDL"), "1");
+  return on;
+}
+template <typename... KArgs, typename... Args>
+static void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);     // (errors surface in check_launch)
+}
+
 void init_args(GemmArgs& a) {
   memset(&a, 0, sizeof(a));
   a.num_groups = 1;
@@ -199,7 +224,7 @@ int launch_gemm_bn(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensor
   const long long total = (long long)a.num_groups * m_tiles * n_tiles;
   if (total <= 0) return OVIS_OK;
   const int grid = (int)(total < sms ? total : sms);
-  gemm_tn_kernel<BN><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(ta, ta2, tb, om, a);
+  launch_k(gemm_tn_kernel<BN>, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, ta, ta2, tb, om, a);
   return check_launch("gemm_tn_kernel");
 }
 
@@ -441,7 +466,7 @@ int ovis_init_queries(const float* qf, const float* qe, const float* g, const fl
   CHECK_ARG(qf && qe && g && b && z32 && z16 && ze16 && d32 && d16 && Q > 0 && rows > 0, "bad arguments");
   int rc = device_info(nullptr);
   if (rc) return rc;
-  init_queries_kernel<<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(qf, qe, g, b, z32, (__half*)z16, (__half*)ze16, d32,
+  launch_k(init_queries_kernel, dim3((rows + 7) / 8), dim3(256), 0, (cudaStream_t)stream, qf, qe, g, b, z32, (__half*)z16, (__half*)ze16, d32,
                                                                         (__half*)d16, Q, rows);
   return check_launch("init_queries_kernel");
 }
@@ -589,7 +614,7 @@ int ovis_linear_ln_f16(const void* x, long long rows, int K, const void* w, cons
     r.pe = pe; r.pe_period = pe_period > 0 ? pe_period : 1;
     r.y32 = y32; r.y16 = (__half*)y16; r.ype16 = (__half*)ype16; r.d32 = d32; r.d16 = (__half*)d16;
     r.rows = (int)rows;
-    ln_reduce_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(r);
+    launch_k(ln_reduce_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, (cudaStream_t)stream, r);
     return check_launch("ln_reduce_kernel");
   }
   a.rows_per_group = (int)rows;
@@ -828,14 +853,14 @@ int ovis_xattn(const void* q, const void* k, const void* v, const unsigned int* 
       const int map_words = (tiles + 31) / 32;
       if (skip_on && map_words <= X2_MAP_WORDS && (tiles + chunks - 1) / chunks <= X2_LIST_MAX) {
         uint32_t* map = reinterpret_cast<uint32_t*>(ml_part + (long long)G * splits * 8 * q_pad * 2);
-        xattn_skipmap_kernel<<<dim3(map_words, qtiles, G), 128, 0, (cudaStream_t)stream>>>(bits, flags, map, Q, q_stride, keys,
+        launch_k(xattn_skipmap_kernel, dim3(dim3(map_words, qtiles, G)), dim3(128), 0, (cudaStream_t)stream, bits, flags, map, Q, q_stride, keys,
                                                                                            a.W, X2_MAP_WORDS);
         rc = check_launch("xattn_skipmap_kernel");
         if (rc) return rc;
         a.skipmap = map;
         a.map_words = X2_MAP_WORDS;
       }
-      xattn_tc2_kernel<<<dim3(chunks * 4, qtiles, G), X2_THREADS, X2_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, a);
+      launch_k(xattn_tc2_kernel, dim3(dim3(chunks * 4, qtiles, G)), dim3(X2_THREADS), X2_SMEM, (cudaStream_t)stream, tq, tk, tv, a);
       rc = check_launch("xattn_tc2_kernel");
     } else {
       xattn_tc_kernel<<<dim3(splits, qtiles, G), XT_THREADS, XT_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, a);
@@ -848,11 +873,11 @@ int ovis_xattn(const void* q, const void* k, const void* v, const unsigned int* 
   if (splits <= 8) {
     // Frame decoders (a few hundred keys per group): 2-8 partials per row, one thread per output element pair
     const long long total = (long long)G * Q * 128;
-    xattn_combine_few_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(o_part, ml_part, (__half*)out, Q,
+    launch_k(xattn_combine_few_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, o_part, ml_part, (__half*)out, Q,
                                                                                                 q_pad, splits, total);
     return check_launch("xattn_combine_few_kernel");
   }
-  xattn_combine_kernel<<<dim3(Q, 8, G), 256, 0, (cudaStream_t)stream>>>(o_part, ml_part, (__half*)out, Q, q_pad, splits);
+  launch_k(xattn_combine_kernel, dim3(dim3(Q, 8, G)), dim3(256), 0, (cudaStream_t)stream, o_part, ml_part, (__half*)out, Q, q_pad, splits);
   return check_launch("xattn_combine_kernel");
 }
 
@@ -937,7 +962,7 @@ int ovis_xattn_t(const void* q, const void* k, const void* v, const unsigned int
   const int map_words = (tiles + 31) / 32;
   if (skip_on && blockand && map_words <= X3_MAP_WORDS && (tiles + splits - 1) / splits <= X3_LIST_MAX) {
     uint32_t* map = reinterpret_cast<uint32_t*>(ml_part + (long long)G * splits * 8 * q_pad * 2);
-    xattn_t3_skipmap_kernel<<<dim3(map_words, qtiles, G), 32, 0, (cudaStream_t)stream>>>(blockand, flags, map, Q, q_stride, a.qw, keys,
+    launch_k(xattn_t3_skipmap_kernel, dim3(dim3(map_words, qtiles, G)), dim3(32), 0, (cudaStream_t)stream, blockand, flags, map, Q, q_stride, a.qw, keys,
                                                                                          (keys + 31) / 32, X3_MAP_WORDS);
     rc = check_launch("xattn_t3_skipmap_kernel");
     if (rc) return rc;
@@ -948,20 +973,149 @@ int ovis_xattn_t(const void* q, const void* k, const void* v, const unsigned int
   const int nq_last = Q - (qtiles - 1) * 128;
   const int nch = qtiles == 1 ? ((nq_last + 15) >> 4) : 0;
   const dim3 grid(splits * 4, qtiles, G);
-  if (nch == 7) xattn_tc3_kernel<7><<<grid, X3_THREADS, X3_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, a);
-  else if (nch == 8) xattn_tc3_kernel<8><<<grid, X3_THREADS, X3_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, a);
-  else if (nch == 5) xattn_tc3_kernel<5><<<grid, X3_THREADS, X3_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, a);
-  else xattn_tc3_kernel<0><<<grid, X3_THREADS, X3_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, a);
+  if (nch == 7) launch_k(xattn_tc3_kernel<7>, dim3(grid), dim3(X3_THREADS), X3_SMEM, (cudaStream_t)stream, tq, tk, tv, a);
+  else if (nch == 8) launch_k(xattn_tc3_kernel<8>, dim3(grid), dim3(X3_THREADS), X3_SMEM, (cudaStream_t)stream, tq, tk, tv, a);
+  else if (nch == 5) launch_k(xattn_tc3_kernel<5>, dim3(grid), dim3(X3_THREADS), X3_SMEM, (cudaStream_t)stream, tq, tk, tv, a);
+  else launch_k(xattn_tc3_kernel<0>, dim3(grid), dim3(X3_THREADS), X3_SMEM, (cudaStream_t)stream, tq, tk, tv, a);
   rc = check_launch("xattn_tc3_kernel");
   if (rc) return rc;
   if (splits <= 8) {
     const long long total = (long long)G * Q * 128;
-    xattn_combine_few_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(o_part, ml_part, (__half*)out, Q,
+    launch_k(xattn_combine_few_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, o_part, ml_part, (__half*)out, Q,
                                                                                                 q_pad, splits, total);
     return check_launch("xattn_combine_few_kernel");
   }
-  xattn_combine_kernel<<<dim3(Q, 8, G), 256, 0, (cudaStream_t)stream>>>(o_part, ml_part, (__half*)out, Q, q_pad, splits);
+  launch_k(xattn_combine_kernel, dim3(dim3(Q, 8, G)), dim3(256), 0, (cudaStream_t)stream, o_part, ml_part, (__half*)out, Q, q_pad, splits);
   return check_launch("xattn_combine_kernel");
+}
+
+// ---- query-side chain (chain.cuh): a list of phases executed by one persistent CTA per group
+struct OvisChain {
+  std::vector<ChainPhase> host;
+  int Q = 0, G = 0;
+  bool checked = false;
+};
+
+int ovis_chain_create(int nphases, int G, int Q, void** handle) {
+  CHECK_ARG(nphases > 0 && G > 0 && Q > 0 && Q <= 128 && handle, "bad arguments (at most 128 queries per group)");
+  int rc = device_info(nullptr);
+  if (rc) return rc;
+  OvisChain* c = new OvisChain();
+  c->host.resize(nphases);
+  memset(static_cast<void*>(c->host.data()), 0, sizeof(ChainPhase) * nphases);
+  for (auto& p : c->host) p.kind = -1;
+  c->Q = Q; c->G = G;
+  *handle = c;
+  return OVIS_OK;
+}
+
+static int chain_maps(OvisChain* c, ChainPhase& p, const void* x, int K, int ldx, const void* w, int N) {
+  int rc = make_map_f16(&p.tmA, x, (unsigned long long)c->G * c->Q, (unsigned long long)K, (unsigned long long)ldx, 128);
+  if (rc) return rc;
+  return make_map_f16(&p.tmB, w, (unsigned long long)N, (unsigned long long)K, (unsigned long long)K, 256);
+}
+
+int ovis_chain_set_linear(void* handle, int idx, const void* x, int K, int ldx, const void* w, int N, const float* bias, float scale,
+                          int relu, void* out, int ldo, int out_f32) {
+  OvisChain* c = static_cast<OvisChain*>(handle);
+  CHECK_ARG(c && idx >= 0 && idx < (int)c->host.size() && x && w && out && K > 0 && K % 64 == 0 && N > 0 && ldx >= K && ldo >= N,
+            "bad arguments");
+  CHECK_ARG((N + 255) / 256 <= GEMM_MAX_NTILES, "N too large");
+  ChainPhase& p = c->host[idx];
+  GemmArgs& a = p.args;
+  init_args(a);
+  a.rows_per_group = c->Q; a.num_groups = c->G; a.a_group_stride = c->Q;
+  a.N = N; a.K = K; a.epi = EPI_STORE;
+  for (int t = 0; t < (N + 255) / 256; ++t) {
+    a.out[t] = out_f32 ? (void*)((float*)out + (long long)t * 256) : (void*)((__half*)out + (long long)t * 256);
+    a.bias[t] = bias ? bias + (long long)t * 256 : nullptr;
+  }
+  a.ldo = ldo; a.out_f32 = out_f32; a.relu = relu; a.scale = scale;
+  p.kind = 0;
+  c->checked = false;
+  return chain_maps(c, p, x, K, ldx, w, N);
+}
+
+int ovis_chain_set_linear_ln(void* handle, int idx, const void* x, int K, const void* w, const float* bias, const float* resid,
+                             const float* ln1_g, const float* ln1_b, const float* ln2_g, const float* ln2_b, const float* pe,
+                             int pe_period, float* y32, void* y16, void* ype16, float* d32, void* d16) {
+  OvisChain* c = static_cast<OvisChain*>(handle);
+  CHECK_ARG(c && idx >= 0 && idx < (int)c->host.size() && x && w && bias && resid && ln1_g && ln1_b && K > 0 && K % 64 == 0,
+            "bad arguments");
+  CHECK_ARG((ln2_g == nullptr) == (ln2_b == nullptr) && (!ype16 || (pe && pe_period > 0)), "bad LayerNorm arguments");
+  ChainPhase& p = c->host[idx];
+  GemmArgs& a = p.args;
+  init_args(a);
+  a.rows_per_group = c->Q; a.num_groups = c->G; a.a_group_stride = c->Q;
+  a.N = 256; a.K = K; a.epi = EPI_LN;
+  a.bias[0] = bias; a.resid = resid;
+  a.ln1_g = ln1_g; a.ln1_b = ln1_b; a.ln2_g = ln2_g; a.ln2_b = ln2_b;
+  a.pe = pe; a.pe_period = pe_period > 0 ? pe_period : 1;
+  a.y32 = y32; a.y16 = (__half*)y16; a.ype16 = (__half*)ype16; a.d32 = d32; a.d16 = (__half*)d16;
+  p.kind = 0;
+  c->checked = false;
+  return chain_maps(c, p, x, K, K, w, 256);
+}
+
+int ovis_chain_set_self_attn(void* handle, int idx, const void* qk, const void* v, void* out) {
+  OvisChain* c = static_cast<OvisChain*>(handle);
+  CHECK_ARG(c && idx >= 0 && idx < (int)c->host.size() && qk && v && out, "bad arguments");
+  ChainPhase& p = c->host[idx];
+  p.sa.qk = (const __half*)qk; p.sa.v = (const __half*)v; p.sa.out = (__half*)out; p.sa.Q = c->Q;
+  p.sa.scale_log2 = 0.17677669529663687f * 1.4426950408889634f;   // 32^-1/2 * log2(e)
+  p.kind = 1;
+  c->checked = false;
+  return OVIS_OK;
+}
+
+static int chain_run(void* handle, int first, int count, long long* trace, void* stream);
+
+int ovis_chain_run(void* handle, int first, int count, void* stream) { return chain_run(handle, first, count, nullptr, stream); }
+
+int ovis_chain_run_traced(void* handle, int first, int count, long long* trace, void* stream) {
+  CHECK_ARG(trace, "bad arguments");
+  return chain_run(handle, first, count, trace, stream);
+}
+
+static int chain_run(void* handle, int first, int count, long long* trace, void* stream) {
+  OvisChain* c = static_cast<OvisChain*>(handle);
+  CHECK_ARG(c && first >= 0 && count > 0 && first + count <= (int)c->host.size(), "bad arguments");
+  int sms = 148;
+  int rc = device_info(&sms);
+  if (rc) return rc;
+  if (!c->checked) {
+    for (auto& p : c->host) CHECK_ARG(p.kind >= 0, "a phase of the chain has not been set");
+    c->checked = true;
+  }
+  static bool attr_done[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_done[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CHAIN_SMEM);
+    if (e != cudaSuccess) return fail(OVIS_ERR_CUDA, "%s: cannot raise the shared-memory limit", "gemm_chain_kernel");
+    attr_done[dev] = true;
+  }
+  const int grid = c->G < sms ? c->G : sms;
+  CHECK_ARG(count <= CHAIN_MAX_PHASES, "too many phases in one launch");
+  ChainLaunch cl;                                  // (copied into the launch by cudaLaunchKernel before it returns)
+  memcpy(static_cast<void*>(cl.ph), c->host.data() + first, sizeof(ChainPhase) * count);
+  launch_k(gemm_chain_kernel, dim3(grid), dim3(320), CHAIN_SMEM, (cudaStream_t)stream, cl, count, c->G, trace);
+  return check_launch("gemm_chain_kernel");
+}
+
+int ovis_chain_upload(void* handle) {
+  OvisChain* c = static_cast<OvisChain*>(handle);
+  CHECK_ARG(c, "bad arguments");
+  for (auto& p : c->host) CHECK_ARG(p.kind >= 0, "a phase of the chain has not been set");
+  c->checked = true;
+  return OVIS_OK;
+}
+
+int ovis_chain_destroy(void* handle) {
+  OvisChain* c = static_cast<OvisChain*>(handle);
+  if (!c) return OVIS_OK;
+  delete c;
+  return OVIS_OK;
 }
 
 int ovis_self_attn(const void* qk, const void* v, void* out, int G, int Q, void* stream) {
@@ -985,7 +1139,7 @@ int ovis_self_attn(const void* qk, const void* v, void* out, int G, int Q, void*
         attr_done[dev] = true;
       }
     }
-    self_attn_mma_kernel<<<dim3(8, G), 256, smem, (cudaStream_t)stream>>>(a);
+    launch_k(self_attn_mma_kernel, dim3(dim3(8, G)), dim3(256), smem, (cudaStream_t)stream, a);
     return check_launch("self_attn_mma_kernel");
   }
   const size_t smem = (size_t)Q * 32 * 2 * sizeof(__half);      // K and V of one head: 128 B per row

@@ -20,6 +20,13 @@ enum GemmEpi : int {
   EPI_SIGNBITS_T = 4, // key-major sign bits for xattn_tc3: bits_t[g][r][col/32] bit col%32 = (acc < 0), flags, 32-key block ANDs
 };
 
+#ifdef OVIS_CHAIN_EVTRACE
+__device__ long long* g_ev_base = nullptr;    // profiling builds: event slots of the tile being finished by warp 2 (chain.cuh)
+#define EPI_EV(sub) do { if (warp == 2 && lane == 0 && blockIdx.x == 0 && g_ev_base) g_ev_base[(sub)] = clock64(); } while (0)
+#else
+#define EPI_EV(sub) do {} while (0)
+#endif
+
 constexpr int GEMM_MAX_NTILES = 16;
 constexpr int GEMM_MAX_OUT_MAPS = 16;
 
@@ -123,45 +130,107 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmArgs& args, const C
                                                  : (long long)(g / args.a_row_div) * args.a_group_stride) + r_warp0;
     const bool vec_ok = (((long long)args.ldo * esize) & 15) == 0;
     const bool bias_vec = bias && ((reinterpret_cast<uintptr_t>(bias) & 15) == 0);
-    // Fast path for the HBM-heavy plain projections (K/V projection, in-projections): fp16 output, vector bias, no
-    // scale / activation / residual, full column tile, bulk tensor store.  The generic code below handles every
-    // combination at run time and costs ~30 instructions per element, which made these GEMMs epilogue-issue-bound.
-    if (args.tma_store && !args.out_f32 && args.relu == 0 && args.scale == 1.f && args.resid_st == nullptr && bias_vec &&
-        !args.row_ss_in && !args.row_ss_out && col_base + BN <= args.N) {
+    // Lean path for full column tiles (every GEMM of the decoder): vector bias or none, optional scale / ReLU, fp16 or fp32
+    // output, bulk tensor store or row-coalesced stores.  The generic code below handles ragged tiles, residuals, row
+    // scales and QuickGELU at run time and costs ~30 instructions per element: 8000 cycles per 128 x 256 tile, which made
+    // the HBM-heavy projections epilogue-issue-bound and every small query-side GEMM a 4 us epilogue.
+    if (args.relu <= 1 && args.resid_st == nullptr && !args.row_ss_in && !args.row_ss_out && (bias == nullptr || bias_vec) &&
+        col_base + BN <= args.N && (args.tma_store || vec_ok)) {
+      const bool do_scale = args.scale != 1.f;
+      const float scale = args.scale;
+      const bool do_relu = args.relu == 1;
+      const long long row_bytes = (long long)args.ldo * esize;
+      char* const obase_w = reinterpret_cast<char*>(args.out[nt]) + (grow0 + (lane >> 3)) * row_bytes + (lane & 7) * 16;
+      const int rows_left = args.rows_per_group - r_warp0 - (lane >> 3);      // this lane stores rows it*4 + (lane >> 3)
 #pragma unroll 1
-      for (int u0 = half * (BN / 2); u0 < (half + 1) * (BN / 2); u0 += 64) {
+      for (int u0 = half * (BN / 2); u0 < (half + 1) * (BN / 2); u0 += cols_per_unit) {
         uint32_t va[32], vb[32];
         tmem_ld_32x32_raw(t_acc + u0, va);
-        tmem_ld_32x32_raw(t_acc + u0 + 32, vb);
+        if (!args.out_f32) tmem_ld_32x32_raw(t_acc + u0 + 32, vb);
         tmem_ld_wait();
         reg_fence32(va);
-        reg_fence32(vb);
-        uint4 pk[8];
+        if (!args.out_f32) reg_fence32(vb);
+        EPI_EV(1 + 4 * ((u0 / cols_per_unit) & 1));
+        if (bias) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + u0 + 8 * j));
-          const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + u0 + 8 * j + 4));
-          pk[j] = make_uint4(pack_half2(__uint_as_float(va[8 * j]) + b0.x, __uint_as_float(va[8 * j + 1]) + b0.y),
-                             pack_half2(__uint_as_float(va[8 * j + 2]) + b0.z, __uint_as_float(va[8 * j + 3]) + b0.w),
-                             pack_half2(__uint_as_float(va[8 * j + 4]) + b1.x, __uint_as_float(va[8 * j + 5]) + b1.y),
-                             pack_half2(__uint_as_float(va[8 * j + 6]) + b1.z, __uint_as_float(va[8 * j + 7]) + b1.w));
-          const float4 c0 = __ldg(reinterpret_cast<const float4*>(bias + u0 + 32 + 8 * j));
-          const float4 c1 = __ldg(reinterpret_cast<const float4*>(bias + u0 + 32 + 8 * j + 4));
-          pk[4 + j] = make_uint4(pack_half2(__uint_as_float(vb[8 * j]) + c0.x, __uint_as_float(vb[8 * j + 1]) + c0.y),
-                                 pack_half2(__uint_as_float(vb[8 * j + 2]) + c0.z, __uint_as_float(vb[8 * j + 3]) + c0.w),
-                                 pack_half2(__uint_as_float(vb[8 * j + 4]) + c1.x, __uint_as_float(vb[8 * j + 5]) + c1.y),
-                                 pack_half2(__uint_as_float(vb[8 * j + 6]) + c1.z, __uint_as_float(vb[8 * j + 7]) + c1.w));
+          for (int j = 0; j < 8; ++j) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + u0 + 4 * j));
+            va[4 * j] = __float_as_uint(__uint_as_float(va[4 * j]) + b0.x);
+            va[4 * j + 1] = __float_as_uint(__uint_as_float(va[4 * j + 1]) + b0.y);
+            va[4 * j + 2] = __float_as_uint(__uint_as_float(va[4 * j + 2]) + b0.z);
+            va[4 * j + 3] = __float_as_uint(__uint_as_float(va[4 * j + 3]) + b0.w);
+          }
+          if (!args.out_f32) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + u0 + 32 + 4 * j));
+              vb[4 * j] = __float_as_uint(__uint_as_float(vb[4 * j]) + b0.x);
+              vb[4 * j + 1] = __float_as_uint(__uint_as_float(vb[4 * j + 1]) + b0.y);
+              vb[4 * j + 2] = __float_as_uint(__uint_as_float(vb[4 * j + 2]) + b0.z);
+              vb[4 * j + 3] = __float_as_uint(__uint_as_float(vb[4 * j + 3]) + b0.w);
+            }
+          }
         }
-        if (lane == 0) tma_store_wait_read0();           // the previous unit's bulk store has read the staging buffer
-        __syncwarp();
+        if (do_scale) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) va[j] = __float_as_uint(__uint_as_float(va[j]) * scale);
+          if (!args.out_f32) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) vb[j] = __float_as_uint(__uint_as_float(vb[j]) * scale);
+          }
+        }
+        if (do_relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) va[j] = __float_as_uint(fmaxf(__uint_as_float(va[j]), 0.f));
+          if (!args.out_f32) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) vb[j] = __float_as_uint(fmaxf(__uint_as_float(vb[j]), 0.f));
+          }
+        }
+        uint4 pk[8];
+        if (args.out_f32) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) pk[j] = make_uint4(va[4 * j], va[4 * j + 1], va[4 * j + 2], va[4 * j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            pk[j] = make_uint4(pack_half2(__uint_as_float(va[8 * j]), __uint_as_float(va[8 * j + 1])),
+                               pack_half2(__uint_as_float(va[8 * j + 2]), __uint_as_float(va[8 * j + 3])),
+                               pack_half2(__uint_as_float(va[8 * j + 4]), __uint_as_float(va[8 * j + 5])),
+                               pack_half2(__uint_as_float(va[8 * j + 6]), __uint_as_float(va[8 * j + 7])));
+            pk[4 + j] = make_uint4(pack_half2(__uint_as_float(vb[8 * j]), __uint_as_float(vb[8 * j + 1])),
+                                   pack_half2(__uint_as_float(vb[8 * j + 2]), __uint_as_float(vb[8 * j + 3])),
+                                   pack_half2(__uint_as_float(vb[8 * j + 4]), __uint_as_float(vb[8 * j + 5])),
+                                   pack_half2(__uint_as_float(vb[8 * j + 6]), __uint_as_float(vb[8 * j + 7])));
+          }
+        }
+        EPI_EV(2 + 4 * ((u0 / cols_per_unit) & 1));
+        if (args.tma_store) {
+          if (lane == 0) tma_store_wait_read0();           // the previous unit's bulk store has read the staging buffer
+          __syncwarp();
+        }
 #pragma unroll
         for (int c = 0; c < 8; ++c) st_shared_v4(stg + (uint32_t)((lane * 8 + (c ^ (lane & 7))) << 4), pk[c]);
-        fence_async_proxy();
-        __syncwarp();
-        if (lane == 0) {
-          tma_store_2d(&omaps[nt], stage_smem + (warp - 2) * 4096, u0, (int)grow0);
-          tma_store_commit();
+        EPI_EV(3 + 4 * ((u0 / cols_per_unit) & 1));
+        if (args.tma_store) {
+          fence_async_proxy();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&omaps[nt], stage_smem + (warp - 2) * 4096, u0, (int)grow0);
+            tma_store_commit();
+          }
+        } else {
+          __syncwarp();
+          char* o = obase_w + (long long)u0 * esize;
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int row = it * 4 + (lane >> 3), c = lane & 7;
+            const uint4 val = ld_shared_v4(stg + (uint32_t)((row * 8 + (c ^ (row & 7))) << 4));
+            if (it * 4 < rows_left) *reinterpret_cast<uint4*>(o + it * 4 * row_bytes) = val;
+          }
+          __syncwarp();
         }
+        EPI_EV(4 + 4 * ((u0 / cols_per_unit) & 1));
       }
       return;
     }
@@ -326,7 +395,8 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmArgs& args, const C
       tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
-        float4 rr = row_ok ? __ldg(reinterpret_cast<const float4*>(res + c * 32 + j)) : make_float4(0, 0, 0, 0);
+        // (__ldcg: inside the query-side chain kernel the residual stream was written earlier by the same kernel)
+        float4 rr = row_ok ? __ldcg(reinterpret_cast<const float4*>(res + c * 32 + j)) : make_float4(0, 0, 0, 0);
         float a0 = __uint_as_float(v[j]) + __ldg(bias + c * 32 + j) + rr.x;
         float a1 = __uint_as_float(v[j + 1]) + __ldg(bias + c * 32 + j + 1) + rr.y;
         float a2 = __uint_as_float(v[j + 2]) + __ldg(bias + c * 32 + j + 2) + rr.z;
@@ -610,6 +680,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_begin();   // (the prologue above overlapped the previous kernel's tail; no global read before this point)
   const uint32_t tmem_base = *tmem_holder;
 
   if (warp == 0) {

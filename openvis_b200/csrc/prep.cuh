@@ -151,6 +151,7 @@ __global__ void __launch_bounds__(256)
 init_queries_kernel(const float* __restrict__ qfeat, const float* __restrict__ qembed, const float* __restrict__ g,
                     const float* __restrict__ bta, float* __restrict__ z32, __half* __restrict__ z16,
                     __half* __restrict__ ze16, float* __restrict__ d32, __half* __restrict__ d16, int Q, int rows) {
+  pdl_begin();   // programmatic dependent launch: scheduled while the previous kernel drains, reads nothing before this
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -201,6 +202,7 @@ struct LnReduceArgs {
 
 __global__ void __launch_bounds__(256)
 ln_reduce_kernel(const LnReduceArgs a) {
+  pdl_begin();   // programmatic dependent launch: scheduled while the previous kernel drains, reads nothing before this
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= a.rows) return;

@@ -89,6 +89,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// Kernels of the query-side chain are 5-15 us each and strictly dependent: launched with the
+// programmatic-stream-serialization attribute (capi.cu: launch_k, OVIS_PDL=1), kernel N+1 is scheduled and runs its
+// prologue as soon as every CTA of kernel N has executed launch_dependents, then blocks here until kernel N has completed
+// and flushed.  Without the launch attribute (the default) both instructions are no-ops.
+__device__ __forceinline__ void pdl_begin() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

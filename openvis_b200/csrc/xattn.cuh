@@ -245,6 +245,7 @@ xattn_split_kernel(const XattnArgs a) {
 __global__ void __launch_bounds__(256)
 xattn_combine_kernel(const float* __restrict__ o_part, const float* __restrict__ ml_part, __half* __restrict__ out,
                      int Q, int q_pad, int splits) {
+  pdl_begin();   // programmatic dependent launch: scheduled while the previous kernel drains, reads nothing before this
   __shared__ float sm_m[8], sm_den[8], sm_num[8][32];
   const int q = blockIdx.x, h = blockIdx.y, g = blockIdx.z;
   const int d = threadIdx.x & 31, sl = threadIdx.x >> 5;
@@ -284,6 +285,7 @@ xattn_combine_kernel(const float* __restrict__ o_part, const float* __restrict__
 __global__ void __launch_bounds__(256)
 xattn_combine_few_kernel(const float* __restrict__ o_part, const float* __restrict__ ml_part, __half* __restrict__ out,
                          int Q, int q_pad, int splits, long long total) {
+  pdl_begin();   // programmatic dependent launch: scheduled while the previous kernel drains, reads nothing before this
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;       // ((g * Q + q) * 8 + h) * 16 + d2
   if (e >= total) return;
   const int d2 = (int)(e & 15), h = (int)((e >> 4) & 7);
@@ -415,6 +417,7 @@ self_attn_kernel(const SelfAttnArgs a) {
 constexpr int SA_KB = 64;
 __global__ void __launch_bounds__(256)
 self_attn_mma_kernel(const SelfAttnArgs a) {
+  pdl_begin();   // programmatic dependent launch: scheduled while the previous kernel drains, reads nothing before this
   extern __shared__ __align__(16) __half sm_sa[];          // K [Qp][XA_LD], V [Qp][XA_LD]; Qp = Q rounded up to 64
   const int Q = a.Q;
   const int Qp = (Q + SA_KB - 1) / SA_KB * SA_KB;

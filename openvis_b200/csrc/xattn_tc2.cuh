@@ -56,6 +56,7 @@ constexpr int X2_THREADS = 19 * 32;
 __global__ void __launch_bounds__(128)
 xattn_skipmap_kernel(const uint32_t* __restrict__ bits, const unsigned char* __restrict__ flags, uint32_t* __restrict__ map,
                      int Q, int q_stride, int keys, int W, int map_words) {
+  pdl_begin();   // programmatic dependent launch: scheduled while the previous kernel drains, reads nothing before this
   __shared__ uint32_t s_and[4];
   const int wi = blockIdx.x, qt = blockIdx.y, g = blockIdx.z;
   const int q = qt * 128 + threadIdx.x;
@@ -96,6 +97,7 @@ xattn_skipmap_kernel(const uint32_t* __restrict__ bits, const unsigned char* __r
 __global__ void __launch_bounds__(X2_THREADS, 1)
 xattn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const XattnTcArgs a) {
+  pdl_begin();   // programmatic dependent launch: scheduled while the previous kernel drains, reads nothing before this
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;

@@ -171,6 +171,7 @@ __device__ __forceinline__ float ordered_float(int i) { return __int_as_float(i 
 __global__ void __launch_bounds__(32)
 xattn_t3_skipmap_kernel(const uint32_t* __restrict__ blockand, const unsigned char* __restrict__ flags, uint32_t* __restrict__ map,
                         int Q, int q_stride, int qw, int keys, int W, int map_words) {
+  pdl_begin();   // programmatic dependent launch: scheduled while the previous kernel drains, reads nothing before this
   const int wi = blockIdx.x, qt = blockIdx.y, g = blockIdx.z, lane = threadIdx.x;
   const int nq = min(128, Q - qt * 128);
   // queries of this tile (4 words); a row with flag 0 ignores its mask: nothing can be skipped then
@@ -206,6 +207,7 @@ template <int NCH>
 __global__ void __launch_bounds__(X3_THREADS, 1)
 xattn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const XattnT3Args a) {
+  pdl_begin();   // programmatic dependent launch: scheduled while the previous kernel drains, reads nothing before this
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem + X3_OFF_Q;

@@ -245,6 +245,13 @@ class _B200MaskedDecoderBase(nn.Module):
         self.clips_per_call = 1
         self.debug_capture = None         # tests: set to a list to receive (head, level, bits, flags) clones
         self.use_cuda_graph = os.environ.get("OVIS_NO_CUDA_GRAPH") is None   # replay the layer loop as a CUDA graph (_run_layers)
+        # one launch per layer for everything between two cross-attentions (csrc/chain.cuh; <= 128 queries per group).  One
+        # CTA per group streams the layer's 3.4 MB of weights alone, so the chain wins when there is ONE group per call (a
+        # single clip: the launch-per-op schedule is then ~17 one-tile kernels per layer) and loses when several groups'
+        # rows share the launch-per-op GEMMs (profiles/experiments/chain_r2.md).  None = that rule; True / False force it
+        # (OVIS_CHAIN=1 / 0).
+        env = os.environ.get("OVIS_CHAIN")
+        self.use_chain = None if env is None else env == "1"
         self._wcache = None
         self._pcache = {}
         self._ws = {}
@@ -453,10 +460,101 @@ class _B200MaskedDecoderBase(nn.Module):
         with torch.cuda.device(dev):
             return self._forward_impl(x, mf, mask_features_in, BT, H4, W4, sizes, dev)
 
+    def _build_chain(self, W, ws):
+        """Phase list of the query-side chain: [mask_embed MLP of head 0, q-projection of layer 0], then per layer
+        [out-proj + LN, self-attention in-projections, self-attention, its out-proj + LN, FFN1, FFN2 + LN + decoder_norm,
+        mask_embed MLP of the next head, q-projection of the next layer]."""
+        nl, R = self.num_layers, ws["R"]
+        qscale = (HIDDEN // NHEADS) ** -0.5 * LOG2E
+        me = W["mask_embed"]
+        first, count = [], []
+        n = 4 + sum(10 + (1 if i + 1 < nl else 0) for i in range(nl))
+        ch = L.Chain(n, ws["G"], self.num_queries)
+        k = 0
+
+        def mlp3_and_q(k, hidx, nxt):
+            ch.set_linear(k, ws["d16"][hidx], me[0][0], me[0][1], ws["m1"], relu=True)
+            ch.set_linear(k + 1, ws["m1"], me[1][0], me[1][1], ws["m2"], relu=True)
+            ch.set_linear(k + 2, ws["m2"], me[2][0], me[2][1], ws["me16"])
+            k += 3
+            if nxt is not None:
+                lw = W["layers"][nxt]
+                ch.set_linear(k, ws["ze16"], lw["xq_w"], lw["xq_b"], ws["q16"], scale=qscale)
+                k += 1
+            return k
+
+        pre_first = k
+        k = mlp3_and_q(k, 0, 0)
+        pre_count = k - pre_first
+        for i in range(nl):
+            lw = W["layers"][i]
+            first.append(k)
+            ch.set_linear_ln(k, ws["att16"], lw["xo_w"], lw["xo_b"], ws["z32"], lw["ln_x"], None, W["qe"],
+                             y32=ws["z32"], y16=ws["z16"], ype16=ws["ze16"])
+            ch.set_linear(k + 1, ws["ze16"], lw["sqk_w"], lw["sqk_b"], ws["qk16"])
+            ch.set_linear(k + 2, ws["z16"], lw["sv_w"], lw["sv_b"], ws["v16"])
+            ch.set_self_attn(k + 3, ws["qk16"], ws["v16"], ws["sa16"])
+            ch.set_linear_ln(k + 4, ws["sa16"], lw["so_w"], lw["so_b"], ws["z32"], lw["ln_s"], None, W["qe"],
+                             y32=ws["z32"], y16=ws["z16"], ype16=ws["ze16"])
+            ch.set_linear(k + 5, ws["z16"], lw["f1_w"], lw["f1_b"], ws["h16"], relu=True)
+            ch.set_linear_ln(k + 6, ws["h16"], lw["f2_w"], lw["f2_b"], ws["z32"], lw["ln_f"], W["dn"], W["qe"],
+                             y32=ws["z32"], y16=ws["z16"], ype16=ws["ze16"], d32=ws["d32"], d16=ws["d16"][i + 1])
+            k = mlp3_and_q(k + 7, i + 1, i + 1 if i + 1 < nl else None)
+            count.append(k - first[-1])
+        assert k == n
+        ch.upload()
+        return dict(chain=ch, pre=(pre_first, pre_count), first=first, count=count)
+
+    def _ensure_chain(self, W, ws):
+        """(re)builds the phase list when the workspace is new or the weights changed; never inside a graph capture"""
+        if self._chain_on(ws) and (ws.get("chain") is None or ws.get("chain_W") is not W):
+            ws["chain"], ws["chain_W"] = self._build_chain(W, ws), W
+
+    def _chain_on(self, ws):
+        if self.num_queries > 128:
+            return False
+        return ws["G"] == 1 if self.use_chain is None else bool(self.use_chain)
+
+    def _layer_loop_chain(self, W, ws):
+        """_layer_loop with the query side of every layer as one launch (csrc/chain.cuh)."""
+        G, Tg, N = ws["G"], ws["Tg"], ws["N"]
+        Q, nl = self.num_queries, self.num_layers
+        self._ensure_chain(W, ws)
+        c = ws["chain"]
+        ch = c["chain"]
+        ws["flags"].zero_()
+        L.init_queries(W["qf"], W["qe"], W["dn"][0], W["dn"][1], G, (ws["z32"], ws["z16"], ws["ze16"], ws["d32"], ws["d16"][0]))
+
+        def bits(hidx, level):
+            if ws["use_t"][level]:
+                L.mask_bits_t(ws["gt"][level], G, Tg * N[level], ws["me16"], Q, ws["bits_t"][level], ws["blockand"][level],
+                              ws["flags"][hidx], Q)
+            else:
+                L.mask_bits(ws["gt"][level], G, Tg * N[level], ws["me16"], Q, ws["bits"][level], ws["flags"][hidx], Q)
+            if self.debug_capture is not None:
+                b = _words_from_bits_t(ws["bits_t"][level], Q) if ws["use_t"][level] else ws["bits"][level].clone()
+                self.debug_capture.append((hidx, level, b, ws["flags"][hidx].clone()))
+
+        ch.run(*c["pre"])
+        bits(0, 0)
+        for i in range(nl):
+            l = i % 3
+            if ws["use_t"][l]:
+                L.xattn_t(ws["q16"], ws["k"][i], ws["v"][i], ws["bits_t"][l], ws["blockand"][l], ws["flags"][i], G, Q, Q,
+                          Tg * N[l], ws["splits"][l], ws["o_part"], ws["ml_part"], ws["att16"])
+            else:
+                L.xattn(ws["q16"], ws["k"][i], ws["v"][i], ws["bits"][l], ws["flags"][i], G, Q, Q, Tg * N[l], ws["splits"][l],
+                        ws["o_part"], ws["ml_part"], ws["att16"])
+            ch.run(c["first"][i], c["count"][i])
+            if i + 1 < nl:
+                bits(i + 1, (i + 1) % 3)
+
     def _layer_loop(self, W, ws):
         """Query initialisation, the first head's mask bits and the nine decoder layers.  Everything here reads and writes
         the per-shape workspace and the weight cache only (no caller tensors, no allocation), so it can be replayed as a
         CUDA graph."""
+        if self._chain_on(ws):
+            return self._layer_loop_chain(W, ws)
         G, Tg, N = ws["G"], ws["Tg"], ws["N"]
         Q, C, nl = self.num_queries, HIDDEN, self.num_layers
         ws["flags"].zero_()
@@ -506,6 +604,7 @@ class _B200MaskedDecoderBase(nn.Module):
         """The layer loop is ~130 small dependent launches: issued from Python they are launch-rate bound (2.5 ms of host
         time per call, more than the GPU needs).  After one eager call per workspace the loop is captured into a CUDA
         graph and replayed; tests' bit capture and the bench's per-launch profiling run it eagerly."""
+        self._ensure_chain(W, ws)
         eager = (not self.use_cuda_graph) or self.debug_capture is not None or L.PROFILE is not None
         if eager or not ws.get("warm"):
             ws["warm"] = True

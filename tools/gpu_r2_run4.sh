@@ -8,5 +8,5 @@ import json
 d=[json.loads(l) for l in open('gpurun_out/r2_run4_bench.json') if l.startswith('{')][-1]
 print('value',d['value'],'e2e',d['e2e']['value'],'launches',d['gpu_launches'])
 for k,v in d['kernels'].items(): print(' ',k, round(v['ms_per_step'],2), round(v.get('frac',0),3))
-for k,v in d['other_configs'].items(): print(k, v.get('value'), v.get('e2e'), v.get('gpu_launches'), v.get('error'))
+for k,v in d['other_configs'].items(): print(k, v.get('value'), v.get('e2e'), v.get('gpu_launches'), v.get('error'), {a:b['ms_per_step'] for a,b in (v.get('kernels') or {}).items()})
 PY

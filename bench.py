@@ -679,6 +679,82 @@ def measure(args, name, dev, world, rank, local, steps, warmup, clips, lanes, wa
     return out
 
 
+def measure_next_rows(dev):
+    """The SURVEY section 8(f) rows that exist as device code, timed briefly (CUDA events, after a warm-up call) so that the
+    default line carries a number for each: f-4 OpenVIS crop classifier (ClipAdapter.forward on one part of 5 frames x 100
+    queries at 720 x 1280: every (frame, query) has a non-empty mask = 500 crops through CLIP ViT-B/16) and f-2
+    MSDeformAttn.forward at the pixel decoder's encoder shapes (4 frames, three levels of a 736 x 1280 input)."""
+    import torch
+    from openvis_b200 import _lib as L
+    from openvis_b200.clip_adapter import ClipAdapter, ClipVisualEncoder
+    from openvis_b200.msda import MSDeformAttn
+    from openvis_b200.synthetic import seeded_clip_visual_params
+    pk, _ = peaks()
+    out = {}
+
+    def timed(fn, n):
+        fn()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / n
+
+    try:
+        T, N, H, W, K = 5, 100, 720, 1280, 1196
+        g = torch.Generator(device=dev).manual_seed(11)
+        ad = ClipAdapter(ClipVisualEncoder().load_state_dict(seeded_clip_visual_params(3)))
+        frames = torch.rand(T, 3, H, W, generator=g, device=dev) * 255
+        logits = torch.full((N, T, H, W), -6.0, device=dev)
+        hw = torch.randint(24, 400, (N, T, 2), generator=g, device=dev).cpu()
+        for n in range(N):
+            for t in range(T):
+                h, w = int(hw[n, t, 0]), int(hw[n, t, 1])
+                y0, x0 = (n * 37 + t * 11) % (H - h), (n * 53 + t * 7) % (W - w)
+                logits[n, t, y0:y0 + h, x0:x0 + w] = 6.0
+        text = make_text(K).to(dev)
+        n0 = L.launch_count()
+        ms_all = timed(lambda: ad(frames, text, logits, layout="nt", logits=True), 3)
+        launches = (L.launch_count() - n0) // 4
+        ms_pre = timed(lambda: ad._preprocess_image(frames, logits, layout="nt", logits=True), 3)
+        crops = T * N
+        Lt, Wd = 197, 768
+        flops = crops * (2 * 196 * Wd * Wd + 12 * (2 * Lt * Wd * (3 * Wd + Wd + 4 * Wd + 4 * Wd) + 4 * Lt * Lt * Wd) + 2 * Wd * 512 + 2 * 512 * K)
+        ms_vit = ms_all - ms_pre
+        out["f4_crop_classifier"] = {
+            "workload": "openvis_crop_classifier_5x720x1280_q100_k1196 (one part of open_vocabulary_inference, openvis.py:112-122)",
+            "crops": crops, "ms": ms_all, "crops_per_s": crops / ms_all * 1e3, "frames_per_s": T / ms_all * 1e3,
+            "ms_preprocess": ms_pre, "preprocess_hbm_gbs": (logits.numel() * 4 * 1.0 + frames.numel() * 4) / ms_pre / 1e6,
+            "ms_clip_tower": ms_vit, "tflops_clip_tower": flops / ms_vit / 1e9,
+            "tensor_frac_of_burst_peak": flops / ms_vit / 1e9 / pk.get("bf16_tflops", 1667.8), "gpu_launches": launches}
+        del ad, frames, logits
+    except Exception as e:
+        out["f4_crop_classifier"] = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
+    try:
+        g = torch.Generator(device=dev).manual_seed(12)
+        shapes = torch.tensor([(92, 160), (46, 80), (23, 40)], device=dev)
+        start = torch.cat([shapes.new_zeros(1), (shapes[:, 0] * shapes[:, 1]).cumsum(0)[:-1]])
+        S, Nf = int((shapes[:, 0] * shapes[:, 1]).sum()), 4
+        m = MSDeformAttn(256, 3, 8, 4).to(dev).eval()
+        with torch.no_grad():
+            m.sampling_offsets.weight.normal_(0, 0.02, generator=None)
+        src = torch.randn(Nf, S, 256, generator=g, device=dev)
+        ref = torch.rand(Nf, S, 3, 2, generator=g, device=dev)
+        n0 = L.launch_count()
+        ms = timed(lambda: m(src, ref, src, shapes, start), 5)
+        out["f2_msdeformattn_module"] = {
+            "workload": "MSDeformAttn.forward, 4 frames x (92x160 + 46x80 + 23x40) positions, 8 heads x 3 levels x 4 points",
+            "ms": ms, "ms_per_frame": ms / Nf, "gpu_launches": (L.launch_count() - n0) // 6,
+            "positions_per_s": Nf * S / ms * 1e3}
+    except Exception as e:
+        out["f2_msdeformattn_module"] = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
+    torch.cuda.empty_cache()
+    return out
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -712,6 +788,7 @@ def main():
                 e2e_steps=e2e_steps)
 
     others = None
+    next_rows = None
     if world == 1 and name == DEFAULT_WORKLOAD and not args.no_other_configs:
         others = {}
         for on in OTHER_CONFIGS:
@@ -730,6 +807,10 @@ def main():
                               "gflop_per_frame": algorithmic_flops_per_frame(WORKLOADS[on][1], *WORKLOADS[on][2:5], WORKLOADS[on][6], WORKLOADS[on][7]) / 1e9}
             except Exception as e:                                  # a secondary measurement must not lose the headline
                 others[on] = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
+        try:
+            next_rows = measure_next_rows(dev)
+        except Exception as e:
+            next_rows = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
 
     if rank != 0:
         if world > 1:
@@ -758,7 +839,7 @@ def main():
                        "on; the synthetic N(0,1) features give ~50 % dense masks, so no fully-masked tile exists to skip here"},
             "clocks": r["clocks"], "e2e": r.get("e2e"), "gpu_launches": r["launches"],
             "roofline": r.get("roofline"), "kernels": r.get("kernels"), "cpu_baseline": cpu,
-            "gather": r.get("gather"), "other_configs": others,
+            "gather": r.get("gather"), "other_configs": others, "next_rows": next_rows,
             "whole_path": {"gflop_per_frame": flops_frame / 1e9,
                            "tensor_frac_of_burst_peak": r["value"] / world * flops_frame / 1e12 / pk.get("bf16_tflops", 1667.8)}}
     line["ms_per_frame"] = r["ms_per_step"] / r["frames_per_step"] * world

@@ -187,6 +187,29 @@ int ovis_self_attn(const void* qk_f16, const void* v_f16, void* out_f16, int G, 
  * frames with a non-empty mask, softmax over K.  logits [T][Q][K], valid [T][Q] -> probs [Q][K], qvalid [Q]. */
 int ovis_clip_aggregate(const float* logits, const unsigned char* valid, float* probs, unsigned char* qvalid,
                         int T, int Q, int K, void* stream);
+/* ---- OpenVIS crop classifier front end --------------------------------------------
+ * ClipAdapter._preprocess_image (openvis/modeling/clip_adapter/adapter.py:73-116) and the input half of encode_image
+ * (adapter.py:140-143) + the token assembly of the CLIP visual tower (mask_adapted_clip model.py:327-342); the
+ * transformer blocks themselves are the ovis_rownorm / ovis_linear_act_f16 / ovis_san_attn calls of the SAN side path.
+ *  masks are addressed as masks[t * stride_t + n * stride_n + y * W + x] (elements): the [T][N][H][W] soft masks
+ *  ClipAdapter.forward takes, or with logits = 1 the decoder's [N][T][H][W] mask logits, the sigmoid of openvis.py:118
+ *  applied on load (no transposed fp32 copy).
+ *  ovis_mask_boxes   valid[T * N] = any(mask > thresh), boxes[T * N][4] int32 = (x_min, y_min, x_max + 1, y_max + 1) of the
+ *                    thresholded mask (detectron2 BitMasks.get_bounding_boxes; zeros when empty).  adapter.py:84-92
+ *  ovis_crop_blend   for each of the M valid (frame, query) pairs `ids` [M][2] (row-major order of valid, adapter.py:103):
+ *                    square box anchored at the top-left corner with side max(w, h) (:94-100), torchvision roi_align
+ *                    (spatial_scale 1, sampling_ratio -1, aligned False) of the frame [T][3][H][W] and of the soft mask
+ *                    [T][N][H][W] to R x R, regions = mask_region * frame_region, fp16 [M][3][R][R] (:106-113)
+ *  ovis_clip_patchify regions -> (v / 255 - mean[c]) / std[c] as fp16 rows [M * (R/P)^2][3 * P * P] of the conv1 GEMM
+ *  ovis_clip_embed   x [M * (1 + Lp)][width] fp32 = ln_pre([class_embedding | patch_tokens] + positional_embedding) */
+int ovis_mask_boxes(const float* masks, int T, int N, long long stride_t, long long stride_n, int H, int W, int logits,
+                    float thresh, int* boxes, unsigned char* valid, void* stream);
+int ovis_crop_blend(const float* frames, const float* masks, long long stride_t, long long stride_n, int logits, const int* ids,
+                    const int* boxes, int M, int T, int N, int H, int W, int R, void* regions_f16, void* stream);
+int ovis_clip_patchify(const void* regions_f16, long long M, int R, int P, const float* mean, const float* std, void* out_f16,
+                       void* stream);
+int ovis_clip_embed(const float* patch_tokens, const float* class_embedding, const float* positional_embedding,
+                    const float* ln_g, const float* ln_b, float* x, long long M, int Lp, int width, void* stream);
 /* ---- multi-scale deformable attention, forward ---------------------------------
  * Replaces MSDA.ms_deform_attn_forward (openvis/modeling/pixel_decoder/ops/src/vision.cpp:18-21 ->
  * ms_deform_attn_cuda_forward, src/cuda/ms_deform_attn_cuda.cu:22-84 -> ms_deformable_im2col_gpu_kernel,
@@ -197,6 +220,12 @@ int ovis_clip_aggregate(const float* logits, const unsigned char* valid, float* 
 int ovis_ms_deform_attn_forward(const float* value, const long long* spatial_shapes, const long long* level_start_index,
                                 const float* sampling_loc, const float* attn_weight, float* out, int N, int S, int M, int D,
                                 int Lq, int L, int P, void* stream);
+/* MSDeformAttn.forward between the query projections and the sampling op (ops/modules/ms_deform_attn.py:104-117): `proj`
+ * [rows][M*L*P*3] fp32 is the output of ONE GEMM over the concatenated sampling_offsets | attention_weights weights (columns
+ * [0, 2*M*L*P) offsets in (m, l, p, xy) order, then M*L*P attention logits); softmax over the L*P logits of a head and
+ * sampling_locations = reference_points + offsets / (W_l, H_l) (ref_dim 2) or the reference-box form (ref_dim 4). */
+int ovis_msda_prepare(const float* proj, const float* reference_points, const long long* spatial_shapes, long long rows, int M,
+                      int L, int P, int ref_dim, float* sampling_loc, float* attn_weight, void* stream);
 /* ---- device-side post-processing ----------------------------------------------
  * Top-k over the flattened [Q*K] scores with labels, query indices and per-query entropy:
  * scores.flatten(0, 1).topk(10), labels[topk], topk // num_classes, sum(-s log s)

@@ -55,8 +55,13 @@ SIGNATURES = {
     "ovis_chain_destroy": (_c_int, [_vp]),
     "ovis_self_attn": (_c_int, [_vp, _vp, _vp, _c_int, _c_int, _vp]),
     "ovis_clip_aggregate": (_c_int, [_vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _vp]),
+    "ovis_mask_boxes": (_c_int, [_vp, _c_int, _c_int, _c_ll, _c_ll, _c_int, _c_int, _c_int, _c_float, _vp, _vp, _vp]),
+    "ovis_crop_blend": (_c_int, [_vp, _vp, _c_ll, _c_ll, _c_int, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _vp]),
+    "ovis_clip_patchify": (_c_int, [_vp, _c_ll, _c_int, _c_int, _vp, _vp, _vp, _vp]),
+    "ovis_clip_embed": (_c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _c_ll, _c_int, _c_int, _vp]),
     "ovis_ms_deform_attn_forward": (_c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
                                              _c_int, _vp]),
+    "ovis_msda_prepare": (_c_int, [_vp, _vp, _vp, _c_ll, _c_int, _c_int, _c_int, _c_int, _vp, _vp, _vp]),
     "ovis_topk_scores": (_c_int, [_vp, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp]),
     "ovis_mask_postprocess": (_c_int, [_vp, _c_ll, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
                                        _c_int, _c_int, _vp, _vp]),
@@ -295,6 +300,22 @@ def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_lo
     return out
 
 
+def msda_prepare(proj, reference_points, spatial_shapes, M, L_, P):
+    """proj [N, Lq, M*L*P*3] fp32 (offsets | attention logits), reference_points [N, Lq, L, 2 or 4] fp32 ->
+    (sampling_locations [N, Lq, M, L, P, 2], attention_weights [N, Lq, M, L, P])."""
+    lib = load()
+    _req(proj, torch.float32, "proj")
+    _req(reference_points, torch.float32, "reference_points")
+    _req(spatial_shapes, torch.int64, "spatial_shapes")
+    N, Lq, cols = proj.shape
+    assert cols == M * L_ * P * 3 and reference_points.shape[:3] == (N, Lq, L_)
+    loc = torch.empty(N, Lq, M, L_, P, 2, dtype=torch.float32, device=proj.device)
+    w = torch.empty(N, Lq, M, L_, P, dtype=torch.float32, device=proj.device)
+    _check(lib.ovis_msda_prepare(_p(proj), _p(reference_points), _p(spatial_shapes), N * Lq, M, L_, P, reference_points.shape[-1],
+                                 _p(loc), _p(w), _stream()))
+    return loc, w
+
+
 def topk_scores(scores, k=10):
     """scores [Q, K] fp32 -> (top scores [k], query index [k], label [k], entropy [k]) sorted by score."""
     lib = load()
@@ -502,6 +523,75 @@ def clip_aggregate(logits, valid):
     qv = torch.empty(Q, dtype=torch.uint8, device=logits.device)
     _check(lib.ovis_clip_aggregate(_p(logits), _p(valid), _p(probs), _p(qv), T, Q, K, _stream()))
     return probs, qv.bool()
+
+
+def _mask_view(masks, layout):
+    """(T, N, H, W, stride_t, stride_n) of a mask tensor in layout "tn" ([T, N, H, W]) or "nt" ([N, T, H, W]); the two
+    leading dimensions may be strided views (a slice of frames), the H x W planes must be dense."""
+    if not masks.is_cuda:
+        raise OvisError("masks: expected a CUDA tensor (no CPU path)")
+    if masks.dtype != torch.float32 or masks.dim() != 4:
+        raise OvisError(f"masks: expected a 4-D float32 tensor, got {masks.dtype} {tuple(masks.shape)}")
+    a, b, H, W = masks.shape
+    if masks.stride(3) != 1 or masks.stride(2) != W:
+        raise OvisError("masks: the H x W planes must be contiguous")
+    if layout == "tn":
+        return a, b, H, W, masks.stride(0), masks.stride(1)
+    if layout == "nt":
+        return b, a, H, W, masks.stride(1), masks.stride(0)
+    raise OvisError(f"unknown mask layout {layout!r}")
+
+
+def mask_boxes(masks, thresh=0.5, layout="tn", logits=False):
+    """masks fp32: [T, N, H, W] soft masks (layout "tn") or [N, T, H, W] (layout "nt"); logits=True applies the sigmoid on load.
+    Returns (valid [T, N] bool, boxes [T, N, 4] int32 = x_min, y_min, x_max + 1, y_max + 1)."""
+    lib = load()
+    T, N, H, W, st, sn = _mask_view(masks, layout)
+    boxes = torch.empty(T * N, 4, dtype=torch.int32, device=masks.device)
+    valid = torch.empty(T * N, dtype=torch.uint8, device=masks.device)
+    _check(lib.ovis_mask_boxes(_p(masks), T, N, st, sn, H, W, int(logits), float(thresh), _p(boxes), _p(valid), _stream()))
+    return valid.bool().view(T, N), boxes.view(T, N, 4)
+
+
+def crop_blend(frames, masks, ids, boxes, R, layout="tn", logits=False):
+    """frames [T, 3, H, W] fp32, masks as in mask_boxes, ids [M, 2] int32 (frame, query), boxes [T, N, 4] int32
+    -> regions [M, 3, R, R] fp16."""
+    lib = load()
+    _req(frames, torch.float32, "frames")
+    _req(ids, torch.int32, "ids")
+    _req(boxes, torch.int32, "boxes")
+    T, N, H, W, st, sn = _mask_view(masks, layout)
+    if tuple(frames.shape) != (T, 3, H, W):
+        raise OvisError(f"frames {tuple(frames.shape)} do not match masks {tuple(masks.shape)} ({layout})")
+    M = ids.shape[0]
+    regions = torch.empty(M, 3, R, R, dtype=torch.float16, device=frames.device)
+    for m0 in range(0, M, 65535):
+        m1 = min(M, m0 + 65535)
+        _check(lib.ovis_crop_blend(_p(frames), _p(masks), st, sn, int(logits), _p(ids[m0:m1]), _p(boxes), m1 - m0, T, N, H, W, R,
+                                   _p(regions[m0:m1]), _stream()))
+    return regions
+
+
+def clip_patchify(regions, patch, mean, std):
+    """regions [M, 3, R, R] fp16 (0..255) -> [M * (R/patch)^2, 3 * patch^2] fp16 normalised patch rows."""
+    lib = load()
+    _req(regions, torch.float16, "regions")
+    M, _, R, _ = regions.shape
+    out = torch.empty(M * (R // patch) ** 2, 3 * patch * patch, dtype=torch.float16, device=regions.device)
+    mean_c = (ctypes.c_float * 3)(*[float(v) for v in mean])
+    std_c = (ctypes.c_float * 3)(*[float(v) for v in std])
+    _check(lib.ovis_clip_patchify(_p(regions), M, R, patch, ctypes.cast(mean_c, _vp), ctypes.cast(std_c, _vp), _p(out), _stream()))
+    return out
+
+
+def clip_embed(patch_tokens, cls, pos, ln_g, ln_b, M, Lp):
+    """patch_tokens [M * Lp, W] fp32 -> x [M * (1 + Lp), W] fp32 = ln_pre([cls | tokens] + pos)."""
+    lib = load()
+    _req(patch_tokens, torch.float32, "patch_tokens")
+    Wd = patch_tokens.shape[1]
+    x = torch.empty(M * (1 + Lp), Wd, dtype=torch.float32, device=patch_tokens.device)
+    _check(lib.ovis_clip_embed(_p(patch_tokens), _p(cls), _p(pos), _p(ln_g), _p(ln_b), _p(x), M, Lp, Wd, _stream()))
+    return x
 
 
 def san_attn_bias(bias, grid_hw):

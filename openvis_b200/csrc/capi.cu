@@ -17,6 +17,7 @@
 #include "xattn_tc2.cuh"
 #include "xattn_tc3.cuh"
 #include "chain.cuh"
+#include "crop.cuh"
 #include <vector>
 #include "san_attn.cuh"
 #include "postproc.cuh"
@@ -281,7 +282,8 @@ int launch_gemm(const void* A, long long a_rows, long long a_cols, long long lda
     const int nt = (a.N + bn - 1) / bn;
     const int es = a.out_f32 ? 4 : 2;
     bool ok = a.epi == EPI_STORE && (a.num_groups == 1 || (a.o_group_stride > 0 && a.o_group_stride % 32 == 0)) &&
-              nt <= GEMM_MAX_OUT_MAPS && (((long long)a.ldo * es) % 16) == 0 && !no_tma_store;
+              nt <= GEMM_MAX_OUT_MAPS && (((long long)a.ldo * es) % 16) == 0 && !no_tma_store &&
+              !(a.resid_st && a.out_f32);   // fp32 residual: the lean epilogue adds it in its row-coalesced store loop
     for (int t = 0; ok && t < nt; ++t) ok = (reinterpret_cast<uintptr_t>(a.out[t]) & 15) == 0;
     if (ok) {
       for (int t = 0; t < nt; ++t) {
@@ -1165,6 +1167,60 @@ int ovis_clip_aggregate(const float* logits, const unsigned char* valid, float* 
   return check_launch("clip_aggregate_kernel");
 }
 
+// ---- OpenVIS crop classifier front end (crop.cuh)
+int ovis_mask_boxes(const float* masks, int T, int N, long long stride_t, long long stride_n, int H, int W, int logits,
+                    float thresh, int* boxes, unsigned char* valid, void* stream) {
+  const long long count = (long long)T * N;
+  CHECK_ARG(masks && boxes && valid && T > 0 && N > 0 && count < (1ll << 31) && H > 0 && W > 0, "bad arguments");
+  CHECK_ARG(thresh > 0.f && thresh < 1.f, "threshold must be inside (0, 1)");
+  if (logits) thresh = logf(thresh / (1.f - thresh));       // sigmoid(x) > thresh  <=>  x > logit(thresh)
+  CHECK_ARG((reinterpret_cast<uintptr_t>(boxes) & 15) == 0, "boxes must be 16-byte aligned");
+  int rc = device_info(nullptr);
+  if (rc) return rc;
+  mask_boxes_kernel<<<(unsigned)count, 256, 0, (cudaStream_t)stream>>>(masks, N, stride_t, stride_n, H, W, thresh, boxes, valid);
+  return check_launch("mask_boxes_kernel");
+}
+
+int ovis_crop_blend(const float* frames, const float* masks, long long stride_t, long long stride_n, int logits, const int* ids,
+                    const int* boxes, int M, int T, int N, int H, int W, int R, void* regions_f16, void* stream) {
+  CHECK_ARG(frames && masks && ids && boxes && regions_f16 && M > 0 && M <= 65535 && T > 0 && N > 0 && H > 0 && W > 0 && R > 0,
+            "bad arguments (at most 65535 regions per call)");
+  CHECK_ARG((reinterpret_cast<uintptr_t>(boxes) & 15) == 0, "boxes must be 16-byte aligned");
+  int rc = device_info(nullptr);
+  if (rc) return rc;
+  CropArgs a;
+  a.frames = frames; a.masks = masks; a.ids = ids; a.boxes = boxes; a.regions = (__half*)regions_f16;
+  a.N = N; a.H = H; a.W = W; a.R = R;
+  a.stride_t = stride_t; a.stride_n = stride_n; a.logits = logits;
+  crop_blend_kernel<<<dim3((R * R + 255) / 256, M), 256, 0, (cudaStream_t)stream>>>(a);
+  return check_launch("crop_blend_kernel");
+}
+
+int ovis_clip_patchify(const void* regions_f16, long long M, int R, int P, const float* mean, const float* std, void* out_f16,
+                       void* stream) {
+  CHECK_ARG(regions_f16 && out_f16 && mean && std && M > 0 && R > 0 && P > 0 && R % P == 0, "bad arguments");
+  const long long rows = M * (R / P) * (R / P);
+  CHECK_ARG(rows < (1ll << 31), "too many patches");
+  int rc = device_info(nullptr);
+  if (rc) return rc;
+  patchify_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>((const __half*)regions_f16, (__half*)out_f16, R, P, mean[0],
+                                                                   mean[1], mean[2], 1.f / std[0], 1.f / std[1], 1.f / std[2], rows);
+  return check_launch("patchify_kernel");
+}
+
+int ovis_clip_embed(const float* patch_tokens, const float* class_embedding, const float* positional_embedding,
+                    const float* ln_g, const float* ln_b, float* x, long long M, int Lp, int width, void* stream) {
+  CHECK_ARG(patch_tokens && class_embedding && positional_embedding && ln_g && ln_b && x && M > 0 && Lp > 0, "bad arguments");
+  CHECK_ARG(width > 0 && width % 32 == 0 && width <= 1024, "width must be a multiple of 32, at most 1024");
+  const long long rows = M * (1 + Lp);
+  CHECK_ARG(rows < (1ll << 33), "too many tokens");
+  int rc = device_info(nullptr);
+  if (rc) return rc;
+  clip_embed_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(patch_tokens, class_embedding, positional_embedding,
+                                                                                  ln_g, ln_b, x, Lp, width, rows);
+  return check_launch("clip_embed_kernel");
+}
+
 int ovis_ms_deform_attn_forward(const float* value, const long long* spatial_shapes, const long long* level_start_index,
                                 const float* sampling_loc, const float* attn_weight, float* out, int N, int S, int M, int D,
                                 int Lq, int L, int P, void* stream) {
@@ -1200,6 +1256,20 @@ int ovis_ms_deform_attn_forward(const float* value, const long long* spatial_sha
   CHECK_ARG(blocks < (1ll << 31), "too many outputs for one launch");
   msda_forward_scalar_kernel<<<(unsigned)blocks, 256, 0, st>>>(a);
   return check_launch("msda_forward_scalar_kernel");
+}
+
+int ovis_msda_prepare(const float* proj, const float* reference_points, const long long* spatial_shapes, long long rows, int M,
+                      int L, int P, int ref_dim, float* sampling_loc, float* attn_weight, void* stream) {
+  CHECK_ARG(proj && reference_points && spatial_shapes && sampling_loc && attn_weight, "null pointer");
+  CHECK_ARG(rows > 0 && M > 0 && L > 0 && P > 0 && (ref_dim == 2 || ref_dim == 4), "bad sizes (reference points are 2- or 4-d)");
+  CHECK_ARG(rows * M < (1ll << 38), "too many queries");
+  int rc = device_info(nullptr);
+  if (rc) return rc;
+  MsdaPrepArgs a;
+  a.proj = proj; a.ref = reference_points; a.shapes = spatial_shapes; a.loc = sampling_loc; a.weight = attn_weight;
+  a.rows = rows; a.M = M; a.L = L; a.P = P; a.ref_dim = ref_dim;
+  msda_prepare_kernel<<<(unsigned)((rows * M + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a);
+  return check_launch("msda_prepare_kernel");
 }
 
 int ovis_topk_scores(const float* scores, int Q, int K, int k, float* out_scores, int* out_query, int* out_label,

@@ -134,12 +134,18 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmArgs& args, const C
     // output, bulk tensor store or row-coalesced stores.  The generic code below handles ragged tiles, residuals, row
     // scales and QuickGELU at run time and costs ~30 instructions per element: 8000 cycles per 128 x 256 tile, which made
     // the HBM-heavy projections epilogue-issue-bound and every small query-side GEMM a 4 us epilogue.
-    if (args.relu <= 1 && args.resid_st == nullptr && !args.row_ss_in && !args.row_ss_out && (bias == nullptr || bias_vec) &&
-        col_base + BN <= args.N && (args.tma_store || vec_ok)) {
+    // (fp32 residual: added in the row-coalesced store loop, where each lane holds 16 contiguous bytes of one row)
+    const bool resid_ok = args.resid_st == nullptr ||
+                          (args.out_f32 && !args.tma_store && ((reinterpret_cast<uintptr_t>(args.resid_st) & 15) == 0));
+    if (resid_ok && !args.row_ss_in && !args.row_ss_out && (bias == nullptr || bias_vec) && col_base + BN <= args.N &&
+        (args.tma_store || vec_ok)) {
       const bool do_scale = args.scale != 1.f;
       const float scale = args.scale;
       const bool do_relu = args.relu == 1;
+      const bool do_gelu = args.relu == 2;
       const long long row_bytes = (long long)args.ldo * esize;
+      const char* const rbase_w = args.resid_st == nullptr ? nullptr
+          : reinterpret_cast<const char*>(args.resid_st) + (grow0 + (lane >> 3)) * row_bytes + (long long)nt * BN * esize + (lane & 7) * 16;
       char* const obase_w = reinterpret_cast<char*>(args.out[nt]) + (grow0 + (lane >> 3)) * row_bytes + (lane & 7) * 16;
       const int rows_left = args.rows_per_group - r_warp0 - (lane >> 3);      // this lane stores rows it*4 + (lane >> 3)
 #pragma unroll 1
@@ -187,6 +193,20 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmArgs& args, const C
             for (int j = 0; j < 32; ++j) vb[j] = __float_as_uint(fmaxf(__uint_as_float(vb[j]), 0.f));
           }
         }
+        if (do_gelu) {   // QuickGELU x * sigmoid(1.702 x) (CLIP blocks, model.py:232-234)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float x = __uint_as_float(va[j]);
+            va[j] = __float_as_uint(__fdividef(x, 1.f + __expf(-1.702f * x)));
+          }
+          if (!args.out_f32) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float x = __uint_as_float(vb[j]);
+              vb[j] = __float_as_uint(__fdividef(x, 1.f + __expf(-1.702f * x)));
+            }
+          }
+        }
         uint4 pk[8];
         if (args.out_f32) {
 #pragma unroll
@@ -225,8 +245,15 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmArgs& args, const C
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             const int row = it * 4 + (lane >> 3), c = lane & 7;
-            const uint4 val = ld_shared_v4(stg + (uint32_t)((row * 8 + (c ^ (row & 7))) << 4));
-            if (it * 4 < rows_left) *reinterpret_cast<uint4*>(o + it * 4 * row_bytes) = val;
+            uint4 val = ld_shared_v4(stg + (uint32_t)((row * 8 + (c ^ (row & 7))) << 4));
+            if (it * 4 < rows_left) {
+              if (rbase_w) {       // (may alias the output: each 16-byte chunk is read and written by the same lane)
+                const float4 q4 = *reinterpret_cast<const float4*>(rbase_w + (long long)u0 * esize + it * 4 * row_bytes);
+                val.x = __float_as_uint(__uint_as_float(val.x) + q4.x); val.y = __float_as_uint(__uint_as_float(val.y) + q4.y);
+                val.z = __float_as_uint(__uint_as_float(val.z) + q4.z); val.w = __float_as_uint(__uint_as_float(val.w) + q4.w);
+              }
+              *reinterpret_cast<uint4*>(o + it * 4 * row_bytes) = val;
+            }
           }
           __syncwarp();
         }

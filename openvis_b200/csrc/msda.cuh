@@ -117,4 +117,53 @@ msda_forward_scalar_kernel(const MsdaArgs a) {
   a.out[idx] = acc;
 }
 
+// MSDeformAttn.forward between the query projections and the sampling op (ops/modules/ms_deform_attn.py:104-117):
+// proj [rows][M * L * P * 3] fp32 = one GEMM's output, columns [0, 2 * MLP) the sampling offsets laid out (m, l, p, xy),
+// columns [2 * MLP, 3 * MLP) the attention logits (m, l, p).  One thread per (row, head): softmax over the L * P logits,
+// sampling_locations = reference_points + offsets / (W_l, H_l)   (2-d reference points), or
+//                    = reference_points[:2] + offsets / P * reference_points[2:] * 0.5   (reference boxes).
+struct MsdaPrepArgs {
+  const float* proj;
+  const float* ref;          // [rows][L][ref_dim]
+  const long long* shapes;   // [L][2] (H, W)
+  float* loc;                // [rows][M][L][P][2]
+  float* weight;             // [rows][M][L][P]
+  long long rows;
+  int M, L, P, ref_dim;
+};
+
+__global__ void __launch_bounds__(256)
+msda_prepare_kernel(const MsdaPrepArgs a) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= a.rows * a.M) return;
+  const int m = (int)(idx % a.M);
+  const long long row = idx / a.M;
+  const int LP = a.L * a.P, MLP = a.M * LP;
+  const float* off = a.proj + row * 3ll * MLP + (long long)m * LP * 2;
+  const float* lg = a.proj + row * 3ll * MLP + 2ll * MLP + (long long)m * LP;
+  float mx = -INFINITY;
+  for (int i = 0; i < LP; ++i) mx = fmaxf(mx, lg[i]);
+  float sum = 0.f;
+  for (int i = 0; i < LP; ++i) sum += expf(lg[i] - mx);
+  const float inv = 1.f / sum;
+  float* wo = a.weight + (row * a.M + m) * LP;
+  float* lo = a.loc + (row * a.M + m) * LP * 2;
+  for (int l = 0; l < a.L; ++l) {
+    const float* r = a.ref + (row * a.L + l) * a.ref_dim;
+    const float Hl = (float)a.shapes[2 * l], Wl = (float)a.shapes[2 * l + 1];
+    for (int p = 0; p < a.P; ++p) {
+      const int i = l * a.P + p;
+      wo[i] = expf(lg[i] - mx) * inv;
+      const float ox = off[2 * i], oy = off[2 * i + 1];
+      if (a.ref_dim == 2) {
+        lo[2 * i] = r[0] + ox / Wl;
+        lo[2 * i + 1] = r[1] + oy / Hl;
+      } else {
+        lo[2 * i] = r[0] + ox / (float)a.P * r[2] * 0.5f;
+        lo[2 * i + 1] = r[1] + oy / (float)a.P * r[3] * 0.5f;
+      }
+    }
+  }
+}
+
 }  // namespace ovis

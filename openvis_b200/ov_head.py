@@ -169,6 +169,22 @@ class SideAdapterBlocks:
         self._w = W
         return self
 
+    def _run_blocks(self, X, n, Q, Lp, pooled):
+        """The residual attention blocks `self.blocks` in place on the fp32 token matrix X [n * (Q + 1 + Lp), W]
+        (ResidualAttentionBlock.forward, mask_adapted_clip model.py:237-268; BiasedResidualAttentionBlock,
+        side_adapter.py:70-78 when `pooled` carries the SOS rows' attention bias)."""
+        att16 = torch.empty(X.shape[0], X.shape[1], dtype=torch.float16, device=X.device)
+        for i in self.blocks:
+            p = self._w[i]
+            _, y16 = L.rownorm(X, p["ln1"][0], p["ln1"][1], layer_norm=True, want32=False)
+            qkv = L.linear_f16(y16, p["in_w"], p["in_b"])
+            L.san_attn(qkv, pooled, att16, n, Q, Lp, self.heads)
+            L.linear_act_f16(att16, p["out_w"], p["out_b"], resid=X, out=X, out_f32=True)
+            _, y16 = L.rownorm(X, p["ln2"][0], p["ln2"][1], layer_norm=True, want32=False)
+            h16 = L.linear_act_f16(y16, p["fc_w"], p["fc_b"], act=2)
+            L.linear_act_f16(h16, p["pj_w"], p["pj_b"], resid=X, out=X, out_f32=True)
+        return X
+
     @torch.no_grad()
     def post_blocks(self, feats, attn_bias, return_tokens=False):
         """feats = (cls_token [1, n, W], pix_feat [n, W, h, w]); attn_bias [n, heads, Q, H', W'] fp32 (or a one-element
@@ -197,16 +213,7 @@ class SideAdapterBlocks:
                 if attn_bias.shape[1] == 1:
                     attn_bias = attn_bias.expand(-1, self.heads, -1, -1, -1)
                 pooled = L.san_pool_bias(attn_bias.float().contiguous(), (h, w))
-            att16 = torch.empty(n * Lt, Wd, dtype=torch.float16, device=pix.device)
-            for i in self.blocks:
-                p = self._w[i]
-                _, y16 = L.rownorm(X, p["ln1"][0], p["ln1"][1], layer_norm=True, want32=False)
-                qkv = L.linear_f16(y16, p["in_w"], p["in_b"])
-                L.san_attn(qkv, pooled, att16, n, Q, Lp, self.heads)
-                L.linear_act_f16(att16, p["out_w"], p["out_b"], resid=X, out=X, out_f32=True)
-                _, y16 = L.rownorm(X, p["ln2"][0], p["ln2"][1], layer_norm=True, want32=False)
-                h16 = L.linear_act_f16(y16, p["fc_w"], p["fc_b"], act=2)
-                L.linear_act_f16(h16, p["pj_w"], p["pj_b"], resid=X, out=X, out_f32=True)
+            self._run_blocks(X, n, Q, Lp, pooled)
             return X if return_tokens else x[:, :Q].contiguous()
 
     @torch.no_grad()

@@ -97,6 +97,47 @@ def seeded_clip_block_params(seed=0, width=768, blocks=(9, 10, 11)):
     return out
 
 
+def seeded_clip_visual_params(seed=0, width=768, layers=12, patch=16, resolution=224, output_dim=512):
+    """Deterministic state dict of a CLIP VisionTransformer (mask_adapted_clip model.py:288-325 key names: conv1.weight,
+    class_embedding, positional_embedding, ln_pre.*, transformer.resblocks.*, ln_post.*, proj) with the initial scales of
+    the reference model (width^-0.5 embeddings and projection) and near-identity LayerNorms."""
+    g = torch.Generator().manual_seed(seed)
+    scale = width ** -0.5
+    out = {"conv1.weight": (3 * patch * patch) ** -0.5 * torch.randn(width, 3, patch, patch, generator=g),
+           "class_embedding": scale * torch.randn(width, generator=g),
+           "positional_embedding": scale * torch.randn((resolution // patch) ** 2 + 1, width, generator=g),
+           "ln_pre.weight": 1.0 + 0.1 * torch.randn(width, generator=g), "ln_pre.bias": 0.02 * torch.randn(width, generator=g),
+           "ln_post.weight": 1.0 + 0.1 * torch.randn(width, generator=g), "ln_post.bias": 0.02 * torch.randn(width, generator=g),
+           "proj": scale * torch.randn(width, output_dim, generator=g)}
+    for k, v in seeded_clip_block_params(seed + 1, width, tuple(range(layers))).items():
+        out["transformer.resblocks." + k] = v
+    return out
+
+
+def seeded_crop_inputs(T=2, N=5, H=320, W=416, seed=0):
+    """Frames [T, 3, H, W] in 0..255 (smooth colour fields + noise) and mask logits [N, T, H, W]: query 0 covers most of the
+    image (crop side > 224: more than one roi_align sample per bin), query 1 a small box near the right border (the square
+    crop box leaves the image), query 2 an ellipse, query 3 is empty everywhere, query 4 is non-empty in frame 0 only."""
+    g = torch.Generator().manual_seed(seed)
+    yy, xx = torch.meshgrid(torch.arange(H, dtype=torch.float32), torch.arange(W, dtype=torch.float32), indexing="ij")
+    frames = torch.stack([torch.stack([127.5 + 100 * torch.sin(xx / (17 + 3 * c + t) + c) * torch.cos(yy / (23 + 2 * c) + t)
+                                       for c in range(3)]) for t in range(T)])
+    frames = (frames + 12 * torch.randn(T, 3, H, W, generator=g)).clamp(0, 255).round()
+    logits = torch.full((N, T, H, W), -6.0)
+    for t in range(T):
+        logits[0, t, 10 + t:H - 14, 8:W - 20 - t] = 5.0
+        logits[1, t, 40:90 + 5 * t, W - 36:W - 2] = 4.0
+        e = ((yy - H / 2 - 9 * t) / 60) ** 2 + ((xx - W / 3) / 35) ** 2
+        logits[2, t] = 4.0 * (1.0 - e)
+    if N > 4:
+        logits[4, 0, H - 50:H - 20, 30:75] = 3.0
+    logits = logits + 0.3 * torch.randn(N, T, H, W, generator=g)
+    logits[3] = -6.0
+    if N > 4:
+        logits[4, 1:] = -6.0
+    return frames, logits
+
+
 def seeded_params(shapes, seed=0):
     """Deterministic weights that do not need the reference to regenerate: names in sorted order, one
     torch.Generator.  Scales mimic the reference's inits (xavier-like for matrices, N(0,1) embeddings,

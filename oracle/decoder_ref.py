@@ -355,6 +355,26 @@ def ms_deform_attn(value, spatial_shapes, sampling_locations, attention_weights)
     return out.reshape(N, Lq, M * D)
 
 
+def ms_deform_attn_module(P, query, reference_points, input_flatten, spatial_shapes, padding_mask=None, n_heads=8, n_points=4):
+    """MSDeformAttn.forward (openvis/modeling/pixel_decoder/ops/modules/ms_deform_attn.py:83-125): P holds the module's
+    state dict (sampling_offsets / attention_weights / value_proj / output_proj .weight / .bias); spatial_shapes [L, 2]."""
+    N, Lq, C = query.shape
+    L_ = spatial_shapes.shape[0]
+    lin = lambda x, n: x @ P[n + ".weight"].T + P[n + ".bias"]
+    value = lin(input_flatten, "value_proj")
+    if padding_mask is not None:
+        value = value.masked_fill(padding_mask[..., None], 0.0)
+    value = value.view(N, -1, n_heads, C // n_heads)
+    off = lin(query, "sampling_offsets").view(N, Lq, n_heads, L_, n_points, 2)
+    w = lin(query, "attention_weights").view(N, Lq, n_heads, L_ * n_points).softmax(-1).view(N, Lq, n_heads, L_, n_points)
+    if reference_points.shape[-1] == 2:
+        norm = torch.stack([spatial_shapes[..., 1], spatial_shapes[..., 0]], -1).float()
+        loc = reference_points[:, :, None, :, None, :] + off / norm[None, None, None, :, None, :]
+    else:
+        loc = reference_points[:, :, None, :, None, :2] + off / n_points * reference_points[:, :, None, :, None, 2:] * 0.5
+    return lin(ms_deform_attn(value, spatial_shapes, loc, w), "output_proj")
+
+
 def video_postprocess(pred_cls, pred_masks, padded_size, img_size, out_hw, topk=10):
     """VideoMaskFormer.postprocess + inference_video (video_maskformer.py:215-229, 262-298) on pred_cls [Q, K] scores and
     stride-4 pred_masks [Q, T, h4, w4]: up-sample to the padded size, top-k over Q*K, crop, resize, > 0.

@@ -271,6 +271,93 @@ def make_resampler_fixture(t=4, Q=12, pseed=21, bseed=6):
     print("wrote temporal_resampler", {k: v.shape for k, v in rec.items()})
 
 
+def msda_module_case(seed=13, ref_dim=2):
+    """Seeded MSDeformAttn module parameters + an encoder-style call (queries = all positions of three levels, one
+    reference point per level, a padding mask on the last columns of the second sample)."""
+    g = torch.Generator().manual_seed(seed)
+    shapes = torch.tensor([(8, 12), (4, 6), (2, 3)])
+    start = torch.cat([shapes.new_zeros(1), (shapes[:, 0] * shapes[:, 1]).cumsum(0)[:-1]])
+    S = int((shapes[:, 0] * shapes[:, 1]).sum())
+    N, C, M, L_, P_ = 2, 256, 8, 3, 4
+    P = {"sampling_offsets.weight": 0.05 * torch.randn(M * L_ * P_ * 2, C, generator=g),
+         "sampling_offsets.bias": 1.5 * torch.randn(M * L_ * P_ * 2, generator=g),
+         "attention_weights.weight": 0.1 * torch.randn(M * L_ * P_, C, generator=g),
+         "attention_weights.bias": 0.1 * torch.randn(M * L_ * P_, generator=g),
+         "value_proj.weight": C ** -0.5 * torch.randn(C, C, generator=g), "value_proj.bias": 0.02 * torch.randn(C, generator=g),
+         "output_proj.weight": C ** -0.5 * torch.randn(C, C, generator=g), "output_proj.bias": 0.02 * torch.randn(C, generator=g)}
+    query = torch.randn(N, S, C, generator=g)
+    src = torch.randn(N, S, C, generator=g)
+    ref = torch.rand(N, S, L_, ref_dim, generator=g)
+    if ref_dim == 4:
+        ref[..., 2:] = 0.1 + 0.3 * ref[..., 2:]
+    pad = torch.zeros(N, S, dtype=torch.bool)
+    pad[1, -20:] = True
+    return P, query, ref, src, shapes, start, pad
+
+
+def make_msda_module_fixture():
+    """tests/golden/msda_module.npz: the reference MSDeformAttn.forward (ops/modules/ms_deform_attn.py:83-125) on
+    msda_module_case(), for 2-d reference points and for reference boxes."""
+    cls = R.msda_module()
+    rec = {}
+    for ref_dim in (2, 4):
+        P, query, ref, src, shapes, start, pad = msda_module_case(ref_dim=ref_dim)
+        m = cls(d_model=256, n_levels=3, n_heads=8, n_points=4).eval()
+        m.load_state_dict(P)
+        with torch.no_grad():
+            rec[f"out{ref_dim}"] = m(query, ref, src, shapes, start, pad)[:, :, ::2].numpy()     # every second channel
+    np.savez_compressed(os.path.join(GOLDEN, "msda_module.npz"), **rec)
+    print("wrote msda_module", {k: v.shape for k, v in rec.items()})
+
+
+def clip_adapter_case(seed=3, K=7):
+    """Seeded inputs of the crop classifier fixture: (visual params, frames, mask logits, text matrix)."""
+    from openvis_b200.synthetic import seeded_clip_visual_params, seeded_crop_inputs
+    P = seeded_clip_visual_params(seed)
+    frames, logits = seeded_crop_inputs(seed=seed)
+    text = torch.nn.functional.normalize(torch.randn(K, 512, generator=torch.Generator().manual_seed(seed + 7)), dim=-1)
+    return P, frames, logits, text
+
+
+def run_reference_clip_adapter(fp32):
+    """The reference ClipAdapter's own _preprocess_image / encode_image / cal_sim_logits (adapter.py:73-147) and
+    OpenVIS.open_vocabulary_inference (openvis.py:110-147) on clip_adapter_case(); fp32 = its `.half()` sections in fp32."""
+    import types
+    P, frames, logits, text = clip_adapter_case()
+    a = R.clip_adapter(P)
+    ov = R.ov_tails()
+    with torch.no_grad(), R.on_cpu(fp32=fp32):
+        masks = logits.sigmoid().transpose(0, 1).contiguous()
+        regions, valid = a._preprocess_image(frames, masks)
+        feats = a.encode_image(regions.float())
+        sim = a.cal_sim_logits(text, feats)
+
+        def clip_adapter(part_frames, class_names, part_masks):
+            r, v = a._preprocess_image(part_frames, part_masks)
+            if r is None:
+                return None, v
+            return a.cal_sim_logits(text, a.encode_image(r.float())), v
+
+        self_ = types.SimpleNamespace(clip_adapter=clip_adapter, device="cpu")
+        probs, kept = ov.open_vocabulary_inference(self_, torch.ones(logits.shape[0]), logits, frames, list(range(text.shape[0])))
+    return dict(valid=valid, regions=regions.float(), feats=feats, sim=sim, probs=probs, kept_shape=torch.tensor(kept.shape))
+
+
+def make_clip_adapter_fixture():
+    """tests/golden/clip_adapter.npz: the reference's outputs evaluated in fp32 (pins oracle/clip_ref.py) and as written
+    (fp16 roi_align on the CPU; the band the fp16 sections move the results by).  Regions are stored sub-sampled."""
+    f32 = run_reference_clip_adapter(True)
+    f16 = run_reference_clip_adapter(False)
+    rec = dict(valid=f32["valid"].numpy(), regions_sub=f32["regions"][:, :, 3::7, 2::7].numpy(),
+               regions_mean=f32["regions"].mean(dim=(-1, -2)).numpy(), feats=f32["feats"].numpy(), sim=f32["sim"].numpy(),
+               probs=f32["probs"].numpy(), kept_shape=f32["kept_shape"].numpy(),
+               regions_sub_h=f16["regions"][:, :, 3::7, 2::7].numpy(), sim_h=f16["sim"].numpy(), probs_h=f16["probs"].numpy())
+    np.savez_compressed(os.path.join(GOLDEN, "clip_adapter.npz"), **rec)
+    print("wrote clip_adapter", {k: v.shape for k, v in rec.items()},
+          "fp16-vs-fp32 band: regions", float(np.abs(rec["regions_sub"] - rec["regions_sub_h"]).max()),
+          "sim", float(np.abs(rec["sim"] - rec["sim_h"]).max()), "probs", float(np.abs(rec["probs"] - rec["probs_h"]).max()))
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     for case in DECODER_CASES:
@@ -281,6 +368,8 @@ def main():
     make_temporal_match_fixture()
     make_resampler_fixture()
     make_ov_tails_fixture()
+    make_clip_adapter_fixture()
+    make_msda_module_fixture()
 
 
 if __name__ == "__main__":

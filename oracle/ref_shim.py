@@ -164,6 +164,61 @@ def side_adapter_module():
     return ns
 
 
+class _BitMasks:
+    """Stand-in for detectron2.structures.BitMasks (not installed here), restated from its published definition
+    (detectron2/structures/masks.py:88-209): `.tensor` [M, H, W] bool; get_bounding_boxes() -> object with `.tensor` [M, 4]
+    = [x_min, y_min, x_max + 1, y_max + 1] of the non-zero pixels, zeros for an empty mask."""
+
+    def __init__(self, tensor):
+        self.tensor = torch.as_tensor(tensor).to(torch.bool)
+
+    def get_bounding_boxes(self):
+        boxes = torch.zeros(self.tensor.shape[0], 4, dtype=torch.float32)
+        x_any = torch.any(self.tensor, dim=1)
+        y_any = torch.any(self.tensor, dim=2)
+        for idx in range(self.tensor.shape[0]):
+            x = torch.where(x_any[idx, :])[0]
+            y = torch.where(y_any[idx, :])[0]
+            if len(x) > 0 and len(y) > 0:
+                boxes[idx, :] = torch.as_tensor([x[0], y[0], x[-1] + 1, y[-1] + 1], dtype=torch.float32)
+        return types.SimpleNamespace(tensor=boxes)
+
+
+def clip_adapter(visual_state_dict=None):
+    """The reference's ClipAdapter (openvis/modeling/clip_adapter/adapter.py:34-147), unmodified, around the vendored
+    mask_adapted_clip CLIP (ViT-B/16) -- `visual_state_dict` (e.g. synthetic.seeded_clip_visual_params) replaces the visual
+    tower's random initialisation.  torchvision's roi_align is the real one; detectron2's BitMasks is `_BitMasks` above.
+    Returns the adapter instance (CPU, eval)."""
+    san = side_adapter_module()                   # installs the clip / refclip packages and the seeded build_clip_model
+    _mod("detectron2.structures", BitMasks=_BitMasks)
+    ad = _load("refclip", _CLIP_DIR, "adapter")
+    ad.build_clip_model = sys.modules["refclip.utils"].build_clip_model
+    a = ad.ClipAdapter("ViT-B/16").eval()
+    if visual_state_dict is not None:
+        missing, unexpected = a.clip_model.visual.load_state_dict(visual_state_dict, strict=False)
+        assert not unexpected and set(missing) <= {"mask_embedding"}, (missing, unexpected)
+    return a
+
+
+class on_cpu:
+    """Context for running reference code that hard-codes `.cuda()` (adapter.py:92) in this GPU-less container, and --
+    `fp32=True` -- for evaluating its `.half()` sections (adapter.py:106, 109) in fp32."""
+
+    def __init__(self, fp32=False):
+        self.fp32 = fp32
+
+    def __enter__(self):
+        self._cuda, self._half = torch.Tensor.cuda, torch.Tensor.half
+        torch.Tensor.cuda = lambda t, *a, **k: t
+        if self.fp32:
+            torch.Tensor.half = lambda t, *a, **k: t.float()
+        return self
+
+    def __exit__(self, *exc):
+        torch.Tensor.cuda, torch.Tensor.half = self._cuda, self._half
+        return False
+
+
 def msda_core_pytorch():
     """The reference's own pure-PyTorch multi-scale deformable attention (``ms_deform_attn_core_pytorch``,
     ops/functions/ms_deform_attn_func.py:55-77).  Its module refuses to import without the compiled extension, so an
@@ -179,6 +234,22 @@ def msda_core_pytorch():
     m = _load("refmsda", d, "ms_deform_attn_func")
     _loaded["msda"] = m.ms_deform_attn_core_pytorch
     return _loaded["msda"]
+
+
+def msda_module():
+    """The reference's MSDeformAttn module class (ops/modules/ms_deform_attn.py:35-125), unmodified.  Without the compiled
+    extension its forward takes its own `except:` branch (:118-121), i.e. ms_deform_attn_core_pytorch."""
+    if "msda_module" in _loaded:
+        return _loaded["msda_module"]
+    if not available():
+        raise RuntimeError(f"reference not found under {REF_ROOT}")
+    _mod("MultiScaleDeformableAttention")
+    ops = os.path.join(REF_ROOT, "openvis/modeling/pixel_decoder/ops")
+    pkg = _mod("refops")
+    pkg.__path__ = [ops]
+    m = importlib.import_module("refops.modules.ms_deform_attn")
+    _loaded["msda_module"] = m.MSDeformAttn
+    return m.MSDeformAttn
 
 
 def temporal():

@@ -56,3 +56,31 @@ def test_pixel_decoder_shape():
     out = _run(value, shapes, loc, w)
     ref = O.ms_deform_attn(value, shapes, loc, w)
     assert torch.allclose(out, ref, rtol=1e-4, atol=1e-6), (out - ref).abs().max().item()
+
+
+@pytest.mark.parametrize("ref_dim", [2, 4])
+def test_module_forward_against_reference_golden_and_oracle(golden_dir, ref_dim):
+    """MSDeformAttn.forward (ops/modules/ms_deform_attn.py:83-125) as four launches -- value projection, one GEMM for the
+    sampling offsets and attention logits, softmax + sampling locations, the sampling kernel, output projection -- with
+    the reference module's own state dict, against its committed output and the oracle restatement."""
+    import os
+    from oracle import decoder_ref as O
+    from oracle.make_golden import msda_module_case
+    from openvis_b200.msda import MSDeformAttn
+    g = np.load(os.path.join(golden_dir, "msda_module.npz"))
+    P, query, ref, src, shapes, start, pad = msda_module_case(ref_dim=ref_dim)
+    m = MSDeformAttn(d_model=256, n_levels=3, n_heads=8, n_points=4).eval()
+    m.load_state_dict(P)                                   # the reference's parameter names
+    m = m.cuda()
+    n0 = L.launch_count()
+    out = m(query.cuda(), ref.cuda(), src.cuda(), shapes.cuda(), start.cuda(), pad.cuda()).cpu()
+    assert L.launch_count() - n0 >= 5
+    want = O.ms_deform_attn_module(P, query, ref, src, shapes, pad)
+    # fp16 GEMM operands (three projections in a row), outputs of magnitude ~1: a sampling location that moves by an
+    # fp16 ulp of the offsets shifts a bilinear sample, so the check is on the bulk and on the worst case separately
+    d = (out - want).abs()
+    assert (d <= 1e-2 + 1e-2 * want.abs()).float().mean().item() > 0.999, d.max().item()
+    assert d.max().item() < 6e-2, d.max().item()
+    assert np.abs(out[:, :, ::2].numpy() - g[f"out{ref_dim}"]).max() < 6e-2
+    with pytest.raises(L.OvisError):
+        m(query, ref, src, shapes, start, pad)                # CPU tensors: no CPU path

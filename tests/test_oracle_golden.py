@@ -235,3 +235,38 @@ def test_register_into_reference_registry_and_builder():
     finally:
         ref.registry.clear()
         ref.registry.update(saved)
+
+
+def test_clip_adapter_oracle_against_reference_golden(golden_dir):
+    """Row f-4: oracle/clip_ref.py (mask boxes, roi_align, blend, CLIP visual tower, logits, per-query aggregation) against
+    the outputs of the reference's own ClipAdapter + OpenVIS.open_vocabulary_inference (tests/golden/clip_adapter.npz,
+    generated by oracle/make_golden.py:make_clip_adapter_fixture with the `.half()` sections evaluated in fp32)."""
+    from oracle import clip_ref as C
+    from oracle.make_golden import clip_adapter_case
+    g = np.load(os.path.join(golden_dir, "clip_adapter.npz"))
+    P, frames, logits, text = clip_adapter_case()
+    masks = logits.sigmoid().transpose(0, 1).contiguous()
+    with torch.no_grad():
+        regions, valid, _ = C.preprocess_image(frames, masks, half_io=False)
+        assert np.array_equal(valid.numpy(), g["valid"])
+        assert np.abs(regions[:, :, 3::7, 2::7].numpy() - g["regions_sub"]).max() < 1e-3
+        assert np.abs(regions.mean(dim=(-1, -2)).numpy() - g["regions_mean"]).max() < 1e-3
+        f = C.encode_image(P, regions)
+        assert np.abs(f.numpy() - g["feats"]).max() < 1e-5
+        assert np.abs((100 * f @ text.T).numpy() - g["sim"]).max() < 1e-3
+        probs, qv = C.open_vocabulary_inference(P, logits, frames, text)        # fp16-rounded regions, like the reference as written
+        assert tuple(probs.shape) == tuple(g["probs"].shape) and int(qv.sum()) == int(g["kept_shape"][0])
+        assert np.abs(probs.numpy() - g["probs"]).max() < 1e-3
+        # the reference as written (fp16 roi_align) stays inside the band its own fp16 sections open
+        assert np.abs(probs.numpy() - g["probs_h"]).max() < 2e-2
+
+
+@pytest.mark.parametrize("ref_dim", [2, 4])
+def test_msda_module_oracle_against_reference_golden(golden_dir, ref_dim):
+    """Row f-2: oracle.decoder_ref.ms_deform_attn_module against the reference MSDeformAttn.forward's committed output
+    (tests/golden/msda_module.npz, every second channel)."""
+    from oracle.make_golden import msda_module_case
+    g = np.load(os.path.join(golden_dir, "msda_module.npz"))
+    P, query, ref, src, shapes, start, pad = msda_module_case(ref_dim=ref_dim)
+    out = O.ms_deform_attn_module(P, query, ref, src, shapes, pad)
+    assert np.abs(out[:, :, ::2].numpy() - g[f"out{ref_dim}"]).max() < 1e-5

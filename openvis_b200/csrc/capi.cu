@@ -20,6 +20,7 @@
 #include "crop.cuh"
 #include <vector>
 #include "san_attn.cuh"
+#include "san_attn_tc.cuh"
 #include "postproc.cuh"
 #include "msda.cuh"
 #include "temporal.cuh"
@@ -1322,8 +1323,30 @@ int ovis_san_attn(const void* qkv, const float* pooled, void* out, int B, int Q,
   cudaGetDevice(&dev);
   SanAttnArgs a;
   a.qkv = (const __half*)qkv; a.pooled = pooled; a.out = (__half*)out;
-  a.Q = Q; a.L = L; a.heads = heads;
+  a.Q = Q; a.L = L; a.heads = heads; a.B = B;
   a.scale_log2 = 0.125f * 1.4426950408889634f;   // 64^-1/2 * log2(e)
+  // OVIS_SAN_ATTN=mma: the mma.sync kernel (A/B and checking); default: tcgen05 kernel for up to 256 keys (CLS + patches)
+  static const bool force_mma = getenv("OVIS_SAN_ATTN") && !strcmp(getenv("OVIS_SAN_ATTN"), "mma");
+  if (!simt && !force_mma && 1 + L <= ST_MAX_KEYS && heads <= 65535 && B <= 65535 &&
+      (long long)B * (Q + 1 + L) < (1ll << 31) && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+    CUtensorMap tm;
+    rc = make_map_f16(&tm, qkv, (unsigned long long)B * (Q + 1 + L), (unsigned long long)3 * heads * 64,
+                      (unsigned long long)3 * heads * 64, 128);
+    if (rc) return rc;
+    static bool attr_tc[64] = {false};
+    if (!attr_tc[dev]) {
+      cudaError_t e = cudaFuncSetAttribute(san_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM);
+      if (e != cudaSuccess) return fail(OVIS_ERR_CUDA, "%s: cannot raise the shared-memory limit", "san_attn_tc_kernel");
+      attr_tc[dev] = true;
+    }
+    int sms = 148;
+    rc = device_info(&sms);
+    if (rc) return rc;
+    const long long items = (long long)B * heads;
+    san_attn_tc_kernel<<<(unsigned)(items < sms ? items : sms), ST_THREADS, ST_SMEM, (cudaStream_t)stream>>>(tm, a);
+    return check_launch("san_attn_tc_kernel");
+  }
   if (!simt) {
     const int ntiles = (1 + L + SA_KT - 1) / SA_KT;
     const size_t smem2 = (size_t)ntiles * SA_KT * SA_LD * 2 * sizeof(__half);

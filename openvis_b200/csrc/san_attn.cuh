@@ -20,6 +20,7 @@ struct SanAttnArgs {
   __half* out;           // [B*(Q+1+L)][heads*64]
   int Q, L, heads;
   float scale_log2;      // 64^-1/2 * log2(e)
+  int B;                 // images (san_attn_tc_kernel's persistent grid)
 };
 
 __global__ void __launch_bounds__(256)

@@ -76,7 +76,7 @@ class MSDeformAttn(torch.nn.Module):
 
     @torch.no_grad()
     def forward(self, query, reference_points, input_flatten, input_spatial_shapes, input_level_start_index,
-                input_padding_mask=None):
+                input_padding_mask=None, _skip_output_proj=False, _query_f16=None):
         if not query.is_cuda:
             raise L.OvisError("openvis_b200 has no CPU path: inputs must be CUDA tensors on an sm_100 device")
         N, Len_q, C = query.shape
@@ -90,11 +90,142 @@ class MSDeformAttn(torch.nn.Module):
             value = L.linear_f16(L.cast_f16(input_flatten.float().reshape(N * Len_in, C).contiguous()), W["vw"], W["vb"], out_f32=True)
             if input_padding_mask is not None:
                 value = value.masked_fill(input_padding_mask.reshape(-1, 1), 0.0)
-            proj = L.linear_f16(L.cast_f16(query.float().reshape(N * Len_q, C).contiguous()), W["qw"], W["qb"], out_f32=True)
+            q16 = _query_f16 if _query_f16 is not None else L.cast_f16(query.float().reshape(N * Len_q, C).contiguous())
+            proj = L.linear_f16(q16, W["qw"], W["qb"], out_f32=True)
             shapes = input_spatial_shapes.long().contiguous()
             loc, w = L.msda_prepare(proj.view(N, Len_q, -1), reference_points.float().contiguous(), shapes, self.n_heads,
                                     self.n_levels, self.n_points)
             out = L.ms_deform_attn_forward(value.view(N, Len_in, self.n_heads, C // self.n_heads), shapes,
                                            input_level_start_index.long().contiguous(), loc, w)
+            if _skip_output_proj:
+                return out                  # [N, Len_q, C] fp32: the caller fuses output_proj into its residual + LayerNorm
             out = L.linear_f16(L.cast_f16(out.view(N * Len_q, C)), W["ow"], W["ob"], out_f32=True)
             return out.view(N, Len_q, C)
+
+
+class MSDeformAttnTransformerEncoderLayer(torch.nn.Module):
+    """Drop-in for the reference encoder layer at inference (pixel_decoder/msdeformattn.py:107-146): ``self_attn`` /
+    ``norm1`` / ``linear1`` / ``linear2`` / ``norm2`` keep their names.  ``output_proj`` + residual + ``norm1`` and
+    ``linear2`` + residual + ``norm2`` are one GEMM each with the LayerNorm in the epilogue (``ovis_linear_ln_f16``), which
+    also emits the fp16 operand of the next GEMM and ``src + pos`` for the next layer's query projections."""
+
+    def __init__(self, d_model=256, d_ffn=1024, dropout=0.1, activation="relu", n_levels=4, n_heads=8, n_points=4):
+        super().__init__()
+        if d_model != 256 or activation != "relu":
+            raise NotImplementedError("openvis_b200: d_model = 256 and ReLU (every shipped pixel-decoder config)")
+        self.self_attn = MSDeformAttn(d_model, n_levels, n_heads, n_points)
+        self.norm1 = torch.nn.LayerNorm(d_model)
+        self.linear1 = torch.nn.Linear(d_model, d_ffn)
+        self.linear2 = torch.nn.Linear(d_ffn, d_model)
+        self.norm2 = torch.nn.LayerNorm(d_model)
+        self._wc = None
+
+    def _weights(self):
+        ps = (self.linear1.weight, self.linear1.bias, self.linear2.weight, self.linear2.bias, self.norm1.weight, self.norm1.bias,
+              self.norm2.weight, self.norm2.bias)
+        key = tuple((p.data_ptr(), p._version) for p in ps)
+        if self._wc is None or self._wc[0] != key:
+            f = lambda t: t.detach().float().contiguous()
+            self._wc = (key, dict(w1=L.cast_f16(f(ps[0])), b1=f(ps[1]), w2=L.cast_f16(f(ps[2])), b2=f(ps[3]),
+                                  n1=(f(ps[4]), f(ps[5])), n2=(f(ps[6]), f(ps[7]))))
+        return self._wc[1]
+
+    @torch.no_grad()
+    def forward(self, src, pos, reference_points, spatial_shapes, level_start_index, padding_mask=None, _state=None):
+        """`_state` (encoder-internal): (src fp32 [rows, C], src fp16, (src + pos) fp16, pos table [S, C] or None) of the
+        previous layer's epilogue, so that no operand is converted twice."""
+        N, S, C = src.shape
+        with torch.cuda.device(src.device):
+            W, A = self._weights(), self.self_attn._weights()
+            if _state is None:
+                x32 = src.float().reshape(N * S, C).contiguous()
+                x16 = L.cast_f16(x32)
+                q16 = x16 if pos is None else L.cast_f16((src + pos).float().reshape(N * S, C).contiguous())
+                pe = None
+            else:
+                x32, x16, q16, pe = _state
+            att = self.self_attn(src, reference_points, x32.view(N, S, C), spatial_shapes, level_start_index, padding_mask,
+                                 _skip_output_proj=True, _query_f16=q16)
+            y32 = torch.empty_like(x32)
+            y16 = torch.empty_like(x16)
+            L.linear_ln_f16(L.cast_f16(att.view(N * S, C)), A["ow"], A["ob"], x32, W["n1"], y32=y32, y16=y16)
+            h16 = L.linear_f16(y16, W["w1"], W["b1"], relu=True)
+            o32, o16 = torch.empty_like(x32), torch.empty_like(x16)
+            oq16 = torch.empty_like(x16) if pe is not None else None
+            L.linear_ln_f16(h16, W["w2"], W["b2"], y32, W["n2"], pe=pe, y32=o32, y16=o16, ype16=oq16)
+            self._last_state = (o32, o16, oq16 if oq16 is not None else o16, pe)
+            return o32.view(N, S, C)
+
+
+class MSDeformAttnTransformerEncoder(torch.nn.Module):
+    """pixel_decoder/msdeformattn.py:149-177: the layer stack + reference points of every position at every level."""
+
+    def __init__(self, encoder_layer, num_layers):
+        super().__init__()
+        import copy
+        self.layers = torch.nn.ModuleList([copy.deepcopy(encoder_layer) for _ in range(num_layers)])
+        self.num_layers = num_layers
+
+    @staticmethod
+    def get_reference_points(spatial_shapes, valid_ratios, device):
+        ref_list = []
+        for lvl, (H_, W_) in enumerate(spatial_shapes):
+            H_, W_ = int(H_), int(W_)
+            ref_y, ref_x = torch.meshgrid(torch.linspace(0.5, H_ - 0.5, H_, dtype=torch.float32, device=device),
+                                          torch.linspace(0.5, W_ - 0.5, W_, dtype=torch.float32, device=device), indexing="ij")
+            ref_y = ref_y.reshape(-1)[None] / (valid_ratios[:, None, lvl, 1] * H_)
+            ref_x = ref_x.reshape(-1)[None] / (valid_ratios[:, None, lvl, 0] * W_)
+            ref_list.append(torch.stack((ref_x, ref_y), -1))
+        reference_points = torch.cat(ref_list, 1)
+        return reference_points[:, :, None] * valid_ratios[:, None]
+
+    @torch.no_grad()
+    def forward(self, src, spatial_shapes, level_start_index, valid_ratios, pos=None, padding_mask=None):
+        if not src.is_cuda:
+            raise L.OvisError("openvis_b200 has no CPU path: inputs must be CUDA tensors on an sm_100 device")
+        N, S, C = src.shape
+        reference_points = self.get_reference_points(spatial_shapes, valid_ratios, device=src.device).contiguous()
+        state = None
+        # the position term is usually the same table for every sample (sine embedding + level embedding): then the
+        # LayerNorm epilogue adds it for the next layer's query operand
+        shared_pos = pos is not None and (pos.shape[0] == 1 or bool((pos == pos[:1]).all()))
+        out = src
+        with torch.cuda.device(src.device):
+            for i, layer in enumerate(self.layers):
+                if i == 0 and shared_pos:
+                    x32 = src.float().reshape(N * S, C).contiguous()
+                    state = (x32, L.cast_f16(x32), L.cast_f16((src + pos).float().reshape(N * S, C).contiguous()),
+                             pos[0].float().contiguous())
+                out = layer(out, pos, reference_points, spatial_shapes, level_start_index, padding_mask,
+                            _state=state if shared_pos else None)
+                state = layer._last_state if shared_pos else None
+        return out
+
+
+class MSDeformAttnTransformerEncoderOnly(torch.nn.Module):
+    """pixel_decoder/msdeformattn.py:38-104: flattens the multi-scale maps, adds the level embedding to the position
+    embeddings and runs the encoder; returns (memory, spatial_shapes, level_start_index)."""
+
+    def __init__(self, d_model=256, nhead=8, num_encoder_layers=6, dim_feedforward=1024, dropout=0.1, activation="relu",
+                 num_feature_levels=4, enc_n_points=4):
+        super().__init__()
+        self.d_model, self.nhead = d_model, nhead
+        layer = MSDeformAttnTransformerEncoderLayer(d_model, dim_feedforward, dropout, activation, num_feature_levels, nhead,
+                                                    enc_n_points)
+        self.encoder = MSDeformAttnTransformerEncoder(layer, num_encoder_layers)
+        self.level_embed = torch.nn.Parameter(torch.zeros(num_feature_levels, d_model))
+
+    @torch.no_grad()
+    def forward(self, srcs, pos_embeds):
+        src_flatten, pos_flatten, shapes = [], [], []
+        for lvl, (src, pos_embed) in enumerate(zip(srcs, pos_embeds)):
+            shapes.append(tuple(src.shape[-2:]))
+            src_flatten.append(src.flatten(2).transpose(1, 2))
+            pos_flatten.append(pos_embed.flatten(2).transpose(1, 2) + self.level_embed[lvl].view(1, 1, -1))
+        src_flatten, pos_flatten = torch.cat(src_flatten, 1), torch.cat(pos_flatten, 1)
+        spatial_shapes = torch.as_tensor(shapes, dtype=torch.long, device=src_flatten.device)
+        level_start_index = torch.cat((spatial_shapes.new_zeros((1,)), spatial_shapes.prod(1).cumsum(0)[:-1]))
+        # masks are all-False in the reference (msdeformattn.py:77): every valid ratio is 1
+        valid_ratios = torch.ones(src_flatten.shape[0], len(shapes), 2, device=src_flatten.device)
+        memory = self.encoder(src_flatten, spatial_shapes, level_start_index, valid_ratios, pos_flatten, None)
+        return memory, spatial_shapes, level_start_index

@@ -416,3 +416,27 @@ def test_san_pool_bias_and_attention():
     L.san_attn(qkv, None, out, B, Q, Lp, heads)
     ref0 = ((q[:, :, Q:] @ k[:, :, Q:].transpose(-1, -2) / 8).softmax(-1) @ v[:, :, Q:]).permute(0, 2, 1, 3).reshape(B, Lp + 1, W)
     assert _maxerr(out.view(B, Lt, W)[:, Q:], ref0) < 4e-3
+
+
+@pytest.mark.parametrize("B,Q,gh,gw", [(40, 0, 14, 14), (30, 100, 14, 14), (17, 200, 14, 14), (5, 3, 15, 17), (3, 0, 5, 3)])
+def test_san_attention_many_items_per_cta(B, Q, gh, gw):
+    """ovis_san_attn on the persistent tcgen05 kernel with several (image, head) items per CTA -- two query tiles per item
+    for the plain CLIP tower (Q = 0, 197 tokens), three / four with 100 / 200 SOS tokens, 256 keys (the maximum), a tiny
+    grid -- against the fp64 formulation, and against the mma.sync checker kernel's structure (same pooled biases)."""
+    from oracle import decoder_ref as O
+    heads = 12
+    Lp, W = gh * gw, heads * 64
+    Lt = Q + 1 + Lp
+    qkv = _randn(B * Lt, 3 * W, seed=5).half()
+    out = torch.empty(B * Lt, W, dtype=torch.float16, device="cuda")
+    pooled = None
+    q, k, v = (t.reshape(B, Lt, heads, 64).permute(0, 2, 1, 3).double() for t in qkv.view(B, Lt, 3 * W).split(W, dim=-1))
+    if Q > 0:
+        bias = _randn(B, heads, Q, 2 * gh, 2 * gw, seed=6, scale=3.0)
+        pooled = L.san_pool_bias(bias, (gh, gw))
+        full = O.san_build_attn_bias(bias.cpu(), (gh, gw)).cuda().double().view(B, heads, Lt, Lt)
+        ref = ((q @ k.transpose(-1, -2) / 8 + full).softmax(-1) @ v).permute(0, 2, 1, 3).reshape(B * Lt, W)
+    else:
+        ref = ((q @ k.transpose(-1, -2) / 8).softmax(-1) @ v).permute(0, 2, 1, 3).reshape(B * Lt, W)
+    L.san_attn(qkv, pooled, out, B, Q, Lp, heads)
+    assert _maxerr(out, ref) < 4e-3, _maxerr(out, ref)

@@ -273,6 +273,26 @@ int ovis_match_compose(const int* pi, long long* indices, int B, int T, int n, v
 int ovis_reorder_queries_f32(const float* in, const long long* idx, float* out, int B, int T, int n, long long inner,
                              long long stride_b, long long stride_t, long long stride_q, void* stream);
 
+/* ---- pixel-decoder glue -----------------------------------------------------
+ * GroupNorm(32, 256) on a token-major map (the `nn.GroupNorm(32, conv_dim)` after every projection / lateral / output
+ * convolution, openvis/modeling/pixel_decoder/msdeformattn.py:227-236, 278-299).
+ * ovis_gn_stats: x [B][S][256] fp32 -> stats [B][32][2] double (sum, sum of squares per sample and group; the caller zeroes
+ * it).  ovis_gn_apply: y = (x - mean) * rstd * gamma + beta, then optionally `+ bilinear(add)` (F.interpolate(...,
+ * mode="bilinear", align_corners=False) of an hs x ws map to the H x W positions, msdeformattn.py:342-343, 371; element
+ * (b, c, p) of the added map at add[b*add_bs + c*add_cs + p*add_ps], so token-major and NCHW maps are both served), then
+ * optionally ReLU; row (b, r) is written to row b*out_bs + out_off + r of out32 (fp32) and / or out16 (fp16). */
+int ovis_gn_stats(const float* x, double* stats, int B, int S, void* stream);
+int ovis_gn_apply(const float* x, const double* stats, const float* gamma, const float* beta, float eps, int B, int H, int W,
+                  int relu, const float* add, long long add_bs, long long add_cs, long long add_ps, int hs, int ws,
+                  float* out32, void* out16, long long out_bs, long long out_off, void* stream);
+/* Token-major rows in_off .. in_off+N of each of B blocks of in_bs rows of C floats -> out [B][C][N] fp32: the NCHW maps
+ * forward_features returns (`z.transpose(1, 2).view(bs, -1, h, w)`, msdeformattn.py:358-359). */
+int ovis_tokens_to_nchw_f32(const float* in, float* out, int B, int C, int N, long long in_bs, long long in_off, void* stream);
+/* A operand of a 3x3 / padding-1 convolution as a GEMM (the FPN output convolution, msdeformattn.py:284-292):
+ * in [B][H][W][C] f16 -> out [B*H*W][9*C] f16, out[(b,y,x)][(ky*3+kx)*C + c] = in[b][y+ky-1][x+kx-1][c] (zero outside);
+ * the weight is laid out [C_out][(ky, kx, C_in)].  C % 8 == 0. */
+int ovis_conv3x3_unfold_f16(const void* in_f16, void* out_f16, int B, int H, int W, int C, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

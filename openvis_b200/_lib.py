@@ -72,6 +72,11 @@ SIGNATURES = {
     "ovis_match_embeds": (_c_int, [_vp, _c_int, _c_int, _c_int, _c_int, _vp, _vp, _vp]),
     "ovis_match_compose": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _vp]),
     "ovis_reorder_queries_f32": (_c_int, [_vp, _vp, _vp, _c_int, _c_int, _c_int, _c_ll, _c_ll, _c_ll, _c_ll, _vp]),
+    "ovis_gn_stats": (_c_int, [_vp, _vp, _c_int, _c_int, _vp]),
+    "ovis_gn_apply": (_c_int, [_vp, _vp, _vp, _vp, _c_float, _c_int, _c_int, _c_int, _c_int, _vp, _c_ll, _c_ll, _c_ll, _c_int, _c_int,
+                               _vp, _vp, _c_ll, _c_ll, _vp]),
+    "ovis_tokens_to_nchw_f32": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_ll, _c_ll, _vp]),
+    "ovis_conv3x3_unfold_f16": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _vp]),
 }
 
 _lib = None
@@ -660,4 +665,53 @@ def reorder_queries(x, idx, layout="btq"):
         sb, st, sq = T * inner, inner, B * T * inner
     out = torch.empty_like(x)
     _check(lib.ovis_reorder_queries_f32(_p(x), _p(idx), _p(out), B, T, n, inner, sb, st, sq, _stream()))
+    return out
+
+
+# ------------------------------------------------------------------------------------------ pixel-decoder glue (row f-2)
+def group_norm_tokens(x, B, H, W, gamma, beta, eps=1e-5, relu=False, add=None, add_layout=None, out32=None, out16=None,
+                      out_bs=None, out_off=0):
+    """GroupNorm(32, 256) of x [B*H*W, 256] fp32 (token-major) (+ bilinear(add) + ReLU).  add_layout = ("tokens", rows per
+    sample, first row, hs, ws) for a token-major fp32 map, ("nchw", hs, ws) for a [B, 256, hs, ws] one.  Row (b, r) goes to
+    row b*out_bs + out_off + r of out32 / out16."""
+    lib = load()
+    _req(x, torch.float32, "x")
+    S = H * W
+    assert x.shape == (B * S, 256)
+    stats = torch.zeros(B, 32, 2, dtype=torch.float64, device=x.device)
+    _check(lib.ovis_gn_stats(_p(x), _p(stats), B, S, _stream()))
+    a_ptr, a_bs, a_cs, a_ps, hs, ws = None, 0, 0, 0, 0, 0
+    if add is not None:
+        _req(add, torch.float32, "add")
+        if add_layout[0] == "tokens":
+            _, rows, first, hs, ws = add_layout
+            a_ptr, a_bs, a_cs, a_ps = add.data_ptr() + first * 256 * 4, rows * 256, 1, 256
+        else:
+            _, hs, ws = add_layout
+            assert add.shape == (B, 256, hs, ws)
+            a_ptr, a_bs, a_cs, a_ps = add.data_ptr(), 256 * hs * ws, hs * ws, 1
+    if out32 is None and out16 is None:
+        out16 = torch.empty(B * S, 256, dtype=torch.float16, device=x.device)
+    _check(lib.ovis_gn_apply(_p(x), _p(stats), _p(gamma), _p(beta), float(eps), B, H, W, int(relu), a_ptr, a_bs, a_cs, a_ps, hs, ws,
+                             _p(out32), _p(out16), S if out_bs is None else out_bs, out_off, _stream()))
+    return out32, out16
+
+
+def tokens_to_nchw(x, B, C, N, in_bs, in_off, out=None):
+    lib = load()
+    _req(x, torch.float32, "x")
+    if out is None:
+        out = torch.empty(B, C, N, dtype=torch.float32, device=x.device)
+    _check(lib.ovis_tokens_to_nchw_f32(_p(x), _p(out), B, C, N, in_bs, in_off, _stream()))
+    return out
+
+
+def conv3x3_unfold_f16(x, B, H, W, out=None):
+    """x [B*H*W, C] fp16 (token-major maps) -> [B*H*W, 9*C] fp16."""
+    lib = load()
+    assert x.dtype == torch.float16 and x.is_contiguous()
+    C = x.shape[-1]
+    if out is None:
+        out = torch.empty(B * H * W, 9 * C, dtype=torch.float16, device=x.device)
+    _check(lib.ovis_conv3x3_unfold_f16(_p(x), _p(out), B, H, W, C, _stream()))
     return out

@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libopenvis_b200.so")
 SOURCES = ["capi.cu"]
-HEADERS = ["ptx.cuh", "gemm_tn.cuh", "prep.cuh", "prep_tma.cuh", "xattn.cuh", "xattn_tc.cuh", "xattn_tc2.cuh", "xattn_tc3.cuh", "chain.cuh", "crop.cuh", "san_attn.cuh", "san_attn_tc.cuh", "postproc.cuh", "msda.cuh", "temporal.cuh", os.path.join("..", "..", "include", "openvis_b200.h")]
+HEADERS = ["ptx.cuh", "gemm_tn.cuh", "prep.cuh", "prep_tma.cuh", "xattn.cuh", "xattn_tc.cuh", "xattn_tc2.cuh", "xattn_tc3.cuh", "chain.cuh", "crop.cuh", "san_attn.cuh", "san_attn_tc.cuh", "postproc.cuh", "msda.cuh", "temporal.cuh", "pixdec.cuh", os.path.join("..", "..", "include", "openvis_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-Wno-format-truncation"]
 

@@ -24,6 +24,7 @@
 #include "postproc.cuh"
 #include "msda.cuh"
 #include "temporal.cuh"
+#include "pixdec.cuh"
 
 using namespace ovis;
 
@@ -1439,4 +1440,61 @@ int ovis_reorder_queries_f32(const float* in, const long long* idx, float* out, 
   if (rc) return rc;
   reorder_queries_kernel<<<dim3(n, T, B), 128, 0, (cudaStream_t)stream>>>(in, idx, out, T, n, inner, stride_b, stride_t, stride_q);
   return check_launch("reorder_queries_kernel");
+}
+
+int ovis_gn_stats(const float* x, double* stats, int B, int S, void* stream) {
+  CHECK_ARG(x && stats && B > 0 && S > 0 && B <= 65535, "bad arguments");
+  CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0, "x must be 16-byte aligned");
+  int sms = 0;
+  int rc = device_info(&sms);
+  if (rc) return rc;
+  // about four CTAs per SM over the whole batch, at least 32 rows each
+  int per = (int)(((long long)S * B + 4ll * sms - 1) / (4ll * sms));
+  per = ((per < 32 ? 32 : per) + 3) / 4 * 4;
+  gn_stats_kernel<<<dim3((S + per - 1) / per, B), 256, 0, (cudaStream_t)stream>>>(x, stats, S, per);
+  return check_launch("gn_stats_kernel");
+}
+
+int ovis_gn_apply(const float* x, const double* stats, const float* gamma, const float* beta, float eps, int B, int H, int W,
+                  int relu, const float* add, long long add_bs, long long add_cs, long long add_ps, int hs, int ws,
+                  float* out32, void* out16, long long out_bs, long long out_off, void* stream) {
+  CHECK_ARG(x && stats && gamma && beta && B > 0 && H > 0 && W > 0 && B <= 65535 && (out32 || out16), "bad arguments");
+  CHECK_ARG(!add || (hs > 0 && ws > 0 && add_ps > 0 && add_cs > 0), "the added map needs its size and strides");
+  CHECK_ARG(!add || add_cs != 1 || (add_ps % 4 == 0 && add_bs % 4 == 0 && (reinterpret_cast<uintptr_t>(add) & 15) == 0),
+            "a token-major added map must be 16-byte aligned");
+  CHECK_ARG(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out32) | reinterpret_cast<uintptr_t>(out16) |
+              reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta)) & 15) == 0, "pointers must be 16-byte aligned");
+  int sms = 0;
+  int rc = device_info(&sms);
+  if (rc) return rc;
+  GnApplyArgs a;
+  a.x = x; a.stats = stats; a.gamma = gamma; a.beta = beta; a.eps = eps; a.S = H * W; a.W = W; a.relu = relu;
+  a.add = add; a.add_bs = add_bs; a.add_cs = add_cs; a.add_ps = add_ps; a.hs = hs; a.ws = ws;
+  a.out32 = out32; a.out16 = (__half*)out16; a.out_bs = out_bs; a.out_off = out_off;
+  const int S = H * W;
+  int gx = (S + 7) / 8;
+  const int cap = (8 * sms + B - 1) / B;
+  if (gx > cap) gx = cap;
+  gn_apply_kernel<<<dim3(gx, B), 256, 0, (cudaStream_t)stream>>>(a);
+  return check_launch("gn_apply_kernel");
+}
+
+int ovis_tokens_to_nchw_f32(const float* in, float* out, int B, int C, int N, long long in_bs, long long in_off, void* stream) {
+  CHECK_ARG(in && out && B > 0 && C > 0 && N > 0 && B <= 65535 && in_bs >= in_off + N && in_off >= 0, "bad arguments");
+  int rc = device_info(nullptr);
+  if (rc) return rc;
+  tokens_to_nchw_kernel<<<dim3((N + 31) / 32, (C + 31) / 32, B), 256, 0, (cudaStream_t)stream>>>(in, out, C, N, in_bs, in_off);
+  return check_launch("tokens_to_nchw_kernel");
+}
+
+int ovis_conv3x3_unfold_f16(const void* in, void* out, int B, int H, int W, int C, void* stream) {
+  CHECK_ARG(in && out && B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "bad arguments");
+  CHECK_ARG(((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0, "pointers must be 16-byte aligned");
+  int rc = device_info(nullptr);
+  if (rc) return rc;
+  const long long total = (long long)B * H * W * 9 * (C / 8);
+  CHECK_ARG((total + 255) / 256 < (1ll << 31), "too many elements for one launch");
+  conv3x3_unfold_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const __half*)in, (__half*)out, H, W,
+                                                                                             C / 8, total);
+  return check_launch("conv3x3_unfold_kernel");
 }

@@ -335,6 +335,8 @@ class _B200MaskedDecoderBase(nn.Module):
         if hasattr(self, "class_embed"):
             ce = self.class_embed
             W["class_embed"] = [(f16(m.weight), f32(m.bias)) for m in (ce.layers if isinstance(ce, MLP) else [ce])]
+        if hasattr(self, "object_embed"):
+            W["object_embed"] = [(f16(m.weight), f32(m.bias)) for m in self.object_embed.layers]
         if self.SAN:
             W["attn_embed"] = [(f16(m.weight), f32(m.bias)) for m in self.attn_embed.layers]
             W["attn_mlp"] = [(f16(m.weight.flatten(1)), f32(m.bias)) for m in self.attn_mlp.layers]
@@ -822,6 +824,64 @@ class EmbeddingFrameMultiScaleMaskedTransformerDecoder(_EmbeddingMixin, _B200Mas
 @TRANSFORMER_DECODER_REGISTRY.register()
 @_configurable_new
 class ProposalFrameMultiScaleMaskedTransformerDecoder(_ProposalMixin, _B200MaskedDecoderBase):
+    VIDEO = False
+
+
+class _ZeroShotMixin:
+    """ZeroShotMultiScaleMaskedTransformerDecoder (zero_shot_mask2former_transformer_decoder.py:44-143, 172-277): a still-image
+    decoder -- every image of the batch is its own attention group and the outputs carry no frame axis.  There is no
+    class_embed: `pred_logits` IS the decoder_norm embedding (the zero-shot classifier consumes it, :256-265) and a two-layer
+    `object_embed` MLP gives the 2-way objectness `pred_object_logits` (:142, 249)."""
+
+    def __init__(self, mask_classification=True, **kwargs):
+        kwargs.pop("num_frames", None)
+        super().__init__(mask_classification=False, **kwargs)
+        self.mask_classification = mask_classification
+        self.object_embed = MLP(kwargs["hidden_dim"], kwargs["hidden_dim"], 2, 2)
+
+    @classmethod
+    def from_config(cls, cfg, in_channels, mask_classification):
+        """zero_shot_...:145-170 (no num_frames)."""
+        m = cfg.MODEL.MASK_FORMER
+        assert m.DEC_LAYERS >= 1
+        return dict(in_channels=in_channels, mask_classification=mask_classification, num_classes=cfg.MODEL.SEM_SEG_HEAD.NUM_CLASSES,
+                    hidden_dim=m.HIDDEN_DIM, num_queries=m.NUM_OBJECT_QUERIES, nheads=m.NHEADS, dim_feedforward=m.DIM_FEEDFORWARD,
+                    dec_layers=m.DEC_LAYERS - 1, pre_norm=m.PRE_NORM, enforce_input_project=m.ENFORCE_INPUT_PROJ,
+                    mask_dim=cfg.MODEL.SEM_SEG_HEAD.MASK_DIM)
+
+    def _full_masks(self, W, ws, hidx, BT, H4, W4, posflags=None):
+        """einsum("bqc,bchw->bqhw") (:251), one group per image: out[b][q][p]."""
+        Q, M = self.num_queries, ws["M"]
+        me = self._mlp3(W["mask_embed"], ws["d16"][hidx], ws["m1"], ws["m2"], ws["me16"])
+        out = torch.empty(BT, Q, H4, W4, dtype=torch.float32, device=me.device)
+        L.mask_logits(ws["ft"], BT, M, me, Q, Q, out, Q * M, M, posflags=posflags, rows_per_frame=M if posflags is not None else 0)
+        return out
+
+    def _class_outputs(self, W, ws, hidx, BT, san):
+        x = ws["d16"][hidx]
+        (w0, b0), (w1, b1) = W["object_embed"]
+        obj = L.linear_f16(L.linear_f16(x, w0, b0, relu=True), w1, b1, out_f32=True)
+        # the embedding of the last head is available in fp32; earlier heads (aux_outputs) keep their fp16 operand copy
+        emb = ws["d32"].clone() if hidx == self.num_layers else x.float()
+        return obj, emb
+
+    def _pack_head(self, d, cls, masks, BT):
+        Q = self.num_queries
+        if self.mask_classification:
+            d["pred_object_logits"] = cls[0].view(BT, Q, 2)
+            d["pred_logits"] = cls[1].view(BT, Q, HIDDEN)
+        d["pred_masks"] = masks
+
+    def _pack_outputs(self, out, cls, pred_masks, pred_embeds, x, mask_features, sizes, p2, pz, BT, san):
+        out["pred_object_logits"] = cls[0].view(BT, self.num_queries, 2)
+        out["pred_logits"] = cls[1].view(BT, self.num_queries, HIDDEN)
+        out["pred_masks"] = pred_masks
+        out["pred_embeds"] = pred_embeds.view(BT, self.num_queries, HIDDEN)
+
+
+@TRANSFORMER_DECODER_REGISTRY.register()
+@_configurable_new
+class ZeroShotMultiScaleMaskedTransformerDecoder(_ZeroShotMixin, _B200MaskedDecoderBase):
     VIDEO = False
 
 

@@ -6,7 +6,8 @@ import torch
 def decoder_param_shapes(kind="frame", Q=100, C=256, F_=2048, L=9, num_classes=1, clip_heads=12, clip_dims=512):
     """state_dict contract of the reference decoders.  kind: frame / video / san_frame / san_video,
     or embedding_{frame,video} (class_embed = MLP(C, 2*clip_dims, clip_dims, 2), video_..._decoder.py:513-515) /
-    proposal_{frame,video} (class_embed = Linear(C, 2), :536-537)."""
+    proposal_{frame,video} (class_embed = Linear(C, 2), :536-537) / zero_shot (object_embed = MLP(C, C, 2, 2), no class_embed,
+    zero_shot_mask2former_transformer_decoder.py:142)."""
     s = {}
     for i in range(L):
         for pre, att in ((f"transformer_self_attention_layers.{i}", "self_attn"),
@@ -40,6 +41,11 @@ def decoder_param_shapes(kind="frame", Q=100, C=256, F_=2048, L=9, num_classes=1
             o = C * clip_heads if i == 2 else C
             s[f"attn_mlp.layers.{i}.weight"] = (o, C, 1, 1)
             s[f"attn_mlp.layers.{i}.bias"] = (o,)
+    elif kind == "zero_shot":
+        s["object_embed.layers.0.weight"] = (C, C)
+        s["object_embed.layers.0.bias"] = (C,)
+        s["object_embed.layers.1.weight"] = (2, C)
+        s["object_embed.layers.1.bias"] = (2,)
     elif kind.startswith("embedding"):
         s["class_embed.layers.0.weight"] = (2 * clip_dims, C)
         s["class_embed.layers.0.bias"] = (2 * clip_dims,)
@@ -218,3 +224,72 @@ def seeded_resampler_params(seed=0, **kw):
             t = (torch.rand(shp, generator=g) * 2 - 1) * bound
         out[name] = t
     return out
+
+
+def pixel_decoder_param_shapes(in_channels=(256, 512, 1024, 2048), C=256, F_=1024, L=6, M=8, P=4):
+    """state_dict names / shapes of the reference MSDeformAttnPixelDecoder (pixel_decoder/msdeformattn.py:182-306) with
+    res2..res5 inputs, the three coarsest fed to the deformable encoder and one FPN level (res2), norm "GN"."""
+    s = {}
+    for i, cin in enumerate(in_channels[:0:-1]):              # res5, res4, res3
+        s[f"input_proj.{i}.0.weight"] = (C, cin, 1, 1)
+        s[f"input_proj.{i}.0.bias"] = (C,)
+        s[f"input_proj.{i}.1.weight"] = (C,)
+        s[f"input_proj.{i}.1.bias"] = (C,)
+    s["transformer.level_embed"] = (3, C)
+    for i in range(L):
+        pre = f"transformer.encoder.layers.{i}"
+        s[f"{pre}.self_attn.sampling_offsets.weight"] = (M * 3 * P * 2, C)
+        s[f"{pre}.self_attn.sampling_offsets.bias"] = (M * 3 * P * 2,)
+        s[f"{pre}.self_attn.attention_weights.weight"] = (M * 3 * P, C)
+        s[f"{pre}.self_attn.attention_weights.bias"] = (M * 3 * P,)
+        for n in ("value_proj", "output_proj"):
+            s[f"{pre}.self_attn.{n}.weight"] = (C, C)
+            s[f"{pre}.self_attn.{n}.bias"] = (C,)
+        s[f"{pre}.linear1.weight"] = (F_, C)
+        s[f"{pre}.linear1.bias"] = (F_,)
+        s[f"{pre}.linear2.weight"] = (C, F_)
+        s[f"{pre}.linear2.bias"] = (C,)
+        for n in ("norm1", "norm2"):
+            s[f"{pre}.{n}.weight"] = (C,)
+            s[f"{pre}.{n}.bias"] = (C,)
+    s["mask_features.weight"] = (C, C, 1, 1)
+    s["mask_features.bias"] = (C,)
+    s["adapter_1.weight"] = (C, in_channels[0], 1, 1)
+    s["adapter_1.norm.weight"] = (C,)
+    s["adapter_1.norm.bias"] = (C,)
+    s["layer_1.weight"] = (C, C, 3, 3)
+    s["layer_1.norm.weight"] = (C,)
+    s["layer_1.norm.bias"] = (C,)
+    return s
+
+
+def seeded_pixel_decoder_params(seed=0, **kw):
+    """Deterministic pixel-decoder weights: xavier-like matrices / convolutions (fan = channels x kernel area), norm weights
+    near 1, sampling-offset biases of a pixel or two (the reference initialises them to a ring of unit steps)."""
+    g = torch.Generator().manual_seed(seed)
+    shapes = pixel_decoder_param_shapes(**kw)
+    out = {}
+    for name in sorted(shapes):
+        shp = shapes[name]
+        if len(shp) == 1 and (".norm" in name or name.endswith(".1.weight") or name.endswith(".1.bias")):
+            t = (1.0 if name.endswith("weight") else 0.0) + 0.1 * torch.randn(shp, generator=g)
+        elif name.endswith("sampling_offsets.bias"):
+            t = 1.5 * torch.randn(shp, generator=g)
+        elif name.endswith("sampling_offsets.weight"):
+            t = 0.03 * torch.randn(shp, generator=g)
+        elif name.endswith(".bias"):
+            t = 0.05 * torch.randn(shp, generator=g)
+        elif name == "transformer.level_embed":
+            t = torch.randn(shp, generator=g)
+        else:
+            area = shp[2] * shp[3] if len(shp) == 4 else 1
+            bound = math.sqrt(6.0 / ((shp[0] + shp[1]) * area))
+            t = (torch.rand(shp, generator=g) * 2 - 1) * bound
+        out[name] = t
+    return out
+
+
+def seeded_backbone_features(T, Hp, Wp, in_channels=(256, 512, 1024, 2048), seed=77):
+    """N(0,1) stand-ins for the backbone's res2..res5 maps (strides 4 / 8 / 16 / 32) of a [T, 3, Hp, Wp] batch."""
+    g = torch.Generator().manual_seed(seed)
+    return {f"res{i + 2}": torch.randn(T, c, Hp // (4 << i), Wp // (4 << i), generator=g) for i, c in enumerate(in_channels)}

@@ -137,6 +137,9 @@ def decoder_forward(params, x, mask_features, kind="frame", nheads=8, num_layers
       kind="frame"     FrameMultiScaleMaskedTransformerDecoder.forward            (frame_...:52-137)
       kind="san_frame" SideAdapterFrameMultiScaleMaskedTransformerDecoder.forward (side_adapter_frame...:57-149)
       kind="san_video" SideAdapterVideoMultiScaleMaskedTransformerDecoder.forward (side_adapter_video...:51-120)
+      kind="zero_shot" ZeroShotMultiScaleMaskedTransformerDecoder.forward (zero_shot_...:172-265): a still-image decoder
+                       (every image its own group, no frame axis in the outputs) whose class output is the decoder_norm
+                       embedding itself plus a 2-way `object_embed` MLP
     x: list of 3 [T, C, h_l, w_l] (coarsest first); mask_features [T, C, H4, W4].
     Returns the reference's output dict (same keys / shapes) plus, when return_attn_masks,
     "attn_masks": list of L+1 bool tensors [G, Q, keys] (True = blocked, before the full-row fix).
@@ -146,6 +149,7 @@ def decoder_forward(params, x, mask_features, kind="frame", nheads=8, num_layers
     mask_features = mask_features.to(dtype)
     video = kind.endswith("video")          # (embedding_* / proposal_* kinds differ only in their class_embed parameters)
     san = kind in ("san_frame", "san_video")
+    zs = kind == "zero_shot"
     T, C = mask_features.shape[:2]
     if num_layers is None:
         num_layers = 1 + max(int(k.split(".")[1]) for k in P if k.startswith("transformer_ffn_layers."))
@@ -181,6 +185,8 @@ def decoder_forward(params, x, mask_features, kind="frame", nheads=8, num_layers
                 cls = torch.einsum("bqc,tnchw->btnqhw", ae, attn_features)           # b = 1
             else:
                 cls = torch.einsum("bqc,bnchw->bnqhw", ae, attn_features)
+        elif zs:
+            cls = (mlp(P, "object_embed", D, 2), D)                                  # zero_shot_...:249, 265
         elif "class_embed.weight" in P:
             cls = D @ P["class_embed.weight"].T + P["class_embed.bias"]
         elif "class_embed.layers.0.weight" in P:
@@ -220,6 +226,14 @@ def decoder_forward(params, x, mask_features, kind="frame", nheads=8, num_layers
         pred_cls.append(cls), pred_mask.append(m), attn_masks.append(blocked)
 
     out = {}
+    if zs:                                                         # zero_shot_...:236-243, 268-277
+        out = {"pred_object_logits": pred_cls[-1][0], "pred_logits": pred_cls[-1][1], "pred_masks": pred_mask[-1],
+               "pred_embeds": D,
+               "aux_outputs": [{"pred_object_logits": a[0], "pred_logits": a[1], "pred_masks": b}
+                               for a, b in zip(pred_cls[:-1], pred_mask[:-1])]}
+        if return_attn_masks:
+            out["attn_masks"] = attn_masks
+        return out
     if not video:
         # '(b t) q h w -> b q t h w' with b = 1 (frame_...:113-121)
         pred_mask = [m.permute(1, 0, 2, 3)[None] for m in pred_mask]

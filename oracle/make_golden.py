@@ -69,6 +69,26 @@ def make_decoder_fixture(name, kind, T, Hp, Wp, Q, pseed, iseed):
     print("wrote", name, {k: v.shape for k, v in rec.items()})
 
 
+def make_zero_shot_fixture(T=2, Hp=128, Wp=192, Q=100, pseed=8, iseed=1243):
+    """tests/golden/dec_zero_shot_q100.npz: the reference's ZeroShotMultiScaleMaskedTransformerDecoder
+    (zero_shot_mask2former_transformer_decoder.py:172-277) on seeded weights / inputs."""
+    kw = R.decoder_kwargs(num_queries=Q)
+    kw.pop("num_frames")
+    m = R.zero_shot_decoder()(**kw).eval()
+    m.load_state_dict(O.seeded_params(O.decoder_param_shapes("zero_shot", Q=Q), pseed))
+    x, mf = O.seeded_inputs(T, Hp, Wp, seed=iseed)
+    with torch.no_grad():
+        out = m(x, mf)
+    rec = dict(meta=np.array([T, Hp, Wp, Q, pseed, iseed]), pred_object_logits=out["pred_object_logits"].numpy(),
+               pred_logits=out["pred_logits"].numpy(), pred_embeds=out["pred_embeds"].numpy(),
+               pred_masks=out["pred_masks"].numpy().astype(np.float16),
+               aux0_pred_masks=out["aux_outputs"][0]["pred_masks"].numpy().astype(np.float16),
+               aux4_pred_object_logits=out["aux_outputs"][4]["pred_object_logits"].numpy(),
+               aux4_pred_logits=out["aux_outputs"][4]["pred_logits"].numpy())
+    np.savez_compressed(os.path.join(GOLDEN, "dec_zero_shot_q100.npz"), **rec)
+    print("wrote dec_zero_shot_q100", {k: v.shape for k, v in rec.items()})
+
+
 def make_san_tail_fixture():
     """SideAdapter._build_attn_biases + post_encode_image tail + cal_sim_logits on seeded inputs
     (side_adapter.py:201-207, 234-270).  The three CLIP blocks in between are out of scope, so the tail
@@ -358,6 +378,54 @@ def make_clip_adapter_fixture():
           "sim", float(np.abs(rec["sim"] - rec["sim_h"]).max()), "probs", float(np.abs(rec["probs"] - rec["probs_h"]).max()))
 
 
+PIXDEC_CH = (64, 128, 192, 256)
+
+
+def pixel_decoder_case(seed=5, layers=2, T=2, Hp=64, Wp=96):
+    """Seeded pixel-decoder weights (narrow stand-in backbone channels, 2 encoder layers) + res2..res5 maps."""
+    from openvis_b200.synthetic import seeded_backbone_features, seeded_pixel_decoder_params
+    P = seeded_pixel_decoder_params(seed, in_channels=PIXDEC_CH, L=layers)
+    feats = seeded_backbone_features(T, Hp, Wp, in_channels=PIXDEC_CH, seed=seed + 70)
+    return P, feats
+
+
+def pixel_decoder_extra(T=2, seed=21):
+    """extra_features of the SAN-fused call (mask_former_head.py:120): one map per encoder level (res5, res4, res3 order), the
+    middle one at another resolution so that the reference interpolates it."""
+    g = torch.Generator().manual_seed(seed)
+    return [torch.randn(T, 256, h, w, generator=g) for (h, w) in ((2, 3), (7, 5), (8, 12))]
+
+
+def reference_pixel_decoder(P, layers=2):
+    ns = R.pixel_decoder()
+    shape = {f"res{i + 2}": ns.ShapeSpec(channels=c, stride=4 << i) for i, c in enumerate(PIXDEC_CH)}
+    m = ns.MSDeformAttnPixelDecoder(shape, transformer_dropout=0.0, transformer_nheads=8, transformer_dim_feedforward=1024,
+                                    transformer_enc_layers=layers, conv_dim=256, mask_dim=256, norm="GN",
+                                    transformer_in_features=["res3", "res4", "res5"], common_stride=4).eval()
+    m.load_state_dict(P)
+    return m
+
+
+def make_pixel_decoder_fixture():
+    """tests/golden/pixel_decoder.npz: the reference MSDeformAttnPixelDecoder.forward_features (msdeformattn.py:329-380) and,
+    separately, its MSDeformAttnTransformerEncoderOnly (:76-104) on pixel_decoder_case()."""
+    P, feats = pixel_decoder_case()
+    m = reference_pixel_decoder(P)
+    with torch.no_grad():
+        mf, o0, ms = m.forward_features(feats)
+        mf_ex, _, ms_ex = m.forward_features(feats, pixel_decoder_extra())
+        g = torch.Generator().manual_seed(11)
+        srcs = [torch.randn(2, 256, h, w, generator=g) for (h, w) in ((2, 3), (4, 6), (8, 12))]
+        pos = [m.pe_layer(s_) for s_ in srcs]
+        mem, shapes, start = m.transformer(srcs, pos)
+    rec = dict(mask_features=mf.numpy(), ms0=ms[0].numpy(), ms1=ms[1].numpy(), ms2=ms[2].numpy(), enc_memory=mem.numpy(),
+               mask_features_ex=mf_ex[:, ::4].numpy(), ms1_ex=ms_ex[1].numpy(),
+               enc_shapes=shapes.numpy(), enc_start=start.numpy())
+    assert torch.equal(o0, ms[0])
+    np.savez_compressed(os.path.join(GOLDEN, "pixel_decoder.npz"), **rec)
+    print("wrote pixel_decoder", {k: v.shape for k, v in rec.items()})
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     for case in DECODER_CASES:
@@ -370,6 +438,8 @@ def main():
     make_ov_tails_fixture()
     make_clip_adapter_fixture()
     make_msda_module_fixture()
+    make_pixel_decoder_fixture()
+    make_zero_shot_fixture()
 
 
 if __name__ == "__main__":

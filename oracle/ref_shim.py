@@ -55,6 +55,42 @@ class _Registry(dict):
         return deco if obj is None else deco(obj)
 
 
+class _Conv2d(torch.nn.Conv2d):
+    """Stand-in for detectron2.layers.Conv2d, restated from its published definition (detectron2/layers/wrappers.py):
+    torch.nn.Conv2d with optional `norm` and `activation` applied after the convolution."""
+
+    def __init__(self, *args, **kwargs):
+        norm = kwargs.pop("norm", None)
+        activation = kwargs.pop("activation", None)
+        super().__init__(*args, **kwargs)
+        self.norm = norm
+        self.activation = activation
+
+    def forward(self, x):
+        x = torch.nn.functional.conv2d(x, self.weight, self.bias, self.stride, self.padding, self.dilation, self.groups)
+        if self.norm is not None:
+            x = self.norm(x)
+        if self.activation is not None:
+            x = self.activation(x)
+        return x
+
+
+class _ShapeSpec:
+    """Stand-in for detectron2.layers.ShapeSpec (channels / height / width / stride record)."""
+
+    def __init__(self, channels=None, height=None, width=None, stride=None):
+        self.channels, self.height, self.width, self.stride = channels, height, width, stride
+
+
+def _get_norm(norm, out_channels):
+    """detectron2.layers.get_norm for the two values the shipped configs use: "" -> None, "GN" -> GroupNorm(32, C)."""
+    if norm is None or norm == "":
+        return None
+    if norm == "GN":
+        return torch.nn.GroupNorm(32, out_channels)
+    raise NotImplementedError(norm)
+
+
 def _c2_xavier_fill(m):
     torch.nn.init.kaiming_uniform_(m.weight, a=1)
     if m.bias is not None:
@@ -66,7 +102,7 @@ def _install_stubs():
         return  # a real detectron2 is importable: leave it alone
     _mod("detectron2", _ovis_stub=True)
     _mod("detectron2.config", configurable=lambda f=None, **k: f)
-    _mod("detectron2.layers", Conv2d=torch.nn.Conv2d)
+    _mod("detectron2.layers", Conv2d=_Conv2d, ShapeSpec=_ShapeSpec, get_norm=_get_norm)
     _mod("detectron2.utils")
     _mod("detectron2.utils.registry", Registry=_Registry)
     _mod("detectron2.utils.comm", get_local_rank=lambda: 0, synchronize=lambda: None)
@@ -252,6 +288,29 @@ def msda_module():
     return m.MSDeformAttn
 
 
+def pixel_decoder():
+    """The reference's MSDeformAttnPixelDecoder / MSDeformAttnTransformerEncoderOnly (openvis/modeling/pixel_decoder/
+    msdeformattn.py:38-380), unmodified; its MSDeformAttn runs ms_deform_attn_core_pytorch (no compiled extension)."""
+    if "pixdec" in _loaded:
+        return _loaded["pixdec"]
+    if not available():
+        raise RuntimeError(f"reference not found under {REF_ROOT}")
+    _install_stubs()
+    _mod("MultiScaleDeformableAttention")
+    m = sys.modules.get("detectron2.modeling")
+    if m is None or not hasattr(m, "SEM_SEG_HEADS_REGISTRY"):
+        _mod("detectron2.modeling", SEM_SEG_HEADS_REGISTRY=_Registry("SEM_SEG_HEADS"))
+    d = os.path.join(REF_ROOT, "openvis/modeling/pixel_decoder")
+    _mod("refpix").__path__ = [d]
+    _mod("refpix.ops").__path__ = [os.path.join(d, "ops")]
+    mod = importlib.import_module("refpix.msdeformattn")
+    ns = types.SimpleNamespace(MSDeformAttnPixelDecoder=mod.MSDeformAttnPixelDecoder,
+                               MSDeformAttnTransformerEncoderOnly=mod.MSDeformAttnTransformerEncoderOnly,
+                               ShapeSpec=_ShapeSpec)
+    _loaded["pixdec"] = ns
+    return ns
+
+
 def temporal():
     """The reference's temporal-association code, unmodified: ``match_via_embeds`` /
     ``batch_video_match_via_embeds`` (openvis/modeling/minvis.py:28-72), ``batch_index`` (openvis/utils/index.py:4-19)
@@ -326,6 +385,12 @@ def ov_tails():
         zero_shot_forward=extract_function("openvis/ov2seg.py", "ZeroShotClassifier.forward"))
     _loaded["ov"] = ns
     return ns
+
+
+def zero_shot_decoder():
+    """ZeroShotMultiScaleMaskedTransformerDecoder of the reference (zero_shot_mask2former_transformer_decoder.py:15-277)."""
+    decoders()
+    return _load("refdec", _DEC_DIR, "zero_shot_mask2former_transformer_decoder").ZeroShotMultiScaleMaskedTransformerDecoder
 
 
 def embedding_decoders():

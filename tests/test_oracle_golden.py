@@ -270,3 +270,60 @@ def test_msda_module_oracle_against_reference_golden(golden_dir, ref_dim):
     P, query, ref, src, shapes, start, pad = msda_module_case(ref_dim=ref_dim)
     out = O.ms_deform_attn_module(P, query, ref, src, shapes, pad)
     assert np.abs(out[:, :, ::2].numpy() - g[f"out{ref_dim}"]).max() < 1e-5
+
+
+def test_pixel_decoder_oracle_against_reference_golden(golden_dir):
+    """oracle.pixel_decoder_ref (row f-2: input projections + GroupNorm, deformable encoder, FPN level, mask features) against
+    the outputs of the reference's own MSDeformAttnPixelDecoder / MSDeformAttnTransformerEncoderOnly
+    (tests/golden/pixel_decoder.npz, oracle.make_golden.make_pixel_decoder_fixture)."""
+    from oracle import pixel_decoder_ref as PO
+    from oracle.make_golden import pixel_decoder_case, pixel_decoder_extra
+    g = np.load(os.path.join(golden_dir, "pixel_decoder.npz"))
+    P, feats = pixel_decoder_case()
+    mf, o0, ms = PO.pixel_decoder_forward(P, feats)
+    assert np.abs(mf.numpy() - g["mask_features"]).max() < 2e-5
+    for i in range(3):
+        assert np.abs(ms[i].numpy() - g[f"ms{i}"]).max() < 2e-5
+    assert o0 is ms[0]
+    mf, _, ms = PO.pixel_decoder_forward(P, feats, pixel_decoder_extra())
+    assert np.abs(mf[:, ::4].numpy() - g["mask_features_ex"]).max() < 2e-5
+    assert np.abs(ms[1].numpy() - g["ms1_ex"]).max() < 2e-5
+    gen = torch.Generator().manual_seed(11)
+    srcs = [torch.randn(2, 256, h, w, generator=gen) for (h, w) in ((2, 3), (4, 6), (8, 12))]
+    pos = [O.sine_pos_2d(*s.shape[-2:])[None].expand(2, -1, -1, -1) for s in srcs]
+    mem, shapes = PO.encoder_only(P, srcs, pos)
+    assert np.abs(mem.numpy() - g["enc_memory"]).max() < 2e-5
+    assert np.array_equal(shapes.numpy(), g["enc_shapes"])
+
+
+@pytest.mark.skipif(not R.available(), reason="reference not mounted")
+def test_pixel_decoder_oracle_against_live_reference():
+    """A larger live case (three encoder layers, 96 x 160 input) against the reference's own module."""
+    from oracle import pixel_decoder_ref as PO
+    from oracle.make_golden import pixel_decoder_case, reference_pixel_decoder
+    P, feats = pixel_decoder_case(seed=9, layers=3, T=1, Hp=96, Wp=160)
+    m = reference_pixel_decoder(P, layers=3)
+    with torch.no_grad():
+        mf, o0, ms = m.forward_features(feats)
+    mf2, _, ms2 = PO.pixel_decoder_forward(P, feats)
+    assert (mf - mf2).abs().max() < 5e-5
+    for a, b in zip(ms, ms2):
+        assert (a - b).abs().max() < 5e-5
+
+
+def test_zero_shot_decoder_oracle_against_reference_golden(golden_dir):
+    """kind="zero_shot" of the oracle against the reference's own ZeroShotMultiScaleMaskedTransformerDecoder
+    (tests/golden/dec_zero_shot_q100.npz, oracle.make_golden.make_zero_shot_fixture)."""
+    g = np.load(os.path.join(golden_dir, "dec_zero_shot_q100.npz"))
+    T, Hp, Wp, Q, pseed, iseed = [int(v) for v in g["meta"]]
+    P = O.seeded_params(O.decoder_param_shapes("zero_shot", Q=Q), pseed)
+    x, mf = O.seeded_inputs(T, Hp, Wp, seed=iseed)
+    out = O.decoder_forward(P, x, mf, kind="zero_shot")
+    assert set(out) == {"pred_object_logits", "pred_logits", "pred_masks", "pred_embeds", "aux_outputs", "attn_masks"}
+    for k in ("pred_object_logits", "pred_logits", "pred_embeds"):
+        _close(out[k], g[k], atol=2e-5)
+    _close(out["pred_masks"], g["pred_masks"], atol=3e-2, rtol=2e-3)
+    _close(out["aux_outputs"][0]["pred_masks"], g["aux0_pred_masks"], atol=3e-2, rtol=2e-3)
+    _close(out["aux_outputs"][4]["pred_logits"], g["aux4_pred_logits"], atol=2e-5)
+    _close(out["aux_outputs"][4]["pred_object_logits"], g["aux4_pred_object_logits"], atol=2e-5)
+    assert len(out["aux_outputs"]) == 9 and set(out["aux_outputs"][0]) == {"pred_object_logits", "pred_logits", "pred_masks"}

@@ -122,3 +122,42 @@ def test_embedding_proposal_decoders_match_reference_golden(name, kind, golden_d
     pl, gl = out["pred_logits"].cpu(), g("pred_logits")
     assert pl.shape == gl.shape and _frac(pl, gl, 0.05) >= 0.97
     assert _frac(out["aux_outputs"][0]["pred_masks"].cpu(), g("aux0_pred_masks"), 0.08) >= 0.9999
+
+
+def _build_zero_shot(Q=100, pseed=0):
+    kw = dict(in_channels=256, mask_classification=True, num_classes=1, hidden_dim=256, num_queries=Q, nheads=8,
+              dim_feedforward=2048, dec_layers=9, pre_norm=False, mask_dim=256, enforce_input_project=False)
+    m = D.TRANSFORMER_DECODER_REGISTRY["ZeroShotMultiScaleMaskedTransformerDecoder"](**kw)
+    P = O.seeded_params(O.decoder_param_shapes("zero_shot", Q=Q), pseed)
+    m.load_state_dict(P)
+    return m.cuda().eval(), P
+
+
+def test_zero_shot_decoder_vs_oracle_and_reference_golden(golden_dir):
+    """zero_shot_mask2former_transformer_decoder.py:172-277: a batch of 4 images at 384 x 640 against the oracle (strict bars),
+    then the reference's own outputs on the small fixture."""
+    m, P = _build_zero_shot()
+    x, mf = O.seeded_inputs(4, 384, 640, seed=91)
+    ref = O.decoder_forward(P, x, mf, kind="zero_shot", return_attn_masks=False)
+    out = m([t.cuda() for t in x], mf.cuda())
+    assert {"pred_object_logits", "pred_logits", "pred_masks", "pred_embeds", "aux_outputs"} <= set(out)
+    pm, rm = out["pred_masks"].cpu(), ref["pred_masks"]
+    assert pm.shape == rm.shape == (4, 100, 96, 160)
+    assert _frac(pm, rm, 0.25) >= 0.999 and ((pm > 0) == (rm > 0)).float().mean().item() >= 0.999
+    for k in ("pred_logits", "pred_embeds", "pred_object_logits"):
+        a, b = out[k].cpu(), ref[k]
+        assert a.shape == b.shape and (a - b).abs().max().item() <= 3e-2, (k, (a - b).abs().max().item())
+    aux = out["aux_outputs"][4]
+    assert set(aux) == {"pred_object_logits", "pred_logits", "pred_masks"}
+    assert _frac(aux["pred_logits"].cpu(), ref["aux_outputs"][4]["pred_logits"], 3e-2) >= 0.999
+    assert _frac(aux["pred_object_logits"].cpu(), ref["aux_outputs"][4]["pred_object_logits"], 3e-2) >= 0.999
+    gold = np.load(os.path.join(golden_dir, "dec_zero_shot_q100.npz"))
+    T, Hp, Wp, Q, pseed, iseed = [int(v) for v in gold["meta"]]
+    m, _ = _build_zero_shot(Q, pseed)
+    x, mf = O.seeded_inputs(T, Hp, Wp, seed=iseed)
+    out = m([t.cuda() for t in x], mf.cuda())
+    g = lambda k: torch.as_tensor(gold[k]).float()
+    assert _frac(out["pred_masks"].cpu(), g("pred_masks"), 0.25) >= 0.95             # small input: LOOSE set (test_decoder_gpu)
+    assert _frac(out["pred_logits"].cpu(), g("pred_logits"), 0.05) >= 0.97
+    assert _frac(out["pred_object_logits"].cpu(), g("pred_object_logits"), 0.05) >= 0.97
+    assert _frac(out["aux_outputs"][0]["pred_masks"].cpu(), g("aux0_pred_masks"), 0.08) >= 0.9999

@@ -1,0 +1,149 @@
+"""the pixel decoder on the device (openvis_b200.pixel_decoder / msda encoder modules, csrc/pixdec.cuh)
+against the committed outputs of the reference's own MSDeformAttnPixelDecoder / MSDeformAttnTransformerEncoderOnly
+(tests/golden/pixel_decoder.npz) and the oracle restatement (oracle/pixel_decoder_ref.py), reference state dict loaded by name.
+Operands are fp16 with fp32 accumulation; GroupNorm / LayerNorm / softmax / sampling arithmetic are fp32."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from openvis_b200 import _lib as L  # noqa: E402
+from openvis_b200.pixel_decoder import MSDeformAttnPixelDecoder, ShapeSpec  # noqa: E402
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    L.device_check()
+
+
+def _band(out, ref, atol, rtol, frac, hard, what):
+    out, ref = torch.as_tensor(out).float().cpu(), torch.as_tensor(ref).float().cpu()
+    assert out.shape == ref.shape, (what, out.shape, ref.shape)
+    err = (out - ref).abs()
+    ok = (err <= atol + rtol * ref.abs()).float().mean().item()
+    print(f"{what}: max err {err.max().item():.3e} (|ref| max {ref.abs().max().item():.2f}), within band {ok:.5f}")
+    assert ok >= frac and err.max().item() <= hard, (what, err.max().item(), ok)
+
+
+@pytest.mark.parametrize("mode", ["plain", "relu", "add_tokens", "add_nchw"])
+def test_group_norm_tokens_against_torch(mode):
+    """GroupNorm(32, 256) on token-major maps (+ bilinear top-down term, + ReLU) vs torch.nn.functional in fp64."""
+    g = torch.Generator().manual_seed(3)
+    B, H, W = 3, 13, 20
+    x = (2.0 * torch.randn(B, 256, H, W, generator=g) + 0.7).cuda()
+    gamma, beta = (1 + 0.1 * torch.randn(256, generator=g)).cuda(), (0.1 * torch.randn(256, generator=g)).cuda()
+    ref = F.group_norm(x.double(), 32, gamma.double(), beta.double(), 1e-5)
+    tok = x.permute(0, 2, 3, 1).reshape(B * H * W, 256).contiguous()
+    add, lay = None, None
+    if mode.startswith("add"):
+        hs, ws = 7, 10
+        a = torch.randn(B, 256, hs, ws, generator=g).cuda()
+        ref = ref + F.interpolate(a.double(), size=(H, W), mode="bilinear", align_corners=False)
+        if mode == "add_tokens":           # rows 5 .. 5 + hs*ws of blocks of 100 rows
+            blk = torch.zeros(B, 100, 256, device="cuda")
+            blk[:, 5:5 + hs * ws] = a.permute(0, 2, 3, 1).reshape(B, hs * ws, 256)
+            add, lay = blk, ("tokens", 100, 5, hs, ws)
+        else:
+            add, lay = a, ("nchw", hs, ws)
+    if mode == "relu":
+        ref = ref.relu()
+    o32 = torch.zeros(B * (H * W + 4) , 256, device="cuda")
+    _, o16 = L.group_norm_tokens(tok, B, H, W, gamma, beta, relu=mode == "relu", add=add, add_layout=lay, out32=o32,
+                                 out16=torch.empty(B * (H * W + 4), 256, dtype=torch.float16, device="cuda"), out_bs=H * W + 4,
+                                 out_off=3)
+    torch.cuda.synchronize()
+    got = o32.view(B, H * W + 4, 256)[:, 3:3 + H * W].reshape(B, H, W, 256).permute(0, 3, 1, 2)
+    assert (got.double() - ref).abs().max().item() < 2e-5
+    assert o32.view(B, H * W + 4, 256)[:, :3].abs().max().item() == 0            # rows outside the window untouched
+    got16 = o16.view(B, H * W + 4, 256)[:, 3:3 + H * W].reshape(B, H, W, 256).permute(0, 3, 1, 2)
+    assert (got16.double() - ref).abs().max().item() < 4e-3
+
+
+def test_conv3x3_unfold_gemm_and_nchw_store():
+    """3x3 / padding-1 convolution = unfold + tcgen05 GEMM (K = 2304) vs F.conv2d on the fp16-rounded operands; NCHW store."""
+    g = torch.Generator().manual_seed(4)
+    B, H, W = 2, 9, 14
+    x = torch.randn(B, 256, H, W, generator=g).half().cuda()
+    w = (torch.randn(256, 256, 3, 3, generator=g) * 0.03).half().cuda()
+    ref = F.conv2d(x.double(), w.double(), padding=1)
+    tok = x.permute(0, 2, 3, 1).reshape(B * H * W, 256).contiguous()
+    u = L.conv3x3_unfold_f16(tok, B, H, W)
+    # operand check: tap (ky, kx) of position (y, x)
+    u5 = u.view(B, H, W, 9, 256)
+    assert torch.equal(u5[1, 4, 6, 5], tok.view(B, H, W, 256)[1, 4, 7]) and u5[0, 0, 0, 0].abs().max().item() == 0
+    assert u5[0, H - 1, W - 1, 8].abs().max().item() == 0 and torch.equal(u5[:, :, :, 4], tok.view(B, H, W, 256))
+    y = L.linear_f16(u, w.permute(0, 2, 3, 1).reshape(256, -1).contiguous(), None, out_f32=True)
+    out = L.tokens_to_nchw(y, B, 256, H * W, H * W, 0).view(B, 256, H, W)
+    torch.cuda.synchronize()
+    assert torch.equal(out, y.view(B, H * W, 256).transpose(1, 2).reshape(B, 256, H, W))
+    assert (out.double() - ref).abs().max().item() < 2e-3
+
+
+def _build(P, channels, layers):
+    shape = {f"res{i + 2}": ShapeSpec(channels=c, stride=4 << i) for i, c in enumerate(channels)}
+    m = MSDeformAttnPixelDecoder(shape, transformer_enc_layers=layers)
+    m.load_state_dict(P, strict=True)
+    return m.cuda()
+
+
+def test_encoder_only_against_reference_golden(golden_dir):
+    """MSDeformAttnTransformerEncoderOnly.forward (msdeformattn.py:76-104), two layers, three levels."""
+    from oracle.make_golden import PIXDEC_CH, pixel_decoder_case
+    from openvis_b200.decoder import sine_pos_2d
+    g = np.load(os.path.join(golden_dir, "pixel_decoder.npz"))
+    P, _ = pixel_decoder_case()
+    m = _build(P, PIXDEC_CH, 2)
+    gen = torch.Generator().manual_seed(11)
+    srcs = [torch.randn(2, 256, h, w, generator=gen).cuda() for (h, w) in ((2, 3), (4, 6), (8, 12))]
+    pos = [sine_pos_2d(*s.shape[-2:], "cuda").t().reshape(1, 256, *s.shape[-2:]).expand(2, -1, -1, -1) for s in srcs]
+    mem, shapes, start = m.transformer(srcs, pos)
+    assert np.array_equal(shapes.cpu().numpy(), g["enc_shapes"]) and np.array_equal(start.cpu().numpy(), g["enc_start"])
+    _band(mem, g["enc_memory"], 2e-2, 2e-2, 0.999, 0.15, "encoder memory")
+
+
+def test_pixel_decoder_against_reference_golden(golden_dir):
+    """forward_features (msdeformattn.py:329-380), with and without extra_features."""
+    from oracle.make_golden import PIXDEC_CH, pixel_decoder_case, pixel_decoder_extra
+    g = np.load(os.path.join(golden_dir, "pixel_decoder.npz"))
+    P, feats = pixel_decoder_case()
+    m = _build(P, PIXDEC_CH, 2)
+    cf = {k: v.cuda() for k, v in feats.items()}
+    mf, o0, ms = m.forward_features(cf)
+    assert o0 is ms[0] and len(ms) == 3 and mf.is_contiguous()
+    for i in range(3):
+        _band(ms[i], g[f"ms{i}"], 2e-2, 2e-2, 0.999, 0.15, f"multi_scale_features[{i}]")
+    _band(mf, g["mask_features"], 2e-2, 2e-2, 0.999, 0.15, "mask_features")
+    mf, _, ms = m.forward_features(cf, [e.cuda() for e in pixel_decoder_extra()])
+    _band(ms[1], g["ms1_ex"], 2e-2, 2e-2, 0.999, 0.15, "multi_scale_features[1] (extra)")
+    _band(mf[:, ::4], g["mask_features_ex"], 2e-2, 2e-2, 0.999, 0.15, "mask_features (extra)")
+
+
+def test_pixel_decoder_feeds_the_decoder_at_a_real_shape():
+    """Six encoder layers, ResNet-50 channel counts, 3 frames of 384 x 640: against the oracle restatement, then straight into
+    the Video decoder (the tensors have exactly the layout / strides the decoder's contract asks for)."""
+    from oracle import pixel_decoder_ref as PO
+    from openvis_b200.decoder import VideoMultiScaleMaskedTransformerDecoder
+    from openvis_b200.synthetic import (decoder_param_shapes, seeded_backbone_features, seeded_params,
+                                        seeded_pixel_decoder_params)
+    ch = (256, 512, 1024, 2048)
+    P = seeded_pixel_decoder_params(2, in_channels=ch, L=6)
+    feats = seeded_backbone_features(3, 384, 640, in_channels=ch, seed=31)
+    m = _build(P, ch, 6)
+    m.unfold_frames = 2                                                  # exercises the chunked 3x3 convolution (2 + 1 frames)
+    mf, _, ms = m.forward_features({k: v.cuda() for k, v in feats.items()})
+    rmf, _, rms = PO.pixel_decoder_forward(P, feats)
+    for i in range(3):
+        _band(ms[i], rms[i], 3e-2, 3e-2, 0.999, 0.3, f"multi_scale_features[{i}]")
+    _band(mf, rmf, 3e-2, 3e-2, 0.999, 0.3, "mask_features")
+    dec = VideoMultiScaleMaskedTransformerDecoder(in_channels=256, mask_classification=True, num_classes=40, hidden_dim=256,
+                                                  num_queries=100, nheads=8, dim_feedforward=2048, dec_layers=9, pre_norm=False,
+                                                  mask_dim=256, enforce_input_project=False, num_frames=3).eval().cuda()
+    dec.load_state_dict(seeded_params(decoder_param_shapes("video", num_classes=40), seed=0), strict=True)
+    out = dec(ms, mf)
+    assert out["pred_masks"].shape == (1, 100, 3, 96, 160) and torch.isfinite(out["pred_masks"]).all()

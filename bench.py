@@ -751,6 +751,31 @@ def measure_next_rows(dev):
             "positions_per_s": Nf * S / ms * 1e3}
     except Exception as e:
         out["f2_msdeformattn_module"] = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
+    try:
+        # the whole pixel decoder (input projections + GroupNorm, six deformable encoder layers, FPN level, mask features) on
+        # ResNet-50-shaped backbone maps of 12 frames of 736 x 1280, handed straight to the Video decoder
+        from openvis_b200.pixel_decoder import MSDeformAttnPixelDecoder, ShapeSpec
+        from openvis_b200.synthetic import seeded_pixel_decoder_params
+        ch, Nf, Hp, Wp = (256, 512, 1024, 2048), 12, 736, 1280
+        pd = MSDeformAttnPixelDecoder({f"res{i + 2}": ShapeSpec(channels=c, stride=4 << i) for i, c in enumerate(ch)})
+        pd.load_state_dict(seeded_pixel_decoder_params(2, in_channels=ch))
+        pd = pd.to(dev)
+        g = torch.Generator(device=dev).manual_seed(13)
+        feats = {f"res{i + 2}": torch.randn(Nf, c, Hp // (4 << i), Wp // (4 << i), generator=g, device=dev) for i, c in enumerate(ch)}
+        n0 = L.launch_count()
+        ms = timed(lambda: pd.forward_features(feats), 3)
+        S = sum((Hp // s) * (Wp // s) for s in (8, 16, 32))
+        M4 = (Hp // 4) * (Wp // 4)
+        flops = Nf * (2 * 256 * sum(c * (Hp // (4 << i)) * (Wp // (4 << i)) for i, c in enumerate(ch))     # 1x1 projections
+                      + 6 * S * 2 * 256 * (256 + 288 + 256 + 2 * 1024)                                     # encoder GEMMs
+                      + M4 * 2 * 256 * (9 * 256 + 256))                                                   # 3x3 + mask features
+        out["f2_pixel_decoder"] = {
+            "workload": "MSDeformAttnPixelDecoder.forward_features, 12 frames of 736x1280, ResNet-50 channel counts, 6 encoder layers",
+            "ms": ms, "frames_per_s": Nf / ms * 1e3, "gpu_launches": (L.launch_count() - n0) // 4,
+            "gemm_tflops": flops / ms / 1e9, "tensor_frac_of_burst_peak": flops / ms / 1e9 / pk.get("bf16_tflops", 1667.8)}
+        del pd, feats
+    except Exception as e:
+        out["f2_pixel_decoder"] = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
     torch.cuda.empty_cache()
     return out
 

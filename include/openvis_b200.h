@@ -226,6 +226,13 @@ int ovis_ms_deform_attn_forward(const float* value, const long long* spatial_sha
  * sampling_locations = reference_points + offsets / (W_l, H_l) (ref_dim 2) or the reference-box form (ref_dim 4). */
 int ovis_msda_prepare(const float* proj, const float* reference_points, const long long* spatial_shapes, long long rows, int M,
                       int L, int P, int ref_dim, float* sampling_loc, float* attn_weight, void* stream);
+/* The same two steps fused (the pixel decoder's encoder path): softmax + sampling locations in registers, fp16 value map
+ * [N][S][M][32] (the value projection's fp16 output), fp32 bilinear weights / accumulation, fp16 rows out [N*Lq][M*32] = the
+ * A operand of output_proj.  proj as for ovis_msda_prepare; reference_points [N or 1][Lq][L][ref_dim] with ref_batch_stride
+ * floats between samples (0 = one table for every sample).  Head width 32, L*P <= 16. */
+int ovis_msda_fused_f16(const void* value_f16, const float* proj, const float* reference_points, long long ref_batch_stride,
+                        const long long* spatial_shapes, const long long* level_start_index, void* out_f16, int N, int S, int M,
+                        int Lq, int L, int P, int ref_dim, void* stream);
 /* ---- device-side post-processing ----------------------------------------------
  * Top-k over the flattened [Q*K] scores with labels, query indices and per-query entropy:
  * scores.flatten(0, 1).topk(10), labels[topk], topk // num_classes, sum(-s log s)

@@ -62,6 +62,7 @@ SIGNATURES = {
     "ovis_ms_deform_attn_forward": (_c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
                                              _c_int, _vp]),
     "ovis_msda_prepare": (_c_int, [_vp, _vp, _vp, _c_ll, _c_int, _c_int, _c_int, _c_int, _vp, _vp, _vp]),
+    "ovis_msda_fused_f16": (_c_int, [_vp, _vp, _vp, _c_ll, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _vp]),
     "ovis_topk_scores": (_c_int, [_vp, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp]),
     "ovis_mask_postprocess": (_c_int, [_vp, _c_ll, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
                                        _c_int, _c_int, _vp, _vp]),
@@ -319,6 +320,22 @@ def msda_prepare(proj, reference_points, spatial_shapes, M, L_, P):
     _check(lib.ovis_msda_prepare(_p(proj), _p(reference_points), _p(spatial_shapes), N * Lq, M, L_, P, reference_points.shape[-1],
                                  _p(loc), _p(w), _stream()))
     return loc, w
+
+
+def msda_fused_f16(value16, proj, reference_points, spatial_shapes, level_start_index, N, S, Lq, M, L_, P):
+    """value16 [N*S, M*32] fp16, proj [N*Lq, 3*M*L*P] fp32, reference_points [N or 1, Lq, L, 2 or 4] fp32 -> [N*Lq, M*32] fp16."""
+    lib = load()
+    assert value16.dtype == torch.float16 and value16.is_contiguous() and value16.shape == (N * S, M * 32)
+    _req(proj, torch.float32, "proj")
+    _req(reference_points, torch.float32, "reference_points")
+    _req(spatial_shapes, torch.int64, "spatial_shapes")
+    _req(level_start_index, torch.int64, "level_start_index")
+    assert proj.shape == (N * Lq, 3 * M * L_ * P) and reference_points.shape[1:3] == (Lq, L_) and reference_points.shape[0] in (1, N)
+    rd = reference_points.shape[-1]
+    out = torch.empty(N * Lq, M * 32, dtype=torch.float16, device=proj.device)
+    _check(lib.ovis_msda_fused_f16(_p(value16), _p(proj), _p(reference_points), 0 if reference_points.shape[0] == 1 else Lq * L_ * rd,
+                                   _p(spatial_shapes), _p(level_start_index), _p(out), N, S, M, Lq, L_, P, rd, _stream()))
+    return out
 
 
 def topk_scores(scores, k=10):

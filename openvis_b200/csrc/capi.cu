@@ -593,26 +593,43 @@ int ovis_linear_ln_f16(const void* x, long long rows, int K, const void* w, cons
   const long long rows_pad = ((rows + 127) / 128) * 128;
   const int S = K / 256;
   static const bool no_split = getenv("OVIS_LN_NO_SPLIT") != nullptr;     // A/B testing only
-  if (!no_split && split_ws && K % 256 == 0 && rows <= 16384 && split_ws_floats >= (long long)S * rows_pad * 256) {
+  // Many rows (the pixel decoder's encoder: frames x 19 320 positions): the row-serial epilogue's thread-per-row stores are
+  // uncoalesced, so with a workspace the product is stored plainly (TMA, fp32) and the same row-parallel kernel finishes.
+  const bool many = !no_split && split_ws && rows > 16384 && split_ws_floats >= rows_pad * 256;
+  if (many) {
     a.rows_per_group = (int)rows;
-    a.num_groups = S;
-    a.a_group_stride = 0;
-    a.a_k_mod = S;
-    a.a_k_offset_stride = 256;
-    a.b_k_mod = S;
-    a.b_k_offset_stride = 256;
-    a.o_group_stride = (int)rows_pad;
+    a.a_group_stride = (int)rows;
     a.N = 256;
-    a.K = 256;
+    a.K = K;
     a.epi = EPI_STORE;
     a.out[0] = split_ws;
-    a.out[1] = split_ws + 128;
     a.ldo = 256;
     a.out_f32 = 1;
-    int rc = launch_gemm(x, rows, K, K, w, 256, K, a, 128, (cudaStream_t)stream);
+    int rc = launch_gemm(x, rows, K, K, w, 256, K, a, 256, (cudaStream_t)stream);
     if (rc) return rc;
+  }
+  if (many || (!no_split && split_ws && K % 256 == 0 && rows <= 16384 && split_ws_floats >= (long long)S * rows_pad * 256)) {
+    if (!many) {
+      a.rows_per_group = (int)rows;
+      a.num_groups = S;
+      a.a_group_stride = 0;
+      a.a_k_mod = S;
+      a.a_k_offset_stride = 256;
+      a.b_k_mod = S;
+      a.b_k_offset_stride = 256;
+      a.o_group_stride = (int)rows_pad;
+      a.N = 256;
+      a.K = 256;
+      a.epi = EPI_STORE;
+      a.out[0] = split_ws;
+      a.out[1] = split_ws + 128;
+      a.ldo = 256;
+      a.out_f32 = 1;
+      int rc = launch_gemm(x, rows, K, K, w, 256, K, a, 128, (cudaStream_t)stream);
+      if (rc) return rc;
+    }
     LnReduceArgs r;
-    r.part = split_ws; r.S = S; r.part_stride = rows_pad;
+    r.part = split_ws; r.S = many ? 1 : S; r.part_stride = rows_pad;
     r.bias = bias; r.resid = resid;
     r.ln1_g = ln1_g; r.ln1_b = ln1_b; r.ln2_g = ln2_g; r.ln2_b = ln2_b;
     r.pe = pe; r.pe_period = pe_period > 0 ? pe_period : 1;
@@ -1272,6 +1289,25 @@ int ovis_msda_prepare(const float* proj, const float* reference_points, const lo
   a.rows = rows; a.M = M; a.L = L; a.P = P; a.ref_dim = ref_dim;
   msda_prepare_kernel<<<(unsigned)((rows * M + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a);
   return check_launch("msda_prepare_kernel");
+}
+
+int ovis_msda_fused_f16(const void* value, const float* proj, const float* reference_points, long long ref_bs,
+                        const long long* spatial_shapes, const long long* level_start_index, void* out, int N, int S, int M,
+                        int Lq, int L, int P, int ref_dim, void* stream) {
+  CHECK_ARG(value && proj && reference_points && spatial_shapes && level_start_index && out, "null pointer");
+  CHECK_ARG(N > 0 && S > 0 && M > 0 && Lq > 0 && L > 0 && P > 0 && (ref_dim == 2 || ref_dim == 4) && ref_bs >= 0, "bad sizes");
+  CHECK_ARG(L * P <= 16, "at most 16 sampling points per head (L * P)");
+  CHECK_ARG(((reinterpret_cast<uintptr_t>(value) | reinterpret_cast<uintptr_t>(out)) & 15) == 0 &&
+            (reinterpret_cast<uintptr_t>(proj) & 7) == 0 && (M * L * P) % 2 == 0, "alignment");
+  int rc = device_info(nullptr);
+  if (rc) return rc;
+  MsdaFusedArgs a;
+  a.value = (const __half*)value; a.proj = proj; a.ref = reference_points; a.ref_bs = ref_bs; a.shapes = spatial_shapes;
+  a.start = level_start_index; a.out = (__half*)out; a.N = N; a.S = S; a.M = M; a.Lq = Lq; a.L = L; a.P = P; a.ref_dim = ref_dim;
+  const long long blocks = ((long long)N * Lq * M * 4 + 255) / 256;
+  CHECK_ARG(blocks < (1ll << 31), "too many queries for one launch");
+  msda_fused_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
+  return check_launch("msda_fused_kernel");
 }
 
 int ovis_topk_scores(const float* scores, int Q, int K, int k, float* out_scores, int* out_query, int* out_label,

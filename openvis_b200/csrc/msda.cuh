@@ -11,6 +11,7 @@
 // (location, weight) triples are read once per group and broadcast with shuffles.  The value map of a frame (20 MB at
 // 736 x 1280) lives in L2, so the op is gather-bound there.
 #pragma once
+#include <cuda_fp16.h>
 #include "ptx.cuh"
 
 namespace ovis {
@@ -163,6 +164,130 @@ msda_prepare_kernel(const MsdaPrepArgs a) {
         lo[2 * i + 1] = r[1] + oy / (float)a.P * r[3] * 0.5f;
       }
     }
+  }
+}
+
+// MSDeformAttn.forward from the two projection GEMMs to the operand of output_proj in ONE kernel (the module path of the
+// pixel decoder's encoder, ops/modules/ms_deform_attn.py:98-122): 4 lanes own a (row, head); they softmax the head's L * P
+// logits and form the sampling locations in registers (what msda_prepare_kernel writes to memory), then gather the fp16
+// value map as 16-byte channel octets (one bilinear corner of a head = one contiguous 64-byte read) with fp32 weights and
+// accumulators, and store the fp16 rows the output projection consumes.  D = 32 channels per head, L * P <= 16.
+struct MsdaFusedArgs {
+  const __half* value;       // [N][S][M][32] fp16 (value_proj output)
+  const float* proj;         // [N * Lq][3 * M * L * P] fp32: offsets (m, l, p, xy) | logits (m, l, p)
+  const float* ref;          // [N or 1][Lq][L][ref_dim]
+  long long ref_bs;          // floats between the reference points of consecutive samples (0: shared)
+  const long long* shapes;   // [L][2] (H, W)
+  const long long* start;    // [L]
+  __half* out;               // [N * Lq][M * 32] fp16
+  int N, S, M, Lq, L, P, ref_dim;
+};
+
+__global__ void __launch_bounds__(256)
+msda_fused_kernel(const MsdaFusedArgs a) {
+  constexpr int LPG = 4, D = 32;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane & (LPG - 1);
+  const int gbase = lane - sub;
+  const long long group = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / LPG;
+  const long long groups = (long long)a.N * a.Lq * a.M;
+  const bool ok = group < groups;
+  const long long gi = ok ? group : groups - 1;
+  const int m = (int)(gi % a.M);
+  const long long row = gi / a.M;                 // (sample, query)
+  const int b = (int)(row / a.Lq);
+  const long long q = row - (long long)b * a.Lq;
+  const int LP = a.L * a.P, MLP = a.M * LP;
+  const float* off = a.proj + row * 3ll * MLP + (long long)m * LP * 2;
+  const float* lg = a.proj + row * 3ll * MLP + 2ll * MLP + (long long)m * LP;
+  const float* rp = a.ref + (long long)b * a.ref_bs + q * a.L * a.ref_dim;
+  // point i lives in lane i % 4, slot i / 4
+  float lw[4], lx[4], ly[4];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    const int i = s * LPG + sub;
+    lw[s] = -INFINITY; lx[s] = 0.f; ly[s] = 0.f;
+    if (i < LP) {
+      lw[s] = __ldg(lg + i);
+      const float2 o = __ldg(reinterpret_cast<const float2*>(off) + i);
+      const int l = i / a.P;
+      const float* r = rp + l * a.ref_dim;
+      if (a.ref_dim == 2) {
+        lx[s] = __ldg(r) + o.x / (float)__ldg(a.shapes + 2 * l + 1);
+        ly[s] = __ldg(r + 1) + o.y / (float)__ldg(a.shapes + 2 * l);
+      } else {
+        lx[s] = __ldg(r) + o.x / (float)a.P * __ldg(r + 2) * 0.5f;
+        ly[s] = __ldg(r + 1) + o.y / (float)a.P * __ldg(r + 3) * 0.5f;
+      }
+      mx = fmaxf(mx, lw[s]);
+    }
+  }
+  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+  float sum = 0.f;
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    lw[s] = (s * LPG + sub < LP) ? expf(lw[s] - mx) : 0.f;
+    sum += lw[s];
+  }
+  sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+  sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+  const float inv = 1.f / sum;
+  const int row_stride = a.M * D;                 // halves between consecutive positions
+  const __half* vb = a.value + (long long)b * a.S * row_stride + m * D + sub * 8;
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    if (s * LPG >= LP) break;
+#pragma unroll
+    for (int j = 0; j < LPG; ++j) {
+      const float x = __shfl_sync(0xffffffffu, lx[s], gbase + j);
+      const float y = __shfl_sync(0xffffffffu, ly[s], gbase + j);
+      const float w = __shfl_sync(0xffffffffu, lw[s], gbase + j) * inv;
+      const int i = s * LPG + j;
+      if (i >= LP) continue;
+      const int l = i / a.P;
+      const int H = (int)__ldg(a.shapes + 2 * l), W = (int)__ldg(a.shapes + 2 * l + 1);
+      const float h_im = y * H - 0.5f, w_im = x * W - 0.5f;
+      if (h_im > -1.f && w_im > -1.f && h_im < H && w_im < W) {
+        const int h_low = (int)floorf(h_im), w_low = (int)floorf(w_im);
+        const float lh = h_im - h_low, lw2 = w_im - w_low;
+        const float hh = 1.f - lh, hw = 1.f - lw2;
+        const __half* vl = vb + (long long)__ldg(a.start + l) * row_stride;
+        uint4 c[4];
+        float cw[4] = {w * hh * hw, w * hh * lw2, w * lh * hw, w * lh * lw2};
+        const bool in[4] = {h_low >= 0 && w_low >= 0, h_low >= 0 && w_low + 1 <= W - 1, h_low + 1 <= H - 1 && w_low >= 0,
+                            h_low + 1 <= H - 1 && w_low + 1 <= W - 1};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          c[k] = make_uint4(0u, 0u, 0u, 0u);
+          if (in[k]) c[k] = __ldg(reinterpret_cast<const uint4*>(vl + ((long long)(h_low + (k >> 1)) * W + w_low + (k & 1)) * row_stride));
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const __half2* hp = reinterpret_cast<const __half2*>(&c[k]);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f = __half22float2(hp[e]);
+            acc[2 * e] += cw[k] * f.x;
+            acc[2 * e + 1] += cw[k] * f.y;
+          }
+        }
+      }
+    }
+  }
+  if (ok) {
+    const __half2 h0 = __floats2half2_rn(acc[0], acc[1]), h1 = __floats2half2_rn(acc[2], acc[3]);
+    const __half2 h2 = __floats2half2_rn(acc[4], acc[5]), h3 = __floats2half2_rn(acc[6], acc[7]);
+    uint4 u;
+    u.x = *reinterpret_cast<const unsigned*>(&h0);
+    u.y = *reinterpret_cast<const unsigned*>(&h1);
+    u.z = *reinterpret_cast<const unsigned*>(&h2);
+    u.w = *reinterpret_cast<const unsigned*>(&h3);
+    *reinterpret_cast<uint4*>(a.out + gi * D + sub * 8) = u;
   }
 }
 

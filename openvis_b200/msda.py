@@ -47,9 +47,11 @@ class MSDeformAttnFunction(torch.autograd.Function):
 class MSDeformAttn(torch.nn.Module):
     """Drop-in for the reference ``MSDeformAttn`` at inference (ops/modules/ms_deform_attn.py:35-125): same constructor,
     parameter names (``sampling_offsets``, ``attention_weights``, ``value_proj``, ``output_proj``) and ``forward`` arguments,
-    so a reference state dict loads with ``load_state_dict``.  Four launches + the casts: value projection (tcgen05 GEMM,
-    fp16 operands, fp32 accumulate and output) -- ONE GEMM for sampling_offsets | attention_weights -- softmax + sampling
-    locations (``ovis_msda_prepare``) -- the sampling kernel -- output projection."""
+    so a reference state dict loads with ``load_state_dict``.  Four launches: value projection (tcgen05 GEMM, fp16 operands
+    and output, fp32 accumulate) -- ONE GEMM for sampling_offsets | attention_weights (fp32 out) -- ``ovis_msda_fused_f16``
+    (softmax + sampling locations in registers, bilinear gather of the fp16 value map with fp32 weights / accumulators, fp16
+    rows out) -- output projection.  Head widths other than 32 take the fp32 value map through ``ovis_msda_prepare`` +
+    ``ovis_ms_deform_attn_forward``."""
 
     def __init__(self, d_model=256, n_levels=4, n_heads=8, n_points=4):
         super().__init__()
@@ -61,6 +63,7 @@ class MSDeformAttn(torch.nn.Module):
         self.attention_weights = torch.nn.Linear(d_model, n_heads * n_levels * n_points)
         self.value_proj = torch.nn.Linear(d_model, d_model)
         self.output_proj = torch.nn.Linear(d_model, d_model)
+        self.fused = True       # False: value map in fp32 + separate softmax / location kernel (A/B, other head widths)
         self._wc = None
 
     def _weights(self):
@@ -76,30 +79,41 @@ class MSDeformAttn(torch.nn.Module):
 
     @torch.no_grad()
     def forward(self, query, reference_points, input_flatten, input_spatial_shapes, input_level_start_index,
-                input_padding_mask=None, _skip_output_proj=False, _query_f16=None):
+                input_padding_mask=None, _skip_output_proj=False, _query_f16=None, _input_f16=None, _trusted=False):
         if not query.is_cuda:
             raise L.OvisError("openvis_b200 has no CPU path: inputs must be CUDA tensors on an sm_100 device")
         N, Len_q, C = query.shape
         _, Len_in, _ = input_flatten.shape
-        if int((input_spatial_shapes[:, 0] * input_spatial_shapes[:, 1]).sum()) != Len_in:
+        # (the encoder validates its shapes once per call: this check reads the device tensor back, i.e. synchronises)
+        if not _trusted and int((input_spatial_shapes[:, 0] * input_spatial_shapes[:, 1]).sum()) != Len_in:
             raise ValueError("input_spatial_shapes do not add up to the flattened input length")
         if reference_points.shape[-1] not in (2, 4):
             raise ValueError(f"Last dim of reference_points must be 2 or 4, but get {reference_points.shape[-1]} instead.")
         with torch.cuda.device(query.device):
             W = self._weights()
-            value = L.linear_f16(L.cast_f16(input_flatten.float().reshape(N * Len_in, C).contiguous()), W["vw"], W["vb"], out_f32=True)
-            if input_padding_mask is not None:
-                value = value.masked_fill(input_padding_mask.reshape(-1, 1), 0.0)
+            x16 = _input_f16 if _input_f16 is not None else L.cast_f16(input_flatten.float().reshape(N * Len_in, C).contiguous())
             q16 = _query_f16 if _query_f16 is not None else L.cast_f16(query.float().reshape(N * Len_q, C).contiguous())
             proj = L.linear_f16(q16, W["qw"], W["qb"], out_f32=True)
             shapes = input_spatial_shapes.long().contiguous()
-            loc, w = L.msda_prepare(proj.view(N, Len_q, -1), reference_points.float().contiguous(), shapes, self.n_heads,
-                                    self.n_levels, self.n_points)
-            out = L.ms_deform_attn_forward(value.view(N, Len_in, self.n_heads, C // self.n_heads), shapes,
-                                           input_level_start_index.long().contiguous(), loc, w)
+            start = input_level_start_index.long().contiguous()
+            if C // self.n_heads == 32 and self.n_levels * self.n_points <= 16 and self.fused:
+                # fp16 value map, softmax + sampling locations + gather in one kernel, fp16 rows for output_proj
+                value = L.linear_f16(x16, W["vw"], W["vb"])
+                if input_padding_mask is not None:
+                    value = value.masked_fill(input_padding_mask.reshape(-1, 1), 0.0)
+                out16 = L.msda_fused_f16(value, proj, reference_points.float().contiguous(), shapes, start, N, Len_in, Len_q,
+                                         self.n_heads, self.n_levels, self.n_points)
+            else:
+                value = L.linear_f16(x16, W["vw"], W["vb"], out_f32=True)
+                if input_padding_mask is not None:
+                    value = value.masked_fill(input_padding_mask.reshape(-1, 1), 0.0)
+                loc, w = L.msda_prepare(proj.view(N, Len_q, -1), reference_points.float().expand(N, -1, -1, -1).contiguous(), shapes, self.n_heads,
+                                        self.n_levels, self.n_points)
+                out = L.ms_deform_attn_forward(value.view(N, Len_in, self.n_heads, C // self.n_heads), shapes, start, loc, w)
+                out16 = L.cast_f16(out.view(N * Len_q, C))
             if _skip_output_proj:
-                return out                  # [N, Len_q, C] fp32: the caller fuses output_proj into its residual + LayerNorm
-            out = L.linear_f16(L.cast_f16(out.view(N * Len_q, C)), W["ow"], W["ob"], out_f32=True)
+                return out16                # [N * Len_q, C] fp16: the caller fuses output_proj into its residual + LayerNorm
+            out = L.linear_f16(out16, W["ow"], W["ob"], out_f32=True)
             return out.view(N, Len_q, C)
 
 
@@ -131,7 +145,7 @@ class MSDeformAttnTransformerEncoderLayer(torch.nn.Module):
         return self._wc[1]
 
     @torch.no_grad()
-    def forward(self, src, pos, reference_points, spatial_shapes, level_start_index, padding_mask=None, _state=None):
+    def forward(self, src, pos, reference_points, spatial_shapes, level_start_index, padding_mask=None, _state=None, _split_ws=None):
         """`_state` (encoder-internal): (src fp32 [rows, C], src fp16, (src + pos) fp16, pos table [S, C] or None) of the
         previous layer's epilogue, so that no operand is converted twice."""
         N, S, C = src.shape
@@ -144,15 +158,15 @@ class MSDeformAttnTransformerEncoderLayer(torch.nn.Module):
                 pe = None
             else:
                 x32, x16, q16, pe = _state
-            att = self.self_attn(src, reference_points, x32.view(N, S, C), spatial_shapes, level_start_index, padding_mask,
-                                 _skip_output_proj=True, _query_f16=q16)
+            att16 = self.self_attn(src, reference_points, x32.view(N, S, C), spatial_shapes, level_start_index, padding_mask,
+                                   _skip_output_proj=True, _query_f16=q16, _input_f16=x16, _trusted=_state is not None)
             y32 = torch.empty_like(x32)
             y16 = torch.empty_like(x16)
-            L.linear_ln_f16(L.cast_f16(att.view(N * S, C)), A["ow"], A["ob"], x32, W["n1"], y32=y32, y16=y16)
+            L.linear_ln_f16(att16, A["ow"], A["ob"], x32, W["n1"], y32=y32, y16=y16, split_ws=_split_ws)
             h16 = L.linear_f16(y16, W["w1"], W["b1"], relu=True)
             o32, o16 = torch.empty_like(x32), torch.empty_like(x16)
             oq16 = torch.empty_like(x16) if pe is not None else None
-            L.linear_ln_f16(h16, W["w2"], W["b2"], y32, W["n2"], pe=pe, y32=o32, y16=o16, ype16=oq16)
+            L.linear_ln_f16(h16, W["w2"], W["b2"], y32, W["n2"], pe=pe, y32=o32, y16=o16, ype16=oq16, split_ws=_split_ws)
             self._last_state = (o32, o16, oq16 if oq16 is not None else o16, pe)
             return o32.view(N, S, C)
 
@@ -180,24 +194,34 @@ class MSDeformAttnTransformerEncoder(torch.nn.Module):
         return reference_points[:, :, None] * valid_ratios[:, None]
 
     @torch.no_grad()
-    def forward(self, src, spatial_shapes, level_start_index, valid_ratios, pos=None, padding_mask=None):
+    def forward(self, src, spatial_shapes, level_start_index, valid_ratios, pos=None, padding_mask=None, _reference_points=None):
+        """`_reference_points` (pixel decoder: cached per input size) [1 or N, S, L, 2] replaces get_reference_points."""
         if not src.is_cuda:
             raise L.OvisError("openvis_b200 has no CPU path: inputs must be CUDA tensors on an sm_100 device")
         N, S, C = src.shape
-        reference_points = self.get_reference_points(spatial_shapes, valid_ratios, device=src.device).contiguous()
+        if _reference_points is None:
+            if int((spatial_shapes[:, 0] * spatial_shapes[:, 1]).sum()) != S:
+                raise ValueError("spatial_shapes do not add up to the flattened input length")
+            reference_points = self.get_reference_points(spatial_shapes, valid_ratios, device=src.device).contiguous()
+        else:
+            reference_points = _reference_points
         state = None
         # the position term is usually the same table for every sample (sine embedding + level embedding): then the
         # LayerNorm epilogue adds it for the next layer's query operand
         shared_pos = pos is not None and (pos.shape[0] == 1 or bool((pos == pos[:1]).all()))
         out = src
         with torch.cuda.device(src.device):
+            # fp32 scratch of the linear + LayerNorm products (split-K partials for few rows, the plain product for many)
+            rows_pad = (N * S + 127) // 128 * 128
+            d_ffn = self.layers[0].linear1.out_features
+            split_ws = torch.empty((d_ffn // 256 if N * S <= 16384 else 1) * rows_pad * 256, dtype=torch.float32, device=src.device)
             for i, layer in enumerate(self.layers):
                 if i == 0 and shared_pos:
                     x32 = src.float().reshape(N * S, C).contiguous()
                     state = (x32, L.cast_f16(x32), L.cast_f16((src + pos).float().reshape(N * S, C).contiguous()),
                              pos[0].float().contiguous())
                 out = layer(out, pos, reference_points, spatial_shapes, level_start_index, padding_mask,
-                            _state=state if shared_pos else None)
+                            _state=state if shared_pos else None, _split_ws=split_ws)
                 state = layer._last_state if shared_pos else None
         return out
 

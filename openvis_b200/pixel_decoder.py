@@ -82,6 +82,7 @@ class MSDeformAttnPixelDecoder(nn.Module):
         self.layer_1 = _ConvGN(conv_dim, conv_dim, 3, padding=1)
         self.unfold_frames = 4          # frames per 3x3-unfold GEMM (bounds the [frames*H*W, 2304] scratch)
         self._wc = None
+        self._tc = None
         self.eval()
 
     @classmethod
@@ -112,6 +113,25 @@ class MSDeformAttnPixelDecoder(nn.Module):
             self._wc = (key, W)
         return self._wc[1]
 
+    def _tables(self, shapes, starts, dev):
+        """Input-size-dependent constants, cached: position table (sine embedding + level embedding) [1, S, 256], the shape /
+        start-index tensors, and the encoder's reference points for all-valid maps (msdeformattn.py:155-169 with every valid
+        ratio = 1: the pixel centres, identical for every level and frame) [1, S, 3, 2]."""
+        le = self.transformer.level_embed
+        key = (tuple(shapes), str(dev), le.data_ptr(), le._version)
+        if self._tc is None or self._tc[0] != key:
+            lef = le.detach().float()
+            pos = torch.cat([sine_pos_2d(h, w, dev) + lef[l][None, :] for l, (h, w) in enumerate(shapes)], 0)[None].contiguous()
+            pts = []
+            for (h, w) in shapes:
+                y = (torch.arange(h, dtype=torch.float32, device=dev) + 0.5) / h
+                x = (torch.arange(w, dtype=torch.float32, device=dev) + 0.5) / w
+                pts.append(torch.stack([x[None, :].expand(h, w), y[:, None].expand(h, w)], -1).reshape(h * w, 2))
+            ref = torch.cat(pts, 0)[None, :, None, :].expand(1, -1, len(shapes), 2).contiguous()
+            self._tc = (key, (pos, torch.as_tensor(shapes, dtype=torch.long, device=dev),
+                              torch.as_tensor(starts, dtype=torch.long, device=dev), ref))
+        return self._tc[1]
+
     @torch.no_grad()
     def forward_features(self, features, extra_features=None):
         if self.training:
@@ -141,12 +161,8 @@ class MSDeformAttnPixelDecoder(nn.Module):
                 L.group_norm_tokens(y, B, h, w, g, b, eps, add=add, add_layout=lay, out32=src.view(B * S, 256), out_bs=S,
                                     out_off=starts[i])
             # ---- deformable encoder; position term = sine embedding + level embedding, one table for every frame
-            le = self.transformer.level_embed.detach().float()
-            pos = torch.cat([sine_pos_2d(h, w, dev) + le[l][None, :] for l, (h, w) in enumerate(shapes)], 0)[None]
-            spatial_shapes = torch.as_tensor(shapes, dtype=torch.long, device=dev)
-            level_start = torch.as_tensor(starts, dtype=torch.long, device=dev)
-            valid = torch.ones(B, 3, 2, device=dev)
-            mem = self.transformer.encoder(src, spatial_shapes, level_start, valid, pos, None).reshape(B * S, 256)
+            pos, spatial_shapes, level_start, ref = self._tables(shapes, starts, dev)
+            mem = self.transformer.encoder(src, spatial_shapes, level_start, None, pos, None, _reference_points=ref).reshape(B * S, 256)
             # ---- maps returned in the reference's layout
             out = [L.tokens_to_nchw(mem, B, 256, h * w, S, starts[i]).view(B, 256, h, w) for i, (h, w) in enumerate(shapes)]
             # ---- FPN level (res2): lateral conv + GN + top-down bilinear addition, 3x3 output conv + GN + ReLU

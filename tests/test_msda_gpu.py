@@ -58,11 +58,13 @@ def test_pixel_decoder_shape():
     assert torch.allclose(out, ref, rtol=1e-4, atol=1e-6), (out - ref).abs().max().item()
 
 
+@pytest.mark.parametrize("fused", [True, False])
 @pytest.mark.parametrize("ref_dim", [2, 4])
-def test_module_forward_against_reference_golden_and_oracle(golden_dir, ref_dim):
-    """MSDeformAttn.forward (ops/modules/ms_deform_attn.py:83-125) as four launches -- value projection, one GEMM for the
-    sampling offsets and attention logits, softmax + sampling locations, the sampling kernel, output projection -- with
-    the reference module's own state dict, against its committed output and the oracle restatement."""
+def test_module_forward_against_reference_golden_and_oracle(golden_dir, ref_dim, fused):
+    """MSDeformAttn.forward (ops/modules/ms_deform_attn.py:83-125) -- value projection, one GEMM for the sampling offsets and
+    attention logits, then either the fused kernel (softmax + sampling locations + gather of the fp16 value map) or
+    ovis_msda_prepare + the fp32 sampling kernel, output projection -- with the reference module's own state dict, against its
+    committed output and the oracle restatement."""
     import os
     from oracle import decoder_ref as O
     from oracle.make_golden import msda_module_case
@@ -72,9 +74,10 @@ def test_module_forward_against_reference_golden_and_oracle(golden_dir, ref_dim)
     m = MSDeformAttn(d_model=256, n_levels=3, n_heads=8, n_points=4).eval()
     m.load_state_dict(P)                                   # the reference's parameter names
     m = m.cuda()
+    m.fused = fused
     n0 = L.launch_count()
     out = m(query.cuda(), ref.cuda(), src.cuda(), shapes.cuda(), start.cuda(), pad.cuda()).cpu()
-    assert L.launch_count() - n0 >= 5
+    assert L.launch_count() - n0 >= (6 if fused else 8)
     want = O.ms_deform_attn_module(P, query, ref, src, shapes, pad)
     # fp16 GEMM operands (three projections in a row), outputs of magnitude ~1: a sampling location that moves by an
     # fp16 ulp of the offsets shifts a bilinear sample, so the check is on the bulk and on the worst case separately

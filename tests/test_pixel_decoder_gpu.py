@@ -104,7 +104,7 @@ def test_encoder_only_against_reference_golden(golden_dir):
     pos = [sine_pos_2d(*s.shape[-2:], "cuda").t().reshape(1, 256, *s.shape[-2:]).expand(2, -1, -1, -1) for s in srcs]
     mem, shapes, start = m.transformer(srcs, pos)
     assert np.array_equal(shapes.cpu().numpy(), g["enc_shapes"]) and np.array_equal(start.cpu().numpy(), g["enc_start"])
-    _band(mem, g["enc_memory"], 2e-2, 2e-2, 0.999, 0.15, "encoder memory")
+    _band(mem, g["enc_memory"], 5e-3, 5e-3, 0.999, 2e-2, "encoder memory")
 
 
 def test_pixel_decoder_against_reference_golden(golden_dir):
@@ -117,11 +117,11 @@ def test_pixel_decoder_against_reference_golden(golden_dir):
     mf, o0, ms = m.forward_features(cf)
     assert o0 is ms[0] and len(ms) == 3 and mf.is_contiguous()
     for i in range(3):
-        _band(ms[i], g[f"ms{i}"], 2e-2, 2e-2, 0.999, 0.15, f"multi_scale_features[{i}]")
-    _band(mf, g["mask_features"], 2e-2, 2e-2, 0.999, 0.15, "mask_features")
+        _band(ms[i], g[f"ms{i}"], 5e-3, 5e-3, 0.999, 2e-2, f"multi_scale_features[{i}]")
+    _band(mf, g["mask_features"], 5e-3, 5e-3, 0.999, 2e-2, "mask_features")
     mf, _, ms = m.forward_features(cf, [e.cuda() for e in pixel_decoder_extra()])
-    _band(ms[1], g["ms1_ex"], 2e-2, 2e-2, 0.999, 0.15, "multi_scale_features[1] (extra)")
-    _band(mf[:, ::4], g["mask_features_ex"], 2e-2, 2e-2, 0.999, 0.15, "mask_features (extra)")
+    _band(ms[1], g["ms1_ex"], 5e-3, 5e-3, 0.999, 2e-2, "multi_scale_features[1] (extra)")
+    _band(mf[:, ::4], g["mask_features_ex"], 5e-3, 5e-3, 0.999, 2e-2, "mask_features (extra)")
 
 
 def test_pixel_decoder_feeds_the_decoder_at_a_real_shape():
@@ -139,8 +139,8 @@ def test_pixel_decoder_feeds_the_decoder_at_a_real_shape():
     mf, _, ms = m.forward_features({k: v.cuda() for k, v in feats.items()})
     rmf, _, rms = PO.pixel_decoder_forward(P, feats)
     for i in range(3):
-        _band(ms[i], rms[i], 3e-2, 3e-2, 0.999, 0.3, f"multi_scale_features[{i}]")
-    _band(mf, rmf, 3e-2, 3e-2, 0.999, 0.3, "mask_features")
+        _band(ms[i], rms[i], 1e-2, 1e-2, 0.999, 3e-2, f"multi_scale_features[{i}]")
+    _band(mf, rmf, 1e-2, 1e-2, 0.999, 3e-2, "mask_features")
     dec = VideoMultiScaleMaskedTransformerDecoder(in_channels=256, mask_classification=True, num_classes=40, hidden_dim=256,
                                                   num_queries=100, nheads=8, dim_feedforward=2048, dec_layers=9, pre_norm=False,
                                                   mask_dim=256, enforce_input_project=False, num_frames=3).eval().cuda()

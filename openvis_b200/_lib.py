@@ -232,6 +232,7 @@ def rownorm(x, g=None, b=None, layer_norm=False, l2=False, want32=True, want16=T
     return o32, o16
 
 
+@_timed("ov_tail")
 def rowstats(x, g=None, b=None, layer_norm=False, want_ss=True, zero=None, groups=None):
     """x [rows, D] fp32 -> (fp16 copy (after LayerNorm when asked), ss [rows] = its rows' sums of squares or None);
     `zero` [rows] fp32 is cleared (accumulator for linear_rowscale_f16(row_ss_out=...)).
@@ -246,6 +247,7 @@ def rowstats(x, g=None, b=None, layer_norm=False, want_ss=True, zero=None, group
     return o16, ss
 
 
+@_timed("ov_tail")
 def linear_rowscale_f16(x, w, bias=None, scale=1.0, row_ss_in=None, row_ss_out=None, out=None, out_f32=False):
     """(x @ w^T + bias) * scale, rows divided by sqrt(row_ss_in) when given; row_ss_out += output rows' sums of squares."""
     lib = load()
@@ -338,6 +340,7 @@ def msda_fused_f16(value16, proj, reference_points, spatial_shapes, level_start_
     return out
 
 
+@_timed("postproc")
 def topk_scores(scores, k=10):
     """scores [Q, K] fp32 -> (top scores [k], query index [k], label [k], entropy [k]) sorted by score."""
     lib = load()
@@ -350,6 +353,7 @@ def topk_scores(scores, k=10):
     return vs, qi, lb, en
 
 
+@_timed("postproc")
 def mask_postprocess(masks, query, pad_hw, img_hw, out_hw, out=None):
     """masks [Q, T, h4, w4] fp32 stride-4 logits (a frame slice of a larger [Q, T', h4, w4] tensor is fine),
     query [n] int32 -> bits [n, T, out_h, ceil(out_w/32)] int32."""
@@ -535,6 +539,7 @@ def self_attn(qk, v, out, G, Q):
     _check(lib.ovis_self_attn(_p(qk), _p(v), _p(out), G, Q, _stream()))
 
 
+@_timed("ov_tail")
 def clip_aggregate(logits, valid):
     """logits [T, Q, K] fp32, valid [T, Q] bool/uint8 -> (probs [Q, K], qvalid [Q] bool)."""
     lib = load()

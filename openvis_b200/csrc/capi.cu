@@ -202,6 +202,7 @@ void init_args(GemmArgs& a) {
   a.a_row_div = 1;
   a.b_k_mod = 1;
   a.kps = 1;
+  a.a_prefetch = 0;
   a.b_row_div = 1;
   a.scale = 1.f;
   a.pe_period = 1;
@@ -328,6 +329,8 @@ int launch_gemm(const void* A, long long a_rows, long long a_cols, long long lda
     int kps = kps_env > 0 ? kps_env : (bn == 256 ? 1 : 4);
     while (kps > 1 && (kblocks % kps != 0 || (bn == 256 ? 4 : 8) % kps != 0)) kps >>= 1;
     a.kps = kps < 1 ? 1 : kps;
+    static const int pf_env = getenv("OVIS_GEMM_PF") ? atoi(getenv("OVIS_GEMM_PF")) : -1;    // A/B testing
+    a.a_prefetch = pf_env >= 0 ? pf_env : 0;    // (measured: no gain for kv_proj, -12 % for mask_logits: profiles/experiments/gemm_bs_r2.md)
   }
   if (a.K <= 256 && m_tiles_total >= 64 && !no_bs)
     return bn == 256 ? launch_gemm_bs<256>(ta, ta2, tb, *omp, a, sms, st) : launch_gemm_bs<128>(ta, ta2, tb, *omp, a, sms, st);

@@ -24,6 +24,8 @@ if which in ("all", "kv"):
     ms = timeit(lambda: L.kv_proj_f16(xk, xv, w, outs, biases))
     byts = rows * 256 * 2 * 2 + rows * 1536 * 2
     print(f"kv_proj L2 rows={rows}: {ms*1e3:.1f} us  {2*rows*1536*256/ms/1e9:.1f} TFLOP/s  {byts/ms/1e6:.1f} GB/s")
+    ms = timeit(lambda: L.kv_proj_f16(xk, xv, w, outs, None))
+    print(f"kv_proj L2 (no bias): {ms*1e3:.1f} us  {2*rows*1536*256/ms/1e9:.1f} TFLOP/s  {byts/ms/1e6:.1f} GB/s")
     del xk, xv, outs
 if which in ("all", "ml"):
     rows = T * M

@@ -61,6 +61,7 @@ struct GemmArgs {
   int a_alt;              // 1: n-tiles with ((nt >> a_alt_shift) & 1) read their A operand from the second tensor map
   int a_alt_shift;        //    (key / value operands; shift 1 when a 256-wide output is split into two 128-wide tiles)
   int tma_store;          // 1: EPI_STORE writes through GemmOutMaps (single group, 16-byte aligned pitch)
+  int a_prefetch;         // B-stationary kernel: A tiles pulled into L2 ahead of the ring (0 = off)
   int kps;                // B-stationary kernel: k-blocks requested together per ring barrier (1, 2 or 4; divides K/64)
   // fused L2-normalisation of the OV heads (kernel 3 of the path): normalize(f) @ text^T = (f @ text^T) / ||f|| row by row
   const float* row_ss_in; // optional [rows]: sum of squares of the A rows (or of the producing GEMM's output rows): the
@@ -885,7 +886,15 @@ gemm_tn_bs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           // the ring's barriers work on groups of `kps` k-block slots: the boxes of a group (the 128-byte column slices of
           // the same 128 rows) are requested back to back, so DRAM sees whole 512-byte rows instead of four visits
           const int kps = args.kps, ngroups = STAGES / kps;
+          // Optional (A/B, OVIS_GEMM_PF): the A tiles this CTA will need are pulled into L2 `pf` tiles ahead of the ring.
+          // Measured: no gain for kv_proj, a loss for mask_logits (profiles/experiments/gemm_bs_r2.md), so the default is 0.
+          const int pf = args.a_prefetch;
+          for (int d = 0; d < pf; ++d)
+            if (r0 + d * R < m_tiles)
+              for (int kb = 0; kb < k_blocks; ++kb) tma_prefetch_2d(ta, a_col + kb * Cfg::BK, a_row0 + (r0 + d * R) * Cfg::BM);
           for (int mt = r0; mt < m_tiles; mt += R) {
+            if (pf > 0 && mt + pf * R < m_tiles)
+              for (int kb = 0; kb < k_blocks; ++kb) tma_prefetch_2d(ta, a_col + kb * Cfg::BK, a_row0 + (mt + pf * R) * Cfg::BM);
             for (int kb = 0; kb < k_blocks; kb += kps) {
               mbar_wait(&empty_bar[stage], phase ^ 1);
               mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(kps * Cfg::A_BYTES));

@@ -165,3 +165,33 @@ def test_shared_operands_bookkeeping():
     gc.collect()
     assert r() is None                                                        # the decoder did not keep it alive
     assert m.shared_operands(mf, torch.zeros(1)) is None
+
+
+def test_pixel_decoder_state_dict_contract_and_config():
+    """MSDeformAttnPixelDecoder: parameter names / shapes of the reference (msdeformattn.py:182-306), (cfg, input_shape)
+    construction like @configurable (:308-327), scope errors, registry."""
+    from types import SimpleNamespace as NS
+    from openvis_b200 import pixel_decoder as PD
+    from openvis_b200.synthetic import pixel_decoder_param_shapes
+    shape = {f"res{i + 2}": PD.ShapeSpec(channels=c, stride=4 << i) for i, c in enumerate((256, 512, 1024, 2048))}
+    cfg = NS(MODEL=NS(SEM_SEG_HEAD=NS(IN_FEATURES=["res2", "res3", "res4", "res5"], CONVS_DIM=256, MASK_DIM=256, NORM="GN",
+                                      TRANSFORMER_ENC_LAYERS=6, DEFORMABLE_TRANSFORMER_ENCODER_IN_FEATURES=["res3", "res4", "res5"],
+                                      COMMON_STRIDE=4, PIXEL_DECODER_NAME="MSDeformAttnPixelDecoder"),
+                      MASK_FORMER=NS(DROPOUT=0.0, NHEADS=8)))
+    m = PD.build_pixel_decoder(cfg, shape)
+    want = pixel_decoder_param_shapes()
+    got = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    assert got == want
+    assert m.in_features == ["res2", "res3", "res4", "res5"] and m.transformer_in_features == ["res3", "res4", "res5"]
+    assert m.num_fpn_levels == 1 and m.maskformer_num_feature_levels == 3 and not m.training
+    reg = {}
+    PD.register_into(reg)
+    assert reg["MSDeformAttnPixelDecoder"] is PD.MSDeformAttnPixelDecoder
+    import pytest
+    with pytest.raises(NotImplementedError):
+        PD.MSDeformAttnPixelDecoder(shape, conv_dim=128)
+    with pytest.raises(NotImplementedError):
+        PD.MSDeformAttnPixelDecoder({**shape, "res2": PD.ShapeSpec(channels=96, stride=4)})
+    import torch
+    with pytest.raises(Exception):                      # CPU tensors: no CPU path
+        m.forward_features({k: torch.zeros(1, v.channels, 64 // v.stride, 64 // v.stride) for k, v in shape.items()})

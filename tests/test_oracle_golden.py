@@ -327,3 +327,31 @@ def test_zero_shot_decoder_oracle_against_reference_golden(golden_dir):
     _close(out["aux_outputs"][4]["pred_logits"], g["aux4_pred_logits"], atol=2e-5)
     _close(out["aux_outputs"][4]["pred_object_logits"], g["aux4_pred_object_logits"], atol=2e-5)
     assert len(out["aux_outputs"]) == 9 and set(out["aux_outputs"][0]) == {"pred_object_logits", "pred_logits", "pred_masks"}
+
+
+@pytest.mark.skipif(not R.available(), reason="reference not mounted")
+def test_pixel_decoder_registers_into_reference_registry_and_builder():
+    """register_into on the registry object the reference's own msdeformattn.py registered its class in, then the reference's
+    own build_pixel_decoder (msdeformattn.py:22-35) builds the B200 class from (cfg, input_shape)."""
+    import sys
+    from types import SimpleNamespace as NS
+    from openvis_b200 import pixel_decoder as PD
+    ns = R.pixel_decoder()
+    ref_mod = sys.modules["refpix.msdeformattn"]
+    reg = ref_mod.SEM_SEG_HEADS_REGISTRY
+    assert reg["MSDeformAttnPixelDecoder"] is ns.MSDeformAttnPixelDecoder
+    try:
+        PD.register_into(reg)
+        shape = {f"res{i + 2}": ns.ShapeSpec(channels=c, stride=4 << i) for i, c in enumerate((256, 512, 1024, 2048))}
+        cfg = NS(MODEL=NS(SEM_SEG_HEAD=NS(IN_FEATURES=["res2", "res3", "res4", "res5"], CONVS_DIM=256, MASK_DIM=256, NORM="GN",
+                                          TRANSFORMER_ENC_LAYERS=6, DEFORMABLE_TRANSFORMER_ENCODER_IN_FEATURES=["res3", "res4", "res5"],
+                                          COMMON_STRIDE=4, PIXEL_DECODER_NAME="MSDeformAttnPixelDecoder"),
+                          MASK_FORMER=NS(DROPOUT=0.0, NHEADS=8)))
+        m = ref_mod.build_pixel_decoder(cfg, shape)
+        assert isinstance(m, PD.MSDeformAttnPixelDecoder)
+        ref = ns.MSDeformAttnPixelDecoder(shape, transformer_dropout=0.0, transformer_nheads=8, transformer_dim_feedforward=1024,
+                                          transformer_enc_layers=6, conv_dim=256, mask_dim=256, norm="GN",
+                                          transformer_in_features=["res3", "res4", "res5"], common_stride=4)
+        m.load_state_dict(ref.state_dict(), strict=True)          # the reference's own state dict loads by name
+    finally:
+        reg["MSDeformAttnPixelDecoder"] = ns.MSDeformAttnPixelDecoder

@@ -164,6 +164,16 @@ int ovis_xattn_t(const void* q_f16, const void* k_f16, const void* v_f16, const 
  * (ovis_chain_upload), then runs of at most 12 consecutive phases are launched: ovis_chain_run(handle, first, count,
  * stream); the phases of a run travel as the launch's kernel parameter. */
 int ovis_chain_create(int nphases, int G, int Q, void** handle);
+/* wide = 1 (before any phase is set): every phase's 128-row tiles are spread over all CTAs of ONE cooperative launch and a
+ * grid-wide barrier separates the phases -- for calls with many groups (Frame decoders: a group per frame), where the
+ * one-CTA-per-group chain would serialise a layer on a few SMs.  Same phases, same results. */
+int ovis_chain_set_wide(void* handle, int wide);
+/* wide chains: fp32 workspace of >= (K_max / 256) * ceil128(G * Q) * 256 floats for the linear + LayerNorm phases (K slices ->
+ * partial products -> row-parallel reduction + LayerNorm instead of the row-serial epilogue); set before those phases. */
+int ovis_chain_set_scratch(void* handle, float* ws, long long floats);
+/* wide chains: plain GEMM phase idx (already set) does not feed phase idx + 1, so no barrier separates them and their tiles go
+ * to different CTAs (K/V-style sibling projections, the next layer's query projection beside the mask-embed MLP). */
+int ovis_chain_set_parallel(void* handle, int idx, int parallel);
 int ovis_chain_set_linear(void* handle, int idx, const void* x_f16, int K, int ldx, const void* w_f16, int N,
                           const float* bias, float scale, int relu, void* out, int ldo, int out_f32);
 int ovis_chain_set_linear_ln(void* handle, int idx, const void* x_f16, int K, const void* w_f16, const float* bias,

@@ -46,6 +46,9 @@ SIGNATURES = {
     "ovis_mask_bits_t": (_c_int, [_vp, _c_int, _c_int, _vp, _c_int, _vp, _vp, _vp, _c_int, _vp]),
     "ovis_xattn_t": (_c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp]),
     "ovis_chain_create": (_c_int, [_c_int, _c_int, _c_int, ctypes.POINTER(_vp)]),
+    "ovis_chain_set_wide": (_c_int, [_vp, _c_int]),
+    "ovis_chain_set_scratch": (_c_int, [_vp, _vp, _c_ll]),
+    "ovis_chain_set_parallel": (_c_int, [_vp, _c_int, _c_int]),
     "ovis_chain_set_linear": (_c_int, [_vp, _c_int, _vp, _c_int, _c_int, _vp, _c_int, _vp, _c_float, _c_int, _vp, _c_int, _c_int]),
     "ovis_chain_set_linear_ln": (_c_int, [_vp, _c_int, _vp, _c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _c_int, _vp, _vp, _vp, _vp, _vp]),
     "ovis_chain_set_self_attn": (_c_int, [_vp, _c_int, _vp, _vp, _vp]),
@@ -456,12 +459,20 @@ class Chain:
     """Query-side chain (csrc/chain.cuh): phases set once on fixed operands, then runs of consecutive phases are single
     launches (one persistent CTA per group of Q <= 128 query rows)."""
 
-    def __init__(self, nphases, G, Q):
+    def __init__(self, nphases, G, Q, wide=False):
+        """wide: phases spread over all CTAs of one cooperative launch with grid barriers between them (many groups)."""
         self._lib = load()
         h = _vp()
         _check(self._lib.ovis_chain_create(int(nphases), int(G), int(Q), ctypes.byref(h)))
         self._h = h
         self._keep = []              # operands must stay where they are for the life of the chain
+        if wide:
+            _check(self._lib.ovis_chain_set_wide(h, 1))
+
+    def set_scratch(self, ws):
+        _req(ws, torch.float32, "scratch")
+        self._keep.append(ws)
+        _check(self._lib.ovis_chain_set_scratch(self._h, _p(ws), ws.numel()))
 
     def set_linear(self, idx, x, w, bias, out, scale=1.0, relu=False, out_f32=False):
         assert x.dtype == torch.float16 and w.dtype == torch.float16 and x.stride(-1) == 1 and w.is_contiguous()
@@ -474,6 +485,10 @@ class Chain:
         _check(self._lib.ovis_chain_set_linear_ln(self._h, idx, _p(x), x.shape[1], _p(w), _p(bias), _p(resid), _p(ln1[0]), _p(ln1[1]),
                                                   _p(ln2[0]) if ln2 else None, _p(ln2[1]) if ln2 else None, _p(pe),
                                                   pe.shape[0] if pe is not None else 0, _p(y32), _p(y16), _p(ype16), _p(d32), _p(d16)))
+
+    def set_parallel(self, idx, parallel=True):
+        """wide chains: phase idx (a plain GEMM, already set) runs beside phase idx + 1 (no barrier between them)"""
+        _check(self._lib.ovis_chain_set_parallel(self._h, int(idx), int(parallel)))
 
     def set_self_attn(self, idx, qk, v, out):
         self._keep += [qk, v, out]

@@ -1018,10 +1018,14 @@ struct OvisChain {
   std::vector<ChainPhase> host;
   int Q = 0, G = 0;
   bool checked = false;
+  bool wide = false;              // phases spread over all CTAs, grid barrier between them (gemm_chain_wide_kernel)
+  unsigned int* bar = nullptr;    // wide: {arrival count, generation}
+  float* split_ws = nullptr;      // wide: fp32 scratch of the split linear + LayerNorm phases
+  long long split_ws_floats = 0;
 };
 
 int ovis_chain_create(int nphases, int G, int Q, void** handle) {
-  CHECK_ARG(nphases > 0 && G > 0 && Q > 0 && Q <= 128 && handle, "bad arguments (at most 128 queries per group)");
+  CHECK_ARG(nphases > 0 && G > 0 && Q > 0 && Q <= 256 && handle, "bad arguments (at most 256 queries per group)");
   int rc = device_info(nullptr);
   if (rc) return rc;
   OvisChain* c = new OvisChain();
@@ -1030,6 +1034,36 @@ int ovis_chain_create(int nphases, int G, int Q, void** handle) {
   for (auto& p : c->host) p.kind = -1;
   c->Q = Q; c->G = G;
   *handle = c;
+  return OVIS_OK;
+}
+
+int ovis_chain_set_wide(void* handle, int wide) {
+  OvisChain* c = static_cast<OvisChain*>(handle);
+  CHECK_ARG(c, "bad arguments");
+  for (auto& p : c->host) CHECK_ARG(p.kind < 0, "the mode must be chosen before the phases are set");
+  if (wide && !c->bar) {
+    if (cudaMalloc(&c->bar, 2 * sizeof(unsigned int)) != cudaSuccess || cudaMemset(c->bar, 0, 2 * sizeof(unsigned int)) != cudaSuccess) {
+      cudaGetLastError();
+      return fail(OVIS_ERR_CUDA, "%s: cannot allocate the grid barrier", "ovis_chain_set_wide");
+    }
+  }
+  c->wide = wide != 0;
+  return OVIS_OK;
+}
+
+int ovis_chain_set_parallel(void* handle, int idx, int parallel) {
+  OvisChain* c = static_cast<OvisChain*>(handle);
+  CHECK_ARG(c && idx >= 0 && idx + 1 < (int)c->host.size(), "bad arguments");
+  CHECK_ARG(c->host[idx].kind == 0, "only a plain GEMM phase (already set) can run beside its successor");
+  c->host[idx].par = parallel ? 1 : 0;
+  return OVIS_OK;
+}
+
+int ovis_chain_set_scratch(void* handle, float* ws, long long floats) {
+  OvisChain* c = static_cast<OvisChain*>(handle);
+  CHECK_ARG(c && ws && floats > 0 && (reinterpret_cast<uintptr_t>(ws) & 15) == 0, "bad arguments");
+  c->split_ws = ws;
+  c->split_ws_floats = floats;
   return OVIS_OK;
 }
 
@@ -1049,6 +1083,7 @@ int ovis_chain_set_linear(void* handle, int idx, const void* x, int K, int ldx, 
   GemmArgs& a = p.args;
   init_args(a);
   a.rows_per_group = c->Q; a.num_groups = c->G; a.a_group_stride = c->Q;
+  if (c->wide) { a.rows_per_group = c->G * c->Q; a.num_groups = 1; a.a_group_stride = c->G * c->Q; }
   a.N = N; a.K = K; a.epi = EPI_STORE;
   for (int t = 0; t < (N + 255) / 256; ++t) {
     a.out[t] = out_f32 ? (void*)((float*)out + (long long)t * 256) : (void*)((__half*)out + (long long)t * 256);
@@ -1071,6 +1106,7 @@ int ovis_chain_set_linear_ln(void* handle, int idx, const void* x, int K, const 
   GemmArgs& a = p.args;
   init_args(a);
   a.rows_per_group = c->Q; a.num_groups = c->G; a.a_group_stride = c->Q;
+  if (c->wide) { a.rows_per_group = c->G * c->Q; a.num_groups = 1; a.a_group_stride = c->G * c->Q; }
   a.N = 256; a.K = K; a.epi = EPI_LN;
   a.bias[0] = bias; a.resid = resid;
   a.ln1_g = ln1_g; a.ln1_b = ln1_b; a.ln2_g = ln2_g; a.ln2_b = ln2_b;
@@ -1078,6 +1114,28 @@ int ovis_chain_set_linear_ln(void* handle, int idx, const void* x, int K, const 
   a.y32 = y32; a.y16 = (__half*)y16; a.ype16 = (__half*)ype16; a.d32 = d32; a.d16 = (__half*)d16;
   p.kind = 0;
   c->checked = false;
+  if (c->wide) {
+    // the wide chain never takes the row-serial LayerNorm epilogue (25-40 us per phase): K slices of 256 -> fp32 partials
+    // (plain stores), grid barrier, row-parallel reduction + LayerNorm by every warp of the launch (kind 3)
+    const long long rows = (long long)c->G * c->Q, rows_pad = (rows + 127) / 128 * 128;
+    const int S = K / 256;
+    CHECK_ARG(K % 256 == 0, "the wide chain's linear + LayerNorm needs K % 256 == 0");
+    CHECK_ARG(c->split_ws && c->split_ws_floats >= (long long)S * rows_pad * 256, "ovis_chain_set_scratch: workspace missing or too small");
+    init_args(a);
+    a.rows_per_group = (int)rows; a.num_groups = S; a.a_group_stride = 0;
+    a.a_k_mod = S; a.a_k_offset_stride = 256; a.b_k_mod = S; a.b_k_offset_stride = 256;
+    a.o_group_stride = (int)rows_pad;
+    a.N = 256; a.K = 256; a.epi = EPI_STORE;
+    a.out[0] = c->split_ws; a.ldo = 256; a.out_f32 = 1;
+    LnReduceArgs& r = p.lnr;
+    r.part = c->split_ws; r.S = S; r.part_stride = rows_pad;
+    r.bias = bias; r.resid = resid;
+    r.ln1_g = ln1_g; r.ln1_b = ln1_b; r.ln2_g = ln2_g; r.ln2_b = ln2_b;
+    r.pe = pe; r.pe_period = pe_period > 0 ? pe_period : 1;
+    r.y32 = y32; r.y16 = (__half*)y16; r.ype16 = (__half*)ype16; r.d32 = d32; r.d16 = (__half*)d16;
+    r.rows = (int)rows;
+    p.kind = 3;
+  }
   return chain_maps(c, p, x, K, K, w, 256);
 }
 
@@ -1119,10 +1177,58 @@ static int chain_run(void* handle, int first, int count, long long* trace, void*
     if (e != cudaSuccess) return fail(OVIS_ERR_CUDA, "%s: cannot raise the shared-memory limit", "gemm_chain_kernel");
     attr_done[dev] = true;
   }
-  const int grid = c->G < sms ? c->G : sms;
   CHECK_ARG(count <= CHAIN_MAX_PHASES, "too many phases in one launch");
+  CHECK_ARG(c->wide || c->Q <= 128, "the one-CTA-per-group chain takes at most 128 queries per group");
   ChainLaunch cl;                                  // (copied into the launch by cudaLaunchKernel before it returns)
   memcpy(static_cast<void*>(cl.ph), c->host.data() + first, sizeof(ChainPhase) * count);
+  if (c->wide) {
+    CHECK_ARG(!trace, "the wide chain has no trace mode");
+    static bool wattr_done[64] = {false};
+    if (!wattr_done[dev]) {
+      cudaError_t e = cudaFuncSetAttribute(gemm_chain_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CHAIN_SMEM);
+      if (e != cudaSuccess) return fail(OVIS_ERR_CUDA, "%s: cannot raise the shared-memory limit", "gemm_chain_wide_kernel");
+      wattr_done[dev] = true;
+    }
+    // as many CTAs as the busiest phase has tiles (or groups), within the SM budget; a COOPERATIVE launch, so that all of
+    // them are resident together -- the grid barrier must never wait for a CTA that cannot be scheduled
+    long long most = c->G;
+    for (int i = 0; i < count; ++i) {
+      const ChainPhase& p = cl.ph[i];
+      if (p.kind == 0 || p.kind == 3) {
+        const long long it = (long long)((p.args.rows_per_group + 127) / 128) * ((p.args.N + 255) / 256) * p.args.num_groups;
+        if (it > most) most = it;
+      } else if ((long long)c->G * 8 > most) {
+        most = (long long)c->G * 8;
+      }
+    }
+    static const int wide_cap = getenv("OVIS_CHAIN_CTAS") ? atoi(getenv("OVIS_CHAIN_CTAS")) : 0;
+    int cap = wide_cap > 0 && wide_cap < sms ? wide_cap : sms;
+    const int grid = (int)(most < cap ? most : cap);
+    // phases that run beside their successor: the successor's items start on the CTAs after this phase's
+    cl.ph[count - 1].par = 0;
+    for (int i = 0, off = 0; i < count; ++i) {
+      ChainPhase& p = cl.ph[i];
+      p.cta_off = off % grid;
+      if (p.par) {
+        off += (int)((long long)((p.args.rows_per_group + 127) / 128) * ((p.args.N + 255) / 256) * p.args.num_groups % grid);
+      } else {
+        off = 0;
+      }
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(320);
+    cfg.dynamicSmemBytes = CHAIN_SMEM;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, gemm_chain_wide_kernel, cl, count, c->G, c->bar);
+    return check_launch("gemm_chain_wide_kernel");
+  }
+  const int grid = c->G < sms ? c->G : sms;
   launch_k(gemm_chain_kernel, dim3(grid), dim3(320), CHAIN_SMEM, (cudaStream_t)stream, cl, count, c->G, trace);
   return check_launch("gemm_chain_kernel");
 }
@@ -1138,6 +1244,7 @@ int ovis_chain_upload(void* handle) {
 int ovis_chain_destroy(void* handle) {
   OvisChain* c = static_cast<OvisChain*>(handle);
   if (!c) return OVIS_OK;
+  if (c->bar) cudaFree(c->bar);
   delete c;
   return OVIS_OK;
 }

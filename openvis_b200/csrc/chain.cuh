@@ -9,6 +9,7 @@
 // launches per layer (5-15 us each, most of them one busy tile per SM) into one.
 #pragma once
 #include "gemm_tn.cuh"
+#include "prep.cuh"
 #include "xattn.cuh"
 
 namespace ovis {
@@ -18,7 +19,10 @@ struct alignas(128) ChainPhase {
   CUtensorMap tmB;        // [N][K] fp16 weights, box 256 rows x 64
   GemmArgs args;          // kind 0: rows_per_group = Q, a_group_stride = Q, num_groups = G
   SelfAttnArgs sa;        // kind 1
-  int kind;               // 0 GEMM phase, 1 self-attention
+  LnReduceArgs lnr;       // kind 3 (wide chain only): row-parallel bias + residual + LayerNorm(s) over the GEMM's fp32 partials
+  int kind;               // 0 GEMM phase, 1 self-attention, 3 split-K GEMM -> grid barrier -> LayerNorm reduction
+  int par;                // wide chain: independent of the NEXT phase -> no barrier after this one (both run side by side)
+  int cta_off;            // wide chain: CTA that takes this phase's item 0 (set by the launch: parallel phases get disjoint CTAs)
 };
 
 // The phases of one launch travel as a kernel parameter (constant bank): TMA descriptors read from plain global memory made
@@ -43,12 +47,14 @@ constexpr int CHAIN_SMEM = GemmCfg<256>::SMEM_BYTES;
 #endif
 
 // one warp = one head of one group: K / V of the head in the warp's own shared-memory slab, flash loop over 64-key blocks
-__device__ __forceinline__ void chain_self_attn_head(const SelfAttnArgs& a, int g, int head, __half* slab, int lane) {
+// (fill: `nthr` threads, thread `tid`, copy K / V of (g, head) into the slab; tiles: the caller's warp takes the 16-row query
+//  tiles mt0, mt0 + mtstep, ...)
+__device__ __forceinline__ void chain_self_attn_fill(const SelfAttnArgs& a, int g, int head, __half* slab, int tid, int nthr) {
   const int Q = a.Q;
   const int Qp = (Q + SA_KB - 1) / SA_KB * SA_KB;
   __half* sk = slab;
   __half* sv = slab + (size_t)Qp * XA_LD;
-  for (int i = lane; i < Qp * 4; i += 32) {
+  for (int i = tid; i < Qp * 4; i += nthr) {
     const int row = i >> 2, ch = i & 3;
     uint4 kv = make_uint4(0u, 0u, 0u, 0u), vv = make_uint4(0u, 0u, 0u, 0u);
     if (row < Q) {
@@ -59,10 +65,17 @@ __device__ __forceinline__ void chain_self_attn_head(const SelfAttnArgs& a, int 
     *reinterpret_cast<uint4*>(sk + row * XA_LD + ch * 8) = kv;
     *reinterpret_cast<uint4*>(sv + row * XA_LD + ch * 8) = vv;
   }
-  __syncwarp();
+}
+
+__device__ __forceinline__ void chain_self_attn_tiles(const SelfAttnArgs& a, int g, int head, const __half* slab, int lane,
+                                                      int mt0, int mtstep) {
+  const int Q = a.Q;
+  const int Qp = (Q + SA_KB - 1) / SA_KB * SA_KB;
+  const __half* sk = slab;
+  const __half* sv = slab + (size_t)Qp * XA_LD;
   const int quad = lane >> 2, tq = lane & 3;
   const int mtiles = (Q + 15) >> 4;
-  for (int mt = 0; mt < mtiles; ++mt) {
+  for (int mt = mt0; mt < mtiles; mt += mtstep) {
     uint32_t qf[2][4];
 #pragma unroll
     for (int ks = 0; ks < 2; ++ks)
@@ -159,6 +172,12 @@ __device__ __forceinline__ void chain_self_attn_head(const SelfAttnArgs& a, int 
       }
     }
   }
+}
+
+__device__ __forceinline__ void chain_self_attn_head(const SelfAttnArgs& a, int g, int head, __half* slab, int lane) {
+  chain_self_attn_fill(a, g, head, slab, lane, 32);
+  __syncwarp();
+  chain_self_attn_tiles(a, g, head, slab, lane, 0, 1);
 }
 
 __global__ void __launch_bounds__(320, 1)
@@ -279,6 +298,176 @@ gemm_chain_kernel(const __grid_constant__ ChainLaunch cl, int nphases, int G, lo
       __syncthreads();
     }
     if (trace && threadIdx.x == 0 && g == 0) trace[nphases] = clock64();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// "Wide" chain: the same phase list, but every phase's tiles are spread over ALL CTAs of the launch and a grid-wide barrier
+// replaces the CTA-wide one.  For calls with many groups (Frame decoders: one group per frame, thousands of query rows) the
+// one-CTA-per-group chain serialises a layer's tiles on a few SMs, and the launch-per-op schedule pays ~14 dependent
+// launches of 5-15 us per layer; here a layer is ONE cooperative launch whose phases cost their own latency chain plus a
+// ~1.5 us barrier.  Rules that keep it correct without L1 invalidations:
+//   * operands written by other CTAs are only ever read through TMA (L2) or ld.global.cg (self-attention);
+//   * the residual stream (fp32, read with plain loads by the LayerNorm epilogue) is produced AND consumed by LayerNorm
+//     phases only, and a LayerNorm phase has one column tile, so tile mt always belongs to CTA mt % gridDim.x.
+__device__ __forceinline__ void chain_grid_barrier(unsigned int* bar, unsigned int nblocks) {
+  __threadfence();                                   // this thread's global writes of the phase
+  asm volatile("fence.proxy.async;" ::: "memory");
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    volatile unsigned int* gen = bar + 1;
+    const unsigned int g0 = *gen;                    // generation before arriving
+    __threadfence();
+    if (atomicAdd(bar, 1u) == nblocks - 1) {
+      bar[0] = 0u;                                   // self-resetting: replayable from a captured graph
+      __threadfence();
+      atomicAdd(bar + 1, 1u);
+    } else {
+      while (*gen == g0) __nanosleep(20);
+    }
+    __threadfence();
+  }
+  __syncthreads();
+  asm volatile("fence.proxy.async;" ::: "memory");   // the next phase's bulk loads see the other CTAs' writes
+}
+
+__global__ void __launch_bounds__(320, 1)
+gemm_chain_wide_kernel(const __grid_constant__ ChainLaunch cl, int nphases, int G, unsigned int* __restrict__ bar) {
+  using Cfg = GemmCfg<256>;
+  constexpr int STAGES = Cfg::STAGES;
+  constexpr int BN = 256;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* stage_smem = smem + STAGES * Cfg::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_smem + Cfg::STAGING_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* tfull_bar = bars + 2 * STAGES;
+  uint64_t* tempty_bar = bars + 2 * STAGES + 2;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 8);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_holder, Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  int stage = 0;
+  uint32_t phase = 0;
+  int acc = 0;
+  uint32_t acc_phase = 0;
+  long long pf_frame = -1;
+  uint32_t pf_set = 0;
+
+  for (int p = 0; p < nphases; ++p) {
+    const ChainPhase* ph = &cl.ph[p];
+    const GemmArgs& args = ph->args;
+    if (ph->kind == 0 || ph->kind == 3) {
+      // items = (group, row tile, column tile); a "group" is a K slice of the split linear + LayerNorm phases
+      const int n_tiles = (args.N + BN - 1) / BN;
+      const int m_tiles = (args.rows_per_group + Cfg::BM - 1) / Cfg::BM;
+      const int per_group = m_tiles * n_tiles;
+      const int items = per_group * args.num_groups;
+      const int k_blocks = args.K / Cfg::BK;
+      const int cta = (int)((blockIdx.x + gridDim.x - (unsigned)ph->cta_off) % gridDim.x);
+      if (warp == 0) {
+        if (lane == 0) {
+          tma_prefetch_desc(&ph->tmA);
+          tma_prefetch_desc(&ph->tmB);
+          for (int it = cta; it < items; it += gridDim.x) {
+            const int g = it / per_group, r = it - g * per_group;
+            const int mt = r % m_tiles, nt = r / m_tiles;
+            const int a_col = (g % args.a_k_mod) * args.a_k_offset_stride;
+            const int b_col = (g % args.b_k_mod) * args.b_k_offset_stride;
+            const int a_row = (g / args.a_row_div) * args.a_group_stride + mt * Cfg::BM;
+            const int b_row = (g / args.b_row_div) * args.b_group_stride + nt * BN;
+            for (int kb = 0; kb < k_blocks; ++kb) {
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+              uint8_t* sb = sa + Cfg::A_BYTES;
+              mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+              tma_load_2d(sa, &ph->tmA, &full_bar[stage], a_col + kb * Cfg::BK, a_row);
+              tma_load_2d(sb, &ph->tmB, &full_bar[stage], b_col + kb * Cfg::BK, b_row);
+              if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      } else if (warp == 1) {
+        if (lane == 0) {
+          constexpr uint32_t idesc = umma_idesc_f16(Cfg::BM, BN);
+          for (int it = cta; it < items; it += gridDim.x) {
+            mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * BN;
+            for (int kb = 0; kb < k_blocks; ++kb) {
+              mbar_wait(&full_bar[stage], phase);
+              tc_fence_after();
+              const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+              const uint64_t adesc = umma_desc_k_sw128(sa);
+              const uint64_t bdesc = umma_desc_k_sw128(sa + Cfg::A_BYTES);
+#pragma unroll
+              for (int k = 0; k < Cfg::BK / 16; ++k) umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              umma_commit(&empty_bar[stage]);
+              if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(&tfull_bar[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+          }
+        }
+      } else {
+        for (int it = cta; it < items; it += gridDim.x) {
+          const int g = it / per_group, r = it - g * per_group;
+          const int mt = r % m_tiles, nt = r / m_tiles;
+          mbar_wait(&tfull_bar[acc], acc_phase);
+          tc_fence_after();
+          gemm_epilogue_tile<BN>(args, nullptr, nt, mt, g, warp, lane, tmem_base + acc * BN, stage_smem, pf_frame, pf_set);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+      }
+      if (ph->kind == 3) {
+        // the K slices' fp32 partials -> bias + residual + LayerNorm(s), one warp per row, every warp of the launch.  A row is
+        // always finished by the same warp of the same CTA (its residual is that warp's own earlier write).
+        chain_grid_barrier(bar, gridDim.x);
+        const int nw = gridDim.x * 10;
+        for (int row = blockIdx.x * 10 + warp; row < ph->lnr.rows; row += nw) ln_reduce_row<true>(ph->lnr, row, lane);
+      }
+    } else {
+      // self-attention: a CTA takes one (group, head) at a time; K / V of the head sit in the idle TMA ring, the eight
+      // non-issuing warps split the 16-row query tiles
+      const int items = G * 8;
+      __half* slab = reinterpret_cast<__half*>(smem);
+      for (int it = blockIdx.x; it < items; it += gridDim.x) {
+        const int g = it >> 3, head = it & 7;
+        if (warp >= 2) chain_self_attn_fill(ph->sa, g, head, slab, threadIdx.x - 64, 256);
+        __syncthreads();
+        if (warp >= 2) chain_self_attn_tiles(ph->sa, g, head, slab, lane, warp - 2, 8);
+        __syncthreads();
+      }
+    }
+    if (p + 1 < nphases && !ph->par) chain_grid_barrier(bar, gridDim.x);
   }
 
   tc_fence_before();

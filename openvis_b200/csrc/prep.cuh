@@ -200,22 +200,23 @@ struct LnReduceArgs {
   int rows;
 };
 
-__global__ void __launch_bounds__(256)
-ln_reduce_kernel(const LnReduceArgs a) {
-  pdl_begin();   // programmatic dependent launch: scheduled while the previous kernel drains, reads nothing before this
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (row >= a.rows) return;
+// one warp finishes one row.  COHERENT: partials / residual are read through L2 (ld.global.cg) -- for callers that run in
+// the same launch as the producers of those rows (the wide query-side chain, csrc/chain.cuh)
+template <bool COHERENT>
+__device__ __forceinline__ void ln_reduce_row(const LnReduceArgs& a, const int row, const int lane) {
   const int c0 = lane * 4, c1 = 128 + lane * 4;
   auto ld4 = [](const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); };
+  auto ld4c = [](const float* p) {
+    return COHERENT ? __ldcg(reinterpret_cast<const float4*>(p)) : __ldg(reinterpret_cast<const float4*>(p));
+  };
   float z[8];
   {
     const float4 b0 = ld4(a.bias + c0), b1 = ld4(a.bias + c1);
-    const float4 r0 = ld4(a.resid + (long long)row * 256 + c0), r1 = ld4(a.resid + (long long)row * 256 + c1);
+    const float4 r0 = ld4c(a.resid + (long long)row * 256 + c0), r1 = ld4c(a.resid + (long long)row * 256 + c1);
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     for (int s = 0; s < a.S; ++s) {
       const float* p = a.part + ((long long)s * a.part_stride + row) * 256;
-      const float4 p0 = ld4(p + c0), p1 = ld4(p + c1);
+      const float4 p0 = ld4c(p + c0), p1 = ld4c(p + c1);
       acc[0] += p0.x; acc[1] += p0.y; acc[2] += p0.z; acc[3] += p0.w;
       acc[4] += p1.x; acc[5] += p1.y; acc[6] += p1.z; acc[7] += p1.w;
     }
@@ -259,6 +260,14 @@ ln_reduce_kernel(const LnReduceArgs a) {
     if (a.d32) st32(a.d32, z);
     if (a.d16) st16(a.d16, z);
   }
+}
+
+__global__ void __launch_bounds__(256)
+ln_reduce_kernel(const LnReduceArgs a) {
+  pdl_begin();   // programmatic dependent launch: scheduled while the previous kernel drains, reads nothing before this
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= a.rows) return;
+  ln_reduce_row<false>(a, row, threadIdx.x & 31);
 }
 
 // Row-wise LayerNorm (optional) + L2 normalisation (optional) to fp16 / fp32, one warp per row.

@@ -245,13 +245,19 @@ class _B200MaskedDecoderBase(nn.Module):
         self.clips_per_call = 1
         self.debug_capture = None         # tests: set to a list to receive (head, level, bits, flags) clones
         self.use_cuda_graph = os.environ.get("OVIS_NO_CUDA_GRAPH") is None   # replay the layer loop as a CUDA graph (_run_layers)
-        # one launch per layer for everything between two cross-attentions (csrc/chain.cuh; <= 128 queries per group).  One
-        # CTA per group streams the layer's 3.4 MB of weights alone, so the chain wins when there is ONE group per call (a
-        # single clip: the launch-per-op schedule is then ~17 one-tile kernels per layer) and loses when several groups'
-        # rows share the launch-per-op GEMMs (profiles/experiments/chain_r2.md).  None = that rule; True / False force it
-        # (OVIS_CHAIN=1 / 0).
+        # One launch per layer for everything between two cross-attentions (csrc/chain.cuh).  Two forms:
+        #   "wide"  -- the layer's phases as ONE cooperative launch, every phase's tiles spread over all CTAs, grid barriers
+        #              between dependent phases, LayerNorms as split-K partials + a row-parallel reduction: 118-124 us per
+        #              layer at 100-400 query rows against 135-186 us for the launch-per-op schedule; loses beyond ~2000
+        #              rows, where the separate kernels already fill the GPU (profiles/experiments/chain_r2.md);
+        #   "group" -- one CTA per group (<= 128 queries) runs the layer alone (round-2 first version, 254-265 us per layer;
+        #              kept for A/B).
+        # use_chain: None = wide up to WIDE_CHAIN_AUTO_ROWS query rows, else launch per op; "wide" / True ("group") / False
+        # force a schedule (OVIS_CHAIN=wide / 1 / 0; OVIS_CHAIN_WIDE_DEFAULT=0 restores the round-2a rule: group chain for
+        # single-group calls).
         env = os.environ.get("OVIS_CHAIN")
-        self.use_chain = None if env is None else env == "1"
+        self.use_chain = None if env is None else ("wide" if env == "wide" else env == "1")
+        self.wide_chain_default = os.environ.get("OVIS_CHAIN_WIDE_DEFAULT", "1") == "1"
         self._wcache = None
         self._pcache = {}
         self._ws = {}
@@ -471,19 +477,24 @@ class _B200MaskedDecoderBase(nn.Module):
         me = W["mask_embed"]
         first, count = [], []
         n = 4 + sum(10 + (1 if i + 1 < nl else 0) for i in range(nl))
-        ch = L.Chain(n, ws["G"], self.num_queries)
+        wide = self._chain_mode(ws) == "wide"
+        ch = L.Chain(n, ws["G"], self.num_queries, wide=wide)
+        if wide:
+            ch.set_scratch(ws["split"])
         k = 0
 
         def mlp3_and_q(k, hidx, nxt):
-            ch.set_linear(k, ws["d16"][hidx], me[0][0], me[0][1], ws["m1"], relu=True)
-            ch.set_linear(k + 1, ws["m1"], me[1][0], me[1][1], ws["m2"], relu=True)
-            ch.set_linear(k + 2, ws["m2"], me[2][0], me[2][1], ws["me16"])
-            k += 3
+            # (the next layer's query projection does not depend on the mask-embed MLP: first, and beside its first layer)
             if nxt is not None:
                 lw = W["layers"][nxt]
                 ch.set_linear(k, ws["ze16"], lw["xq_w"], lw["xq_b"], ws["q16"], scale=qscale)
+                if wide:
+                    ch.set_parallel(k)
                 k += 1
-            return k
+            ch.set_linear(k, ws["d16"][hidx], me[0][0], me[0][1], ws["m1"], relu=True)
+            ch.set_linear(k + 1, ws["m1"], me[1][0], me[1][1], ws["m2"], relu=True)
+            ch.set_linear(k + 2, ws["m2"], me[2][0], me[2][1], ws["me16"])
+            return k + 3
 
         pre_first = k
         k = mlp3_and_q(k, 0, 0)
@@ -494,6 +505,8 @@ class _B200MaskedDecoderBase(nn.Module):
             ch.set_linear_ln(k, ws["att16"], lw["xo_w"], lw["xo_b"], ws["z32"], lw["ln_x"], None, W["qe"],
                              y32=ws["z32"], y16=ws["z16"], ype16=ws["ze16"])
             ch.set_linear(k + 1, ws["ze16"], lw["sqk_w"], lw["sqk_b"], ws["qk16"])
+            if wide:
+                ch.set_parallel(k + 1)                       # the key / query and the value projections side by side
             ch.set_linear(k + 2, ws["z16"], lw["sv_w"], lw["sv_b"], ws["v16"])
             ch.set_self_attn(k + 3, ws["qk16"], ws["v16"], ws["sa16"])
             ch.set_linear_ln(k + 4, ws["sa16"], lw["so_w"], lw["so_b"], ws["z32"], lw["ln_s"], None, W["qe"],
@@ -509,13 +522,28 @@ class _B200MaskedDecoderBase(nn.Module):
 
     def _ensure_chain(self, W, ws):
         """(re)builds the phase list when the workspace is new or the weights changed; never inside a graph capture"""
-        if self._chain_on(ws) and (ws.get("chain") is None or ws.get("chain_W") is not W):
-            ws["chain"], ws["chain_W"] = self._build_chain(W, ws), W
+        mode = self._chain_mode(ws)
+        if mode and (ws.get("chain") is None or ws.get("chain_W") is not W or ws.get("chain_mode") != mode):
+            ws["chain"], ws["chain_W"], ws["chain_mode"] = self._build_chain(W, ws), W, mode
+
+    WIDE_CHAIN_MAX_ROWS = 16384          # what the wide chain can take (its split workspace)
+    WIDE_CHAIN_AUTO_ROWS = 2048          # where it beats the launch-per-op schedule (profiles/experiments/chain_r2.md)
+
+    def _chain_mode(self, ws):
+        """None (launch per op), "group" (one CTA per group runs a layer's query side: single-group calls) or "wide" (the
+        layer's tiles spread over all CTAs of one cooperative launch, grid barriers between the phases: many groups)."""
+        wide_ok = self.num_queries <= 256 and ws["R"] <= self.WIDE_CHAIN_MAX_ROWS and ws.get("split") is not None
+        uc = self.use_chain
+        if uc is None:
+            if self.wide_chain_default and wide_ok and ws["R"] <= self.WIDE_CHAIN_AUTO_ROWS:
+                return "wide"
+            return "group" if ws["G"] == 1 and self.num_queries <= 128 else None
+        if uc == "wide":
+            return "wide" if wide_ok else None
+        return "group" if uc and self.num_queries <= 128 else None
 
     def _chain_on(self, ws):
-        if self.num_queries > 128:
-            return False
-        return ws["G"] == 1 if self.use_chain is None else bool(self.use_chain)
+        return self._chain_mode(ws) is not None
 
     def _layer_loop_chain(self, W, ws):
         """_layer_loop with the query side of every layer as one launch (csrc/chain.cuh)."""

@@ -324,8 +324,9 @@ def test_cuda_graph_replay_equals_eager(kind):
     assert per_call > 50, per_call                      # replayed launches are still counted (one group: chained layers)
 
 
+@pytest.mark.parametrize("mode", [True, "wide"])
 @pytest.mark.parametrize("kind,T", [("video", 2), ("frame", 3), ("san_frame", 2)])
-def test_query_side_chain_equals_launch_per_op(kind, T):
+def test_query_side_chain_equals_launch_per_op(kind, T, mode):
     """The query-side chain (one launch per layer: csrc/chain.cuh) against the launch-per-operation schedule on the same
     weights and inputs: same kernels' arithmetic, only the LayerNorm GEMMs take the fused-epilogue path instead of the
     split-K one, so the results agree to fp32 summation order (at the config-1 resolution: tiny inputs amplify a single
@@ -340,7 +341,7 @@ def test_query_side_chain_equals_launch_per_op(kind, T):
     a = m(xs, mfs)
     n_ops = L.launch_count() - n0
     ref = {k: a[k].clone() for k in ("pred_masks",) + (("pred_logits",) if "pred_logits" in a else ("class_attn_biases",))}
-    m.use_chain = True
+    m.use_chain = mode               # True: one CTA per group; "wide": tiles over all CTAs + grid barriers (cooperative launch)
     n0 = L.launch_count()
     b = m(xs, mfs)
     n_chain = L.launch_count() - n0

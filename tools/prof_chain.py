@@ -7,7 +7,7 @@ import torch
 from openvis_b200 import _lib as L, decoder as D
 from openvis_b200.synthetic import decoder_param_shapes, seeded_params
 
-NAMES = ["xo+LN", "sqk", "sv", "self_attn", "so+LN", "ffn1", "ffn2+LN+dn", "me0", "me1", "me2", "xq(next)"]
+NAMES = ["xo+LN", "sqk", "sv", "self_attn", "so+LN", "ffn1", "ffn2+LN+dn", "xq(next)", "me0", "me1", "me2"]
 
 
 def ev(fn, n=20):
@@ -20,7 +20,7 @@ def ev(fn, n=20):
     return e0.elapsed_time(e1) / n * 1e3
 
 
-for kind, T, clips, Hp, Wp in (("video", 8, 4, 128, 192), ("frame", 144, 1, 128, 192), ("video", 2, 1, 128, 192)):
+for kind, T, clips, Hp, Wp in (("video", 8, 4, 128, 192), ("frame", 144, 1, 128, 192), ("frame", 36, 1, 128, 192), ("video", 2, 1, 128, 192)):
     kw = dict(in_channels=256, mask_classification=True, num_classes=1, hidden_dim=256, num_queries=100, nheads=8,
               dim_feedforward=2048, dec_layers=9, pre_norm=False, mask_dim=256, enforce_input_project=False, num_frames=2)
     cls = D.VideoMultiScaleMaskedTransformerDecoder if kind == "video" else D.FrameMultiScaleMaskedTransformerDecoder
@@ -60,3 +60,13 @@ for kind, T, clips, Hp, Wp in (("video", 8, 4, 128, 192), ("frame", 144, 1, 128,
         m._mlp3(W["mask_embed"], ws["d16"][4], ws["m1"], ws["m2"], ws["me16"])
         L.linear_f16(ws["ze16"], lw["xq_w"], lw["xq_b"], scale=0.25, out=ws["q16"])
     print(f"    launch-per-op schedule of the same layer: {ev(ops):.1f} us")
+    # the wide chain (tiles of every phase over all CTAs of one cooperative launch, grid barriers between phases)
+    m.use_chain = "wide"
+    m(x, mf)
+    cw = ws["chain"]
+    assert ws["chain_mode"] == "wide"
+    chw = cw["chain"]
+    fw, nw = cw["first"][3], cw["count"][3]
+    perw = [ev(lambda j=j: chw.run(fw + j, 1)) for j in range(nw)]
+    print(f"    wide chain: {ev(lambda: chw.run(fw, nw)):.1f} us as one launch; phases alone: " +
+          ", ".join(f"{NAMES[j]} {perw[j]:.1f}" for j in range(nw)) + f"  (sum {sum(perw):.1f})")

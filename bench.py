@@ -691,17 +691,21 @@ def measure_next_rows(dev):
     from openvis_b200.synthetic import seeded_clip_visual_params
     pk, _ = peaks()
     out = {}
+    torch.cuda.empty_cache()
 
     def timed(fn, n):
+        """median device time of n calls after a warm-up call (per-call CUDA events: one call that has to go back to
+        cudaMalloc -- the caching allocator after the big sweeps -- must not triple the figure)"""
         fn()
         torch.cuda.synchronize(dev)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(n):
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+        for a, b in ev:
+            a.record()
             fn()
-        e1.record()
+            b.record()
         torch.cuda.synchronize(dev)
-        return e0.elapsed_time(e1) / n
+        ts = sorted(a.elapsed_time(b) for a, b in ev)
+        return ts[len(ts) // 2]
 
     try:
         T, N, H, W, K = 5, 100, 720, 1280, 1196
@@ -762,8 +766,9 @@ def measure_next_rows(dev):
         pd = pd.to(dev)
         g = torch.Generator(device=dev).manual_seed(13)
         feats = {f"res{i + 2}": torch.randn(Nf, c, Hp // (4 << i), Wp // (4 << i), generator=g, device=dev) for i, c in enumerate(ch)}
+        torch.cuda.empty_cache()
         n0 = L.launch_count()
-        ms = timed(lambda: pd.forward_features(feats), 3)
+        ms = timed(lambda: pd.forward_features(feats), 5)
         S = sum((Hp // s) * (Wp // s) for s in (8, 16, 32))
         M4 = (Hp // 4) * (Wp // 4)
         flops = Nf * (2 * 256 * sum(c * (Hp // (4 << i)) * (Wp // (4 << i)) for i, c in enumerate(ch))     # 1x1 projections
@@ -771,7 +776,7 @@ def measure_next_rows(dev):
                       + M4 * 2 * 256 * (9 * 256 + 256))                                                   # 3x3 + mask features
         out["f2_pixel_decoder"] = {
             "workload": "MSDeformAttnPixelDecoder.forward_features, 12 frames of 736x1280, ResNet-50 channel counts, 6 encoder layers",
-            "ms": ms, "frames_per_s": Nf / ms * 1e3, "gpu_launches": (L.launch_count() - n0) // 4,
+            "ms": ms, "frames_per_s": Nf / ms * 1e3, "gpu_launches": (L.launch_count() - n0) // 6,
             "gemm_tflops": flops / ms / 1e9, "tensor_frac_of_burst_peak": flops / ms / 1e9 / pk.get("bf16_tflops", 1667.8)}
         del pd, feats
     except Exception as e:

@@ -1201,8 +1201,10 @@ static int chain_run(void* handle, int first, int count, long long* trace, void*
         most = (long long)c->G * 8;
       }
     }
+    // (cap: half of the SMs by default, so that the wide launches of TWO calls in flight fit side by side whatever the
+    //  driver's scheduling of cooperative grids from different streams is; OVIS_CHAIN_CTAS overrides)
     static const int wide_cap = getenv("OVIS_CHAIN_CTAS") ? atoi(getenv("OVIS_CHAIN_CTAS")) : 0;
-    int cap = wide_cap > 0 && wide_cap < sms ? wide_cap : sms;
+    int cap = wide_cap > 0 ? (wide_cap < sms ? wide_cap : sms) : (sms / 2 > 0 ? sms / 2 : 1);
     const int grid = (int)(most < cap ? most : cap);
     // phases that run beside their successor: the successor's items start on the CTAs after this phase's
     cl.ph[count - 1].par = 0;

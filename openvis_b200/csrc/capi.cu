@@ -1448,6 +1448,13 @@ int ovis_mask_postprocess(const float* masks, long long q_stride, const int* que
   a.pad_h = pad_h; a.pad_w = pad_w; a.img_h = img_h; a.img_w = img_w; a.out_h = out_h; a.out_w = out_w;
   a.words = (out_w + 31) / 32;
   CHECK_ARG((long long)n_sel * T <= 65535 && (out_h + MP_ROWS - 1) / MP_ROWS <= 65535, "too many planes / rows for one launch");
+  // output = image size and an exact x4 first interpolation (the evaluation default): fixed-fraction fast path
+  static const bool no_x4 = getenv("OVIS_POST_X4") && atoi(getenv("OVIS_POST_X4")) == 0;     // A/B testing
+  if (!no_x4 && out_h == img_h && out_w == img_w && pad_h == 4 * h4 && pad_w == 4 * w4) {
+    dim3 gridx((a.words * 32 + 255) / 256, (h4 + 1 + MPX_PAIRS - 1) / MPX_PAIRS, n_sel * T);
+    mask_postprocess_x4_kernel<<<gridx, 256, 0, (cudaStream_t)stream>>>(a);
+    return check_launch("mask_postprocess_x4_kernel");
+  }
   dim3 grid((a.words * 32 + 255) / 256, (out_h + MP_ROWS - 1) / MP_ROWS, n_sel * T);
   mask_postprocess_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
   return check_launch("mask_postprocess_kernel");

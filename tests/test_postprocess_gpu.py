@@ -50,3 +50,25 @@ def test_packed_masks_roundtrip():
     bits = (pad.view(2, 3, 5, words, 32).long() << torch.arange(32)).sum(-1)
     bits = torch.where(bits >= 2 ** 31, bits - 2 ** 32, bits).to(torch.int32)
     assert torch.equal(PP.PackedMasks(bits, 70).unpack(), m)
+
+
+@pytest.mark.parametrize("T,pad,img", [(3, (96, 160), (90, 160)), (2, (736, 1280), (720, 1280)), (1, (64, 96), (64, 96)), (2, (32, 64), (29, 37))])
+def test_x4_fast_path_against_torch_and_general_kernel(T, pad, img, monkeypatch):
+    """output = image size with an exact x4 first interpolation takes mask_postprocess_x4_kernel: against F.interpolate + crop
+    (the reference's arithmetic) including the first / last two rows and columns (clamped samples), ragged widths, and bit for
+    bit against the general kernel except at |logit| ~ 0."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(11)
+    Q = 12
+    masks = (torch.randn(Q, T, pad[0] // 4, pad[1] // 4, generator=g) * 4).cuda()
+    qi = torch.tensor([3, 0, 11, 7, 5, 1, 2, 9, 10, 4], dtype=torch.int32).cuda()
+    n0 = L.launch_count()
+    bits = L.mask_postprocess(masks, qi, pad, img, img)
+    assert L.launch_count() - n0 == 1
+    got = PP.PackedMasks(bits, img[1]).unpack().cpu()
+    up = F.interpolate(masks[qi.long()], size=pad, mode="bilinear", align_corners=False)[:, :, :img[0], :img[1]].cpu()
+    want = up > 0
+    diff = got != want
+    assert got.shape == want.shape and bool((~diff | (up.abs() < 1e-4)).all()), int(diff.sum())
+    # rows / columns 0, 1 and the last ones exercise the clamped samples
+    assert torch.equal(got[..., :2, :][up[..., :2, :].abs() > 1e-4], want[..., :2, :][up[..., :2, :].abs() > 1e-4])

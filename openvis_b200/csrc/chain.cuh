@@ -322,17 +322,18 @@ __device__ __forceinline__ void chain_grid_barrier(unsigned int* bar, unsigned i
   asm volatile("fence.proxy.async;" ::: "memory");
   __syncthreads();
   if (threadIdx.x == 0) {
-    volatile unsigned int* gen = bar + 1;
-    const unsigned int g0 = *gen;                    // generation before arriving
-    __threadfence();
-    if (atomicAdd(bar, 1u) == nblocks - 1) {
-      bar[0] = 0u;                                   // self-resetting: replayable from a captured graph
-      __threadfence();
-      atomicAdd(bar + 1, 1u);
+    unsigned int g0, g1;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(g0) : "l"(bar + 1) : "memory");     // generation before arriving
+    unsigned int prev;
+    asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(prev) : "l"(bar) : "memory");
+    if (prev == nblocks - 1) {
+      asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(bar), "r"(0u) : "memory");   // self-resetting: replayable from a graph
+      asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar + 1) : "memory");
     } else {
-      while (*gen == g0) __nanosleep(20);
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(g1) : "l"(bar + 1) : "memory");
+      } while (g1 == g0);
     }
-    __threadfence();
   }
   __syncthreads();
   asm volatile("fence.proxy.async;" ::: "memory");   // the next phase's bulk loads see the other CTAs' writes

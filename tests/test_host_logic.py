@@ -195,3 +195,29 @@ def test_pixel_decoder_state_dict_contract_and_config():
     import torch
     with pytest.raises(Exception):                      # CPU tensors: no CPU path
         m.forward_features({k: torch.zeros(1, v.channels, 64 // v.stride, 64 // v.stride) for k, v in shape.items()})
+
+
+def test_chain_mode_selection():
+    """decoder._chain_mode: wide chain up to WIDE_CHAIN_AUTO_ROWS query rows (and <= 256 queries, workspace present), the
+    one-CTA-per-group chain only when forced (or as the round-2a rule with the wide default off), launch per op otherwise."""
+    from openvis_b200 import decoder as D
+    kw = dict(in_channels=256, mask_classification=True, num_classes=1, hidden_dim=256, nheads=8, dim_feedforward=2048,
+              dec_layers=9, pre_norm=False, mask_dim=256, enforce_input_project=False, num_frames=2)
+    m = D.FrameMultiScaleMaskedTransformerDecoder(num_queries=100, **kw)
+    ws = lambda G, R, split=True: {"G": G, "R": R, "split": object() if split else None}
+    assert m.use_chain is None and m.wide_chain_default
+    assert m._chain_mode(ws(1, 100)) == "wide" and m._chain_mode(ws(4, 400)) == "wide" and m._chain_mode(ws(20, 2000)) == "wide"
+    assert m._chain_mode(ws(36, 3600)) is None and m._chain_mode(ws(144, 14400)) is None
+    assert m._chain_mode(ws(4, 400, split=False)) is None
+    m.use_chain = "wide"
+    assert m._chain_mode(ws(144, 14400)) == "wide" and m._chain_mode(ws(200, 20000)) is None
+    m.use_chain = True
+    assert m._chain_mode(ws(144, 14400)) == "group"
+    m.use_chain = False
+    assert m._chain_mode(ws(1, 100)) is None and not m._chain_on(ws(1, 100))
+    m.use_chain, m.wide_chain_default = None, False
+    assert m._chain_mode(ws(1, 100)) == "group" and m._chain_mode(ws(4, 400)) is None
+    m200 = D.FrameMultiScaleMaskedTransformerDecoder(num_queries=200, **kw)
+    assert m200._chain_mode(ws(2, 400)) == "wide"              # 200-query groups fit the wide chain's CTA-wide self-attention
+    m200.use_chain = True
+    assert m200._chain_mode(ws(2, 400)) is None                # ... but not the one-warp-per-head group chain

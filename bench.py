@@ -778,9 +778,28 @@ def measure_next_rows(dev):
             "workload": "MSDeformAttnPixelDecoder.forward_features, 12 frames of 736x1280, ResNet-50 channel counts, 6 encoder layers",
             "ms": ms, "frames_per_s": Nf / ms * 1e3, "gpu_launches": (L.launch_count() - n0) // 6,
             "gemm_tflops": flops / ms / 1e9, "tensor_frac_of_burst_peak": flops / ms / 1e9 / pk.get("bf16_tflops", 1667.8)}
-        del pd, feats
+        # pixel decoder -> Video decoder: through the reference's fp32 NCHW maps, and through the fp16 token-major hand-off
+        from openvis_b200.decoder import VideoMultiScaleMaskedTransformerDecoder
+        from openvis_b200.synthetic import decoder_param_shapes, seeded_params
+        dec = VideoMultiScaleMaskedTransformerDecoder(in_channels=256, mask_classification=True, num_classes=40, hidden_dim=256,
+                                                      num_queries=100, nheads=8, dim_feedforward=2048, dec_layers=9, pre_norm=False,
+                                                      mask_dim=256, enforce_input_project=False, num_frames=Nf).eval().to(dev)
+        dec.load_state_dict(seeded_params(decoder_param_shapes("video", num_classes=40), seed=0))
+
+        def nchw():
+            mf, _, ms = pd.forward_features(feats)
+            return dec(ms, mf)
+
+        ms_nchw = timed(nchw, 5)
+        ms_tok = timed(lambda: dec.forward_tokens(pd.forward_tokens(feats)), 5)
+        out["f2_pixel_decoder_to_decoder"] = {
+            "workload": "pixel decoder + Video decoder, one 12-frame 736x1280 clip (device-resident backbone maps)",
+            "ms_nchw_fp32_interface": ms_nchw, "frames_per_s_nchw": Nf / ms_nchw * 1e3,
+            "ms_token_handoff_fp16": ms_tok, "frames_per_s_token_handoff": Nf / ms_tok * 1e3}
+        del pd, feats, dec
     except Exception as e:
-        out["f2_pixel_decoder"] = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
+        out["f2_pixel_decoder"] = out.get("f2_pixel_decoder") or {"error": f"{type(e).__name__}: {str(e)[:200]}"}
+        out.setdefault("f2_pixel_decoder_to_decoder", {"error": f"{type(e).__name__}: {str(e)[:200]}"})
     torch.cuda.empty_cache()
     return out
 

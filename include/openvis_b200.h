@@ -310,6 +310,15 @@ int ovis_tokens_to_nchw_f32(const float* in, float* out, int B, int C, int N, lo
  * the weight is laid out [C_out][(ky, kx, C_in)].  C % 8 == 0. */
 int ovis_conv3x3_unfold_f16(const void* in_f16, void* out_f16, int B, int H, int W, int C, void* stream);
 
+/* ---- token-major hand-off pixel decoder -> masked decoder (no NCHW fp32 round trip; 256 channels) -----------------------
+ * ovis_tokens_pool_f16: ft [B][H][W][256] f16 -> g [B][H/s][W/s][256] f16 = fp32 mean of the centre 2x2 pixels of every s x s
+ * block: the operand of the intermediate mask heads (F.interpolate(outputs_mask, size=attn_mask_target_size, "bilinear"),
+ * frame_...decoder.py:146, for an integer factor s).
+ * ovis_tokens_add_pos_f16: xp[b][n][:] = f16(xt[b][n][:] + pos[n][:] + pos_t[b][:]) -- the `memory + pos` key operand
+ * (video_...decoder.py:115-116) from token-major f16 features; pos [N][256], pos_t [B][256] or null. */
+int ovis_tokens_pool_f16(const void* ft_f16, void* g_f16, int B, int H, int W, int s, void* stream);
+int ovis_tokens_add_pos_f16(const void* xt_f16, const float* pos, const float* pos_t, void* xp_f16, int B, int N, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

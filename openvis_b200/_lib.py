@@ -81,6 +81,8 @@ SIGNATURES = {
                                _vp, _vp, _c_ll, _c_ll, _vp]),
     "ovis_tokens_to_nchw_f32": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_ll, _c_ll, _vp]),
     "ovis_conv3x3_unfold_f16": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _vp]),
+    "ovis_tokens_pool_f16": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _vp]),
+    "ovis_tokens_add_pos_f16": (_c_int, [_vp, _vp, _vp, _vp, _c_int, _c_int, _vp]),
 }
 
 _lib = None
@@ -751,4 +753,27 @@ def conv3x3_unfold_f16(x, B, H, W, out=None):
     if out is None:
         out = torch.empty(B * H * W, 9 * C, dtype=torch.float16, device=x.device)
     _check(lib.ovis_conv3x3_unfold_f16(_p(x), _p(out), B, H, W, C, _stream()))
+    return out
+
+
+@_timed("prep")
+def tokens_pool_f16(ft, B, H, W, s, out):
+    """ft [B*H*W, 256] fp16 token-major -> out [B*(H/s)*(W/s), 256] fp16: mean of the centre 2x2 pixels of every s x s block."""
+    lib = load()
+    assert ft.dtype == torch.float16 and out.dtype == torch.float16 and ft.is_contiguous() and out.is_contiguous()
+    assert ft.numel() == B * H * W * 256 and out.numel() == B * (H // s) * (W // s) * 256
+    _check(lib.ovis_tokens_pool_f16(_p(ft), _p(out), B, H, W, s, _stream()))
+    return out
+
+
+@_timed("prep")
+def tokens_add_pos_f16(xt, pos, pos_t, out):
+    """xt [B, N, 256] fp16 + pos [N, 256] fp32 (+ pos_t [B, 256] fp32) -> out fp16 [B, N, 256]."""
+    lib = load()
+    assert xt.dtype == torch.float16 and out.dtype == torch.float16 and xt.is_contiguous() and out.is_contiguous()
+    _req(pos, torch.float32, "pos")
+    _req(pos_t, torch.float32, "pos_t")
+    B, N = xt.shape[0], xt.shape[1]
+    assert pos.shape == (N, 256) and (pos_t is None or pos_t.shape == (B, 256)) and out.numel() == xt.numel()
+    _check(lib.ovis_tokens_add_pos_f16(_p(xt), _p(pos), _p(pos_t), _p(out), B, N, _stream()))
     return out

@@ -1653,3 +1653,26 @@ int ovis_conv3x3_unfold_f16(const void* in, void* out, int B, int H, int W, int 
                                                                                              C / 8, total);
   return check_launch("conv3x3_unfold_kernel");
 }
+
+int ovis_tokens_pool_f16(const void* ft, void* g, int B, int H, int W, int s, void* stream) {
+  CHECK_ARG(ft && g && B > 0 && H > 0 && W > 0 && s >= 2 && s % 2 == 0 && H % s == 0 && W % s == 0, "bad arguments");
+  CHECK_ARG(((reinterpret_cast<uintptr_t>(ft) | reinterpret_cast<uintptr_t>(g)) & 15) == 0, "pointers must be 16-byte aligned");
+  int rc = device_info(nullptr);
+  if (rc) return rc;
+  const long long total = (long long)B * (H / s) * (W / s) * 32;
+  CHECK_ARG((total + 255) / 256 < (1ll << 31), "too many elements for one launch");
+  tokens_pool_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const __half*)ft, (__half*)g, H, W, s, total);
+  return check_launch("tokens_pool_kernel");
+}
+
+int ovis_tokens_add_pos_f16(const void* xt, const float* pos, const float* pos_t, void* xp, int B, int N, void* stream) {
+  CHECK_ARG(xt && pos && xp && B > 0 && N > 0, "bad arguments");
+  CHECK_ARG(((reinterpret_cast<uintptr_t>(xt) | reinterpret_cast<uintptr_t>(xp) | reinterpret_cast<uintptr_t>(pos) |
+              reinterpret_cast<uintptr_t>(pos_t)) & 15) == 0, "pointers must be 16-byte aligned");
+  int rc = device_info(nullptr);
+  if (rc) return rc;
+  const long long total = (long long)B * N * 32;
+  CHECK_ARG((total + 255) / 256 < (1ll << 31), "too many elements for one launch");
+  tokens_add_pos_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const __half*)xt, pos, pos_t, (__half*)xp, N, total);
+  return check_launch("tokens_add_pos_kernel");
+}

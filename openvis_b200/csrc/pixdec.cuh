@@ -187,4 +187,66 @@ conv3x3_unfold_kernel(const __half* __restrict__ in, __half* __restrict__ out, i
   reinterpret_cast<uint4*>(out)[i] = v;
 }
 
+// ---- token-major hand-off from the pixel decoder to the masked decoder (no NCHW fp32 round trip) ------------------------
+// g_l of the decoder's mask head (bilinear down-sampling by an integer factor = mean of the centre 2x2
+// pixels of each s x s block) from the token-major fp16 mask features: ft [B][H][W][256] -> g [B][H/s][W/s][256], fp32 mean.
+__global__ void __launch_bounds__(256)
+tokens_pool_kernel(const __half* __restrict__ ft, __half* __restrict__ g, int H, int W, int s, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // (b, y, x, 8-channel group)
+  if (i >= total) return;
+  const int c8 = (int)(i & 31);
+  long long t = i >> 5;
+  const int Ws = W / s, Hs = H / s;
+  const int x = (int)(t % Ws);
+  t /= Ws;
+  const int y = (int)(t % Hs);
+  const long long b = t / Hs;
+  const int y0 = y * s + s / 2 - 1, x0 = x * s + s / 2 - 1;
+  const uint4* base = reinterpret_cast<const uint4*>(ft) + ((b * H + y0) * (long long)W + x0) * 32 + c8;
+  const uint4 v00 = __ldg(base), v01 = __ldg(base + 32), v10 = __ldg(base + (long long)W * 32), v11 = __ldg(base + (long long)W * 32 + 32);
+  uint4 o;
+  const __half2* a = reinterpret_cast<const __half2*>(&v00);
+  const __half2* bq = reinterpret_cast<const __half2*>(&v01);
+  const __half2* c = reinterpret_cast<const __half2*>(&v10);
+  const __half2* d = reinterpret_cast<const __half2*>(&v11);
+  __half2* po = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 fa = __half22float2(a[e]), fb = __half22float2(bq[e]), fc = __half22float2(c[e]), fd = __half22float2(d[e]);
+    po[e] = __floats2half2_rn(0.25f * ((fa.x + fb.x) + (fc.x + fd.x)), 0.25f * ((fa.y + fb.y) + (fc.y + fd.y)));
+  }
+  reinterpret_cast<uint4*>(g)[i] = o;
+}
+
+// key operand of the decoder's cross-attention from token-major fp16 features: xp[b][n][:] = fp16(xt[b][n][:] + pos[n][:] + pos_t[b][:])
+// (level embedding + 2-D sine position per token, frame term of the 3-D embedding per frame; pos_t may be null)
+__global__ void __launch_bounds__(256)
+tokens_add_pos_kernel(const __half* __restrict__ xt, const float* __restrict__ pos, const float* __restrict__ pos_t,
+                      __half* __restrict__ xp, int N, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // (b, n, 8-channel group)
+  if (i >= total) return;
+  const int c8 = (int)(i & 31);
+  const long long bn = i >> 5;
+  const int n = (int)(bn % N);
+  const long long b = bn / N;
+  const uint4 v = __ldg(reinterpret_cast<const uint4*>(xt) + i);
+  const float4 p0 = __ldg(reinterpret_cast<const float4*>(pos + (long long)n * 256 + c8 * 8));
+  const float4 p1 = __ldg(reinterpret_cast<const float4*>(pos + (long long)n * 256 + c8 * 8) + 1);
+  float p[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+  if (pos_t) {
+    const float4 t0 = __ldg(reinterpret_cast<const float4*>(pos_t + b * 256 + c8 * 8));
+    const float4 t1 = __ldg(reinterpret_cast<const float4*>(pos_t + b * 256 + c8 * 8) + 1);
+    p[0] += t0.x; p[1] += t0.y; p[2] += t0.z; p[3] += t0.w; p[4] += t1.x; p[5] += t1.y; p[6] += t1.z; p[7] += t1.w;
+  }
+  const __half2* h = reinterpret_cast<const __half2*>(&v);
+  uint4 o;
+  __half2* po = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 f = __half22float2(h[e]);
+    po[e] = __floats2half2_rn(f.x + p[2 * e], f.y + p[2 * e + 1]);
+  }
+  reinterpret_cast<uint4*>(xp)[i] = o;
+}
+
 }  // namespace ovis

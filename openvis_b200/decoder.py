@@ -649,7 +649,25 @@ class _B200MaskedDecoderBase(nn.Module):
         ws["graph"].replay()
         L.add_launch_count(ws["graph_launches"])
 
-    def _forward_impl(self, x, mf, mask_features_in, BT, H4, W4, sizes, dev):
+    def forward_tokens(self, tokens):
+        """Video decoders: the forward pass on the token-major fp16 hand-off of `pixel_decoder.MSDeformAttnPixelDecoder.
+        forward_tokens` (`DecoderTokens`) instead of fp32 NCHW maps -- same layers, same outputs; the layout kernels are replaced
+        by a centre-2x2 pooling of the fp16 mask features and a position add (0.7 GB of traffic per 36-frame 720 x 1280 clip
+        instead of 4.9 GB).  The g_l operands are then means of fp16-rounded mask features (the NCHW path averages in fp32
+        before rounding): mask bits agree to the same 99.9 % bar (tests/test_pixel_decoder_gpu.py)."""
+        if self.training:
+            raise RuntimeError("openvis_b200 decoders are inference-only: call .eval()")
+        if not self.VIDEO or self.SAN:
+            raise NotImplementedError("forward_tokens: Video decoders (the Frame / SAN variants return NCHW-derived extras)")
+        BT, H4, W4 = tokens.ft.shape[0], tokens.H4, tokens.W4
+        sizes = [tuple(s_) for s_ in tokens.sizes]
+        if H4 % 8 or W4 % 8 or sizes != [(H4 // s_, W4 // s_) for s_ in (8, 4, 2)] or tokens.ft.shape[1:] != (H4 * W4, HIDDEN):
+            raise NotImplementedError("forward_tokens: strides 32 / 16 / 8 / 4 of a /32-padded input, 256 channels")
+        dev = tokens.ft.device
+        with torch.no_grad(), torch.cuda.device(dev):
+            return self._forward_impl(None, None, None, BT, H4, W4, sizes, dev, tokens=tokens)
+
+    def _forward_impl(self, x, mf, mask_features_in, BT, H4, W4, sizes, dev, tokens=None):
         W = self._weights()
         ws = self._workspace(BT, H4, W4, dev)
         padd, p2, pz = self._pos_tables(BT // self._groups(BT), sizes, dev)
@@ -661,12 +679,23 @@ class _B200MaskedDecoderBase(nn.Module):
         Q, C, nl = self.num_queries, HIDDEN, self.num_layers
 
         # ---- layout preparation (HBM-bound, once per call)
-        for l in range(3):
-            if x[l].shape[-1] % 4 == 0:
-                L.nchw_to_tokens_hw_f16(x[l], out=ws["xt"][l], out_pos=ws["xp"][l], pos_cn=padd[l], pos_t=pz)
-            else:                                      # odd widths: no 16-byte row pitch for the tensor maps
-                L.nchw_to_tokens_f16(x[l], out=ws["xt"][l], out_pos=ws["xp"][l], pos=padd[l].t().contiguous(), pos_t=pz)
-        L.maskfeat_prep(mf, (ws["ft"], ws["gt"][0], ws["gt"][1], ws["gt"][2]))
+        xt, ft = ws["xt"], ws["ft"]
+        if tokens is not None:
+            xt, ft = [t.reshape(BT * n, C) for t, n in zip(tokens.xt, N)], tokens.ft.reshape(BT * M, C)
+            pk = ("tok", id(padd))
+            if pk not in self._pcache:                       # token-major copies of the position tables (cached with them)
+                self._pcache[pk] = [p.t().contiguous() for p in padd]
+            for l, s_ in enumerate((8, 4, 2)):
+                L.tokens_pool_f16(ft, BT, H4, W4, s_, ws["gt"][l])
+                L.tokens_add_pos_f16(tokens.xt[l], self._pcache[pk][l], pz, ws["xp"][l])
+        else:
+            for l in range(3):
+                if x[l].shape[-1] % 4 == 0:
+                    L.nchw_to_tokens_hw_f16(x[l], out=ws["xt"][l], out_pos=ws["xp"][l], pos_cn=padd[l], pos_t=pz)
+                else:                                      # odd widths: no 16-byte row pitch for the tensor maps
+                    L.nchw_to_tokens_f16(x[l], out=ws["xt"][l], out_pos=ws["xp"][l], pos=padd[l].t().contiguous(), pos_t=pz)
+            L.maskfeat_prep(mf, (ws["ft"], ws["gt"][0], ws["gt"][1], ws["gt"][2]))
+        ws["ft_cur"] = ft                                  # the final / lazy mask heads read the mask features from here
         # ---- key / value projections of all layers, one launch per level
         for l in range(3):
             ids = W["kv_layers"][l]
@@ -676,7 +705,7 @@ class _B200MaskedDecoderBase(nn.Module):
             for i in ids:
                 outs += [ws["k"][i], ws["v"][i]]
                 biases += [W["layers"][i]["xk_b"], W["layers"][i]["v_bias"]]
-            L.kv_proj_f16(ws["xp"][l], ws["xt"][l], W["kv_w"][l], outs, biases)
+            L.kv_proj_f16(ws["xp"][l], xt[l], W["kv_w"][l], outs, biases)
 
         san = self._san_prepare(W, ws, BT, H4, W4) if self.SAN else None
 
@@ -709,7 +738,8 @@ class _B200MaskedDecoderBase(nn.Module):
             list(aux)
         out["aux_outputs"] = aux
         # (weak references: remembering which tensors the operand copies belong to must not keep GBs of them alive)
-        self._last = dict(gen=gen, mf=weakref.ref(mask_features_in), mf_ver=mask_features_in._version, ft=ws["ft"],
+        self._last = dict(gen=gen, mf=weakref.ref(mask_features_in) if mask_features_in is not None else (lambda: None),
+                          mf_ver=mask_features_in._version if mask_features_in is not None else -1, ft=ws["ft_cur"],
                           af32=weakref.ref(san["attn_feats"]) if san else None,
                           af_ver=san["attn_feats"]._version if san else None, af16=ws.get("af16"))
         return out
@@ -736,12 +766,12 @@ class _B200MaskedDecoderBase(nn.Module):
         if self.VIDEO:
             # [clips, Q, Tg, H, W]: out[g][q][t*M + p]
             out = torch.empty(G, Q, Tg, H4, W4, dtype=torch.float32, device=me.device)
-            L.mask_logits(ws["ft"], G, Tg * M, me, Q, Q, out, Q * Tg * M, Tg * M,
+            L.mask_logits(ws.get("ft_cur", ws["ft"]), G, Tg * M, me, Q, Q, out, Q * Tg * M, Tg * M,
                           posflags=posflags, rows_per_frame=M if posflags is not None else 0)
         else:
             # frames as groups, written as [1, Q, T, H, W]: out[q][g*M + p]
             out = torch.empty(1, Q, BT, H4, W4, dtype=torch.float32, device=me.device)
-            L.mask_logits(ws["ft"], G, M, me, Q, Q, out, M, BT * M,
+            L.mask_logits(ws.get("ft_cur", ws["ft"]), G, M, me, Q, Q, out, M, BT * M,
                           posflags=posflags, rows_per_frame=M if posflags is not None else 0)
         return out
 
@@ -882,7 +912,7 @@ class _ZeroShotMixin:
         Q, M = self.num_queries, ws["M"]
         me = self._mlp3(W["mask_embed"], ws["d16"][hidx], ws["m1"], ws["m2"], ws["me16"])
         out = torch.empty(BT, Q, H4, W4, dtype=torch.float32, device=me.device)
-        L.mask_logits(ws["ft"], BT, M, me, Q, Q, out, Q * M, M, posflags=posflags, rows_per_frame=M if posflags is not None else 0)
+        L.mask_logits(ws.get("ft_cur", ws["ft"]), BT, M, me, Q, Q, out, Q * M, M, posflags=posflags, rows_per_frame=M if posflags is not None else 0)
         return out
 
     def _class_outputs(self, W, ws, hidx, BT, san):

@@ -33,6 +33,15 @@ class ShapeSpec:
         self.channels, self.height, self.width, self.stride = channels, height, width, stride
 
 
+class DecoderTokens:
+    """Token-major hand-off from `MSDeformAttnPixelDecoder.forward_tokens` to a B200 decoder's `forward_tokens`: what the
+    decoder's own layout kernels would otherwise rebuild from the fp32 NCHW maps.  xt[l] [BT, h_l*w_l, 256] fp16 (multi-scale
+    features, coarsest first), ft [BT, H/4*W/4, 256] fp16 (mask features), sizes [(h_l, w_l)], (H4, W4)."""
+
+    def __init__(self, xt, ft, sizes, H4, W4):
+        self.xt, self.ft, self.sizes, self.H4, self.W4 = xt, ft, sizes, H4, W4
+
+
 class _ConvGN(nn.Conv2d):
     """Parameter container with the names of detectron2's Conv2d wrapper: .weight (.bias) and .norm.{weight, bias}."""
 
@@ -133,7 +142,15 @@ class MSDeformAttnPixelDecoder(nn.Module):
         return self._tc[1]
 
     @torch.no_grad()
-    def forward_features(self, features, extra_features=None):
+    def forward_tokens(self, features, extra_features=None):
+        """The same computation as forward_features, handed over token-major in fp16 (`DecoderTokens`) for
+        `decoder.forward_tokens`: the multi-scale maps are the encoder's own fp16 rows, the mask-feature convolution stores fp16
+        rows instead of an fp32 NCHW map -- no NCHW store here and no layout pass (2.9 GB read + 2.0 GB written per 36-frame
+        720 x 1280 clip) in the decoder."""
+        return self.forward_features(features, extra_features, _tokens=True)
+
+    @torch.no_grad()
+    def forward_features(self, features, extra_features=None, _tokens=False):
         if self.training:
             raise RuntimeError("openvis_b200 pixel decoder is inference-only: call .eval()")
         names = self.transformer_in_features[::-1]                    # res5, res4, res3: low to high resolution
@@ -163,8 +180,12 @@ class MSDeformAttnPixelDecoder(nn.Module):
             # ---- deformable encoder; position term = sine embedding + level embedding, one table for every frame
             pos, spatial_shapes, level_start, ref = self._tables(shapes, starts, dev)
             mem = self.transformer.encoder(src, spatial_shapes, level_start, None, pos, None, _reference_points=ref).reshape(B * S, 256)
-            # ---- maps returned in the reference's layout
-            out = [L.tokens_to_nchw(mem, B, 256, h * w, S, starts[i]).view(B, 256, h, w) for i, (h, w) in enumerate(shapes)]
+            # ---- maps returned in the reference's layout (token hand-off: the encoder's fp16 rows, level by level)
+            if _tokens:
+                m16 = self.transformer.encoder.layers[-1]._last_state[1].view(B, S, 256)
+                xt = [m16[:, starts[i]:starts[i] + h * w].contiguous() for i, (h, w) in enumerate(shapes)]
+            else:
+                out = [L.tokens_to_nchw(mem, B, 256, h * w, S, starts[i]).view(B, 256, h, w) for i, (h, w) in enumerate(shapes)]
             # ---- FPN level (res2): lateral conv + GN + top-down bilinear addition, 3x3 output conv + GN + ReLU
             H, Wd = x2.shape[-2:]
             wt, g, b, eps = W["lat"]
@@ -186,6 +207,9 @@ class MSDeformAttnPixelDecoder(nn.Module):
             del conv
             # ---- mask features: 1x1 conv, transposed fp32 store = NCHW directly
             wt, bias = W["mf"]
+            if _tokens:
+                ft = L.linear_f16(y16, wt, bias).view(B, H * Wd, 256)
+                return DecoderTokens(xt, ft, [tuple(s_) for s_ in shapes], H, Wd)
             mf = torch.empty(B, 256, H, Wd, dtype=torch.float32, device=dev)
             L.mask_logits(y16, B, H * Wd, wt, 0, 256, mf, 256 * H * Wd, H * Wd, bias=bias)
         return mf, out[0], out[:self.maskformer_num_feature_levels]

@@ -147,3 +147,42 @@ def test_pixel_decoder_feeds_the_decoder_at_a_real_shape():
     dec.load_state_dict(seeded_params(decoder_param_shapes("video", num_classes=40), seed=0), strict=True)
     out = dec(ms, mf)
     assert out["pred_masks"].shape == (1, 100, 3, 96, 160) and torch.isfinite(out["pred_masks"]).all()
+
+
+def test_token_handoff_equals_the_nchw_path():
+    """pixel_decoder.forward_tokens -> decoder.forward_tokens (fp16 token-major hand-off, no NCHW fp32 round trip) against
+    forward_features -> decoder(x, mask_features) on the same weights and inputs, 4 frames of 384 x 640 as two clips."""
+    from openvis_b200.decoder import VideoMultiScaleMaskedTransformerDecoder
+    from openvis_b200.synthetic import (decoder_param_shapes, seeded_backbone_features, seeded_params,
+                                        seeded_pixel_decoder_params)
+    ch = (256, 512, 1024, 2048)
+    P = seeded_pixel_decoder_params(2, in_channels=ch, L=6)
+    feats = {k: v.cuda() for k, v in seeded_backbone_features(4, 384, 640, in_channels=ch, seed=33).items()}
+    pd = _build(P, ch, 6)
+    dec = VideoMultiScaleMaskedTransformerDecoder(in_channels=256, mask_classification=True, num_classes=40, hidden_dim=256,
+                                                  num_queries=100, nheads=8, dim_feedforward=2048, dec_layers=9, pre_norm=False,
+                                                  mask_dim=256, enforce_input_project=False, num_frames=2).eval().cuda()
+    dec.load_state_dict(seeded_params(decoder_param_shapes("video", num_classes=40), seed=0), strict=True)
+    dec.clips_per_call = 2
+    mf, _, ms = pd.forward_features(feats)
+    a = dec(ms, mf)
+    ref = {k: a[k].clone() for k in ("pred_masks", "pred_logits", "mask_valid")}
+    tok = pd.forward_tokens(feats)
+    assert tok.ft.dtype == torch.float16 and tok.ft.shape == (4, 96 * 160, 256) and [t.shape[1] for t in tok.xt] == [12 * 20, 24 * 40, 48 * 80]
+    n0 = L.launch_count()
+    b = dec.forward_tokens(tok)
+    assert L.launch_count() - n0 > 40
+    pm, rm = b["pred_masks"], ref["pred_masks"]
+    assert pm.shape == rm.shape == (2, 100, 2, 96, 160)
+    sign = ((pm > 0) == (rm > 0)).float().mean().item()
+    close = ((pm - rm).abs() <= 0.25).float().mean().item()
+    print(f"token hand-off vs NCHW path: mask sign agreement {sign:.5f}, within 0.25: {close:.5f}, "
+          f"logits max diff {(b['pred_logits'] - ref['pred_logits']).abs().max().item():.3e}")
+    assert sign >= 0.999 and close >= 0.999
+    assert (b["pred_logits"] - ref["pred_logits"]).abs().max().item() <= 3e-2
+    assert (b["mask_valid"] == ref["mask_valid"]).float().mean().item() >= 0.995
+    with pytest.raises(NotImplementedError):
+        from openvis_b200.decoder import FrameMultiScaleMaskedTransformerDecoder
+        FrameMultiScaleMaskedTransformerDecoder(in_channels=256, mask_classification=True, num_classes=1, hidden_dim=256,
+                                                num_queries=100, nheads=8, dim_feedforward=2048, dec_layers=9, pre_norm=False,
+                                                mask_dim=256, enforce_input_project=False, num_frames=2).eval().cuda().forward_tokens(tok)

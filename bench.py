@@ -826,6 +826,10 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # the result gather runs alone at the end of a step: give NCCL all the channels it can use (measured with
+        # tools/prof_gather.py: 2 GPUs 2.90 -> 2.20 ms, 8 GPUs 3.75 -> 3.46 ms for the 64 clips' 2.7 GB)
+        os.environ.setdefault("NCCL_MIN_NCHANNELS", "64")
+        os.environ.setdefault("NCCL_MAX_NCHANNELS", "64")
         dist.init_process_group("nccl", device_id=dev)
     L.device_check()
     torch.set_grad_enabled(False)

@@ -161,3 +161,38 @@ def test_zero_shot_decoder_vs_oracle_and_reference_golden(golden_dir):
     assert _frac(out["pred_logits"].cpu(), g("pred_logits"), 0.05) >= 0.97
     assert _frac(out["pred_object_logits"].cpu(), g("pred_object_logits"), 0.05) >= 0.97
     assert _frac(out["aux_outputs"][0]["pred_masks"].cpu(), g("aux0_pred_masks"), 0.08) >= 0.9999
+
+
+def test_sweep_tail_at_config5_shape_against_oracle():
+    """The tail of one clip of the 64-clip sweep at its own shape (BASELINE configs[4]: 36 frames of 720 x 1280 padded to
+    736 x 1280, Q = 100, LV-VIS vocabulary K = 1196): OpenVIS OV tail (normalise, 100 * f @ text^T, per-query mean over the valid
+    frames, softmax; openvis.py:123-141) -> top-10 over Q * K -> x4 up-sampling / crop / threshold / bit-pack
+    (video_maskformer.py:215-229, 262-298), composed as bench.py composes it, against the oracle."""
+    import torch.nn.functional as F
+    from openvis_b200 import _lib as L
+    from openvis_b200 import postprocess as PP
+    T, Q, K, pad, img = 36, 100, 1196, (736, 1280), (720, 1280)
+    g = torch.Generator().manual_seed(17)
+    feats = torch.randn(T, Q, 512, generator=g)
+    text = torch.nn.functional.normalize(torch.randn(K, 512, generator=g), dim=-1)
+    valid = torch.rand(T, Q, generator=g) > 0.3
+    valid[:, 7] = False                                           # a query without any valid frame
+    valid[:, 11] = False
+    valid[5, 11] = True                                           # ... and one valid in a single frame
+    masks = torch.randn(Q, T, pad[0] // 4, pad[1] // 4, generator=g) * 4
+    probs, qvalid = ClipLogitHead().open_vocabulary_scores(feats.cuda(), valid.to(torch.uint8).cuda(), text.cuda())
+    lg = O.ov_cosine_logits(feats.reshape(-1, 512), text, 100.0)
+    rp, rv = O.openvis_clip_aggregate(lg[valid.flatten()], valid)
+    assert torch.equal(qvalid.cpu().bool(), rv) and probs.shape == (Q, K)
+    assert (probs.cpu()[rv] - rp).abs().max().item() < 5e-3 and probs.cpu()[~rv].abs().max().item() == 0
+    # top-10 + post-processing on the device scores (the selection itself must be the exact top-10 of those scores)
+    vs, qi, lb, en = L.topk_scores(probs, 10)
+    pc = probs.cpu()
+    sc, idx = pc.flatten().topk(10, sorted=True)
+    assert torch.equal(vs.cpu(), sc) and torch.equal(qi.cpu().long(), idx // K) and torch.equal(lb.cpu().long(), idx % K)
+    bits = L.mask_postprocess(masks.cuda(), qi, pad, img, img)                  # output = image size: the x4 fast path
+    got = PP.PackedMasks(bits, img[1]).unpack().cpu()
+    up = F.interpolate(masks[idx // K], size=pad, mode="bilinear", align_corners=False)[:, :, :img[0], :img[1]]
+    diff = got != (up > 0)
+    assert got.shape == (10, T, img[0], img[1]) and bool((~diff | (up.abs() < 1e-4)).all()), int(diff.sum())
+    assert diff.float().mean().item() < 1e-5

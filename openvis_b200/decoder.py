@@ -523,8 +523,11 @@ class _B200MaskedDecoderBase(nn.Module):
     def _ensure_chain(self, W, ws):
         """(re)builds the phase list when the workspace is new or the weights changed; never inside a graph capture"""
         mode = self._chain_mode(ws)
-        if mode and (ws.get("chain") is None or ws.get("chain_W") is not W or ws.get("chain_mode") != mode):
-            ws["chain"], ws["chain_W"], ws["chain_mode"] = self._build_chain(W, ws), W, mode
+        if mode != ws.get("chain_mode", None) or (mode and ws.get("chain_W") is not W):
+            # a captured layer loop belongs to the schedule (and, for the wide chain, to the barrier words) it was captured
+            # with: drop it before the chain it refers to goes away
+            ws["graph"] = None
+            ws["chain"], ws["chain_W"], ws["chain_mode"] = (self._build_chain(W, ws) if mode else None), W, mode
 
     WIDE_CHAIN_MAX_ROWS = 16384          # what the wide chain can take (its split workspace)
     WIDE_CHAIN_AUTO_ROWS = 2048          # where it beats the launch-per-op schedule (profiles/experiments/chain_r2.md)

@@ -221,3 +221,29 @@ def test_chain_mode_selection():
     assert m200._chain_mode(ws(2, 400)) == "wide"              # 200-query groups fit the wide chain's CTA-wide self-attention
     m200.use_chain = True
     assert m200._chain_mode(ws(2, 400)) is None                # ... but not the one-warp-per-head group chain
+
+
+def test_forward_tokens_argument_checks():
+    """decoder.forward_tokens: Video decoders only, strides 32 / 16 / 8 / 4 of a /32-padded input -- rejected before any
+    device work (no GPU needed for the error paths)."""
+    import pytest
+    import torch
+    from openvis_b200 import decoder as D
+    from openvis_b200.pixel_decoder import DecoderTokens
+    kw = dict(in_channels=256, mask_classification=True, num_classes=1, hidden_dim=256, num_queries=100, nheads=8,
+              dim_feedforward=2048, dec_layers=9, pre_norm=False, mask_dim=256, enforce_input_project=False, num_frames=2)
+    H4, W4 = 32, 48
+    ok_sizes = [(H4 // s, W4 // s) for s in (8, 4, 2)]
+    mk = lambda sizes, h4=H4, w4=W4: DecoderTokens([torch.zeros(2, h * w, 256, dtype=torch.float16) for h, w in sizes],
+                                                   torch.zeros(2, h4 * w4, 256, dtype=torch.float16), sizes, h4, w4)
+    v = D.VideoMultiScaleMaskedTransformerDecoder(**kw).eval()
+    with pytest.raises(NotImplementedError):
+        v.forward_tokens(mk([(4, 6), (8, 12), (15, 24)]))                      # not the /2 pyramid of the mask features
+    with pytest.raises(NotImplementedError):
+        v.forward_tokens(mk([(3, 5), (7, 11), (15, 23)], 30, 46))              # H/4, W/4 not multiples of 8
+    with pytest.raises(NotImplementedError):
+        D.FrameMultiScaleMaskedTransformerDecoder(**kw).eval().forward_tokens(mk(ok_sizes))
+    with pytest.raises(NotImplementedError):
+        D.SideAdapterVideoMultiScaleMaskedTransformerDecoder(clip_heads=12, **kw).eval().forward_tokens(mk(ok_sizes))
+    with pytest.raises(RuntimeError):
+        v.train().forward_tokens(mk(ok_sizes))

@@ -247,3 +247,24 @@ def test_forward_tokens_argument_checks():
         D.SideAdapterVideoMultiScaleMaskedTransformerDecoder(clip_heads=12, **kw).eval().forward_tokens(mk(ok_sizes))
     with pytest.raises(RuntimeError):
         v.train().forward_tokens(mk(ok_sizes))
+
+
+def test_bench_workloads_cover_every_baseline_config():
+    """bench.py: one workload per BASELINE.json config (metric / unit as BASELINE names them, the default = the 64-clip scaling
+    sweep on the LV-VIS vocabulary, shapes of the named configs)."""
+    import json
+    import os
+    import bench
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    base = json.load(open(os.path.join(root, "BASELINE.json")))
+    assert len(base["configs"]) == 5 and base["metric"].startswith(bench.METRIC) and bench.UNIT == "frames/s"
+    named = " ".join(bench.BASELINE_CONFIG.values())
+    assert all(f"configs[{i}]" in named for i in range(5))
+    W = bench.WORKLOADS
+    assert set(W) == set(bench.BASELINE_CONFIG) and bench.DEFAULT_WORKLOAD in W and set(bench.OTHER_CONFIGS) <= set(W)
+    pipe, kind, T, Hp, Wp, out_hw, Q, K, total = W[bench.DEFAULT_WORKLOAD]
+    assert (T, out_hw, Q, K, total) == (36, (720, 1280), 100, 1196, 64) and Hp % 32 == 0 and Wp % 32 == 0      # configs[4] on configs[1]'s clip
+    assert W["openvis_video_5x360x640_q100_k40"][2:8] == (5, 384, 640, (360, 640), 100, 40)                      # configs[0]
+    assert W["openvis_video_36x720x1280_q100_k40"][2:8] == (36, 736, 1280, (720, 1280), 100, 40)                 # configs[1]
+    assert W["brivis_frame_36x360x640_q100_k1196"][0] == "brivis" and W["brivis_frame_36x360x640_q100_k1196"][7] == 1196    # configs[2]
+    assert W["san_online_36x720x1280_q200_k1196"][6] == 200                                                      # configs[3]
